@@ -1,0 +1,145 @@
+"""CPU model of the B200 engine's RESTRUCTURED algorithm  --  TEST INFRASTRUCTURE, NOT PRODUCT.
+
+The CUDA engine does not evaluate WaveGlow.infer (model.py:223-274) op by op.  It uses an
+algebraically equivalent form that suits one fused tcgen05 kernel per WN layer:
+
+  * activations are time-major  [B, T', C]  (C contiguous == K-major MMA operand);
+  * the conditioning 1x1 conv (model.py:121) is a K-extension of each layer's dilated conv:
+        in_i(t) = [W_in_i(tap-1) | W_in_i(tap0) | W_in_i(tap+1) | W_cond_i] . [x(t-d); x(t); x(t+d); S(t)]
+    with the two biases folded;
+  * the skip path and the `end` 1x1 conv (model.py:130-137) are folded per layer:
+        end(sum_i skip_i) = sum_i (W_end W_skip_i) acts_i + (W_end sum_i b_skip_i + b_end)
+    so each layer emits only 2h <= 8 "skip-end" channels accumulated in fp32 (`e`);
+  * the residual stream x is carried in the MMA operand dtype (fp16 by default) and updated
+    on the tensor core:  x <- [W_res_i | I] . [acts; x] + b_res_i;
+  * the audio state is time-major [B, T', 8]; live channels are the LAST C slots, so the two
+    early-output concats (model.py:260-271) and the final de-squeeze (model.py:273) are no-ops.
+
+This file restates that pipeline in torch on the CPU with the same rounding points
+(`op_dtype`: torch.float16 / torch.bfloat16 / torch.float32 = no rounding) so that
+  (1) tests can show the restructuring is exact (op_dtype=float32 vs the oracle, ~1e-6), and
+  (2) the tolerance budget of the fp16/bf16 modes is derived on CPU before any GPU run, and
+  (3) per-layer intermediates are available to localise a GPU mismatch.
+"""
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+from . import waveglow_oracle as O
+
+Tensor = torch.Tensor
+
+
+def rnd(x: Tensor, dt: torch.dtype) -> Tensor:
+  return x if dt == torch.float32 else x.to(dt).to(torch.float32)
+
+
+class PackedFlow:
+  """Per-flow packed weights in the engine's layout (fp32 master values, rounded on use)."""
+
+  def __init__(self, w: Dict[str, Tensor], dims: O.ModelDims, k: int):
+    nc, L = dims.n_channels, dims.n_layers
+    p = f"WN.{k}."
+    c = dims.flow_channels[k]
+    h = c // 2
+    self.h, self.c = h, c
+    self.w_start = w[p + "start.weight"][:, :, 0].double()       # [nc, h]
+    self.b_start = w[p + "start.bias"].double()
+    w_end = w[p + "end.weight"][:, :, 0].double()                 # [2h, nc]
+    w_cond = w[p + "cond_layer.weight"][:, :, 0].double()         # [2 nc L, 640]
+    b_cond = w[p + "cond_layer.bias"].double()
+    self.w1: List[Tensor] = []   # [2nc, 3nc + 640]   columns: tap-1 | tap0 | tap+1 | mel
+    self.b1: List[Tensor] = []
+    self.w_res: List[Optional[Tensor]] = []   # [nc, nc]
+    self.b_res: List[Optional[Tensor]] = []
+    self.w_se: List[Tensor] = []   # [2h, nc]  skip-end fold
+    e_bias = w[p + "end.bias"].double().clone()
+    for i in range(L):
+      wi = w[p + f"in_layers.{i}.weight"].double()                # [2nc, nc, 3]
+      cat = torch.cat([wi[:, :, 0], wi[:, :, 1], wi[:, :, 2], w_cond[2 * nc * i: 2 * nc * (i + 1)]], dim=1)
+      self.w1.append(cat.float())
+      self.b1.append((w[p + f"in_layers.{i}.bias"].double() + b_cond[2 * nc * i: 2 * nc * (i + 1)]).float())
+      wrs = w[p + f"res_skip_layers.{i}.weight"][:, :, 0].double()
+      brs = w[p + f"res_skip_layers.{i}.bias"].double()
+      if i < L - 1:
+        self.w_res.append(wrs[:nc].float())
+        self.b_res.append(brs[:nc].float())
+        w_skip, b_skip = wrs[nc:], brs[nc:]
+      else:
+        self.w_res.append(None)
+        self.b_res.append(None)
+        w_skip, b_skip = wrs, brs
+      self.w_se.append((w_end @ w_skip).float())
+      e_bias = e_bias + w_end @ b_skip
+    self.e_bias = e_bias.float()                                  # [2h]: rows [:h] -> b, [h:] -> s
+    self.w_start = self.w_start.float()
+    self.b_start = self.b_start.float()
+    W = w[f"convinv.{k}.conv.weight"][:, :, 0]
+    self.w_inv = W.float().inverse()                              # model.py:51-53
+
+
+def shift_time(x: Tensor, s: int) -> Tensor:
+  """y[:, t] = x[:, t + s] with zeros outside [0, T')  (zero padding of the dilated conv, model.py:100-102)."""
+  if s == 0:
+    return x
+  y = torch.zeros_like(x)
+  T = x.size(1)
+  if abs(s) >= T:
+    return y
+  if s > 0:
+    y[:, : T - s] = x[:, s:]
+  else:
+    y[:, -s:] = x[:, : T + s]
+  return y
+
+
+def wn_layers(pf: PackedFlow, dims: O.ModelDims, x: Tensor, S: Tensor, op_dtype: torch.dtype,
+              trace: Optional[list] = None) -> Tensor:
+  """x: [B,T',nc] (already in op_dtype precision), S: [B,T',640].  Returns e [B,T',2h] fp32 (without e_bias)."""
+  nc = dims.n_channels
+  e = torch.zeros(x.size(0), x.size(1), 2 * pf.h, dtype=torch.float32)
+  for i in range(dims.n_layers):
+    d = 2 ** i
+    a = torch.cat([shift_time(x, -d), x, shift_time(x, d), S], dim=2)          # [B,T',3nc+640]
+    pre = a @ rnd(pf.w1[i], op_dtype).t() + pf.b1[i]                           # fp32 accumulate
+    acts = rnd(torch.tanh(pre[..., :nc]) * torch.sigmoid(pre[..., nc:]), op_dtype)
+    e = e + acts @ rnd(pf.w_se[i], op_dtype).t()
+    if pf.w_res[i] is not None:
+      x = rnd(x + acts @ rnd(pf.w_res[i], op_dtype).t() + pf.b_res[i], op_dtype)
+    if trace is not None:
+      trace.append({"layer": i, "acts": acts.clone(), "x": x.clone(), "e": e.clone()})
+  return e
+
+
+def upsample_squeeze_tm(w: Dict[str, Tensor], dims: O.ModelDims, mel: Tensor, n_samples: Optional[int] = None) -> Tensor:
+  """Time-major squeezed conditioning S[b, t', c*8+j] = up[b, c, 8t'+j]  (model.py:225-232)."""
+  return O.upsample_squeeze(w, dims, mel, n_samples).permute(0, 2, 1).contiguous()
+
+
+def pack_noise(dims: O.ModelDims, zs: Sequence[Tensor], sigma: float) -> Tensor:
+  """Initial audio state [B,T',8]: slots = [z_last_early ... z_first_early, z_init] * sigma."""
+  parts = [sigma * z.permute(0, 2, 1) for z in zs]      # zs order: init, early(k=8), early(k=4)
+  return torch.cat(list(reversed(parts)), dim=2).contiguous()
+
+
+def infer(w: Dict[str, Tensor], dims: O.ModelDims, mel: Tensor, sigma: float, zs: Sequence[Tensor],
+          op_dtype: torch.dtype = torch.float16, trace: Optional[list] = None) -> Tensor:
+  S = rnd(upsample_squeeze_tm(w, dims, mel), op_dtype)
+  state = pack_noise(dims, zs, sigma)                   # [B,T',8] fp32
+  G = dims.n_group
+  for k in reversed(range(dims.n_flows)):
+    pf = PackedFlow(w, dims, k)
+    c, h = pf.c, pf.h
+    a0 = state[..., G - c: G - c + h]
+    a1 = state[..., G - c + h:]
+    x = rnd(a0 @ pf.w_start.t() + pf.b_start, op_dtype)
+    tr = [] if trace is not None else None
+    e = wn_layers(pf, dims, x, S, op_dtype, tr) + pf.e_bias
+    b, s = e[..., :h], e[..., h:]
+    a1 = (a1 - b) * torch.exp(-s)
+    live = torch.cat([a0, a1], dim=2) @ pf.w_inv.t()
+    state = torch.cat([state[..., : G - c], live], dim=2)
+    if trace is not None:
+      trace.append({"flow": k, "layers": tr, "e": e.clone(), "state": state.clone()})
+  return state.reshape(state.size(0), -1)
