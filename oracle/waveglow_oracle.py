@@ -188,7 +188,7 @@ def forward(w: Dict[str, Tensor], dims: ModelDims, mel: Tensor, audio: Tensor) -
       output_audio.append(audio[:, :dims.n_early_size, :])
       audio = audio[:, dims.n_early_size:, :]
     W = w[f"convinv.{k}.conv.weight"]
-    log_det_W = audio.size(0) * audio.size(2) * torch.logdet(W.squeeze(-1))
+    log_det_W = audio.size(0) * audio.size(2) * torch.logdet(W.squeeze())
     audio = F.conv1d(audio, W)
     log_det_W_list.append(log_det_W)
     n_half = audio.size(1) // 2

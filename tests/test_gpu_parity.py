@@ -1,0 +1,194 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI.
+
+Stage-by-stage checks compare the engine's intermediates with oracle/engine_model.py (same restructured
+algorithm, same rounding points); end-to-end checks compare with the golden vectors produced by the
+unmodified reference and, at larger sizes, use size-independent properties."""
+import pytest
+import torch
+
+from oracle import engine_model as E
+from oracle import waveglow_oracle as O
+from tests.helpers import (FP16_MAX_ABS, FP16_MIN_SNR_DB, FP32_MAX_ABS, golden_noise, load_golden, max_abs, snr_db,
+                           synthetic_weights)
+from waveglow_b200.model import WaveGlow
+from waveglow_b200.synthetic import synthetic_mel, synthetic_noise
+
+pytestmark = pytest.mark.gpu
+
+_MODELS = {}
+
+
+def get_model(n_channels: int, precision: str, style: str = "parametrized") -> WaveGlow:
+  key = (n_channels, precision, style)
+  if key not in _MODELS:
+    hp, sd, w, dims = synthetic_weights(n_channels, style)
+    m = WaveGlow(hp, precision=precision).to("cuda:0")
+    m.load_state_dict(sd)
+    _MODELS[key] = WaveGlow.remove_weightnorm(m).eval()
+  return _MODELS[key]
+
+
+def run(model, mel, zs, sigma):
+  out = model.infer_with_noise(mel.cuda(), [z.cuda() for z in zs], sigma)
+  torch.cuda.synchronize()
+  return out.cpu()
+
+
+def test_tcgen05_descriptor_gemm():
+  """TMA(SWIZZLE_128B) -> tcgen05.mma(kind::f16) -> tcgen05.ld in isolation: D = A . B^T."""
+  eng = get_model(256, "fp16").engine()
+  g = torch.Generator().manual_seed(0)
+  for dt in (torch.float16, torch.bfloat16):
+    a = (torch.randn((256, 320), generator=g)).to(dt)
+    b = (torch.randn((512, 320), generator=g)).to(dt)
+    d = eng.debug_gemm(a.cuda(), b.cuda()).cpu()
+    torch.cuda.synchronize()
+    ref = a.double() @ b.double().t()
+    err = float((d.double() - ref).abs().max())
+    print(f"debug gemm {dt}: max err {err:.3e} (ref absmax {float(ref.abs().max()):.2f})")
+    assert err <= 2e-3, f"tcgen05 GEMM mismatch for {dt}: {err}"
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_stagewise_first_flow(precision):
+  """cond (upsample+squeeze), start conv, then every WN layer of the first flow, then the coupling step."""
+  op_dtype = torch.float32 if precision == "fp32" else torch.float16
+  tol = 2e-5 if precision == "fp32" else 6e-3      # intermediates are O(1..10); fp16 has 2^-11 relative steps
+  hp, sd, w, dims = synthetic_weights(256)
+  model = get_model(256, precision)
+  eng = model.engine()
+  B, F = 2, 7            # T' = 224: one full and one ragged 128-tile, dilation 128 reaches across both
+  T = F * 32
+  mel = synthetic_mel(B, F, 31)
+  zs = synthetic_noise(hp, B, T, 32)
+  sigma = 0.8
+  trace = []
+  with torch.no_grad():
+    ref_audio = E.infer(w, dims, mel, sigma, zs, op_dtype, trace)
+  k = dims.n_flows - 1
+  flow_tr = trace[0]
+  assert flow_tr["flow"] == k
+  S_ref = E.rnd(E.upsample_squeeze_tm(w, dims, mel), op_dtype)
+  pf = E.PackedFlow(w, dims, k)
+  state0 = E.pack_noise(dims, zs, sigma)
+  x0_ref = E.rnd(state0[..., 4:6] @ pf.w_start.t() + pf.b_start, op_dtype)
+  failures = []
+
+  def check(name, got, ref, t=tol):
+    err = float((got.double() - ref.double()).abs().max())
+    scale = float(ref.abs().max())
+    print(f"[{precision}] {name}: max err {err:.3e} (ref absmax {scale:.3f})")
+    if not err <= t * max(1.0, scale):
+      failures.append(f"{name}: {err:.3e}")
+
+  try:
+    eng.debug_stop_after(k, -1)
+    run(model, mel, zs, sigma)
+    check("cond", eng.debug_view("cond", B, F).float().view(B, T, 640).cpu(), S_ref)
+    check("x after start", eng.debug_view("x0", B, F).float().view(B, T, 256).cpu(), x0_ref)
+    for i in range(dims.n_layers):
+      eng.debug_stop_after(k, i)
+      run(model, mel, zs, sigma)
+      lt = flow_tr["layers"][i]
+      check(f"e after layer {i}", eng.debug_view("e", B, F).view(B, T, 8).cpu()[..., : 2 * pf.h], lt["e"])
+      if i < dims.n_layers - 1:
+        buf = "x1" if (i + 1) % 2 == 1 else "x0"
+        check(f"x after layer {i}", eng.debug_view(buf, B, F).float().view(B, T, 256).cpu(), lt["x"])
+    eng.debug_stop_after(k, dims.n_layers)
+    state = run(model, mel, zs, sigma).view(B, T, 8)
+    check("state after first flow", state, flow_tr["state"], t=tol)
+  finally:
+    eng.debug_stop_after(-1, 0)
+  out = run(model, mel, zs, sigma)
+  check("final audio vs engine model", out, ref_audio, t=(2e-5 if precision == "fp32" else 2e-3))
+  assert not failures, "; ".join(failures)
+
+
+@pytest.mark.parametrize("name", ["infer_c256_b2_f12", "infer_c256_b1_f40", "infer_c256_b3_f7_ragged",
+                                  "infer_c256_b1_f11_sigma0", "infer_c512_b1_f10"])
+def test_fp32_mode_matches_reference_golden(name):
+  g = load_golden(name)
+  model = get_model(int(g["n_channels"]), "fp32", str(g["weight_style"]))
+  out = run(model, torch.from_numpy(g["mel"]), golden_noise(g), float(g["sigma"]))
+  ref = torch.from_numpy(g["audio"])
+  err = max_abs(ref, out)
+  print(f"fp32 {name}: max-abs {err:.3e}")
+  assert out.shape == ref.shape and err <= FP32_MAX_ABS
+
+
+@pytest.mark.parametrize("name", ["infer_c256_b2_f12", "infer_c256_b1_f40", "infer_c256_b3_f7_ragged",
+                                  "infer_c256_b1_f11_sigma0"])
+def test_fp16_tensor_core_mode_matches_reference_golden(name):
+  g = load_golden(name)
+  model = get_model(256, "fp16", str(g["weight_style"]))
+  out = run(model, torch.from_numpy(g["mel"]), golden_noise(g), float(g["sigma"]))
+  ref = torch.from_numpy(g["audio"])
+  err, snr = max_abs(ref, out), snr_db(ref, out)
+  print(f"fp16 {name}: max-abs {err:.3e}  snr {snr:.1f} dB")
+  assert out.shape == ref.shape
+  assert err <= FP16_MAX_ABS and snr >= FP16_MIN_SNR_DB
+
+
+def test_fp16_vs_oracle_medium_size():
+  """B=4 x 2.3 s: against the oracle itself (CPU, a few seconds)."""
+  hp, sd, w, dims = synthetic_weights(256)
+  model = get_model(256, "fp16")
+  B, F = 4, 200
+  mel = synthetic_mel(B, F, 1001)
+  zs = synthetic_noise(hp, B, F * 32, 9)
+  with torch.no_grad():
+    ref = O.infer(w, dims, mel, 0.666, zs)
+  out = run(model, mel, zs, 0.666)
+  err, snr = max_abs(ref, out), snr_db(ref, out)
+  print(f"fp16 B4 F200: max-abs {err:.3e}  snr {snr:.1f} dB")
+  assert err <= FP16_MAX_ABS and snr >= FP16_MIN_SNR_DB
+
+
+def test_seed_semantics_and_determinism():
+  """model.infer draws its noise from torch's global CUDA generator in the reference's order; same seed, same audio."""
+  model = get_model(256, "fp16")
+  mel = synthetic_mel(1, 16, 5).cuda()
+  torch.manual_seed(123)
+  a = model.infer(mel, sigma=0.7)
+  torch.manual_seed(123)
+  zs = model.draw_noise(1, 16 * 32, mel.device)
+  b = model.infer_with_noise(mel, zs, 0.7)
+  torch.manual_seed(123)
+  c = model.infer(mel, sigma=0.7)
+  assert torch.equal(a, b) and torch.equal(a, c)
+  assert a.shape == (1, 16 * 256) and a.dtype == torch.float32 and a.device == mel.device
+  assert torch.isfinite(a).all()
+
+
+def test_batch_independence_and_locality_full_length():
+  """Size-independent properties at the benchmark's utterance length (10 s, F=861):
+  (1) utterance b of a batch equals the same utterance synthesised alone (no cross-batch interaction);
+  (2) a WN sees +-255 group-steps per flow => changing the mel after frame f0 cannot change audio more than
+      12 flows * 255 group-steps (+ the 4-frame upsampler support) before it."""
+  hp, sd, w, dims = synthetic_weights(256)
+  model = get_model(256, "fp16")
+  B, F = 3, 861
+  mel = synthetic_mel(B, F, 1002)
+  zs = synthetic_noise(hp, B, F * 32, 10)
+  full = run(model, mel, zs, 0.666)
+  assert torch.isfinite(full).all()
+  alone = run(model, mel[1:2], [z[1:2] for z in zs], 0.666)
+  assert torch.equal(full[1:2], alone)
+  f0 = 600
+  mel2 = mel.clone()
+  mel2[:, :, f0:] = synthetic_mel(B, F - f0, 77)
+  full2 = run(model, mel2, zs, 0.666)
+  reach = (12 * 255 + 3 * 32) * 8
+  cut = f0 * 256 - reach
+  assert torch.equal(full[:, :cut], full2[:, :cut])
+  assert not torch.equal(full[:, f0 * 256:], full2[:, f0 * 256:])
+
+
+def test_errors_are_loud():
+  from waveglow_b200.engine import WgError
+  model = get_model(256, "fp16")
+  mel = synthetic_mel(1, 4, 5).cuda()
+  with pytest.raises(WgError, match="noise tensors"):
+    model.infer_with_noise(mel, [torch.zeros(1, 4, 128).cuda()], 1.0)
+  with pytest.raises(ValueError):
+    model.infer_with_noise(torch.zeros(1, 3, 4).cuda(), [], 1.0)

@@ -1,0 +1,121 @@
+"""CPU: the C ABI loads and exports what include/waveglow_b200.h declares; host-side mirror of the reference interface."""
+import ctypes
+import dataclasses
+import os
+import re
+
+import pytest
+import torch
+
+import __graft_entry__ as graft
+from tests.helpers import synthetic_weights
+from waveglow_b200 import engine as wg_engine
+from waveglow_b200.hparams import HParams, get_dataclass_from_dict, overwrite_custom_hparams
+from waveglow_b200.model import WaveGlow
+from waveglow_b200.synthetic import flow_channels, synthetic_noise, synthetic_state_dict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+  graft.build()
+  return wg_engine.load_library()
+
+
+def test_library_exports_every_declared_symbol(lib):
+  header = open(os.path.join(ROOT, "include", "waveglow_b200.h")).read()
+  declared = set(re.findall(r"\b(wg_[a-z_0-9]+)\s*\(", header))
+  declared -= {"wg_status", "wg_precision"}
+  assert {"wg_create", "wg_load_weights", "wg_infer", "wg_forward", "wg_workspace_bytes", "wg_destroy"} <= declared
+  for sym in sorted(declared):
+    assert hasattr(lib, sym), f"{sym} declared in the header but not exported"
+  assert set(wg_engine.EXPORTED_SYMBOLS) <= declared
+  assert b"sm_100a" in lib.wg_version()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_create_fails_loudly_without_gpu(lib):
+  """No CPU fallback: without a device wg_create returns WG_ERR_CUDA and says why."""
+  hp = HParams()
+  cfg = wg_engine._Config(hp.n_mel_channels, hp.n_flows, hp.n_group, hp.n_early_every, hp.n_early_size, hp.n_layers,
+                          hp.n_channels, hp.kernel_size, hp.segment_length, wg_engine.PRECISION_FP16, 0)
+  h = ctypes.c_void_p()
+  rc = lib.wg_create(ctypes.byref(cfg), ctypes.byref(h))
+  assert rc == -3
+  assert b"no CPU fallback" in lib.wg_last_error(h)
+  lib.wg_destroy(h)
+
+
+def test_create_rejects_unsupported_hparams(lib):
+  hp = HParams()
+  cfg = wg_engine._Config(hp.n_mel_channels, hp.n_flows, 4, hp.n_early_every, hp.n_early_size, hp.n_layers,
+                          hp.n_channels, hp.kernel_size, hp.segment_length, wg_engine.PRECISION_FP16, 0)
+  h = ctypes.c_void_p()
+  rc = lib.wg_create(ctypes.byref(cfg), ctypes.byref(h))
+  assert rc == -2 and b"n_group=8" in lib.wg_last_error(h)
+  lib.wg_destroy(h)
+
+
+def test_model_infer_on_cpu_raises():
+  model = WaveGlow(HParams())
+  with pytest.raises(wg_engine.WgError, match="no CPU fallback"):
+    model.infer(torch.zeros(1, 80, 4), sigma=1.0)
+
+
+def test_hparams_field_names_and_overrides():
+  hp = HParams()
+  d = dataclasses.asdict(hp)
+  for name, val in dict(n_mel_channels=80, n_flows=12, n_group=8, n_early_every=4, n_early_size=2, n_layers=8,
+                        n_channels=256, kernel_size=3, segment_length=16000, sampling_rate=22050, sigma=1.0).items():
+    assert d[name] == val
+  hp2 = overwrite_custom_hparams(hp, {"n_channels": "512"})
+  assert hp2.n_channels == 512 and isinstance(hp2.n_channels, int)
+  with pytest.raises(Exception):
+    overwrite_custom_hparams(hp, {"nope": "1"})
+  hp3, ignored = get_dataclass_from_dict({**d, "legacy_field": 3})
+  assert hp3 == hp and ignored == {"legacy_field"}
+
+
+@pytest.mark.parametrize("style", ["parametrized", "legacy"])
+def test_state_dict_layout_and_three_key_styles(style):
+  """The module tree ingests the reference's checkpoint layouts and folds like remove_weightnorm."""
+  hp, sd, w, dims = synthetic_weights(256, style)
+  model = WaveGlow(hp)
+  if style == "parametrized":
+    assert set(model.state_dict().keys()) == set(sd.keys()) and len(sd) == 686
+  res = model.load_state_dict(sd)
+  assert not res.missing_keys and not res.unexpected_keys
+  model = WaveGlow.remove_weightnorm(model)
+  folded_sd = model.state_dict()
+  assert len(folded_sd) == 470
+  for k, v in model.folded_weights().items():
+    assert torch.equal(v, w[k]), k
+  # already-folded checkpoints load too
+  model2 = WaveGlow.remove_weightnorm(WaveGlow(hp))
+  res = model2.load_state_dict(folded_sd)
+  assert not res.missing_keys and not res.unexpected_keys
+
+
+def test_flow_channels_and_noise_shapes():
+  hp = HParams()
+  assert flow_channels(hp) == [8, 8, 8, 8, 6, 6, 6, 6, 4, 4, 4, 4]
+  zs = synthetic_noise(hp, 3, 64, 1)
+  assert [tuple(z.shape) for z in zs] == [(3, 4, 64), (3, 2, 64), (3, 2, 64)]
+  model = WaveGlow.__new__(WaveGlow)
+  torch.nn.Module.__init__(model)
+  model.n_remaining_channels, model.n_flows, model.n_early_every, model.n_early_size = 4, 12, 4, 2
+  torch.manual_seed(5)
+  a = model.draw_noise(2, 32, torch.device("cpu"))
+  from oracle import waveglow_oracle as O
+  torch.manual_seed(5)
+  b = O.draw_noise(O.ModelDims(), 2, 32)
+  assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_synthetic_checkpoint_is_deterministic_and_non_degenerate():
+  hp = HParams()
+  a = synthetic_state_dict(hp, 7)
+  b = synthetic_state_dict(hp, 7)
+  assert all(torch.equal(a[k], b[k]) for k in a)
+  assert float(a["WN.0.end.weight"].abs().max()) > 0   # the reference zero-inits `end`: would hide the WN kernels

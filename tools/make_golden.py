@@ -1,0 +1,99 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) in the build container.
+
+  python tools/make_golden.py
+
+Each fixture holds: the mel input, the pre-drawn noise tensors (drawn from torch's global CPU generator in
+the order the reference draws them), the reference's `WaveGlow.infer` output, and the recipe for the
+weights (`synthetic_state_dict(hparams, weight_seed)` -- deterministic, so the 352 MB checkpoint is not
+committed).  The script asserts that oracle/waveglow_oracle.py reproduces the reference bit-for-bit before
+writing anything, which is what pins the oracle.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+from oracle import waveglow_oracle as O  # noqa: E402
+from ref_loader import load_reference  # noqa: E402
+from waveglow_b200.hparams import HParams  # noqa: E402
+from waveglow_b200.synthetic import synthetic_mel, synthetic_state_dict  # noqa: E402
+
+CASES = [
+  # name, n_channels, batch, frames, sigma, noise seed, mel seed, weight style
+  ("infer_c256_b2_f12", 256, 2, 12, 0.666, 11, 1001, "parametrized"),
+  ("infer_c256_b1_f40", 256, 1, 40, 1.0, 12, 1002, "parametrized"),
+  ("infer_c256_b3_f7_ragged", 256, 3, 7, 0.666, 13, 1003, "legacy"),
+  ("infer_c256_b1_f11_sigma0", 256, 1, 11, 0.0, 14, 1004, "parametrized"),
+  ("infer_c512_b1_f10", 512, 1, 10, 0.666, 15, 1005, "parametrized"),
+]
+FWD_CASES = [
+  # name, n_channels, batch, n_samples, frames, seed
+  ("forward_c256_b2_t2048", 256, 2, 2048, 8, 21),
+  ("forward_c256_b1_t4000", 256, 1, 4000, 16, 22),
+]
+WEIGHT_SEED = 1234
+
+
+def main():
+  WaveGlow, RefHParams = load_reference()
+  out_dir = os.path.join(ROOT, "tests", "golden")
+  os.makedirs(out_dir, exist_ok=True)
+  models = {}
+
+  def get_model(nc, style):
+    key = (nc, style)
+    if key not in models:
+      hp = HParams(n_channels=nc)
+      sd = synthetic_state_dict(hp, WEIGHT_SEED, style=style)
+      m = WaveGlow(RefHParams(n_channels=nc))
+      missing = m.load_state_dict(sd)
+      assert not missing.missing_keys and not missing.unexpected_keys, missing
+      m = WaveGlow.remove_weightnorm(m).eval()
+      models[key] = (m, O.fold_weight_norm(sd), O.ModelDims(n_channels=nc))
+    return models[key]
+
+  for name, nc, B, F, sigma, seed, mel_seed, style in CASES:
+    m, w, dims = get_model(nc, style)
+    mel = synthetic_mel(B, F, mel_seed)
+    torch.manual_seed(seed)
+    with torch.no_grad():
+      ref = m.infer(mel, sigma=sigma)
+    torch.manual_seed(seed)
+    zs = O.draw_noise(dims, B, F * 32)
+    with torch.no_grad():
+      mine = O.infer(w, dims, mel, sigma, zs)
+    assert torch.equal(ref, mine), f"{name}: oracle is not bit-identical to the reference"
+    np.savez_compressed(os.path.join(out_dir, name + ".npz"), mel=mel.numpy(), audio=ref.numpy(), sigma=np.float32(sigma),
+                        n_channels=np.int32(nc), weight_seed=np.int32(WEIGHT_SEED), weight_style=np.array(style),
+                        **{f"z{i}": z.numpy() for i, z in enumerate(zs)})
+    print(f"{name}: audio {tuple(ref.shape)} absmax {ref.abs().max():.3f}  (oracle bit-identical)")
+
+  for name, nc, B, T, F, seed in FWD_CASES:
+    m, w, dims = get_model(nc, "parametrized")
+    mel = synthetic_mel(B, F, 2000 + seed)
+    g = torch.Generator().manual_seed(seed)
+    audio = torch.rand((B, T), generator=g) * 2 - 1
+    with torch.no_grad():
+      z, log_s_list, log_det_W_list = m((mel, audio))
+      z2, ls2, ld2 = O.forward(w, dims, mel, audio)
+    assert torch.equal(z, z2) and all(torch.equal(a, b) for a, b in zip(log_s_list, ls2))
+    # fp32 logdet goes through LAPACK's LU and depends on the operand's memory layout at the last bits;
+    # log_det_W = B * T' * logdet(W) amplifies that by B * T'
+    atol = 2e-6 * B * (T // 8)
+    assert all(torch.allclose(a, b, rtol=1e-5, atol=atol) for a, b in zip(log_det_W_list, ld2))
+    np.savez_compressed(os.path.join(out_dir, name + ".npz"), mel=mel.numpy(), audio_in=audio.numpy(), z=z.numpy(),
+                        log_s_sum=np.array([float(t.double().sum()) for t in log_s_list]),
+                        log_det_w=np.array([float(t) for t in log_det_W_list]),
+                        loss=np.float64(O.loss(z, log_s_list, log_det_W_list, 1.0)),
+                        n_channels=np.int32(nc), weight_seed=np.int32(WEIGHT_SEED),
+                        **{f"log_s{k}": t.numpy() for k, t in enumerate(log_s_list)})
+    print(f"{name}: z {tuple(z.shape)}  (oracle bit-identical)")
+
+
+if __name__ == "__main__":
+  main()

@@ -1,0 +1,783 @@
+// wg_engine.cu -- C ABI (include/waveglow_b200.h), host-side weight packing and launch orchestration
+// of the B200 WaveGlow flow engine.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo
+// -O3 -shared -Xcompiler -fPIC wg_engine.cu -o libwaveglow_b200.so  (no libcuda link: the one driver
+// entry point needed, cuTensorMapEncodeTiled, is fetched through cudaGetDriverEntryPoint).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/waveglow_b200.h"
+#include "wg_kernels.cuh"
+#include "wg_layer_tc.cuh"
+
+namespace {
+
+using namespace wg;
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct FlowPack {
+  int C = 0, h = 0;
+  float e_bias[kGroup] = {0};
+  float w_inv[kGroup * kGroup] = {0};
+  double logdet = 0.0;          // log |det W_k|
+  float w_fwd[kGroup * kGroup] = {0};   // forward 1x1 weight (row-major C x C)
+  float* d_w_start = nullptr;   // [nc, h]
+  float* d_b_start = nullptr;   // [nc]
+};
+
+}  // namespace
+
+struct wg_engine {
+  wg_config cfg{};
+  std::string err;
+  bool loaded = false;
+  int launches = 0;
+  int dbg_flow = -1, dbg_layer = 0;
+  std::vector<int> flowC;             // live channels per flow
+  std::vector<FlowPack> flows;
+  // upsample
+  float* d_up_w = nullptr;            // Wp[32][320][640]
+  float* d_up_b = nullptr;            // [80]
+  // fp16 tensor-core path
+  void* d_w1 = nullptr;               // [flows*layers*512][1408] 16-bit
+  void* d_w2 = nullptr;               // [flows*layers*272][256] 16-bit
+  void* d_ident = nullptr;            // [64][64] 16-bit identity
+  float* d_bias1 = nullptr;           // [flows*layers][512] packed order
+  float* d_bias_res = nullptr;        // [flows*layers][256]
+  CUtensorMap tm_w1{}, tm_w2a{}, tm_w2b{}, tm_ident{};
+  // fp32 path
+  float* d_w1f = nullptr;             // [flows*layers][K1][2nc]
+  float* d_bias1f = nullptr;          // [flows*layers][2nc]
+  float* d_wresf = nullptr;           // [flows*layers][nc][nc]
+  float* d_wsef = nullptr;            // [flows*layers][nc][8]
+  PFN_encodeTiled encode = nullptr;
+  std::vector<cudaEvent_t> ev;        // 2 per flow: around the WN layer launches of the last call
+  int ev_flows = 0;                   // flows recorded by the last call
+  int op_fmt = 0;                     // 0 = fp16 operands, 1 = bf16 (WG_B200_OPERAND=bf16; fails the max-abs gate, kept for study)
+};
+
+namespace {
+
+int fail(wg_engine* e, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (e) e->err = buf;
+  return code;
+}
+
+#define WG_CUDA(e, call)                                                                          \
+  do {                                                                                            \
+    cudaError_t _st = (call);                                                                     \
+    if (_st != cudaSuccess) return fail((e), WG_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_st)); \
+  } while (0)
+
+uint16_t f2h(float f, int fmt) {
+  if (fmt == 1) {  // bf16 round-to-nearest-even
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return static_cast<uint16_t>(u >> 16);
+  }
+  __half h = __float2half_rn(f);   // host-callable
+  uint16_t r;
+  memcpy(&r, &h, 2);
+  return r;
+}
+
+// Gauss-Jordan inverse + log|det| in double.  Returns false if singular.
+bool invert(const double* a, int n, double* inv, double* logabsdet) {
+  std::vector<double> m(n * 2 * n);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      m[i * 2 * n + j] = a[i * n + j];
+      m[i * 2 * n + n + j] = (i == j) ? 1.0 : 0.0;
+    }
+  double lad = 0.0;
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < n; ++r)
+      if (std::fabs(m[r * 2 * n + c]) > std::fabs(m[piv * 2 * n + c])) piv = r;
+    if (m[piv * 2 * n + c] == 0.0) return false;
+    if (piv != c)
+      for (int j = 0; j < 2 * n; ++j) std::swap(m[c * 2 * n + j], m[piv * 2 * n + j]);
+    const double d = m[c * 2 * n + c];
+    lad += std::log(std::fabs(d));
+    for (int j = 0; j < 2 * n; ++j) m[c * 2 * n + j] /= d;
+    for (int r = 0; r < n; ++r) {
+      if (r == c) continue;
+      const double f = m[r * 2 * n + c];
+      if (f != 0.0)
+        for (int j = 0; j < 2 * n; ++j) m[r * 2 * n + j] -= f * m[c * 2 * n + j];
+    }
+  }
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) inv[i * n + j] = m[i * 2 * n + n + j];
+  *logabsdet = lad;
+  return true;
+}
+
+struct HostWeights {
+  std::map<std::string, std::vector<float>> t;
+  std::map<std::string, std::vector<int64_t>> shape;
+};
+
+template <typename T>
+int upload(wg_engine* e, T** dst, const std::vector<T>& src) {
+  if (*dst) {
+    cudaFree(*dst);
+    *dst = nullptr;
+  }
+  WG_CUDA(e, cudaMalloc(reinterpret_cast<void**>(dst), src.size() * sizeof(T)));
+  WG_CUDA(e, cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return WG_OK;
+}
+
+int make_map(wg_engine* e, CUtensorMap* m, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+             const uint32_t* box, CUtensorMapDataType dt) {
+  cuuint64_t gd[4];
+  cuuint64_t gs[3];
+  cuuint32_t bx[4], es[4];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = e->encode(m, dt, rank, base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(e, WG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return WG_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct WsLayout {
+  size_t cond, x0, x1, e, total;
+  size_t elt;   // operand element size
+};
+
+WsLayout ws_layout(const wg_engine* e, int B, int T) {
+  WsLayout L{};
+  L.elt = e->cfg.precision == WG_PRECISION_FP32 ? 4 : 2;
+  const size_t npos = static_cast<size_t>(B) * T;
+  size_t off = 0;
+  L.cond = off;
+  off = align_up(off + npos * kCond * L.elt, 1024);
+  L.x0 = off;
+  off = align_up(off + npos * e->cfg.n_channels * L.elt, 1024);
+  L.x1 = off;
+  off = align_up(off + npos * e->cfg.n_channels * L.elt, 1024);
+  L.e = off;
+  off = align_up(off + npos * kGroup * sizeof(float), 1024);
+  L.total = off;
+  return L;
+}
+
+int frames_to_T(int frames) { return frames * kUpStride / kGroup; }
+
+}  // namespace
+
+extern "C" {
+
+const char* wg_version(void) { return "waveglow_b200 0.1 (sm_100a)"; }
+
+const char* wg_last_error(const wg_engine* e) { return e ? e->err.c_str() : "null engine"; }
+
+int wg_last_launch_count(const wg_engine* e) { return e ? e->launches : 0; }
+
+int wg_create(const wg_config* cfg, wg_engine** out) {
+  if (!cfg || !out) return WG_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  wg_engine* e = new wg_engine();
+  e->cfg = *cfg;
+  *out = e;   // returned even on failure so that wg_last_error works; caller must wg_destroy
+  if (cfg->n_group != kGroup || cfg->n_mel_channels != kMel || cfg->kernel_size != 3)
+    return fail(e, WG_ERR_UNSUPPORTED, "engine is built for n_group=8, n_mel_channels=80, kernel_size=3 (got %d, %d, %d)",
+                cfg->n_group, cfg->n_mel_channels, cfg->kernel_size);
+  if (cfg->n_flows < 1 || cfg->n_flows > 64 || cfg->n_layers < 1 || cfg->n_layers > 16 || cfg->n_early_every < 1 ||
+      cfg->n_early_size < 0 || (cfg->n_early_size & 1))
+    return fail(e, WG_ERR_INVALID_ARGUMENT, "bad n_flows/n_layers/n_early_every/n_early_size");
+  if (cfg->precision == WG_PRECISION_FP16) {
+    if (cfg->n_channels != kNC) return fail(e, WG_ERR_UNSUPPORTED, "fp16 tensor-core path is built for n_channels=256 (got %d)", cfg->n_channels);
+  } else if (cfg->precision == WG_PRECISION_FP32) {
+    if (cfg->n_channels != 256 && cfg->n_channels != 512)
+      return fail(e, WG_ERR_UNSUPPORTED, "fp32 path is built for n_channels in {256, 512} (got %d)", cfg->n_channels);
+  } else {
+    return fail(e, WG_ERR_INVALID_ARGUMENT, "unknown precision %d", cfg->precision);
+  }
+  int n_rem = cfg->n_group;
+  for (int k = 0; k < cfg->n_flows; ++k) {
+    if (k % cfg->n_early_every == 0 && k > 0) n_rem -= cfg->n_early_size;
+    if (n_rem < 2) return fail(e, WG_ERR_INVALID_ARGUMENT, "early outputs exhaust the audio channels at flow %d", k);
+    e->flowC.push_back(n_rem);
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(e, WG_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(e, WG_ERR_INVALID_ARGUMENT, "device %d out of range", cfg->device);
+  cudaDeviceProp prop{};
+  WG_CUDA(e, cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10)
+    return fail(e, WG_ERR_UNSUPPORTED, "device %d is sm_%d%d; kernels are built for sm_100a only", cfg->device, prop.major, prop.minor);
+  WG_CUDA(e, cudaSetDevice(cfg->device));
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  WG_CUDA(e, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return fail(e, WG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  e->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  const char* fmt_env = getenv("WG_B200_OPERAND");
+  e->op_fmt = (fmt_env && strcmp(fmt_env, "bf16") == 0) ? 1 : 0;
+  WG_CUDA(e, cudaFuncSetAttribute(wn_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total + 1024));
+  WG_CUDA(e, cudaFuncSetAttribute(debug_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 49152 + 1024 + 128));
+  WG_CUDA(e, cudaFuncSetAttribute(wn_layer_fp32_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (kF32KC * kF32Pos + kF32KC * 512 + kF32Pos * 256) * 4));
+  WG_CUDA(e, cudaFuncSetAttribute(wn_layer_fp32_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (kF32KC * kF32Pos + kF32KC * 1024 + kF32Pos * 512) * 4));
+  return WG_OK;
+}
+
+void wg_destroy(wg_engine* e) {
+  if (!e) return;
+  for (auto& f : e->flows) {
+    cudaFree(f.d_w_start);
+    cudaFree(f.d_b_start);
+  }
+  for (auto ev : e->ev) cudaEventDestroy(ev);
+  cudaFree(e->d_up_w);
+  cudaFree(e->d_up_b);
+  cudaFree(e->d_w1);
+  cudaFree(e->d_w2);
+  cudaFree(e->d_ident);
+  cudaFree(e->d_bias1);
+  cudaFree(e->d_bias_res);
+  cudaFree(e->d_w1f);
+  cudaFree(e->d_bias1f);
+  cudaFree(e->d_wresf);
+  cudaFree(e->d_wsef);
+  delete e;
+}
+
+int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) {
+  if (!e || !descs || n_descs <= 0) return WG_ERR_INVALID_ARGUMENT;
+  if (!e->encode) return fail(e, WG_ERR_INVALID_ARGUMENT, "engine was not created successfully");
+  WG_CUDA(e, cudaSetDevice(e->cfg.device));
+  const int nc = e->cfg.n_channels, L = e->cfg.n_layers, NF = e->cfg.n_flows;
+  HostWeights hw;
+  for (int i = 0; i < n_descs; ++i) {
+    const wg_weight_desc& d = descs[i];
+    if (!d.name || !d.data || d.ndim < 1 || d.ndim > 4) return fail(e, WG_ERR_WEIGHTS, "bad weight descriptor %d", i);
+    size_t n = 1;
+    std::vector<int64_t> shp;
+    for (int j = 0; j < d.ndim; ++j) {
+      n *= static_cast<size_t>(d.shape[j]);
+      shp.push_back(d.shape[j]);
+    }
+    std::vector<float> buf(n);
+    WG_CUDA(e, cudaMemcpy(buf.data(), d.data, n * sizeof(float), cudaMemcpyDefault));
+    hw.t[d.name] = std::move(buf);
+    hw.shape[d.name] = shp;
+  }
+  auto need = [&](const std::string& name, std::initializer_list<int64_t> shp, const std::vector<float>** out) -> int {
+    auto it = hw.t.find(name);
+    if (it == hw.t.end()) return fail(e, WG_ERR_WEIGHTS, "missing weight '%s'", name.c_str());
+    const auto& s = hw.shape[name];
+    size_t want = 1, have = 1;
+    for (auto v : shp) want *= static_cast<size_t>(v);
+    for (auto v : s) have *= static_cast<size_t>(v);
+    if (want != have) return fail(e, WG_ERR_WEIGHTS, "weight '%s' has %zu elements, expected %zu", name.c_str(), have, want);
+    *out = &it->second;
+    return WG_OK;
+  };
+  int rc;
+  // ---- upsample (model.py:145-150): Wup[ci][co][k] -> Wp[p][m*80+ci][co*8+j], k = 8p + j + 256m
+  {
+    const std::vector<float>*w, *b;
+    if ((rc = need("upsample.weight", {kMel, kMel, kUpK}, &w))) return rc;
+    if ((rc = need("upsample.bias", {kMel}, &b))) return rc;
+    std::vector<float> wp(static_cast<size_t>(kUpPhases) * kUpKdim * kCond);
+    for (int p = 0; p < kUpPhases; ++p)
+      for (int m = 0; m < kUpTaps; ++m)
+        for (int ci = 0; ci < kMel; ++ci)
+          for (int co = 0; co < kMel; ++co)
+            for (int j = 0; j < kGroup; ++j)
+              wp[(static_cast<size_t>(p) * kUpKdim + m * kMel + ci) * kCond + co * kGroup + j] =
+                  (*w)[(static_cast<size_t>(ci) * kMel + co) * kUpK + kGroup * p + j + kUpStride * m];
+    if ((rc = upload(e, &e->d_up_w, wp))) return rc;
+    if ((rc = upload(e, &e->d_up_b, *b))) return rc;
+  }
+  const bool tc = e->cfg.precision == WG_PRECISION_FP16;
+  const int K1 = 3 * nc + kCond;
+  std::vector<uint16_t> w1h, w2h;
+  std::vector<float> bias1, bias_res, w1f, bias1f, wresf, wsef;
+  if (tc) {
+    w1h.assign(static_cast<size_t>(NF) * L * 2 * nc * K1, 0);
+    w2h.assign(static_cast<size_t>(NF) * L * kW2Rows * nc, 0);
+    bias1.assign(static_cast<size_t>(NF) * L * 2 * nc, 0.f);
+    bias_res.assign(static_cast<size_t>(NF) * L * nc, 0.f);
+  } else {
+    w1f.assign(static_cast<size_t>(NF) * L * K1 * 2 * nc, 0.f);
+    bias1f.assign(static_cast<size_t>(NF) * L * 2 * nc, 0.f);
+    wresf.assign(static_cast<size_t>(NF) * L * nc * nc, 0.f);
+    wsef.assign(static_cast<size_t>(NF) * L * nc * kGroup, 0.f);
+  }
+  for (auto& f : e->flows) {
+    cudaFree(f.d_w_start);
+    cudaFree(f.d_b_start);
+  }
+  e->flows.assign(NF, FlowPack());
+  for (int k = 0; k < NF; ++k) {
+    FlowPack& fp = e->flows[k];
+    const int C = e->flowC[k], h = C / 2;
+    fp.C = C;
+    fp.h = h;
+    const std::string p = "WN." + std::to_string(k) + ".";
+    const std::vector<float>*w_start, *b_start, *w_end, *b_end, *w_cond, *b_cond, *w_ci;
+    if ((rc = need(p + "start.weight", {nc, h, 1}, &w_start))) return rc;
+    if ((rc = need(p + "start.bias", {nc}, &b_start))) return rc;
+    if ((rc = need(p + "end.weight", {2 * h, nc, 1}, &w_end))) return rc;
+    if ((rc = need(p + "end.bias", {2 * h}, &b_end))) return rc;
+    if ((rc = need(p + "cond_layer.weight", {2 * nc * L, kCond, 1}, &w_cond))) return rc;
+    if ((rc = need(p + "cond_layer.bias", {2 * nc * L}, &b_cond))) return rc;
+    if ((rc = need("convinv." + std::to_string(k) + ".conv.weight", {C, C, 1}, &w_ci))) return rc;
+    if ((rc = upload(e, &fp.d_w_start, *w_start))) return rc;
+    if ((rc = upload(e, &fp.d_b_start, *b_start))) return rc;
+    {
+      double a[kGroup * kGroup], inv[kGroup * kGroup];
+      for (int i = 0; i < C * C; ++i) {
+        a[i] = (*w_ci)[i];
+        fp.w_fwd[i] = (*w_ci)[i];
+      }
+      if (!invert(a, C, inv, &fp.logdet)) return fail(e, WG_ERR_WEIGHTS, "convinv.%d.conv.weight is singular", k);
+      for (int i = 0; i < C * C; ++i) fp.w_inv[i] = static_cast<float>(inv[i]);
+    }
+    std::vector<double> ebias(2 * h);
+    for (int r = 0; r < 2 * h; ++r) ebias[r] = (*b_end)[r];
+    for (int i = 0; i < L; ++i) {
+      const size_t li = static_cast<size_t>(k) * L + i;
+      const std::vector<float>*w_in, *b_in, *w_rs, *b_rs;
+      const int rs_rows = (i < L - 1) ? 2 * nc : nc;
+      if ((rc = need(p + "in_layers." + std::to_string(i) + ".weight", {2 * nc, nc, 3}, &w_in))) return rc;
+      if ((rc = need(p + "in_layers." + std::to_string(i) + ".bias", {2 * nc}, &b_in))) return rc;
+      if ((rc = need(p + "res_skip_layers." + std::to_string(i) + ".weight", {rs_rows, nc, 1}, &w_rs))) return rc;
+      if ((rc = need(p + "res_skip_layers." + std::to_string(i) + ".bias", {rs_rows}, &b_rs))) return rc;
+      const int skip_row0 = (i < L - 1) ? nc : 0;
+      // skip->end fold: Wse[r][c] = sum_m Wend[r][m] * Wskip[m][c];  e_bias += Wend . b_skip
+      std::vector<double> wse(static_cast<size_t>(2 * h) * nc, 0.0);
+      for (int r = 0; r < 2 * h; ++r) {
+        for (int m = 0; m < nc; ++m) {
+          const double we = (*w_end)[static_cast<size_t>(r) * nc + m];
+          const float* wsk = &(*w_rs)[static_cast<size_t>(skip_row0 + m) * nc];
+          for (int c = 0; c < nc; ++c) wse[static_cast<size_t>(r) * nc + c] += we * wsk[c];
+          ebias[r] += we * (*b_rs)[skip_row0 + m];
+        }
+      }
+      if (tc) {
+        uint16_t* w1 = &w1h[li * 2 * nc * K1];
+        for (int np = 0; np < 2 * nc; ++np) {
+          const int chunk = np / 256, half = (np % 256) / 128, j = np % 128;
+          const int oc = half * nc + chunk * 128 + j;
+          uint16_t* row = w1 + static_cast<size_t>(np) * K1;
+          for (int tap = 0; tap < 3; ++tap)
+            for (int ci = 0; ci < nc; ++ci) row[tap * nc + ci] = f2h((*w_in)[(static_cast<size_t>(oc) * nc + ci) * 3 + tap], e->op_fmt);
+          const float* wc = &(*w_cond)[(static_cast<size_t>(2 * nc) * i + oc) * kCond];
+          for (int m = 0; m < kCond; ++m) row[3 * nc + m] = f2h(wc[m], e->op_fmt);
+          bias1[li * 2 * nc + np] = (*b_in)[oc] + (*b_cond)[2 * nc * i + oc];
+        }
+        uint16_t* w2 = &w2h[li * kW2Rows * nc];
+        if (i < L - 1) {
+          for (int n = 0; n < nc; ++n) {
+            for (int c = 0; c < nc; ++c) w2[static_cast<size_t>(n) * nc + c] = f2h((*w_rs)[static_cast<size_t>(n) * nc + c], e->op_fmt);
+            bias_res[li * nc + n] = (*b_rs)[n];
+          }
+        }
+        for (int r = 0; r < 2 * h; ++r)
+          for (int c = 0; c < nc; ++c) w2[static_cast<size_t>(256 + r) * nc + c] = f2h(static_cast<float>(wse[static_cast<size_t>(r) * nc + c]), e->op_fmt);
+      } else {
+        float* w1 = &w1f[li * K1 * 2 * nc];
+        for (int oc = 0; oc < 2 * nc; ++oc) {
+          for (int tap = 0; tap < 3; ++tap)
+            for (int ci = 0; ci < nc; ++ci)
+              w1[static_cast<size_t>(tap * nc + ci) * 2 * nc + oc] = (*w_in)[(static_cast<size_t>(oc) * nc + ci) * 3 + tap];
+          const float* wc = &(*w_cond)[(static_cast<size_t>(2 * nc) * i + oc) * kCond];
+          for (int m = 0; m < kCond; ++m) w1[static_cast<size_t>(3 * nc + m) * 2 * nc + oc] = wc[m];
+          bias1f[li * 2 * nc + oc] = (*b_in)[oc] + (*b_cond)[2 * nc * i + oc];
+        }
+        if (i < L - 1) {
+          for (int n = 0; n < nc; ++n) {
+            for (int c = 0; c < nc; ++c) wresf[(li * nc + c) * nc + n] = (*w_rs)[static_cast<size_t>(n) * nc + c];
+            bias_res.resize(static_cast<size_t>(NF) * L * nc, 0.f);
+            bias_res[li * nc + n] = (*b_rs)[n];
+          }
+        }
+        for (int r = 0; r < 2 * h; ++r)
+          for (int c = 0; c < nc; ++c) wsef[(li * nc + c) * kGroup + r] = static_cast<float>(wse[static_cast<size_t>(r) * nc + c]);
+      }
+    }
+    for (int r = 0; r < 2 * h; ++r) fp.e_bias[r] = static_cast<float>(ebias[r]);
+  }
+  if (bias_res.empty()) bias_res.assign(static_cast<size_t>(NF) * L * nc, 0.f);
+  if ((rc = upload(e, &e->d_bias_res, bias_res))) return rc;
+  if (tc) {
+    uint16_t* d16 = nullptr;
+    d16 = static_cast<uint16_t*>(e->d_w1);
+    if ((rc = upload(e, &d16, w1h))) return rc;
+    e->d_w1 = d16;
+    d16 = static_cast<uint16_t*>(e->d_w2);
+    if ((rc = upload(e, &d16, w2h))) return rc;
+    e->d_w2 = d16;
+    std::vector<uint16_t> ident(64 * 64, 0);
+    for (int i = 0; i < 64; ++i) ident[i * 64 + i] = f2h(1.0f, e->op_fmt);
+    d16 = static_cast<uint16_t*>(e->d_ident);
+    if ((rc = upload(e, &d16, ident))) return rc;
+    e->d_ident = d16;
+    if ((rc = upload(e, &e->d_bias1, bias1))) return rc;
+    const CUtensorMapDataType dt = e->op_fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    {
+      const uint64_t dims[2] = {static_cast<uint64_t>(K1), static_cast<uint64_t>(NF) * L * 2 * nc};
+      const uint64_t str[1] = {static_cast<uint64_t>(K1) * 2};
+      const uint32_t box[2] = {64, 256};
+      if ((rc = make_map(e, &e->tm_w1, e->d_w1, 2, dims, str, box, dt))) return rc;
+    }
+    {
+      const uint64_t dims[2] = {static_cast<uint64_t>(nc), static_cast<uint64_t>(NF) * L * kW2Rows};
+      const uint64_t str[1] = {static_cast<uint64_t>(nc) * 2};
+      const uint32_t boxa[2] = {64, 256}, boxb[2] = {64, 16};
+      if ((rc = make_map(e, &e->tm_w2a, e->d_w2, 2, dims, str, boxa, dt))) return rc;
+      if ((rc = make_map(e, &e->tm_w2b, e->d_w2, 2, dims, str, boxb, dt))) return rc;
+    }
+    {
+      const uint64_t dims[2] = {64, 64};
+      const uint64_t str[1] = {128};
+      const uint32_t box[2] = {64, 64};
+      if ((rc = make_map(e, &e->tm_ident, e->d_ident, 2, dims, str, box, dt))) return rc;
+    }
+  } else {
+    if ((rc = upload(e, &e->d_w1f, w1f))) return rc;
+    if ((rc = upload(e, &e->d_bias1f, bias1f))) return rc;
+    if ((rc = upload(e, &e->d_wresf, wresf))) return rc;
+    if ((rc = upload(e, &e->d_wsef, wsef))) return rc;
+  }
+  e->loaded = true;
+  return WG_OK;
+}
+
+size_t wg_workspace_bytes(const wg_engine* e, int32_t batch, int32_t frames) {
+  if (!e || batch <= 0 || frames <= 0) return 0;
+  // sized for the forward direction too (up to 768 extra samples = 96 group-steps per utterance)
+  return ws_layout(e, batch, frames_to_T(frames) + (kUpK - kUpStride) / kGroup).total;
+}
+
+int wg_debug_stop_after(wg_engine* e, int32_t flow, int32_t layer) {
+  if (!e) return WG_ERR_INVALID_ARGUMENT;
+  e->dbg_flow = flow;
+  e->dbg_layer = layer;
+  return WG_OK;
+}
+
+int wg_debug_view(const wg_engine* e, const char* name, int32_t batch, int32_t frames, void* workspace, void** ptr,
+                  size_t* bytes) {
+  if (!e || !name || !workspace || !ptr || !bytes) return WG_ERR_INVALID_ARGUMENT;
+  const int T = frames_to_T(frames);
+  const WsLayout L = ws_layout(e, batch, T);
+  const size_t npos = static_cast<size_t>(batch) * T;
+  uint8_t* base = static_cast<uint8_t*>(workspace);
+  if (!strcmp(name, "cond")) {
+    *ptr = base + L.cond;
+    *bytes = npos * kCond * L.elt;
+  } else if (!strcmp(name, "x0")) {
+    *ptr = base + L.x0;
+    *bytes = npos * e->cfg.n_channels * L.elt;
+  } else if (!strcmp(name, "x1")) {
+    *ptr = base + L.x1;
+    *bytes = npos * e->cfg.n_channels * L.elt;
+  } else if (!strcmp(name, "e")) {
+    *ptr = base + L.e;
+    *bytes = npos * kGroup * sizeof(float);
+  } else {
+    return WG_ERR_INVALID_ARGUMENT;
+  }
+  return WG_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+template <typename XT>
+void launch_flow_step(const FlowStepParams& fs, float* state, const float* ebuf, void* x, size_t npos, cudaStream_t st) {
+  const unsigned grid = static_cast<unsigned>((npos + kFsPos - 1) / kFsPos);
+  flow_step_kernel<XT><<<grid, kFsThreads, 0, st>>>(fs, state, ebuf, static_cast<XT*>(x), npos);
+}
+
+// Runs the WN layers of flow k.  x buffers alternate; returns the index of the buffer holding the
+// current residual stream through *cur.  Returns 1 if the debug stop triggered.
+int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout& L, const CUtensorMap* tm_x,
+                  const CUtensorMap* tm_cond, int* cur, cudaStream_t st, bool* stopped) {
+  const int nc = e->cfg.n_channels, NL = e->cfg.n_layers;
+  const bool tc = e->cfg.precision == WG_PRECISION_FP16;
+  void* xb[2] = {ws + L.x0, ws + L.x1};
+  float* ebuf = reinterpret_cast<float*>(ws + L.e);
+  *stopped = false;
+  if (e->ev.size() < static_cast<size_t>(2 * e->cfg.n_flows)) {
+    e->ev.resize(2 * e->cfg.n_flows);
+    for (auto& ev : e->ev) cudaEventCreate(&ev);
+  }
+  cudaEventRecord(e->ev[2 * e->ev_flows], st);
+  struct RecordEnd {
+    wg_engine* e;
+    cudaStream_t st;
+    ~RecordEnd() {
+      cudaEventRecord(e->ev[2 * e->ev_flows + 1], st);
+      e->ev_flows++;
+    }
+  } record_end{e, st};
+  for (int i = 0; i < NL; ++i) {
+    const size_t li = static_cast<size_t>(k) * NL + i;
+    const int has_res = i < NL - 1;
+    if (tc) {
+      LayerTcParams lp{};
+      lp.T = T;
+      lp.dilation = 1 << i;
+      lp.w1_row0 = static_cast<int>(li * 2 * nc);
+      lp.w2_row0 = static_cast<int>(li * kW2Rows);
+      lp.has_res = has_res;
+      lp.accumulate_e = i > 0;
+      lp.fmt = e->op_fmt;
+      lp.bias1 = e->d_bias1 + li * 2 * nc;
+      lp.bias_res = e->d_bias_res + li * nc;
+      lp.e = ebuf;
+      dim3 grid((T + kTileM - 1) / kTileM, B);
+      wn_layer_tc_kernel<<<grid, kTcThreads, TcSmem::total + 1024, st>>>(tm_x[*cur], tm_x[*cur ^ 1], *tm_cond, e->tm_w1,
+                                                                        e->tm_w2a, e->tm_w2b, e->tm_ident, lp);
+    } else {
+      LayerF32Params lp{};
+      lp.T = T;
+      lp.dilation = 1 << i;
+      lp.has_res = has_res;
+      lp.accumulate_e = i > 0;
+      lp.x_in = static_cast<const float*>(xb[*cur]);
+      lp.x_out = static_cast<float*>(xb[*cur ^ 1]);
+      lp.cond = reinterpret_cast<const float*>(ws + L.cond);
+      const size_t K1 = 3 * nc + kCond;
+      lp.w1 = e->d_w1f + li * K1 * 2 * nc;
+      lp.bias1 = e->d_bias1f + li * 2 * nc;
+      lp.wres = e->d_wresf + li * nc * nc;
+      lp.bias_res = e->d_bias_res + li * nc;
+      lp.wse = e->d_wsef + li * nc * kGroup;
+      lp.e = ebuf;
+      dim3 grid((T + kF32Pos - 1) / kF32Pos, B);
+      if (nc == 256)
+        wn_layer_fp32_kernel<256><<<grid, 256, (kF32KC * kF32Pos + kF32KC * 512 + kF32Pos * 256) * 4, st>>>(lp);
+      else
+        wn_layer_fp32_kernel<512><<<grid, 256, (kF32KC * kF32Pos + kF32KC * 1024 + kF32Pos * 512) * 4, st>>>(lp);
+    }
+    e->launches++;
+    if (has_res) *cur ^= 1;
+    if (e->dbg_flow == k && e->dbg_layer == i) {
+      *stopped = true;
+      return WG_OK;
+    }
+  }
+  return WG_OK;
+}
+
+int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CUtensorMap* tm_x, CUtensorMap* tm_cond) {
+  const CUtensorMapDataType dt = e->op_fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const int nc = e->cfg.n_channels;
+  int rc;
+  const uint32_t box[3] = {64, static_cast<uint32_t>(kTileM), 1};
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(nc), static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
+    const uint64_t str[2] = {static_cast<uint64_t>(nc) * 2, static_cast<uint64_t>(nc) * 2 * T};
+    if ((rc = make_map(e, &tm_x[0], ws + L.x0, 3, dims, str, box, dt))) return rc;
+    if ((rc = make_map(e, &tm_x[1], ws + L.x1, 3, dims, str, box, dt))) return rc;
+  }
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(kCond), static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
+    const uint64_t str[2] = {static_cast<uint64_t>(kCond) * 2, static_cast<uint64_t>(kCond) * 2 * T};
+    if ((rc = make_map(e, tm_cond, ws + L.cond, 3, dims, str, box, dt))) return rc;
+  }
+  return WG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wg_infer(wg_engine* e, const float* mel, int32_t batch, int32_t frames, const float* const* z, int32_t n_z,
+             float sigma, float* audio, void* workspace, size_t ws_bytes, void* stream) {
+  if (!e) return WG_ERR_INVALID_ARGUMENT;
+  if (!e->loaded) return fail(e, WG_ERR_WEIGHTS, "wg_load_weights has not been called");
+  if (!mel || !z || !audio || !workspace || batch <= 0 || frames <= 0) return fail(e, WG_ERR_INVALID_ARGUMENT, "null pointer or non-positive size");
+  const int NF = e->cfg.n_flows;
+  int n_early = 0;
+  for (int k = 1; k < NF; ++k)
+    if (k % e->cfg.n_early_every == 0) n_early++;
+  if (n_z != 1 + n_early) return fail(e, WG_ERR_INVALID_ARGUMENT, "expected %d noise tensors, got %d", 1 + n_early, n_z);
+  const int B = batch, T = frames_to_T(frames);
+  const WsLayout L = ws_layout(e, B, T);
+  if (ws_bytes < L.total) return fail(e, WG_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, L.total);
+  if (reinterpret_cast<uintptr_t>(workspace) % 1024) return fail(e, WG_ERR_WORKSPACE, "workspace must be 1024-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  WG_CUDA(e, cudaSetDevice(e->cfg.device));
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const size_t npos = static_cast<size_t>(B) * T;
+  const bool tc = e->cfg.precision == WG_PRECISION_FP16;
+  e->launches = 0;
+  e->ev_flows = 0;
+
+  // 1. noise -> time-major state in the output buffer (live channels are the LAST C slots)
+  {
+    NoiseParams np{};
+    np.n = n_z;
+    int slot = kGroup;
+    // z[0] = init (n_remaining channels) sits last; early outputs are prepended in draw order
+    for (int i = 0; i < n_z; ++i) {
+      const int ch = (i == 0) ? e->flowC[NF - 1] : e->cfg.n_early_size;
+      slot -= ch;
+      if (!z[i]) return fail(e, WG_ERR_INVALID_ARGUMENT, "z[%d] is null", i);
+      np.z[i] = z[i];
+      np.ch[i] = ch;
+      np.slot0[i] = slot;
+    }
+    if (slot != 0) return fail(e, WG_ERR_INVALID_ARGUMENT, "noise channels do not add up to n_group");
+    pack_noise_kernel<<<static_cast<unsigned>((npos + 255) / 256), 256, 0, st>>>(np, sigma, audio, B, T);
+    e->launches++;
+  }
+  // 2. mel upsampler + squeeze -> conditioning, time-major
+  {
+    const int Fq = (T + kUpPhases - 1) / kUpPhases;
+    dim3 grid(kUpPhases, B * ((Fq + kUpFrames - 1) / kUpFrames));
+    if (tc) {
+      if (e->op_fmt == 1)
+        upsample_squeeze_kernel<__nv_bfloat16><<<grid, kUpThreads, 0, st>>>(mel, e->d_up_w, e->d_up_b,
+                                                                           reinterpret_cast<__nv_bfloat16*>(ws + L.cond), B, frames, T);
+      else
+        upsample_squeeze_kernel<__half><<<grid, kUpThreads, 0, st>>>(mel, e->d_up_w, e->d_up_b,
+                                                                    reinterpret_cast<__half*>(ws + L.cond), B, frames, T);
+    } else {
+      upsample_squeeze_kernel<float><<<grid, kUpThreads, 0, st>>>(mel, e->d_up_w, e->d_up_b,
+                                                                 reinterpret_cast<float*>(ws + L.cond), B, frames, T);
+    }
+    e->launches++;
+  }
+  CUtensorMap tm_x[2], tm_cond;
+  if (tc) {
+    int rc = make_act_maps(e, ws, L, B, T, tm_x, &tm_cond);
+    if (rc) return rc;
+  }
+  float* ebuf = reinterpret_cast<float*>(ws + L.e);
+  int cur = 0;
+  auto flow_step = [&](const FlowStepParams& fs, void* xdst) {
+    if (!tc)
+      launch_flow_step<float>(fs, audio, ebuf, xdst, npos, st);
+    else if (e->op_fmt == 1)
+      launch_flow_step<__nv_bfloat16>(fs, audio, ebuf, xdst, npos, st);
+    else
+      launch_flow_step<__half>(fs, audio, ebuf, xdst, npos, st);
+    e->launches++;
+  };
+  void* xb[2] = {ws + L.x0, ws + L.x1};
+  // 3. start conv of the first (last-indexed) flow
+  {
+    FlowStepParams fs{};
+    const FlowPack& f = e->flows[NF - 1];
+    fs.do_finish = 0;
+    fs.do_start = 1;
+    fs.C2 = f.C;
+    fs.h2 = f.h;
+    fs.nc = e->cfg.n_channels;
+    fs.w_start = f.d_w_start;
+    fs.b_start = f.d_b_start;
+    flow_step(fs, xb[cur]);
+  }
+  bool stopped = (e->dbg_flow == NF - 1 && e->dbg_layer == -1);
+  for (int k = NF - 1; k >= 0 && !stopped; --k) {
+    int rc = run_wn_layers(e, k, B, T, ws, L, tm_x, &tm_cond, &cur, st, &stopped);
+    if (rc) return rc;
+    if (stopped) break;
+    FlowStepParams fs{};
+    const FlowPack& f = e->flows[k];
+    fs.do_finish = 1;
+    fs.C = f.C;
+    fs.h = f.h;
+    memcpy(fs.e_bias, f.e_bias, sizeof(fs.e_bias));
+    memcpy(fs.w_inv, f.w_inv, sizeof(fs.w_inv));
+    if (k > 0) {
+      const FlowPack& g = e->flows[k - 1];
+      fs.do_start = 1;
+      fs.C2 = g.C;
+      fs.h2 = g.h;
+      fs.nc = e->cfg.n_channels;
+      fs.w_start = g.d_w_start;
+      fs.b_start = g.d_b_start;
+    }
+    flow_step(fs, xb[cur]);
+    if (e->dbg_flow == k && e->dbg_layer >= e->cfg.n_layers) stopped = true;
+    if (k > 0 && e->dbg_flow == k - 1 && e->dbg_layer == -1) stopped = true;
+  }
+  WG_CUDA(e, cudaGetLastError());
+  return WG_OK;
+}
+
+int wg_profile_layers(wg_engine* e, float* total_ms, int32_t* n_launches) {
+  if (!e || !total_ms || !n_launches) return WG_ERR_INVALID_ARGUMENT;
+  float sum = 0.f;
+  for (int k = 0; k < e->ev_flows; ++k) {
+    float ms = 0.f;
+    WG_CUDA(e, cudaEventSynchronize(e->ev[2 * k + 1]));
+    WG_CUDA(e, cudaEventElapsedTime(&ms, e->ev[2 * k], e->ev[2 * k + 1]));
+    sum += ms;
+  }
+  *total_ms = sum;
+  *n_launches = e->ev_flows * e->cfg.n_layers;
+  return WG_OK;
+}
+
+int wg_forward(wg_engine* e, const float*, int32_t, int32_t, const float*, int32_t, float*, float* const*, float*, float*,
+               void*, size_t, void*) {
+  return fail(e, WG_ERR_UNSUPPORTED, "wg_forward: training-direction flow is not implemented yet in this build");
+}
+
+// Diagnostic: D[M x N] fp32 = A[M x K] . B[N x K]^T with 16-bit device operands (fmt 0 fp16 / 1 bf16).
+// M % 128 == 0, N % 256 == 0, K % 64 == 0.  Exercises TMA(SW128) -> tcgen05.mma -> tcgen05.ld in isolation.
+int wg_debug_gemm(wg_engine* e, const void* A, const void* Bm, float* D, int32_t M, int32_t N, int32_t K, int32_t fmt,
+                  void* stream) {
+  if (!e || !e->encode) return WG_ERR_INVALID_ARGUMENT;
+  if (M % 128 || N % 256 || K % 64) return fail(e, WG_ERR_INVALID_ARGUMENT, "debug gemm needs M%%128==0, N%%256==0, K%%64==0");
+  const CUtensorMapDataType dt = fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap ta, tb;
+  int rc;
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    const uint64_t str[1] = {static_cast<uint64_t>(K) * 2};
+    const uint32_t box[2] = {64, 128};
+    if ((rc = make_map(e, &ta, const_cast<void*>(A), 2, dims, str, box, dt))) return rc;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    const uint64_t str[1] = {static_cast<uint64_t>(K) * 2};
+    const uint32_t box[2] = {64, 256};
+    if ((rc = make_map(e, &tb, const_cast<void*>(Bm), 2, dims, str, box, dt))) return rc;
+  }
+  dim3 grid(M / 128, N / 256);
+  debug_gemm_tc_kernel<<<grid, 192, 2 * 49152 + 1024 + 128, static_cast<cudaStream_t>(stream)>>>(ta, tb, D, M, N, K, fmt);
+  WG_CUDA(e, cudaGetLastError());
+  return WG_OK;
+}
+
+}  // extern "C"

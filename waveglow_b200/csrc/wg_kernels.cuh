@@ -1,0 +1,339 @@
+// wg_kernels.cuh -- the non-tensor-core kernels of the flow engine:
+//   pack_noise_kernel      z lists -> time-major audio state           (model.py:234-244, 260-271)
+//   upsample_squeeze_kernel ConvTranspose1d(80,80,1024,256) + squeeze   (model.py:225-232)
+//   flow_step_kernel       end-bias + affine inverse + 1x1 inverse (+ next flow's start conv)
+//                                                                       (model.py:247-258, 117)
+//   wn_layer_fp32_kernel   one WN layer in fp32 on CUDA cores (correctness mode)  (model.py:123-135)
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace wg {
+
+constexpr int kGroup = 8;        // n_group the engine is built for (state row = 8 fp32 = 32 bytes)
+constexpr int kMel = 80;         // n_mel_channels
+constexpr int kCond = kMel * kGroup;   // 640
+constexpr int kUpK = 1024;       // ConvTranspose1d kernel size (hard-coded in the reference, model.py:145-150)
+constexpr int kUpStride = 256;
+constexpr int kUpTaps = kUpK / kUpStride;           // 4 frames contribute to every sample
+constexpr int kUpPhases = kUpStride / kGroup;       // 32 group-steps per mel frame
+
+template <typename T> __device__ __forceinline__ T from_float(float v);
+template <> __device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_float<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <typename T> __device__ __forceinline__ float to_float(T v);
+template <> __device__ __forceinline__ float to_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_float<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// ------------------------------------------------------------------------------------------ noise
+struct NoiseParams {
+  const float* z[8];   // z[i]: [B, ch[i], T]
+  int ch[8];
+  int slot0[8];        // first state slot of z[i]
+  int n;
+};
+
+// state[b, t, slot0[i] + c] = sigma * z[i][b, c, t]; slots not covered by any z are zeroed.
+__global__ void pack_noise_kernel(NoiseParams p, float sigma, float* __restrict__ state, int B, int T) {
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<size_t>(B) * T) return;
+  const int b = static_cast<int>(idx / T), t = static_cast<int>(idx % T);
+  float row[kGroup];
+#pragma unroll
+  for (int i = 0; i < kGroup; ++i) row[i] = 0.f;
+  for (int i = 0; i < p.n; ++i)
+    for (int c = 0; c < p.ch[i]; ++c) row[p.slot0[i] + c] = sigma * p.z[i][(static_cast<size_t>(b) * p.ch[i] + c) * T + t];
+  float4* dst = reinterpret_cast<float4*>(state + idx * kGroup);
+  dst[0] = make_float4(row[0], row[1], row[2], row[3]);
+  dst[1] = make_float4(row[4], row[5], row[6], row[7]);
+}
+
+// ------------------------------------------------------------------------------------------ upsample
+// S[b, t', c*8 + j] = bias[c] + sum_{m<4, ci<80} mel[b, ci, q - m] * Wup[ci, c, r + 256 m],
+//   sample n = 8 t' + j = 256 q + r,  r = 8 p + j  (p = t' mod 32 is the "phase").
+// Weights are pre-packed as Wp[p][m*80 + ci][c*8 + j] so a block (one phase, 16 frames) streams a dense
+// [320 x 640] slice with coalesced 128-bit loads; each thread owns 4 output columns x 16 frames.
+constexpr int kUpFrames = 16;
+constexpr int kUpThreads = kCond / 4;   // 160
+constexpr int kUpKdim = kUpTaps * kMel; // 320
+
+template <typename OutT>
+__global__ void __launch_bounds__(kUpThreads)
+upsample_squeeze_kernel(const float* __restrict__ mel, const float* __restrict__ wp, const float* __restrict__ bias,
+                        OutT* __restrict__ S, int B, int F, int T /* group-steps kept per utterance */) {
+  __shared__ __align__(16) float mel_s[kUpKdim][kUpFrames];
+  const int p = blockIdx.x;
+  const int Fq = (T + kUpPhases - 1) / kUpPhases;      // frame slots that produce kept group-steps
+  const int groups_per_utt = (Fq + kUpFrames - 1) / kUpFrames;
+  const int b = blockIdx.y / groups_per_utt;
+  const int q0 = (blockIdx.y % groups_per_utt) * kUpFrames;
+  for (int i = threadIdx.x; i < kUpKdim * kUpFrames; i += kUpThreads) {
+    const int k = i / kUpFrames, q = i % kUpFrames;
+    const int m = k / kMel, ci = k % kMel;
+    const int f = q0 + q - m;
+    mel_s[k][q] = (f >= 0 && f < F) ? mel[(static_cast<size_t>(b) * kMel + ci) * F + f] : 0.f;
+  }
+  __syncthreads();
+  float acc[kUpFrames][4];
+#pragma unroll
+  for (int q = 0; q < kUpFrames; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
+  const float4* w4 = reinterpret_cast<const float4*>(wp + static_cast<size_t>(p) * kUpKdim * kCond) + threadIdx.x;
+#pragma unroll 4
+  for (int k = 0; k < kUpKdim; ++k) {
+    const float4 w = __ldg(w4 + static_cast<size_t>(k) * (kCond / 4));
+    const float4* mrow = reinterpret_cast<const float4*>(&mel_s[k][0]);
+#pragma unroll
+    for (int q4 = 0; q4 < kUpFrames / 4; ++q4) {
+      const float4 mv = mrow[q4];
+      const float ms[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[q4 * 4 + u][0] = fmaf(ms[u], w.x, acc[q4 * 4 + u][0]);
+        acc[q4 * 4 + u][1] = fmaf(ms[u], w.y, acc[q4 * 4 + u][1]);
+        acc[q4 * 4 + u][2] = fmaf(ms[u], w.z, acc[q4 * 4 + u][2]);
+        acc[q4 * 4 + u][3] = fmaf(ms[u], w.w, acc[q4 * 4 + u][3]);
+      }
+    }
+  }
+  const int col = threadIdx.x * 4;
+  const float bv = bias[col / kGroup];
+#pragma unroll
+  for (int q = 0; q < kUpFrames; ++q) {
+    const int t = (q0 + q) * kUpPhases + p;
+    if (t < T) {
+      OutT* dst = S + (static_cast<size_t>(b) * T + t) * kCond + col;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) dst[u] = from_float<OutT>(acc[q][u] + bv);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ flow step
+struct FlowStepParams {
+  // "finish" part: flow k
+  int do_finish;
+  int C, h;                   // live channels of flow k, C/2
+  float e_bias[kGroup];       // folded end bias: [:h] -> b, [h:2h] -> s
+  float w_inv[kGroup * kGroup];   // [C x C] row-major inverse 1x1 weight (model.py:51-59)
+  // "start" part: next flow (k-1), or the first flow
+  int do_start;
+  int C2, h2;
+  int nc;
+  const float* w_start;       // [nc, h2]
+  const float* b_start;       // [nc]
+};
+
+constexpr int kFsPos = 64;      // group-steps per block
+constexpr int kFsThreads = 256;
+
+template <typename XT>
+__global__ void __launch_bounds__(kFsThreads)
+flow_step_kernel(FlowStepParams p, float* __restrict__ state, const float* __restrict__ e, XT* __restrict__ x,
+                 size_t n_pos /* B*T */) {
+  __shared__ float a0s[kFsPos][4];
+  const size_t pos0 = static_cast<size_t>(blockIdx.x) * kFsPos;
+  if (threadIdx.x < kFsPos) {
+    const size_t pos = pos0 + threadIdx.x;
+    float row[kGroup];
+    if (pos < n_pos) {
+      const float4* sp = reinterpret_cast<const float4*>(state + pos * kGroup);
+      const float4 s0 = sp[0], s1 = sp[1];
+      row[0] = s0.x; row[1] = s0.y; row[2] = s0.z; row[3] = s0.w;
+      row[4] = s1.x; row[5] = s1.y; row[6] = s1.z; row[7] = s1.w;
+      if (p.do_finish) {
+        const float4* ep = reinterpret_cast<const float4*>(e + pos * kGroup);
+        const float4 e0 = ep[0], e1 = ep[1];
+        const float ev[kGroup] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+        const int base = kGroup - p.C;
+        float v[kGroup];
+#pragma unroll
+        for (int i = 0; i < kGroup; ++i) v[i] = 0.f;
+        for (int i = 0; i < p.h; ++i) {
+          v[i] = row[base + i];
+          const float bb = ev[i] + p.e_bias[i];
+          const float ss = ev[p.h + i] + p.e_bias[p.h + i];
+          v[p.h + i] = (row[base + p.h + i] - bb) / expf(ss);      // model.py:255
+        }
+        for (int i = 0; i < p.C; ++i) {
+          float acc = 0.f;
+          for (int j = 0; j < p.C; ++j) acc = fmaf(p.w_inv[i * p.C + j], v[j], acc);   // model.py:59
+          row[base + i] = acc;
+        }
+        float4* dp = reinterpret_cast<float4*>(state + pos * kGroup);
+        dp[0] = make_float4(row[0], row[1], row[2], row[3]);
+        dp[1] = make_float4(row[4], row[5], row[6], row[7]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kGroup; ++i) row[i] = 0.f;
+    }
+    if (p.do_start) {
+      const int base2 = kGroup - p.C2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a0s[threadIdx.x][j] = (j < p.h2) ? row[base2 + j] : 0.f;
+    }
+  }
+  if (!p.do_start) return;
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.nc; c += kFsThreads) {
+    float w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = (j < p.h2) ? p.w_start[c * p.h2 + j] : 0.f;
+    const float bs = p.b_start[c];
+    for (int i = 0; i < kFsPos; ++i) {
+      const size_t pos = pos0 + i;
+      if (pos >= n_pos) break;
+      float acc = bs;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc = fmaf(w[j], a0s[i][j], acc);              // model.py:117
+      x[pos * p.nc + c] = from_float<XT>(acc);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ fp32 layer
+// One WN layer in fp32 on CUDA cores.  Block = 256 threads, tile = 32 group-steps of one utterance.
+//   W1  [K1 = 3 NC + 640][2 NC]  (k-major rows, natural channel order: tanh half | sigmoid half)
+//   Wres [NC][NC] (k-major), Wse [NC][8]
+struct LayerF32Params {
+  int T, dilation, has_res, accumulate_e;
+  const float* x_in;    // [B,T,NC]
+  float* x_out;         // [B,T,NC]
+  const float* cond;    // [B,T,640]
+  const float* w1;
+  const float* bias1;   // [2 NC]
+  const float* wres;
+  const float* bias_res;
+  const float* wse;
+  float* e;             // [B,T,8]
+};
+
+constexpr int kF32Pos = 32;
+constexpr int kF32KC = 16;
+
+template <int NC>
+__global__ void __launch_bounds__(256, 1) wn_layer_fp32_kernel(const LayerF32Params p) {
+  constexpr int CPT = NC / 64;             // gate channels per thread
+  constexpr int K1 = 3 * NC + kCond;
+  extern __shared__ __align__(16) float sm[];
+  float* As = sm;                           // [KC][32]
+  float* Ws = As + kF32KC * kF32Pos;        // [KC][2 NC]
+  float* acts_s = Ws + kF32KC * 2 * NC;     // [32][NC]
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int t0 = blockIdx.x * kF32Pos, b = blockIdx.y;
+  const size_t ubase = static_cast<size_t>(b) * p.T;
+
+  float acc[8][2 * CPT];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 2 * CPT; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K1; k0 += kF32KC) {
+    // A chunk: As[kk][pos]
+    for (int i = threadIdx.x; i < kF32KC * kF32Pos; i += 256) {
+      const int pos = i % kF32Pos, kk = i / kF32Pos;
+      const int k = k0 + kk;
+      float v = 0.f;
+      if (k < 3 * NC) {
+        const int tap = k / NC, ch = k % NC;
+        const int t = t0 + pos + (tap - 1) * p.dilation;
+        if (t >= 0 && t < p.T) v = p.x_in[(ubase + t) * NC + ch];
+      } else {
+        const int t = t0 + pos;
+        if (t < p.T) v = p.cond[(ubase + t) * kCond + (k - 3 * NC)];
+      }
+      As[kk * kF32Pos + pos] = v;
+    }
+    {
+      const float4* src = reinterpret_cast<const float4*>(p.w1 + static_cast<size_t>(k0) * 2 * NC);
+      float4* dst = reinterpret_cast<float4*>(Ws);
+      for (int i = threadIdx.x; i < kF32KC * 2 * NC / 4; i += 256) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kF32KC; ++kk) {
+      const float4 a_lo = *reinterpret_cast<const float4*>(As + kk * kF32Pos + ty * 8);
+      const float4 a_hi = *reinterpret_cast<const float4*>(As + kk * kF32Pos + ty * 8 + 4);
+      const float a[8] = {a_lo.x, a_lo.y, a_lo.z, a_lo.w, a_hi.x, a_hi.y, a_hi.z, a_hi.w};
+      float w[2 * CPT];
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        w[j] = Ws[kk * 2 * NC + tx * CPT + j];
+        w[CPT + j] = Ws[kk * 2 * NC + NC + tx * CPT + j];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 2 * CPT; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  // gate (model.py:13-20)
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) {
+    const float bt = p.bias1[tx * CPT + j], bs = p.bias1[NC + tx * CPT + j];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float ta = tanhf(acc[i][j] + bt);
+      const float sa = 1.f / (1.f + expf(-(acc[i][CPT + j] + bs)));
+      acts_s[(ty * 8 + i) * NC + tx * CPT + j] = ta * sa;
+    }
+  }
+  __syncthreads();
+  // skip-end: one output per thread
+  {
+    const int pos = threadIdx.x >> 3, j = threadIdx.x & 7;
+    float s = 0.f;
+    for (int k = 0; k < NC; ++k) s = fmaf(acts_s[pos * NC + k], __ldg(p.wse + k * 8 + j), s);
+    const int t = t0 + pos;
+    if (t < p.T) {
+      float* ep = p.e + (ubase + t) * 8 + j;
+      *ep = p.accumulate_e ? (*ep + s) : s;
+    }
+  }
+  if (!p.has_res) return;
+  // residual GEMM: [32 x NC] = acts [32 x NC] . Wres[NC x NC]
+  float r[8][CPT];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) r[i][j] = 0.f;
+  for (int k0 = 0; k0 < NC; k0 += kF32KC) {
+    __syncthreads();
+    {
+      const float4* src = reinterpret_cast<const float4*>(p.wres + static_cast<size_t>(k0) * NC);
+      float4* dst = reinterpret_cast<float4*>(Ws);
+      for (int i = threadIdx.x; i < kF32KC * NC / 4; i += 256) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kF32KC; ++kk) {
+      float w[CPT];
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) w[j] = Ws[kk * NC + tx * CPT + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float a = acts_s[(ty * 8 + i) * NC + k0 + kk];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) r[i][j] = fmaf(a, w[j], r[i][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int t = t0 + ty * 8 + i;
+    if (t < p.T) {
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const size_t o = (ubase + t) * NC + tx * CPT + j;
+        p.x_out[o] = p.x_in[o] + r[i][j] + p.bias_res[tx * CPT + j];      // model.py:131-132
+      }
+    }
+  }
+}
+
+}  // namespace wg

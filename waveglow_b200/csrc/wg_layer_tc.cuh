@@ -1,0 +1,428 @@
+// wg_layer_tc.cuh -- one fused WaveNet coupling layer on tcgen05 tensor cores (sm_100a).
+//
+// Replaces, for a tile of 128 group-steps of one utterance, the body of the WN inner loop
+// (reference src/waveglow/model.py:123-135) plus this layer's share of cond_layer (model.py:121)
+// and of the skip->end path (model.py:130-137):
+//
+//   GEMM1  pre[128 x 512] = [x(t-d) | x(t) | x(t+d) | S(t)] [128 x 1408] . W1^T      (tcgen05, K-major SW128, TMA-fed)
+//   gate   acts = tanh(pre[:, tanh half] + b) * sigmoid(pre[:, sigmoid half] + b)      (TMEM -> registers -> smem fp16)
+//   GEMM2  x'   [128 x 256] = acts . W_res^T + x . I        (residual carried on the tensor core)
+//          e'   [128 x  16] = acts . (W_end W_skip)^T       (skip->end fold, fp32 accumulator in global)
+//
+// Data layout: x, S are time-major fp16 [B, T', C]; the dilation halo comes from three TMA boxes at
+// t-d, t, t+d (out-of-range rows are zero-filled by TMA == the conv's zero padding, model.py:100-102).
+// W1 rows are pre-permuted so that accumulator chunk c (256 TMEM columns) holds
+// [tanh ch 128c..128c+127 | sigmoid ch 128c..128c+127]; the gate therefore reads column j and j+128 of
+// the same TMEM lane.
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..9 = gate / epilogue (thread = one TMEM lane = one group-step, two column halves).
+// TMEM: 512 columns = R0 [0,256) chunk-a accumulator then x', R1 [256,512) chunk-b accumulator then e'.
+#pragma once
+#include "wg_ptx.cuh"
+
+namespace wg {
+
+constexpr int kTcThreads = 320;
+constexpr int kTileM = 128;      // group-steps per CTA
+constexpr int kBlockK = 64;      // 16-bit elements per 128-byte swizzle row
+constexpr int kStages = 3;
+constexpr int kNC = 256;         // WN channels this kernel is built for
+constexpr int kCondC = 640;      // n_mel_channels * n_group
+constexpr int kK1 = 3 * kNC + kCondC;          // 1408
+constexpr int kKB1 = kK1 / kBlockK;            // 22
+constexpr int kW2Rows = 272;                   // 256 residual rows + 16 skip-end rows
+constexpr int kStageABytes = kTileM * 128;     // 16 KB
+constexpr int kStageBBytes = 256 * 128 + 16 * 128;  // 34 KB (W1 uses the first 32 KB)
+constexpr int kStageBytes = kStageABytes + kStageBBytes;   // 51200 (multiple of 1024)
+constexpr int kActsBytes = kTileM * kNC * 2;   // 64 KB, 4 slabs of [128 x 64]
+constexpr int kIdentBytes = 64 * 128;          // 8 KB
+
+struct TcSmem {
+  // offsets inside dynamic smem (after 1024-byte alignment)
+  static constexpr int stage0 = 0;
+  static constexpr int acts = kStages * kStageBytes;                    // 153600
+  static constexpr int ident = acts + kActsBytes;                       // 219136
+  static constexpr int bias1 = ident + kIdentBytes;                     // 227328
+  static constexpr int bias_res = bias1 + 2 * kNC * 4;                  // +2048
+  static constexpr int bars = bias_res + kNC * 4;                       // +1024
+  static constexpr int total = bars + 128;
+};
+static_assert(TcSmem::total + 1024 <= 232448, "shared memory budget exceeded");
+
+struct LayerTcParams {
+  int T;              // group-steps per utterance
+  int dilation;
+  int w1_row0;        // first packed-W1 row of this (flow, layer)
+  int w2_row0;        // first packed-W2 row of this (flow, layer)
+  int has_res;        // 0 for the last layer (no residual output, model.py:107-110)
+  int accumulate_e;   // 0 for the first layer (e' = ...), 1 afterwards (e' = e + ...)
+  int fmt;            // 0 = fp16, 1 = bf16 operands
+  const float* bias1;     // [512] packed order, b_in + b_cond
+  const float* bias_res;  // [256]
+  float* e;               // [B, T, 8] fp32
+};
+
+__device__ __forceinline__ float gate_one(float a, float b) {
+  // tanh(a) * sigmoid(b), sigmoid(b) = 0.5 + 0.5 tanh(b/2)   (model.py:13-20)
+  return ptx::tanh_approx(a) * fmaf(0.5f, ptx::tanh_approx(0.5f * b), 0.5f);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, T, B} box {64,128,1} SW128
+                   const __grid_constant__ CUtensorMap tm_x_out,  // same geometry, other buffer
+                   const __grid_constant__ CUtensorMap tm_cond,   // {640, T, B} box {64,128,1}
+                   const __grid_constant__ CUtensorMap tm_w1,     // {1408, rows} box {64,256}
+                   const __grid_constant__ CUtensorMap tm_w2a,    // {256, rows} box {64,256}
+                   const __grid_constant__ CUtensorMap tm_w2b,    // {256, rows} box {64,16}
+                   const __grid_constant__ CUtensorMap tm_ident,  // {64, 64} box {64,64}
+                   const LayerTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TcSmem::bars);
+  uint64_t* full = bars;                 // [kStages]
+  uint64_t* empty = bars + kStages;      // [kStages]
+  uint64_t* acc_full = bars + 2 * kStages;      // [2]
+  uint64_t* acts_ready = acc_full + 2;          // [2]
+  uint64_t* d2_full = acts_ready + 2;           // [1]
+  uint64_t* ident_full = d2_full + 1;           // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ident_full + 1);
+  float* s_bias1 = reinterpret_cast<float*>(smem + TcSmem::bias1);
+  float* s_bias_res = reinterpret_cast<float*>(smem + TcSmem::bias_res);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int t0 = blockIdx.x * kTileM;
+  const int b = blockIdx.y;
+
+  // ---- one-time setup
+  for (int i = threadIdx.x; i < 2 * kNC; i += kTcThreads) s_bias1[i] = p.bias1[i];
+  for (int i = threadIdx.x; i < kNC; i += kTcThreads) s_bias_res[i] = p.has_res ? p.bias_res[i] : 0.f;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    ptx::mbar_init(&acc_full[0], 1);
+    ptx::mbar_init(&acc_full[1], 1);
+    ptx::mbar_init(&acts_ready[0], 256);
+    ptx::mbar_init(&acts_ready[1], 256);
+    ptx::mbar_init(d2_full, 1);
+    ptx::mbar_init(ident_full, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_g2 = p.has_res ? 8 : 4;   // stage uses of GEMM2 (4 W2 K-blocks [+ 4 x K-blocks for the identity term])
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tm_x_in);
+      ptx::prefetch_tmap(&tm_cond);
+      ptx::prefetch_tmap(&tm_w1);
+      if (p.has_res) {
+        ptx::mbar_arrive_expect_tx(ident_full, kIdentBytes);
+        ptx::tma_load_2d(smem + TcSmem::ident, &tm_ident, ident_full, 0, 0);
+      }
+      int use = 0;
+      for (int chunk = 0; chunk < 2; ++chunk) {
+        for (int kb = 0; kb < kKB1; ++kb, ++use) {
+          const int s = use % kStages;
+          const uint32_t ph = (use / kStages) & 1;
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = smem + TcSmem::stage0 + s * kStageBytes;
+          uint8_t* sb = sa + kStageABytes;
+          ptx::mbar_arrive_expect_tx(&full[s], kStageABytes + 256 * 128);
+          if (kb < 12) {
+            const int tap = kb >> 2;   // 0: t-d, 1: t, 2: t+d
+            ptx::tma_load_3d(sa, &tm_x_in, &full[s], (kb & 3) * kBlockK, t0 + (tap - 1) * p.dilation, b);
+          } else {
+            ptx::tma_load_3d(sa, &tm_cond, &full[s], (kb - 12) * kBlockK, t0, b);
+          }
+          ptx::tma_load_2d(sb, &tm_w1, &full[s], kb * kBlockK, p.w1_row0 + chunk * 256);
+        }
+      }
+      for (int j = 0; j < n_g2; ++j, ++use) {
+        const int s = use % kStages;
+        const uint32_t ph = (use / kStages) & 1;
+        ptx::mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* sa = smem + TcSmem::stage0 + s * kStageBytes;
+        uint8_t* sb = sa + kStageABytes;
+        if (j < 4) {
+          ptx::mbar_arrive_expect_tx(&full[s], kStageBBytes);
+          ptx::tma_load_2d(sb, &tm_w2a, &full[s], j * kBlockK, p.w2_row0);
+          ptx::tma_load_2d(sb + 256 * 128, &tm_w2b, &full[s], j * kBlockK, p.w2_row0 + 256);
+        } else {
+          ptx::mbar_arrive_expect_tx(&full[s], kStageABytes);
+          ptx::tma_load_3d(sa, &tm_x_in, &full[s], (j - 4) * kBlockK, t0, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      const uint32_t idesc256 = ptx::make_idesc_f16(128, 256, p.fmt);
+      const uint32_t idesc64 = ptx::make_idesc_f16(128, 64, p.fmt);
+      const uint32_t idesc16 = ptx::make_idesc_f16(128, 16, p.fmt);
+      const uint32_t stage_addr0 = ptx::smem_u32(smem + TcSmem::stage0);
+      const uint32_t acts_addr = ptx::smem_u32(smem + TcSmem::acts);
+      const uint32_t ident_addr = ptx::smem_u32(smem + TcSmem::ident);
+      int use = 0;
+      for (int chunk = 0; chunk < 2; ++chunk) {
+        const uint32_t d = tmem_base + chunk * 256;
+        for (int kb = 0; kb < kKB1; ++kb, ++use) {
+          const int s = use % kStages;
+          const uint32_t ph = (use / kStages) & 1;
+          ptx::mbar_wait(&full[s], ph);
+          ptx::tc_fence_after_sync();
+          const uint32_t a_addr = stage_addr0 + s * kStageBytes;
+          const uint32_t b_addr = a_addr + kStageABytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            ptx::mma_f16_ss(d, ptx::make_desc_sw128(a_addr + k * 32), ptx::make_desc_sw128(b_addr + k * 32), idesc256,
+                            (kb | k) != 0);
+          }
+          ptx::mma_commit(&empty[s]);
+        }
+        ptx::mma_commit(&acc_full[chunk]);
+      }
+      // GEMM2 needs all of acts (K = 256) and both accumulator regions drained by the gate.
+      ptx::mbar_wait(&acts_ready[0], 0);
+      ptx::mbar_wait(&acts_ready[1], 0);
+      ptx::tc_fence_after_sync();
+      for (int j = 0; j < 4; ++j, ++use) {
+        const int s = use % kStages;
+        const uint32_t ph = (use / kStages) & 1;
+        ptx::mbar_wait(&full[s], ph);
+        ptx::tc_fence_after_sync();
+        const uint32_t b_addr = stage_addr0 + s * kStageBytes + kStageABytes;
+        const uint32_t a_addr = acts_addr + j * (kTileM * 128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ad = ptx::make_desc_sw128(a_addr + k * 32);
+          if (p.has_res) ptx::mma_f16_ss(tmem_base, ad, ptx::make_desc_sw128(b_addr + k * 32), idesc256, (j | k) != 0);
+          ptx::mma_f16_ss(tmem_base + 256, ad, ptx::make_desc_sw128(b_addr + 256 * 128 + k * 32), idesc16, (j | k) != 0);
+        }
+        ptx::mma_commit(&empty[s]);
+      }
+      if (p.has_res) {
+        ptx::mbar_wait(ident_full, 0);
+        for (int j = 0; j < 4; ++j, ++use) {
+          const int s = use % kStages;
+          const uint32_t ph = (use / kStages) & 1;
+          ptx::mbar_wait(&full[s], ph);
+          ptx::tc_fence_after_sync();
+          const uint32_t a_addr = stage_addr0 + s * kStageBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            ptx::mma_f16_ss(tmem_base + j * 64, ptx::make_desc_sw128(a_addr + k * 32),
+                            ptx::make_desc_sw128(ident_addr + k * 32), idesc64, 1);
+          }
+          ptx::mma_commit(&empty[s]);
+        }
+      }
+      ptx::mma_commit(d2_full);
+    }
+  } else {
+    // =============================== gate / epilogue warps ===============================
+    const int q = warp & 3;              // TMEM lane quarter this warp may touch
+    const int hh = (warp - 2) >> 2;      // column half handled by this warp
+    const int row = q * 32 + lane;       // group-step inside the tile == TMEM lane
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint8_t* acts = smem + TcSmem::acts;
+
+    for (int chunk = 0; chunk < 2; ++chunk) {
+      ptx::mbar_wait(&acc_full[chunk], 0);
+      ptx::tc_fence_after_sync();
+      const int slab = 2 * chunk + hh;                 // acts channels [64*slab, 64*slab+64)
+      uint8_t* slab_row = acts + slab * (kTileM * 128) + row * 128;
+      const float* bt = s_bias1 + chunk * 256 + hh * 64;
+      const float* bs = bt + 128;
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        uint32_t vt[16], vs[16];
+        const uint32_t col = chunk * 256 + hh * 64 + g * 16;
+        ptx::tmem_ld16(lane_addr + col, vt);
+        ptx::tmem_ld16(lane_addr + col + 128, vs);
+        ptx::tmem_ld_wait();
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float a0 = gate_one(__uint_as_float(vt[2 * i]) + bt[g * 16 + 2 * i],
+                                    __uint_as_float(vs[2 * i]) + bs[g * 16 + 2 * i]);
+          const float a1 = gate_one(__uint_as_float(vt[2 * i + 1]) + bt[g * 16 + 2 * i + 1],
+                                    __uint_as_float(vs[2 * i + 1]) + bs[g * 16 + 2 * i + 1]);
+          if (p.fmt == 0) {
+            pk[i] = ptx::pack_half2(a0, a1);
+          } else {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
+            pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+        }
+        // 128-byte swizzle: 16-byte chunk index XOR (row mod 8)
+        const int c0 = (2 * g) ^ (row & 7);
+        const int c1 = (2 * g + 1) ^ (row & 7);
+        *reinterpret_cast<uint4*>(slab_row + c0 * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(slab_row + c1 * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      ptx::tc_fence_before_sync();
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&acts_ready[chunk]);
+    }
+
+    // ---- epilogue 2: x' (fp16, via smem + TMA store) and e' (fp32, direct)
+    ptx::mbar_wait(d2_full, 0);
+    ptx::tc_fence_after_sync();
+    const int t = t0 + row;
+    if (hh == 0) {
+      uint32_t ve[8];
+      ptx::tmem_ld8(lane_addr + 256, ve);
+      ptx::tmem_ld_wait();
+      if (t < p.T) {
+        float4* ep = reinterpret_cast<float4*>(p.e + (static_cast<size_t>(b) * p.T + t) * 8);
+        float4 lo = make_float4(__uint_as_float(ve[0]), __uint_as_float(ve[1]), __uint_as_float(ve[2]), __uint_as_float(ve[3]));
+        float4 hi = make_float4(__uint_as_float(ve[4]), __uint_as_float(ve[5]), __uint_as_float(ve[6]), __uint_as_float(ve[7]));
+        if (p.accumulate_e) {
+          const float4 o0 = ep[0], o1 = ep[1];
+          lo.x += o0.x; lo.y += o0.y; lo.z += o0.z; lo.w += o0.w;
+          hi.x += o1.x; hi.y += o1.y; hi.z += o1.z; hi.w += o1.w;
+        }
+        ep[0] = lo;
+        ep[1] = hi;
+      }
+    }
+    if (p.has_res) {
+#pragma unroll 1
+      for (int g = 0; g < 8; ++g) {
+        uint32_t v[16];
+        const int ch0 = hh * 128 + g * 16;          // first residual channel of this group
+        ptx::tmem_ld16(lane_addr + ch0, v);
+        ptx::tmem_ld_wait();
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float a0 = __uint_as_float(v[2 * i]) + s_bias_res[ch0 + 2 * i];
+          const float a1 = __uint_as_float(v[2 * i + 1]) + s_bias_res[ch0 + 2 * i + 1];
+          if (p.fmt == 0) {
+            pk[i] = ptx::pack_half2(a0, a1);
+          } else {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
+            pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+        }
+        const int slab = ch0 >> 6;
+        const int cc = (ch0 & 63) >> 3;             // 16-byte chunk inside the 128-byte row
+        uint8_t* slab_row = acts + slab * (kTileM * 128) + row * 128;
+        *reinterpret_cast<uint4*>(slab_row + ((cc ^ (row & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(slab_row + (((cc + 1) ^ (row & 7)) * 16)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      ptx::fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps only
+      if (warp == 2 && lane == 0) {
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) ptx::tma_store_3d(&tm_x_out, acts + s4 * (kTileM * 128), s4 * kBlockK, t0, b);
+        ptx::tma_store_commit();
+        ptx::tma_store_wait_all();
+      }
+    }
+  }
+
+  // ---- teardown
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Diagnostic GEMM  D[M x N] = A[M x K] . B[N x K]^T  (fp16 in, fp32 out) built from the same TMA /
+// descriptor / tcgen05 pieces as the layer kernel, N = 256 per CTA column, M = 128 per CTA row.
+// Used only by tests (wg_debug_gemm) to validate the descriptor encodings in isolation.
+__global__ void __launch_bounds__(192, 1)
+debug_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a,   // {K, M} box {64,128}
+                     const __grid_constant__ CUtensorMap tm_b,   // {K, N} box {64,256}
+                     float* __restrict__ D, int M, int N, int K, int fmt) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int stage_bytes = 16384 + 32768;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 2;
+  uint64_t* done = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 256;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    ptx::mbar_init(done, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nkb = K / 64;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb & 1;
+        ptx::mbar_wait(&empty[s], ((kb >> 1) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&full[s], stage_bytes);
+        ptx::tma_load_2d(smem + s * stage_bytes, &tm_a, &full[s], kb * 64, m0);
+        ptx::tma_load_2d(smem + s * stage_bytes + 16384, &tm_b, &full[s], kb * 64, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_f16(128, 256, fmt);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb & 1;
+        ptx::mbar_wait(&full[s], (kb >> 1) & 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t a_addr = ptx::smem_u32(smem + s * stage_bytes);
+        for (int k = 0; k < 4; ++k)
+          ptx::mma_f16_ss(tmem_base, ptx::make_desc_sw128(a_addr + k * 32), ptx::make_desc_sw128(a_addr + 16384 + k * 32),
+                          idesc, (kb | k) != 0);
+        ptx::mma_commit(&empty[s]);
+      }
+      ptx::mma_commit(done);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    ptx::mbar_wait(done, 0);
+    ptx::tc_fence_after_sync();
+    for (int g = 0; g < 16; ++g) {
+      uint32_t v[16];
+      ptx::tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 16, v);
+      ptx::tmem_ld_wait();
+      if (m0 + row < M)
+        for (int i = 0; i < 16; ++i) D[static_cast<size_t>(m0 + row) * N + n0 + g * 16 + i] = __uint_as_float(v[i]);
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, 256);
+  }
+}
+
+}  // namespace wg

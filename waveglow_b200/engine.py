@@ -1,0 +1,210 @@
+"""ctypes binding of libwaveglow_b200.so (C ABI: include/waveglow_b200.h).
+
+This is the stub a maintainer of the reference would add: plain pointers and
+sizes cross the boundary, torch is used only for device memory and the current stream.  There is no
+CPU fallback: a missing library or a failing call raises.
+"""
+import ctypes
+import os
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+_LIB_NAME = "libwaveglow_b200.so"
+_lib = None
+
+PRECISION_FP32 = 0
+PRECISION_FP16 = 1
+
+EXPORTED_SYMBOLS = [
+  "wg_create", "wg_load_weights", "wg_workspace_bytes", "wg_infer", "wg_forward", "wg_last_launch_count",
+  "wg_debug_stop_after", "wg_debug_view", "wg_debug_gemm", "wg_profile_layers", "wg_last_error", "wg_version",
+  "wg_destroy",
+]
+
+
+class WgError(RuntimeError):
+  pass
+
+
+class _Config(ctypes.Structure):
+  _fields_ = [(n, ctypes.c_int32) for n in (
+    "n_mel_channels", "n_flows", "n_group", "n_early_every", "n_early_size", "n_layers", "n_channels",
+    "kernel_size", "segment_length", "precision", "device")]
+
+
+class _WeightDesc(ctypes.Structure):
+  _fields_ = [("name", ctypes.c_char_p), ("data", ctypes.c_void_p), ("ndim", ctypes.c_int32),
+              ("shape", ctypes.c_int64 * 4)]
+
+
+def lib_path() -> str:
+  return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+
+
+def load_library() -> ctypes.CDLL:
+  global _lib
+  if _lib is not None:
+    return _lib
+  path = lib_path()
+  if not os.path.isfile(path):
+    raise WgError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                  "(there is no CPU fallback)")
+  lib = ctypes.CDLL(path)
+  vp, i32, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_float
+  lib.wg_create.argtypes = [ctypes.POINTER(_Config), ctypes.POINTER(vp)]
+  lib.wg_create.restype = ctypes.c_int
+  lib.wg_load_weights.argtypes = [vp, ctypes.POINTER(_WeightDesc), i32]
+  lib.wg_load_weights.restype = ctypes.c_int
+  lib.wg_workspace_bytes.argtypes = [vp, i32, i32]
+  lib.wg_workspace_bytes.restype = ctypes.c_size_t
+  lib.wg_infer.argtypes = [vp, vp, i32, i32, ctypes.POINTER(vp), i32, f32, vp, vp, ctypes.c_size_t, vp]
+  lib.wg_infer.restype = ctypes.c_int
+  lib.wg_forward.argtypes = [vp, vp, i32, i32, vp, i32, vp, ctypes.POINTER(vp), vp, vp, vp, ctypes.c_size_t, vp]
+  lib.wg_forward.restype = ctypes.c_int
+  lib.wg_last_launch_count.argtypes = [vp]
+  lib.wg_last_launch_count.restype = ctypes.c_int
+  lib.wg_debug_stop_after.argtypes = [vp, i32, i32]
+  lib.wg_debug_stop_after.restype = ctypes.c_int
+  lib.wg_debug_view.argtypes = [vp, ctypes.c_char_p, i32, i32, vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
+  lib.wg_debug_view.restype = ctypes.c_int
+  lib.wg_debug_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
+  lib.wg_debug_gemm.restype = ctypes.c_int
+  lib.wg_profile_layers.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
+  lib.wg_profile_layers.restype = ctypes.c_int
+  lib.wg_last_error.argtypes = [vp]
+  lib.wg_last_error.restype = ctypes.c_char_p
+  lib.wg_version.argtypes = []
+  lib.wg_version.restype = ctypes.c_char_p
+  lib.wg_destroy.argtypes = [vp]
+  lib.wg_destroy.restype = None
+  _lib = lib
+  return lib
+
+
+class Engine:
+  """One flow engine on one CUDA device."""
+
+  def __init__(self, hparams, precision: int, device: torch.device):
+    self.lib = load_library()
+    self.device = torch.device(device)
+    if self.device.type != "cuda":
+      raise WgError("the B200 engine needs a CUDA device (no CPU fallback)")
+    index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+    self.device = torch.device("cuda", index)
+    cfg = _Config(hparams.n_mel_channels, hparams.n_flows, hparams.n_group, hparams.n_early_every,
+                  hparams.n_early_size, hparams.n_layers, hparams.n_channels, hparams.kernel_size,
+                  hparams.segment_length, precision, index)
+    self.precision = precision
+    self.n_group = hparams.n_group
+    self.n_channels = hparams.n_channels
+    self._h = ctypes.c_void_p()
+    rc = self.lib.wg_create(ctypes.byref(cfg), ctypes.byref(self._h))
+    if rc != 0:
+      msg = self._err()
+      self.close()
+      raise WgError(f"wg_create failed ({rc}): {msg}")
+    self._ws: Optional[torch.Tensor] = None
+
+  def _err(self) -> str:
+    if not self._h:
+      return "no engine"
+    return self.lib.wg_last_error(self._h).decode()
+
+  def _check(self, rc: int, what: str) -> None:
+    if rc != 0:
+      raise WgError(f"{what} failed ({rc}): {self._err()}")
+
+  def close(self) -> None:
+    if getattr(self, "_h", None):
+      self.lib.wg_destroy(self._h)
+      self._h = ctypes.c_void_p()
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass
+
+  def load_weights(self, folded: Dict[str, torch.Tensor]) -> None:
+    """folded: name -> fp32 tensor (any device) in the reference layout after remove_weightnorm."""
+    keep: List[torch.Tensor] = []
+    descs = (_WeightDesc * len(folded))()
+    for i, (name, t) in enumerate(folded.items()):
+      t = t.detach().to(torch.float32).contiguous()
+      keep.append(t)
+      descs[i].name = name.encode()
+      descs[i].data = t.data_ptr()
+      descs[i].ndim = t.dim()
+      for j in range(t.dim()):
+        descs[i].shape[j] = t.size(j)
+    torch.cuda.synchronize(self.device)
+    self._check(self.lib.wg_load_weights(self._h, descs, len(folded)), "wg_load_weights")
+
+  def workspace(self, batch: int, frames: int) -> torch.Tensor:
+    need = self.lib.wg_workspace_bytes(self._h, batch, frames)
+    if self._ws is None or self._ws.numel() < need + 1024:
+      self._ws = None
+      self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+    return self._ws
+
+  @staticmethod
+  def _aligned_ptr(t: torch.Tensor) -> int:
+    return (t.data_ptr() + 1023) // 1024 * 1024
+
+  def infer(self, mel: torch.Tensor, zs: Sequence[torch.Tensor], sigma: float) -> torch.Tensor:
+    """mel [B,80,F] fp32 cuda; zs pre-drawn N(0,1) in the reference order.  Returns audio [B, 256 F]."""
+    if mel.device != self.device:
+      raise WgError(f"mel is on {mel.device}, engine on {self.device}")
+    mel = mel.to(torch.float32).contiguous()
+    B, _, F = mel.shape
+    zs = [z.to(torch.float32).contiguous() for z in zs]
+    audio = torch.empty((B, F * 256), dtype=torch.float32, device=self.device)
+    ws = self.workspace(B, F)
+    zp = (ctypes.c_void_p * len(zs))(*[z.data_ptr() for z in zs])
+    stream = torch.cuda.current_stream(self.device).cuda_stream
+    rc = self.lib.wg_infer(self._h, mel.data_ptr(), B, F, zp, len(zs), float(sigma), audio.data_ptr(),
+                           self._aligned_ptr(ws), ws.numel() - 1024, stream)
+    self._check(rc, "wg_infer")
+    return audio
+
+  def launch_count(self) -> int:
+    return self.lib.wg_last_launch_count(self._h)
+
+  def profile_layers(self):
+    """(ms spent in the WN layer kernels of the last call, number of layer launches) -- synchronises."""
+    ms = ctypes.c_float()
+    n = ctypes.c_int32()
+    self._check(self.lib.wg_profile_layers(self._h, ctypes.byref(ms), ctypes.byref(n)), "wg_profile_layers")
+    return float(ms.value), int(n.value)
+
+  # ---- test hooks
+  def debug_stop_after(self, flow: int, layer: int) -> None:
+    self._check(self.lib.wg_debug_stop_after(self._h, flow, layer), "wg_debug_stop_after")
+
+  def debug_view(self, name: str, batch: int, frames: int) -> torch.Tensor:
+    """Copy of a named workspace buffer as a flat tensor of the right dtype."""
+    ws = self.workspace(batch, frames)
+    ptr = ctypes.c_void_p()
+    nbytes = ctypes.c_size_t()
+    self._check(self.lib.wg_debug_view(self._h, name.encode(), batch, frames, self._aligned_ptr(ws),
+                                       ctypes.byref(ptr), ctypes.byref(nbytes)), "wg_debug_view")
+    off = ptr.value - ws.data_ptr()
+    raw = ws[off: off + nbytes.value].clone()
+    if name == "e" or self.precision == PRECISION_FP32:
+      return raw.view(torch.float32)
+    return raw.view(torch.float16)
+
+  def debug_gemm(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """D = A @ B^T through the TMA -> tcgen05.mma -> tcgen05.ld diagnostic kernel (fp16/bf16 inputs)."""
+    assert a.dtype == b.dtype and a.dtype in (torch.float16, torch.bfloat16)
+    a = a.contiguous()
+    b = b.contiguous()
+    M, K = a.shape
+    N = b.shape[0]
+    d = torch.empty((M, N), dtype=torch.float32, device=self.device)
+    stream = torch.cuda.current_stream(self.device).cuda_stream
+    fmt = 0 if a.dtype == torch.float16 else 1
+    self._check(self.lib.wg_debug_gemm(self._h, a.data_ptr(), b.data_ptr(), d.data_ptr(), M, N, K, fmt, stream),
+                "wg_debug_gemm")
+    return d

@@ -1,0 +1,198 @@
+"""`WaveGlow` -- drop-in for the reference's `waveglow.model.WaveGlow` whose hot path runs on the B200 engine.
+
+The module tree, parameter names and shapes mirror /root/reference/src/waveglow/model.py:142-176 (and
+`WN` 68-113, `Invertible1x1Conv` 23-43) exactly, so `load_state_dict`, `state_dict`, `.to(device)`,
+`.eval()`, `WaveGlow.remove_weightnorm(model)`, `Denoiser(waveglow=model, ...)` and the reference's
+`load_model` work unchanged.  The modules are PARAMETER CONTAINERS only: the arithmetic
+of `infer` (model.py:223-274) is done by hand-written sm_100a kernels behind the C ABI
+(waveglow_b200/engine.py).  There is no torch/CPU fallback: calling `infer` without a CUDA device or
+without the built library raises.
+"""
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import engine as _engine
+from .hparams import HParams
+from .synthetic import flow_channels
+
+
+class Invertible1x1Conv(torch.nn.Module):
+  """Holds the C x C weight of model.py:30-43 (random orthonormal init, det = +1)."""
+
+  def __init__(self, c: int):
+    super().__init__()
+    self.conv = torch.nn.Conv1d(c, c, kernel_size=1, stride=1, padding=0, bias=False)
+    W = torch.linalg.qr(torch.empty(c, c).normal_())[0]
+    if torch.det(W) < 0:
+      W[:, 0] = -1 * W[:, 0]
+    self.conv.weight.data = W.view(c, c, 1)
+
+
+class WN(torch.nn.Module):
+  """Parameter container with the layout of model.py:75-113 (weight-normed start / cond / in / res_skip, plain zero-init end)."""
+
+  def __init__(self, n_in_channels: int, n_mel_channels: int, hparams: HParams):
+    super().__init__()
+    assert hparams.kernel_size % 2 == 1
+    assert hparams.n_channels % 2 == 0
+    self.n_layers = hparams.n_layers
+    self.n_channels = hparams.n_channels
+    wn = torch.nn.utils.parametrizations.weight_norm
+    self.in_layers = torch.nn.ModuleList()
+    self.res_skip_layers = torch.nn.ModuleList()
+    self.start = wn(torch.nn.Conv1d(n_in_channels, self.n_channels, 1), name="weight")
+    end = torch.nn.Conv1d(self.n_channels, 2 * n_in_channels, 1)
+    end.weight.data.zero_()
+    end.bias.data.zero_()
+    self.end = end
+    self.cond_layer = wn(torch.nn.Conv1d(n_mel_channels, 2 * self.n_channels * self.n_layers, 1), name="weight")
+    for i in range(self.n_layers):
+      dilation = 2 ** i
+      padding = int((hparams.kernel_size * dilation - dilation) / 2)
+      self.in_layers.append(wn(torch.nn.Conv1d(self.n_channels, 2 * self.n_channels, hparams.kernel_size,
+                                               dilation=dilation, padding=padding), name="weight"))
+      rs = 2 * self.n_channels if i < self.n_layers - 1 else self.n_channels
+      self.res_skip_layers.append(wn(torch.nn.Conv1d(self.n_channels, rs, 1), name="weight"))
+
+
+def _remove(conv_list: torch.nn.ModuleList) -> torch.nn.ModuleList:
+  out = torch.nn.ModuleList()
+  for conv in conv_list:
+    out.append(torch.nn.utils.parametrize.remove_parametrizations(conv, "weight"))
+  return out
+
+
+class WaveGlow(torch.nn.Module):
+  """Same constructor, attributes and call surface as the reference WaveGlow (model.py:141-297).
+
+  Extra, engine-only knobs:
+    precision: "fp16" (tcgen05 tensor cores, fp16 operands / fp32 accumulate; default) or "fp32"
+               (CUDA-core correctness mode).  Can also be set with `model.set_precision(...)`.
+  """
+
+  def __init__(self, hparams: HParams, precision: str = "fp16"):
+    super().__init__()
+    self.hparams = hparams
+    self.upsample = torch.nn.ConvTranspose1d(hparams.n_mel_channels, hparams.n_mel_channels, 1024, stride=256)
+    assert hparams.n_group % 2 == 0
+    self.n_flows = hparams.n_flows
+    self.n_group = hparams.n_group
+    self.n_early_every = hparams.n_early_every
+    self.n_early_size = hparams.n_early_size
+    self.WN = torch.nn.ModuleList()
+    self.convinv = torch.nn.ModuleList()
+    chans = flow_channels(hparams)
+    for k in range(self.n_flows):
+      self.convinv.append(Invertible1x1Conv(chans[k]))
+      self.WN.append(WN(chans[k] // 2, hparams.n_mel_channels * self.n_group, hparams))
+    self.n_remaining_channels = chans[-1]
+    self._precision = precision
+    self._engine: Optional[_engine.Engine] = None
+    self._packed = False
+
+  # ------------------------------------------------------------------ engine plumbing
+  def set_precision(self, precision: str) -> "WaveGlow":
+    assert precision in ("fp16", "fp32")
+    if precision != self._precision:
+      self._precision = precision
+      self._drop_engine()
+    return self
+
+  def _drop_engine(self) -> None:
+    if self._engine is not None:
+      self._engine.close()
+    self._engine = None
+    self._packed = False
+
+  def invalidate_packed_weights(self) -> None:
+    """Call after changing parameters in place; the reference has the same staleness for its cached
+    `W_inverse` (model.py:49-58).  load_state_dict / remove_weightnorm / .to() call it for you."""
+    self._packed = False
+
+  def load_state_dict(self, *args, **kwargs):
+    res = super().load_state_dict(*args, **kwargs)
+    self._packed = False
+    return res
+
+  def _apply(self, fn, *args, **kwargs):
+    res = super()._apply(fn, *args, **kwargs)
+    self._drop_engine()
+    return res
+
+  def folded_weights(self) -> Dict[str, torch.Tensor]:
+    """name -> folded fp32 weight, keyed like state_dict() after remove_weightnorm (model.py:276-297)."""
+    out: Dict[str, torch.Tensor] = {"upsample.weight": self.upsample.weight, "upsample.bias": self.upsample.bias}
+    for k in range(self.n_flows):
+      wn = self.WN[k]
+      p = f"WN.{k}."
+      out[p + "start.weight"], out[p + "start.bias"] = wn.start.weight, wn.start.bias
+      out[p + "end.weight"], out[p + "end.bias"] = wn.end.weight, wn.end.bias
+      out[p + "cond_layer.weight"], out[p + "cond_layer.bias"] = wn.cond_layer.weight, wn.cond_layer.bias
+      for i in range(wn.n_layers):
+        out[p + f"in_layers.{i}.weight"], out[p + f"in_layers.{i}.bias"] = wn.in_layers[i].weight, wn.in_layers[i].bias
+        out[p + f"res_skip_layers.{i}.weight"] = wn.res_skip_layers[i].weight
+        out[p + f"res_skip_layers.{i}.bias"] = wn.res_skip_layers[i].bias
+      out[f"convinv.{k}.conv.weight"] = self.convinv[k].conv.weight
+    return {n: t.detach() for n, t in out.items()}
+
+  def engine(self) -> _engine.Engine:
+    device = self.upsample.weight.device
+    if device.type != "cuda":
+      raise _engine.WgError("WaveGlow.infer runs on the B200 engine only: move the model to a CUDA device "
+                            "(there is no CPU fallback)")
+    if self._engine is None:
+      prec = _engine.PRECISION_FP16 if self._precision == "fp16" else _engine.PRECISION_FP32
+      self._engine = _engine.Engine(self.hparams, prec, device)
+      self._packed = False
+    if not self._packed:
+      with torch.no_grad():
+        self._engine.load_weights(self.folded_weights())
+      self._packed = True
+    return self._engine
+
+  # ------------------------------------------------------------------ reference call surface
+  def draw_noise(self, batch: int, n_groups: int, device: torch.device) -> List[torch.Tensor]:
+    """N(0,1) from torch's global generator on `device`, in the reference's order, shapes and dtype
+    (model.py:239-243 then 266-270 for k = 8, 4) so a seed means the same thing as in the reference."""
+    zs = [torch.empty(batch, self.n_remaining_channels, n_groups, dtype=torch.float32, device=device).normal_()]
+    for k in reversed(range(self.n_flows)):
+      if k % self.n_early_every == 0 and k > 0:
+        zs.append(torch.empty(batch, self.n_early_size, n_groups, dtype=torch.float32, device=device).normal_())
+    return zs
+
+  def infer_with_noise(self, spect: torch.Tensor, zs: Sequence[torch.Tensor], sigma: float = 1.0) -> torch.Tensor:
+    if spect.dim() != 3 or spect.size(1) != self.hparams.n_mel_channels:
+      raise ValueError(f"spect must be [B, {self.hparams.n_mel_channels}, frames], got {tuple(spect.shape)}")
+    eng = self.engine()
+    with torch.no_grad():
+      return eng.infer(spect, zs, sigma)
+
+  def infer(self, spect: torch.Tensor, sigma: float = 1.0) -> torch.Tensor:
+    """audio[B, 256 * frames] = inverse flow of sigma * N(0,1) conditioned on spect[B, 80, frames] (model.py:223-274)."""
+    n_groups = spect.size(2) * 256 // self.n_group
+    zs = self.draw_noise(spect.size(0), n_groups, spect.device)
+    return self.infer_with_noise(spect, zs, sigma)
+
+  def forward(self, forward_input: Tuple[torch.Tensor, torch.Tensor]):
+    raise NotImplementedError("training-direction flow (model.py:178-221) is not wired to the engine yet")
+
+  @staticmethod
+  def remove_weightnorm(model: "WaveGlow") -> "WaveGlow":
+    """Folds w = g v / ||v|| for start, in_layers, cond_layer, res_skip_layers (model.py:276-297)."""
+    for wnet in model.WN:
+      if torch.nn.utils.parametrize.is_parametrized(wnet.start, "weight"):
+        wnet.start = torch.nn.utils.parametrize.remove_parametrizations(wnet.start, "weight")
+        wnet.in_layers = _remove(wnet.in_layers)
+        wnet.cond_layer = torch.nn.utils.parametrize.remove_parametrizations(wnet.cond_layer, "weight")
+        wnet.res_skip_layers = _remove(wnet.res_skip_layers)
+    model.invalidate_packed_weights()
+    return model
+
+
+def load_model(hparams: HParams, state_dict: Optional[dict], device: torch.device, precision: str = "fp16") -> WaveGlow:
+  """Mirror of train.py:48-55, minus `try_copy_to`'s silent CPU fallback (do not replicate)."""
+  model = WaveGlow(hparams, precision=precision).to(device)
+  if state_dict is not None:
+    model.load_state_dict(state_dict)
+  return model

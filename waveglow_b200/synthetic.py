@@ -95,6 +95,8 @@ def synthetic_state_dict(hp: HParams, seed: int = 1234, end_std: float = 0.02,
     q, _ = torch.linalg.qr(torch.randn((c, c), generator=gen))
     if torch.det(q) < 0:
       q[:, 0] = -q[:, 0]
+    # a trained 1x1 weight is no longer orthonormal: perturb so that W^-1 != W^T and log|det W| != 0
+    q = q @ (torch.eye(c) + 0.03 * torch.randn((c, c), generator=gen))
     sd[f"convinv.{k}.conv.weight"] = q.contiguous().view(c, c, 1)
   return sd
 
