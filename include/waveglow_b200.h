@@ -120,6 +120,10 @@ int wg_profile_layers(wg_engine* e, float* total_ms, int32_t* n_launches);
 int wg_debug_gemm(wg_engine* e, const void* a, const void* b, float* d, int32_t m, int32_t n, int32_t k,
                   int32_t fmt, void* stream);
 
+/* Diagnostics: when set (device pointer to [n_ctas][16] int64), every fused layer launch writes clock64
+ * stamps of its pipeline phases per CTA (slot meaning: tools/timeline.py).  NULL disables (default). */
+int wg_debug_timeline(wg_engine* e, long long* device_buffer);
+
 /* Test/diagnostic hooks (used by tests/ only).
  * wg_debug_stop_after: make the next wg_infer return after flow `flow` (counting down from
  * n_flows-1), WN layer `layer` (-1 = after the start conv, n_layers = after the whole flow incl. the

@@ -63,6 +63,9 @@ struct wg_engine {
   PFN_encodeTiled encode = nullptr;
   std::vector<cudaEvent_t> ev;        // 2 per flow: around the WN layer launches of the last call
   int ev_flows = 0;                   // flows recorded by the last call
+  long long* dbg_timeline = nullptr;  // device buffer for clock64 stamps of layer launches (tests/diagnostics)
+  int num_sms = 148;
+  int dbg_flags = 0;                  // WG_DBG_FLAGS env (diagnostics; see LayerTcParams::dbg_flags)
   int op_fmt = 0;                     // 0 = fp16 operands, 1 = bf16 (WG_B200_OPERAND=bf16; fails the max-abs gate, kept for study)
 };
 
@@ -234,6 +237,7 @@ int wg_create(const wg_config* cfg, wg_engine** out) {
   if (prop.major != 10)
     return fail(e, WG_ERR_UNSUPPORTED, "device %d is sm_%d%d; kernels are built for sm_100a only", cfg->device, prop.major, prop.minor);
   WG_CUDA(e, cudaSetDevice(cfg->device));
+  e->num_sms = prop.multiProcessorCount;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   WG_CUDA(e, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -241,6 +245,8 @@ int wg_create(const wg_config* cfg, wg_engine** out) {
   e->encode = reinterpret_cast<PFN_encodeTiled>(fn);
   const char* fmt_env = getenv("WG_B200_OPERAND");
   e->op_fmt = (fmt_env && strcmp(fmt_env, "bf16") == 0) ? 1 : 0;
+  const char* dbg_env = getenv("WG_DBG_FLAGS");
+  e->dbg_flags = dbg_env ? atoi(dbg_env) : 0;
   WG_CUDA(e, cudaFuncSetAttribute(wn_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total + 1024));
   WG_CUDA(e, cudaFuncSetAttribute(debug_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 49152 + 1024 + 128));
   WG_CUDA(e, cudaFuncSetAttribute(wn_layer_fp32_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -551,6 +557,7 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
     if (tc) {
       LayerTcParams lp{};
       lp.T = T;
+      lp.B = B;
       lp.dilation = 1 << i;
       lp.w1_row0 = static_cast<int>(li * 2 * nc);
       lp.w2_row0 = static_cast<int>(li * kW2Rows);
@@ -560,7 +567,10 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
       lp.bias1 = e->d_bias1 + li * 2 * nc;
       lp.bias_res = e->d_bias_res + li * nc;
       lp.e = ebuf;
-      dim3 grid((T + kTileM - 1) / kTileM, B);
+      lp.timeline = e->dbg_timeline;
+      lp.dbg_flags = e->dbg_flags;
+      const int n_tiles = ((T + kTileM - 1) / kTileM) * B;
+      dim3 grid(n_tiles < e->num_sms ? n_tiles : e->num_sms);
       wn_layer_tc_kernel<<<grid, kTcThreads, TcSmem::total + 1024, st>>>(tm_x[*cur], tm_x[*cur ^ 1], *tm_cond, e->tm_w1,
                                                                         e->tm_w2a, e->tm_w2b, e->tm_ident, lp);
     } else {
@@ -731,6 +741,12 @@ int wg_infer(wg_engine* e, const float* mel, int32_t batch, int32_t frames, cons
     if (k > 0 && e->dbg_flow == k - 1 && e->dbg_layer == -1) stopped = true;
   }
   WG_CUDA(e, cudaGetLastError());
+  return WG_OK;
+}
+
+int wg_debug_timeline(wg_engine* e, long long* device_buffer) {
+  if (!e) return WG_ERR_INVALID_ARGUMENT;
+  e->dbg_timeline = device_buffer;
   return WG_OK;
 }
 

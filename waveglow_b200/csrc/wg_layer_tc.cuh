@@ -17,7 +17,12 @@
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
 // warps 2..9 = gate / epilogue (thread = one TMEM lane = one group-step, two column halves).
-// TMEM: 512 columns = R0 [0,256) chunk-a accumulator then x', R1 [256,512) chunk-b accumulator then e'.
+// The kernel is PERSISTENT (one CTA per SM, tiles strided by gridDim.x) and software-pipelined across
+// tiles.  TMEM: 512 columns = two 256-column regions whose roles alternate per tile:
+//   tile i:  region A(i) <- GEMM1 chunk a, later x';   region B(i) <- GEMM1 chunk b, later e' (16 columns)
+//   A(i+1) = B(i), B(i+1) = A(i): the next tile's GEMM1 starts as soon as the 16 e' columns are read, so
+//   the x' drain + TMA store, the barrier/TMEM setup and the TMA pipeline fill are all off the MMA's
+//   critical path (measured timeline: profiles/).
 #pragma once
 #include "wg_ptx.cuh"
 
@@ -52,6 +57,7 @@ static_assert(TcSmem::total + 1024 <= 232448, "shared memory budget exceeded");
 
 struct LayerTcParams {
   int T;              // group-steps per utterance
+  int B;              // utterances
   int dilation;
   int w1_row0;        // first packed-W1 row of this (flow, layer)
   int w2_row0;        // first packed-W2 row of this (flow, layer)
@@ -61,7 +67,13 @@ struct LayerTcParams {
   const float* bias1;     // [512] packed order, b_in + b_cond
   const float* bias_res;  // [256]
   float* e;               // [B, T, 8] fp32
+  int dbg_flags;          // diagnostics only: bit0 skip GEMM1 B loads, bit1 skip GEMM1 A loads (results invalid)
+  long long* timeline;    // optional [n_ctas][16] clock64 stamps (diagnostics; nullptr in production)
 };
+
+__device__ __forceinline__ void stamp(const LayerTcParams& p, int slot) {
+  if (p.timeline) p.timeline[(static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 16 + slot] = clock64();
+}
 
 __device__ __forceinline__ float gate_one(float a, float b) {
   // tanh(a) * sigmoid(b), sigmoid(b) = 0.5 + 0.5 tanh(b/2)   (model.py:13-20)
@@ -80,22 +92,28 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, T, B}
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TcSmem::bars);
-  uint64_t* full = bars;                 // [kStages]
-  uint64_t* empty = bars + kStages;      // [kStages]
-  uint64_t* acc_full = bars + 2 * kStages;      // [2]
-  uint64_t* acts_ready = acc_full + 2;          // [2]
-  uint64_t* d2_full = acts_ready + 2;           // [1]
+  uint64_t* full = bars;                 // [kStages]  TMA -> MMA
+  uint64_t* empty = bars + kStages;      // [kStages]  MMA -> TMA
+  uint64_t* acc_full = bars + 2 * kStages;      // [2]  MMA -> gate: GEMM1 chunk a / b accumulator complete
+  uint64_t* acts_ready = acc_full + 2;          // [2]  gate -> MMA: acts slabs written, accumulator region drained
+  uint64_t* d2_full = acts_ready + 2;           // [1]  MMA -> epilogue: GEMM2 complete
   uint64_t* ident_full = d2_full + 1;           // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ident_full + 1);
+  uint64_t* e_drained = ident_full + 1;         // [1]  epilogue -> MMA: skip-end columns read (region reusable)
+  uint64_t* res_drained = e_drained + 1;        // [1]  epilogue -> MMA: residual columns read (region reusable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_drained + 1);
   float* s_bias1 = reinterpret_cast<float*>(smem + TcSmem::bias1);
   float* s_bias_res = reinterpret_cast<float*>(smem + TcSmem::bias_res);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int t0 = blockIdx.x * kTileM;
-  const int b = blockIdx.y;
+  const int tiles_per_utt = (p.T + kTileM - 1) / kTileM;
+  const int n_tiles = tiles_per_utt * p.B;
+  // persistent: this CTA processes tiles blockIdx.x, blockIdx.x + gridDim.x, ...  Concurrently running
+  // tiles are therefore neighbours in time, so the dilation halos are served from L2.
+  const int my_tiles = (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
   // ---- one-time setup
+  if (threadIdx.x == 0) stamp(p, 0);
   for (int i = threadIdx.x; i < 2 * kNC; i += kTcThreads) s_bias1[i] = p.bias1[i];
   for (int i = threadIdx.x; i < kNC; i += kTcThreads) s_bias_res[i] = p.has_res ? p.bias_res[i] : 0.f;
   if (threadIdx.x == 0) {
@@ -109,6 +127,8 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, T, B}
     ptx::mbar_init(&acts_ready[1], 256);
     ptx::mbar_init(d2_full, 1);
     ptx::mbar_init(ident_full, 1);
+    ptx::mbar_init(e_drained, 128);
+    ptx::mbar_init(res_drained, 256);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -119,8 +139,6 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, T, B}
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-
-  const int n_g2 = p.has_res ? 8 : 4;   // stage uses of GEMM2 (4 W2 K-blocks [+ 4 x K-blocks for the identity term])
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -133,36 +151,45 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, T, B}
         ptx::tma_load_2d(smem + TcSmem::ident, &tm_ident, ident_full, 0, 0);
       }
       int use = 0;
-      for (int chunk = 0; chunk < 2; ++chunk) {
-        for (int kb = 0; kb < kKB1; ++kb, ++use) {
+      for (int it = 0; it < my_tiles; ++it) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int b = tile / tiles_per_utt;
+        const int t0 = (tile % tiles_per_utt) * kTileM;
+        for (int chunk = 0; chunk < 2; ++chunk) {
+          for (int kb = 0; kb < kKB1; ++kb, ++use) {
+            const int s = use % kStages;
+            const uint32_t ph = (use / kStages) & 1;
+            ptx::mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* sa = smem + TcSmem::stage0 + s * kStageBytes;
+            uint8_t* sb = sa + kStageABytes;
+            const bool skip_b = (p.dbg_flags & 1) && use >= kStages, skip_a = (p.dbg_flags & 2) && use >= kStages;
+            if (skip_a && skip_b) {
+              ptx::mbar_arrive(&full[s]);
+              continue;
+            }
+            ptx::mbar_arrive_expect_tx(&full[s], (skip_a ? 0 : kStageABytes) + (skip_b ? 0 : 256 * 128));
+            if (!skip_a) {
+              if (kb < 12) {
+                const int tap = kb >> 2;   // 0: t-d, 1: t, 2: t+d
+                ptx::tma_load_3d(sa, &tm_x_in, &full[s], (kb & 3) * kBlockK, t0 + (tap - 1) * p.dilation, b);
+              } else {
+                ptx::tma_load_3d(sa, &tm_cond, &full[s], (kb - 12) * kBlockK, t0, b);
+              }
+            }
+            if (!skip_b) ptx::tma_load_2d(sb, &tm_w1, &full[s], kb * kBlockK, p.w1_row0 + chunk * 256);
+          }
+        }
+        // GEMM2: stage j = W2 K-block j (B region) + x(t) K-block j for the identity term (A region)
+        for (int j = 0; j < 4; ++j, ++use) {
           const int s = use % kStages;
           const uint32_t ph = (use / kStages) & 1;
           ptx::mbar_wait(&empty[s], ph ^ 1);
           uint8_t* sa = smem + TcSmem::stage0 + s * kStageBytes;
           uint8_t* sb = sa + kStageABytes;
-          ptx::mbar_arrive_expect_tx(&full[s], kStageABytes + 256 * 128);
-          if (kb < 12) {
-            const int tap = kb >> 2;   // 0: t-d, 1: t, 2: t+d
-            ptx::tma_load_3d(sa, &tm_x_in, &full[s], (kb & 3) * kBlockK, t0 + (tap - 1) * p.dilation, b);
-          } else {
-            ptx::tma_load_3d(sa, &tm_cond, &full[s], (kb - 12) * kBlockK, t0, b);
-          }
-          ptx::tma_load_2d(sb, &tm_w1, &full[s], kb * kBlockK, p.w1_row0 + chunk * 256);
-        }
-      }
-      for (int j = 0; j < n_g2; ++j, ++use) {
-        const int s = use % kStages;
-        const uint32_t ph = (use / kStages) & 1;
-        ptx::mbar_wait(&empty[s], ph ^ 1);
-        uint8_t* sa = smem + TcSmem::stage0 + s * kStageBytes;
-        uint8_t* sb = sa + kStageABytes;
-        if (j < 4) {
-          ptx::mbar_arrive_expect_tx(&full[s], kStageBBytes);
+          ptx::mbar_arrive_expect_tx(&full[s], kStageBBytes + (p.has_res ? kStageABytes : 0));
           ptx::tma_load_2d(sb, &tm_w2a, &full[s], j * kBlockK, p.w2_row0);
           ptx::tma_load_2d(sb + 256 * 128, &tm_w2b, &full[s], j * kBlockK, p.w2_row0 + 256);
-        } else {
-          ptx::mbar_arrive_expect_tx(&full[s], kStageABytes);
-          ptx::tma_load_3d(sa, &tm_x_in, &full[s], (j - 4) * kBlockK, t0, b);
+          if (p.has_res) ptx::tma_load_3d(sa, &tm_x_in, &full[s], j * kBlockK, t0, b);
         }
       }
     }
@@ -176,162 +203,206 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, T, B}
       const uint32_t acts_addr = ptx::smem_u32(smem + TcSmem::acts);
       const uint32_t ident_addr = ptx::smem_u32(smem + TcSmem::ident);
       int use = 0;
-      for (int chunk = 0; chunk < 2; ++chunk) {
-        const uint32_t d = tmem_base + chunk * 256;
-        for (int kb = 0; kb < kKB1; ++kb, ++use) {
-          const int s = use % kStages;
-          const uint32_t ph = (use / kStages) & 1;
-          ptx::mbar_wait(&full[s], ph);
-          ptx::tc_fence_after_sync();
-          const uint32_t a_addr = stage_addr0 + s * kStageBytes;
-          const uint32_t b_addr = a_addr + kStageABytes;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            ptx::mma_f16_ss(d, ptx::make_desc_sw128(a_addr + k * 32), ptx::make_desc_sw128(b_addr + k * 32), idesc256,
-                            (kb | k) != 0);
+      stamp(p, 1);
+      for (int it = 0; it < my_tiles; ++it) {
+        const uint32_t par = it & 1;
+        // TMEM regions alternate between tiles: this tile's chunk-a region is the previous tile's
+        // chunk-b region (free once its 16 skip-end columns are read); this tile's chunk-b region is
+        // the previous tile's chunk-a region (free once x' is drained, long before it is needed).
+        const uint32_t ra = tmem_base + par * 256;
+        const uint32_t rb = tmem_base + (par ^ 1) * 256;
+        const bool tl = (it == 1);     // timeline: steady-state tile
+        for (int chunk = 0; chunk < 2; ++chunk) {
+          if (it > 0) {
+            ptx::mbar_wait(chunk == 0 ? e_drained : res_drained, par ^ 1);
+            ptx::tc_fence_after_sync();
           }
-          ptx::mma_commit(&empty[s]);
-        }
-        ptx::mma_commit(&acc_full[chunk]);
-      }
-      // GEMM2 needs all of acts (K = 256) and both accumulator regions drained by the gate.
-      ptx::mbar_wait(&acts_ready[0], 0);
-      ptx::mbar_wait(&acts_ready[1], 0);
-      ptx::tc_fence_after_sync();
-      for (int j = 0; j < 4; ++j, ++use) {
-        const int s = use % kStages;
-        const uint32_t ph = (use / kStages) & 1;
-        ptx::mbar_wait(&full[s], ph);
-        ptx::tc_fence_after_sync();
-        const uint32_t b_addr = stage_addr0 + s * kStageBytes + kStageABytes;
-        const uint32_t a_addr = acts_addr + j * (kTileM * 128);
+          const uint32_t d = chunk == 0 ? ra : rb;
+          for (int kb = 0; kb < kKB1; ++kb, ++use) {
+            const int s = use % kStages;
+            const uint32_t ph = (use / kStages) & 1;
+            ptx::mbar_wait(&full[s], ph);
+            ptx::tc_fence_after_sync();
+            if (tl && chunk == 0 && kb == 0) stamp(p, 2);
+            const uint32_t a_addr = stage_addr0 + s * kStageBytes;
+            const uint32_t b_addr = a_addr + kStageABytes;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t ad = ptx::make_desc_sw128(a_addr + k * 32);
-          if (p.has_res) ptx::mma_f16_ss(tmem_base, ad, ptx::make_desc_sw128(b_addr + k * 32), idesc256, (j | k) != 0);
-          ptx::mma_f16_ss(tmem_base + 256, ad, ptx::make_desc_sw128(b_addr + 256 * 128 + k * 32), idesc16, (j | k) != 0);
+            for (int k = 0; k < 4; ++k) {
+              ptx::mma_f16_ss(d, ptx::make_desc_sw128(a_addr + k * 32), ptx::make_desc_sw128(b_addr + k * 32), idesc256,
+                              (kb | k) != 0);
+            }
+            ptx::mma_commit(&empty[s]);
+          }
+          ptx::mma_commit(&acc_full[chunk]);
+          if (tl) stamp(p, 3 + chunk);
         }
-        ptx::mma_commit(&empty[s]);
-      }
-      if (p.has_res) {
-        ptx::mbar_wait(ident_full, 0);
+        // GEMM2 needs all of acts (K = 256) and both accumulator regions drained by the gate.
+        ptx::mbar_wait(&acts_ready[0], par);
+        ptx::mbar_wait(&acts_ready[1], par);
+        ptx::tc_fence_after_sync();
+        if (tl) stamp(p, 9);
+        if (p.has_res && it == 0) ptx::mbar_wait(ident_full, 0);
         for (int j = 0; j < 4; ++j, ++use) {
           const int s = use % kStages;
           const uint32_t ph = (use / kStages) & 1;
           ptx::mbar_wait(&full[s], ph);
           ptx::tc_fence_after_sync();
-          const uint32_t a_addr = stage_addr0 + s * kStageBytes;
+          const uint32_t x_addr = stage_addr0 + s * kStageBytes;
+          const uint32_t b_addr = x_addr + kStageABytes;
+          const uint32_t a_addr = acts_addr + j * (kTileM * 128);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            ptx::mma_f16_ss(tmem_base + j * 64, ptx::make_desc_sw128(a_addr + k * 32),
-                            ptx::make_desc_sw128(ident_addr + k * 32), idesc64, 1);
+            const uint64_t ad = ptx::make_desc_sw128(a_addr + k * 32);
+            if (p.has_res) ptx::mma_f16_ss(ra, ad, ptx::make_desc_sw128(b_addr + k * 32), idesc256, (j | k) != 0);
+            ptx::mma_f16_ss(rb, ad, ptx::make_desc_sw128(b_addr + 256 * 128 + k * 32), idesc16, (j | k) != 0);
+          }
+          if (p.has_res) {
+            // x' += x . I : carries the residual stream on the tensor core (columns 64j .. 64j+63)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              ptx::mma_f16_ss(ra + j * 64, ptx::make_desc_sw128(x_addr + k * 32), ptx::make_desc_sw128(ident_addr + k * 32),
+                              idesc64, 1);
+            }
           }
           ptx::mma_commit(&empty[s]);
         }
+        ptx::mma_commit(d2_full);
+        if (tl) stamp(p, 10);
       }
-      ptx::mma_commit(d2_full);
     }
   } else {
     // =============================== gate / epilogue warps ===============================
     const int q = warp & 3;              // TMEM lane quarter this warp may touch
     const int hh = (warp - 2) >> 2;      // column half handled by this warp
     const int row = q * 32 + lane;       // group-step inside the tile == TMEM lane
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint8_t* acts = smem + TcSmem::acts;
+    bool store_pending = false;          // an x' TMA store of the previous tile may still read the staging buffer
 
-    for (int chunk = 0; chunk < 2; ++chunk) {
-      ptx::mbar_wait(&acc_full[chunk], 0);
-      ptx::tc_fence_after_sync();
-      const int slab = 2 * chunk + hh;                 // acts channels [64*slab, 64*slab+64)
-      uint8_t* slab_row = acts + slab * (kTileM * 128) + row * 128;
-      const float* bt = s_bias1 + chunk * 256 + hh * 64;
-      const float* bs = bt + 128;
-#pragma unroll 1
-      for (int g = 0; g < 4; ++g) {
-        uint32_t vt[16], vs[16];
-        const uint32_t col = chunk * 256 + hh * 64 + g * 16;
-        ptx::tmem_ld16(lane_addr + col, vt);
-        ptx::tmem_ld16(lane_addr + col + 128, vs);
-        ptx::tmem_ld_wait();
-        uint32_t pk[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float a0 = gate_one(__uint_as_float(vt[2 * i]) + bt[g * 16 + 2 * i],
-                                    __uint_as_float(vs[2 * i]) + bs[g * 16 + 2 * i]);
-          const float a1 = gate_one(__uint_as_float(vt[2 * i + 1]) + bt[g * 16 + 2 * i + 1],
-                                    __uint_as_float(vs[2 * i + 1]) + bs[g * 16 + 2 * i + 1]);
-          if (p.fmt == 0) {
-            pk[i] = ptx::pack_half2(a0, a1);
-          } else {
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
-            pk[i] = *reinterpret_cast<uint32_t*>(&h2);
-          }
+    for (int it = 0; it < my_tiles; ++it) {
+      const uint32_t par = it & 1;
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int b = tile / tiles_per_utt;
+      const int t0 = (tile % tiles_per_utt) * kTileM;
+      const uint32_t ra = lane_base + par * 256;
+      const uint32_t rb = lane_base + (par ^ 1) * 256;
+      const bool tl = (it == 1) && threadIdx.x == 64;
+
+      for (int chunk = 0; chunk < 2; ++chunk) {
+        ptx::mbar_wait(&acc_full[chunk], par);
+        ptx::tc_fence_after_sync();
+        if (tl) stamp(p, 5 + 2 * chunk);
+        if (chunk == 0 && store_pending) {
+          // the acts buffer doubles as x' staging: wait until the previous tile's TMA store has read it
+          if (warp == 2 && lane == 0) ptx::tma_store_wait_read();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          store_pending = false;
         }
-        // 128-byte swizzle: 16-byte chunk index XOR (row mod 8)
-        const int c0 = (2 * g) ^ (row & 7);
-        const int c1 = (2 * g + 1) ^ (row & 7);
-        *reinterpret_cast<uint4*>(slab_row + c0 * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(slab_row + c1 * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        const uint32_t rc = chunk == 0 ? ra : rb;
+        const int slab = 2 * chunk + hh;                 // acts channels [64*slab, 64*slab+64)
+        uint8_t* slab_row = acts + slab * (kTileM * 128) + row * 128;
+        const float* bt = s_bias1 + chunk * 256 + hh * 64;
+        const float* bs = bt + 128;
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          uint32_t vt[16], vs[16];
+          const uint32_t col = hh * 64 + g * 16;
+          ptx::tmem_ld16(rc + col, vt);
+          ptx::tmem_ld16(rc + col + 128, vs);
+          ptx::tmem_ld_wait();
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float a0 = gate_one(__uint_as_float(vt[2 * i]) + bt[g * 16 + 2 * i],
+                                      __uint_as_float(vs[2 * i]) + bs[g * 16 + 2 * i]);
+            const float a1 = gate_one(__uint_as_float(vt[2 * i + 1]) + bt[g * 16 + 2 * i + 1],
+                                      __uint_as_float(vs[2 * i + 1]) + bs[g * 16 + 2 * i + 1]);
+            if (p.fmt == 0) {
+              pk[i] = ptx::pack_half2(a0, a1);
+            } else {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
+              pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+          }
+          // 128-byte swizzle: 16-byte chunk index XOR (row mod 8)
+          const int c0 = (2 * g) ^ (row & 7);
+          const int c1 = (2 * g + 1) ^ (row & 7);
+          *reinterpret_cast<uint4*>(slab_row + c0 * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(slab_row + c1 * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        ptx::tc_fence_before_sync();
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&acts_ready[chunk]);
+        if (tl) stamp(p, 6 + 2 * chunk);
+      }
+
+      // ---- epilogue 2: e' (fp32, direct; read FIRST so the MMA can reuse that region) and x' (fp16, smem + TMA store)
+      ptx::mbar_wait(d2_full, par);
+      ptx::tc_fence_after_sync();
+      if (tl) stamp(p, 11);
+      const int t = t0 + row;
+      if (hh == 0) {
+        uint32_t ve[8];
+        ptx::tmem_ld8(rb, ve);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before_sync();
+        ptx::mbar_arrive(e_drained);
+        if (t < p.T) {
+          float4* ep = reinterpret_cast<float4*>(p.e + (static_cast<size_t>(b) * p.T + t) * 8);
+          float4 lo = make_float4(__uint_as_float(ve[0]), __uint_as_float(ve[1]), __uint_as_float(ve[2]), __uint_as_float(ve[3]));
+          float4 hi = make_float4(__uint_as_float(ve[4]), __uint_as_float(ve[5]), __uint_as_float(ve[6]), __uint_as_float(ve[7]));
+          if (p.accumulate_e) {
+            const float4 o0 = ep[0], o1 = ep[1];
+            lo.x += o0.x; lo.y += o0.y; lo.z += o0.z; lo.w += o0.w;
+            hi.x += o1.x; hi.y += o1.y; hi.z += o1.z; hi.w += o1.w;
+          }
+          ep[0] = lo;
+          ep[1] = hi;
+        }
+      }
+      if (p.has_res) {
+#pragma unroll 1
+        for (int g = 0; g < 8; ++g) {
+          uint32_t v[16];
+          const int ch0 = hh * 128 + g * 16;          // first residual channel of this group
+          ptx::tmem_ld16(ra + ch0, v);
+          ptx::tmem_ld_wait();
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float a0 = __uint_as_float(v[2 * i]) + s_bias_res[ch0 + 2 * i];
+            const float a1 = __uint_as_float(v[2 * i + 1]) + s_bias_res[ch0 + 2 * i + 1];
+            if (p.fmt == 0) {
+              pk[i] = ptx::pack_half2(a0, a1);
+            } else {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
+              pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+          }
+          const int slab = ch0 >> 6;
+          const int cc = (ch0 & 63) >> 3;             // 16-byte chunk inside the 128-byte row
+          uint8_t* slab_row = acts + slab * (kTileM * 128) + row * 128;
+          *reinterpret_cast<uint4*>(slab_row + ((cc ^ (row & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(slab_row + (((cc + 1) ^ (row & 7)) * 16)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
       }
       ptx::tc_fence_before_sync();
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&acts_ready[chunk]);
-    }
-
-    // ---- epilogue 2: x' (fp16, via smem + TMA store) and e' (fp32, direct)
-    ptx::mbar_wait(d2_full, 0);
-    ptx::tc_fence_after_sync();
-    const int t = t0 + row;
-    if (hh == 0) {
-      uint32_t ve[8];
-      ptx::tmem_ld8(lane_addr + 256, ve);
-      ptx::tmem_ld_wait();
-      if (t < p.T) {
-        float4* ep = reinterpret_cast<float4*>(p.e + (static_cast<size_t>(b) * p.T + t) * 8);
-        float4 lo = make_float4(__uint_as_float(ve[0]), __uint_as_float(ve[1]), __uint_as_float(ve[2]), __uint_as_float(ve[3]));
-        float4 hi = make_float4(__uint_as_float(ve[4]), __uint_as_float(ve[5]), __uint_as_float(ve[6]), __uint_as_float(ve[7]));
-        if (p.accumulate_e) {
-          const float4 o0 = ep[0], o1 = ep[1];
-          lo.x += o0.x; lo.y += o0.y; lo.z += o0.z; lo.w += o0.w;
-          hi.x += o1.x; hi.y += o1.y; hi.z += o1.z; hi.w += o1.w;
+      ptx::mbar_arrive(res_drained);
+      if (p.has_res) {
+        ptx::fence_proxy_async_smem();
+        if (tl) stamp(p, 12);
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps only
+        if (warp == 2 && lane == 0) {
+#pragma unroll
+          for (int s4 = 0; s4 < 4; ++s4) ptx::tma_store_3d(&tm_x_out, acts + s4 * (kTileM * 128), s4 * kBlockK, t0, b);
+          ptx::tma_store_commit();
         }
-        ep[0] = lo;
-        ep[1] = hi;
+        store_pending = true;
       }
     }
-    if (p.has_res) {
-#pragma unroll 1
-      for (int g = 0; g < 8; ++g) {
-        uint32_t v[16];
-        const int ch0 = hh * 128 + g * 16;          // first residual channel of this group
-        ptx::tmem_ld16(lane_addr + ch0, v);
-        ptx::tmem_ld_wait();
-        uint32_t pk[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float a0 = __uint_as_float(v[2 * i]) + s_bias_res[ch0 + 2 * i];
-          const float a1 = __uint_as_float(v[2 * i + 1]) + s_bias_res[ch0 + 2 * i + 1];
-          if (p.fmt == 0) {
-            pk[i] = ptx::pack_half2(a0, a1);
-          } else {
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
-            pk[i] = *reinterpret_cast<uint32_t*>(&h2);
-          }
-        }
-        const int slab = ch0 >> 6;
-        const int cc = (ch0 & 63) >> 3;             // 16-byte chunk inside the 128-byte row
-        uint8_t* slab_row = acts + slab * (kTileM * 128) + row * 128;
-        *reinterpret_cast<uint4*>(slab_row + ((cc ^ (row & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(slab_row + (((cc + 1) ^ (row & 7)) * 16)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      }
-      ptx::fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps only
-      if (warp == 2 && lane == 0) {
-#pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) ptx::tma_store_3d(&tm_x_out, acts + s4 * (kTileM * 128), s4 * kBlockK, t0, b);
-        ptx::tma_store_commit();
-        ptx::tma_store_wait_all();
-      }
+    if (warp == 2 && lane == 0) {
+      ptx::tma_store_wait_all();
+      stamp(p, 13);
     }
   }
 
@@ -340,6 +411,7 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, T, B}
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after_sync();
+    if (lane == 0) stamp(p, 14);
     ptx::tmem_dealloc(tmem_base, 512);
   }
 }

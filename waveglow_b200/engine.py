@@ -18,7 +18,7 @@ PRECISION_FP16 = 1
 
 EXPORTED_SYMBOLS = [
   "wg_create", "wg_load_weights", "wg_workspace_bytes", "wg_infer", "wg_forward", "wg_last_launch_count",
-  "wg_debug_stop_after", "wg_debug_view", "wg_debug_gemm", "wg_profile_layers", "wg_last_error", "wg_version",
+  "wg_debug_stop_after", "wg_debug_view", "wg_debug_gemm", "wg_debug_timeline", "wg_profile_layers", "wg_last_error", "wg_version",
   "wg_destroy",
 ]
 
@@ -70,6 +70,8 @@ def load_library() -> ctypes.CDLL:
   lib.wg_debug_view.restype = ctypes.c_int
   lib.wg_debug_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
   lib.wg_debug_gemm.restype = ctypes.c_int
+  lib.wg_debug_timeline.argtypes = [vp, vp]
+  lib.wg_debug_timeline.restype = ctypes.c_int
   lib.wg_profile_layers.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
   lib.wg_profile_layers.restype = ctypes.c_int
   lib.wg_last_error.argtypes = [vp]
@@ -181,6 +183,9 @@ class Engine:
   # ---- test hooks
   def debug_stop_after(self, flow: int, layer: int) -> None:
     self._check(self.lib.wg_debug_stop_after(self._h, flow, layer), "wg_debug_stop_after")
+
+  def debug_timeline(self, buf: Optional[torch.Tensor]) -> None:
+    self._check(self.lib.wg_debug_timeline(self._h, buf.data_ptr() if buf is not None else None), "wg_debug_timeline")
 
   def debug_view(self, name: str, batch: int, frames: int) -> torch.Tensor:
     """Copy of a named workspace buffer as a flat tensor of the right dtype."""
