@@ -7,6 +7,10 @@ algebraically equivalent form that suits one fused tcgen05 kernel per WN layer:
   * the conditioning 1x1 conv (model.py:121) is a K-extension of each layer's dilated conv:
         in_i(t) = [W_in_i(tap-1) | W_in_i(tap0) | W_in_i(tap+1) | W_cond_i] . [x(t-d); x(t); x(t+d); S(t)]
     with the two biases folded;
+  * (tensor-core mode, `phase_cond=True`) the mel upsampler (ConvTranspose1d, model.py:145-150, 225) is
+    composed INTO the conditioning weights: a group-step t = 32 q + p (frame q, phase p) sees only the 4 mel
+    frames q..q-3, so  W_cond_i . S(t) = V_{i,p} . [mel(q); mel(q-1); mel(q-2); mel(q-3)] + const  with
+    V_{i,p} = W_cond_i . Wup_p  (K = 320 instead of 640; no upsampled tensor is ever formed);
   * the skip path and the `end` 1x1 conv (model.py:130-137) are folded per layer:
         end(sum_i skip_i) = sum_i (W_end W_skip_i) acts_i + (W_end sum_i b_skip_i + b_end)
     so each layer emits only 2h <= 8 "skip-end" channels accumulated in fp32 (`e`);
@@ -35,10 +39,34 @@ def rnd(x: Tensor, dt: torch.dtype) -> Tensor:
   return x if dt == torch.float32 else x.to(dt).to(torch.float32)
 
 
+def upsample_phase_weights(w: Dict[str, Tensor], dims: O.ModelDims) -> Tensor:
+  """Wup_p[p, cj = c*8+j, k = m*80+ci] = Wup[ci, c, 8p + j + 256m]   (float64), p < 32, m < 4."""
+  wup = w["upsample.weight"].double()                      # [ci, c, 1024]
+  n_mel, g = dims.n_mel_channels, dims.n_group
+  phases = 256 // g
+  out = torch.zeros(phases, n_mel * g, 4 * n_mel, dtype=torch.float64)
+  for p in range(phases):
+    for m in range(4):
+      blk = wup[:, :, g * p + 256 * m: g * p + 256 * m + g]      # [ci, c, j]
+      out[p, :, m * n_mel:(m + 1) * n_mel] = blk.permute(1, 2, 0).reshape(n_mel * g, n_mel)
+  return out
+
+
+def mel_windows(mel: Tensor, n_frames_out: int) -> Tensor:
+  """MW[b, q, m*80+ci] = mel[b, ci, q-m] (0 outside [0,F)), q < n_frames_out."""
+  B, n_mel, F = mel.shape
+  mw = torch.zeros(B, n_frames_out, 4 * n_mel, dtype=mel.dtype)
+  for m in range(4):
+    lo, hi = m, min(n_frames_out, F + m)
+    if hi > lo:
+      mw[:, lo:hi, m * n_mel:(m + 1) * n_mel] = mel[:, :, lo - m: hi - m].permute(0, 2, 1)
+  return mw
+
+
 class PackedFlow:
   """Per-flow packed weights in the engine's layout (fp32 master values, rounded on use)."""
 
-  def __init__(self, w: Dict[str, Tensor], dims: O.ModelDims, k: int):
+  def __init__(self, w: Dict[str, Tensor], dims: O.ModelDims, k: int, wup_p: Optional[Tensor] = None):
     nc, L = dims.n_channels, dims.n_layers
     p = f"WN.{k}."
     c = dims.flow_channels[k]
@@ -49,6 +77,8 @@ class PackedFlow:
     w_end = w[p + "end.weight"][:, :, 0].double()                 # [2h, nc]
     w_cond = w[p + "cond_layer.weight"][:, :, 0].double()         # [2 nc L, 640]
     b_cond = w[p + "cond_layer.bias"].double()
+    self.v: List[Tensor] = []    # phase-composed conditioning [32, 2nc, 320] (only when wup_p is given)
+    self.b1p: List[Tensor] = []  # bias for the phase-composed form (adds W_cond . upsample.bias)
     self.w1: List[Tensor] = []   # [2nc, 3nc + 640]   columns: tap-1 | tap0 | tap+1 | mel
     self.b1: List[Tensor] = []
     self.w_res: List[Optional[Tensor]] = []   # [nc, nc]
@@ -60,6 +90,11 @@ class PackedFlow:
       cat = torch.cat([wi[:, :, 0], wi[:, :, 1], wi[:, :, 2], w_cond[2 * nc * i: 2 * nc * (i + 1)]], dim=1)
       self.w1.append(cat.float())
       self.b1.append((w[p + f"in_layers.{i}.bias"].double() + b_cond[2 * nc * i: 2 * nc * (i + 1)]).float())
+      if wup_p is not None:
+        wc = w_cond[2 * nc * i: 2 * nc * (i + 1)]                       # [2nc, 640]
+        self.v.append(torch.einsum("oc,pck->pok", wc, wup_p).float())    # [32, 2nc, 320]
+        b_up = w["upsample.bias"].double().repeat_interleave(dims.n_group)
+        self.b1p.append((self.b1[-1].double() + wc @ b_up).float())
       wrs = w[p + f"res_skip_layers.{i}.weight"][:, :, 0].double()
       brs = w[p + f"res_skip_layers.{i}.bias"].double()
       if i < L - 1:
@@ -95,14 +130,22 @@ def shift_time(x: Tensor, s: int) -> Tensor:
 
 
 def wn_layers(pf: PackedFlow, dims: O.ModelDims, x: Tensor, S: Tensor, op_dtype: torch.dtype,
-              trace: Optional[list] = None) -> Tensor:
-  """x: [B,T',nc] (already in op_dtype precision), S: [B,T',640].  Returns e [B,T',2h] fp32 (without e_bias)."""
+              trace: Optional[list] = None, mw: Optional[Tensor] = None) -> Tensor:
+  """x: [B,T',nc] (already in op_dtype precision), S: [B,T',640] (or None with mw = mel windows [B,F',320]).
+  Returns e [B,T',2h] fp32 (without e_bias)."""
   nc = dims.n_channels
   e = torch.zeros(x.size(0), x.size(1), 2 * pf.h, dtype=torch.float32)
   for i in range(dims.n_layers):
     d = 2 ** i
-    a = torch.cat([shift_time(x, -d), x, shift_time(x, d), S], dim=2)          # [B,T',3nc+640]
-    pre = a @ rnd(pf.w1[i], op_dtype).t() + pf.b1[i]                           # fp32 accumulate
+    if mw is None:
+      a = torch.cat([shift_time(x, -d), x, shift_time(x, d), S], dim=2)          # [B,T',3nc+640]
+      pre = a @ rnd(pf.w1[i], op_dtype).t() + pf.b1[i]                           # fp32 accumulate
+    else:
+      a = torch.cat([shift_time(x, -d), x, shift_time(x, d)], dim=2)
+      pre = a @ rnd(pf.w1[i][:, : 3 * nc], op_dtype).t() + pf.b1p[i]
+      B, T, P = x.size(0), x.size(1), 256 // dims.n_group
+      cond = torch.einsum("bqk,pok->bqpo", mw, rnd(pf.v[i], op_dtype))           # [B,F',32,2nc]
+      pre = pre + cond.reshape(B, -1, 2 * nc)[:, :T]
     acts = rnd(torch.tanh(pre[..., :nc]) * torch.sigmoid(pre[..., nc:]), op_dtype)
     e = e + acts @ rnd(pf.w_se[i], op_dtype).t()
     if pf.w_res[i] is not None:
@@ -124,18 +167,24 @@ def pack_noise(dims: O.ModelDims, zs: Sequence[Tensor], sigma: float) -> Tensor:
 
 
 def infer(w: Dict[str, Tensor], dims: O.ModelDims, mel: Tensor, sigma: float, zs: Sequence[Tensor],
-          op_dtype: torch.dtype = torch.float16, trace: Optional[list] = None) -> Tensor:
-  S = rnd(upsample_squeeze_tm(w, dims, mel), op_dtype)
+          op_dtype: torch.dtype = torch.float16, trace: Optional[list] = None, phase_cond: bool = False) -> Tensor:
   state = pack_noise(dims, zs, sigma)                   # [B,T',8] fp32
   G = dims.n_group
+  if phase_cond:
+    wup_p = upsample_phase_weights(w, dims)
+    S = None
+    mw = rnd(mel_windows(mel, (state.size(1) + 31) // 32), op_dtype)
+  else:
+    wup_p, mw = None, None
+    S = rnd(upsample_squeeze_tm(w, dims, mel), op_dtype)
   for k in reversed(range(dims.n_flows)):
-    pf = PackedFlow(w, dims, k)
+    pf = PackedFlow(w, dims, k, wup_p)
     c, h = pf.c, pf.h
     a0 = state[..., G - c: G - c + h]
     a1 = state[..., G - c + h:]
     x = rnd(a0 @ pf.w_start.t() + pf.b_start, op_dtype)
     tr = [] if trace is not None else None
-    e = wn_layers(pf, dims, x, S, op_dtype, tr) + pf.e_bias
+    e = wn_layers(pf, dims, x, S, op_dtype, tr, mw) + pf.e_bias
     b, s = e[..., :h], e[..., h:]
     a1 = (a1 - b) * torch.exp(-s)
     live = torch.cat([a0, a1], dim=2) @ pf.w_inv.t()

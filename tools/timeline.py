@@ -35,7 +35,7 @@ def main():
   eng = model.engine()
   for _ in range(2):
     model.infer_with_noise(mel, zs, 0.666)
-  n_cta = a.batch * ((a.frames * 32 + 127) // 128)
+  n_cta = 148
   buf = torch.zeros((n_cta, 16), dtype=torch.int64, device=dev)
   eng.debug_timeline(buf)
   eng.debug_stop_after(hp.n_flows - 1, 3)       # stamps of the 4th layer launch (dilation 8) remain
@@ -45,7 +45,8 @@ def main():
   eng.debug_stop_after(-1, 0)
   t = buf.cpu().double()
   t = t[(t[:, 0] > 0) & (t[:, 5] > 0)]           # persistent kernel: one row per CTA; phase stamps are of its 2nd tile
-  print(f"rows with stamps: {t.size(0)}; per-CTA tiles ~ {n_cta / max(1, t.size(0)):.2f}")
+  n_tiles = a.batch * 32 * ((a.frames + 127) // 128)
+  print(f"rows with stamps: {t.size(0)}; tiles {n_tiles}; per-CTA tiles ~ {n_tiles / max(1, t.size(0)):.2f}")
   rel = t[:, 1:15] - t[:, 0:1]
   med = rel.median(dim=0).values
   print(f"CTAs {n_cta}; median cycles since kernel entry of each CTA:")
@@ -59,8 +60,8 @@ def main():
   print(f"steady-state tile: first operands of G1a -> D2 done: median {span.median():.0f} cycles")
   g1a = t[:, 5] - t[:, 2]
   g1b = t[:, 7] - t[:, 5]
-  print(f"G1a (first operands -> acc a done): median {g1a.median():.0f} cycles = {g1a.median() / 88:.1f} per UTCHMMA (ideal 128)")
-  print(f"G1b (acc a done -> acc b done):     median {g1b.median():.0f} cycles = {g1b.median() / 88:.1f} per UTCHMMA")
+  print(f"G1a (first operands -> acc a done): median {g1a.median():.0f} cycles = {g1a.median() / 68:.1f} per UTCHMMA (ideal 128)")
+  print(f"G1b (acc a done -> acc b done):     median {g1b.median():.0f} cycles = {g1b.median() / 68:.1f} per UTCHMMA")
 
 
 if __name__ == "__main__":

@@ -49,12 +49,13 @@ struct wg_engine {
   float* d_up_w = nullptr;            // Wp[32][320][640]
   float* d_up_b = nullptr;            // [80]
   // fp16 tensor-core path
-  void* d_w1 = nullptr;               // [flows*layers*512][1408] 16-bit
+  void* d_w1 = nullptr;               // [flows*layers*512][768] 16-bit  (dilated conv taps, packed row order)
+  void* d_v = nullptr;                // [flows*layers*32*512][320] 16-bit (phase-composed conditioning V = W_cond . Wup_p)
   void* d_w2 = nullptr;               // [flows*layers*272][256] 16-bit
   void* d_ident = nullptr;            // [64][64] 16-bit identity
   float* d_bias1 = nullptr;           // [flows*layers][512] packed order
   float* d_bias_res = nullptr;        // [flows*layers][256]
-  CUtensorMap tm_w1{}, tm_w2a{}, tm_w2b{}, tm_ident{};
+  CUtensorMap tm_w1{}, tm_v{}, tm_w2a{}, tm_w2b{}, tm_ident{};
   // fp32 path
   float* d_w1f = nullptr;             // [flows*layers][K1][2nc]
   float* d_bias1f = nullptr;          // [flows*layers][2nc]
@@ -169,7 +170,8 @@ int make_map(wg_engine* e, CUtensorMap* m, void* base, int rank, const uint64_t*
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t cond, x0, x1, e, total;
+  size_t cond, x0, x1, e, total;   // cond: fp32 mode = upsampled conditioning S [B,T,640]; fp16 mode = mel windows MW [B,Fq,320]
+  size_t cond_bytes;
   size_t elt;   // operand element size
 };
 
@@ -179,7 +181,10 @@ WsLayout ws_layout(const wg_engine* e, int B, int T) {
   const size_t npos = static_cast<size_t>(B) * T;
   size_t off = 0;
   L.cond = off;
-  off = align_up(off + npos * kCond * L.elt, 1024);
+  L.cond_bytes = e->cfg.precision == WG_PRECISION_FP32
+                     ? npos * kCond * L.elt
+                     : static_cast<size_t>(B) * ((T + kUpPhases - 1) / kUpPhases) * kUpKdim * L.elt;
+  off = align_up(off + L.cond_bytes, 1024);
   L.x0 = off;
   off = align_up(off + npos * e->cfg.n_channels * L.elt, 1024);
   L.x1 = off;
@@ -266,6 +271,7 @@ void wg_destroy(wg_engine* e) {
   cudaFree(e->d_up_w);
   cudaFree(e->d_up_b);
   cudaFree(e->d_w1);
+  cudaFree(e->d_v);
   cudaFree(e->d_w2);
   cudaFree(e->d_ident);
   cudaFree(e->d_bias1);
@@ -326,11 +332,17 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
     if ((rc = upload(e, &e->d_up_b, *b))) return rc;
   }
   const bool tc = e->cfg.precision == WG_PRECISION_FP16;
-  const int K1 = 3 * nc + kCond;
+  const int K1 = 3 * nc + kCond;     // fp32 mode: taps | upsampled conditioning
+  const int K1x = 3 * nc;            // fp16 mode: taps only (conditioning goes through V)
   std::vector<uint16_t> w1h, w2h;
+  const std::vector<float>* up_bias = nullptr;
+  if ((rc = need("upsample.bias", {kMel}, &up_bias))) return rc;
   std::vector<float> bias1, bias_res, w1f, bias1f, wresf, wsef;
   if (tc) {
-    w1h.assign(static_cast<size_t>(NF) * L * 2 * nc * K1, 0);
+    w1h.assign(static_cast<size_t>(NF) * L * 2 * nc * K1x, 0);
+    cudaFree(e->d_v);
+    e->d_v = nullptr;
+    WG_CUDA(e, cudaMalloc(&e->d_v, static_cast<size_t>(NF) * L * kUpPhases * 2 * nc * kUpKdim * 2));
     w2h.assign(static_cast<size_t>(NF) * L * kW2Rows * nc, 0);
     bias1.assign(static_cast<size_t>(NF) * L * 2 * nc, 0.f);
     bias_res.assign(static_cast<size_t>(NF) * L * nc, 0.f);
@@ -361,6 +373,19 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
     if ((rc = need("convinv." + std::to_string(k) + ".conv.weight", {C, C, 1}, &w_ci))) return rc;
     if ((rc = upload(e, &fp.d_w_start, *w_start))) return rc;
     if ((rc = upload(e, &fp.d_b_start, *b_start))) return rc;
+    if (tc) {
+      // V = W_cond . Wup_p for all layers and phases of this flow, composed on the device (fp32 accumulate)
+      float* d_wc = nullptr;
+      if ((rc = upload(e, &d_wc, *w_cond))) return rc;
+      dim3 grid(kUpKdim / 64, 2 * nc / 64, L * kUpPhases);
+      const size_t v_off = static_cast<size_t>(k) * L * kUpPhases * 2 * nc * kUpKdim;
+      if (e->op_fmt == 1)
+        compose_cond_kernel<__nv_bfloat16><<<grid, 256>>>(d_wc, e->d_up_w, static_cast<__nv_bfloat16*>(e->d_v) + v_off, nc);
+      else
+        compose_cond_kernel<__half><<<grid, 256>>>(d_wc, e->d_up_w, static_cast<__half*>(e->d_v) + v_off, nc);
+      WG_CUDA(e, cudaDeviceSynchronize());
+      cudaFree(d_wc);
+    }
     {
       double a[kGroup * kGroup], inv[kGroup * kGroup];
       for (int i = 0; i < C * C; ++i) {
@@ -392,16 +417,18 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
         }
       }
       if (tc) {
-        uint16_t* w1 = &w1h[li * 2 * nc * K1];
+        uint16_t* w1 = &w1h[li * 2 * nc * K1x];
         for (int np = 0; np < 2 * nc; ++np) {
           const int chunk = np / 256, half = (np % 256) / 128, j = np % 128;
           const int oc = half * nc + chunk * 128 + j;
-          uint16_t* row = w1 + static_cast<size_t>(np) * K1;
+          uint16_t* row = w1 + static_cast<size_t>(np) * K1x;
           for (int tap = 0; tap < 3; ++tap)
             for (int ci = 0; ci < nc; ++ci) row[tap * nc + ci] = f2h((*w_in)[(static_cast<size_t>(oc) * nc + ci) * 3 + tap], e->op_fmt);
+          // the upsampler's bias enters every kept group-step: fold W_cond . b_up into the layer bias
           const float* wc = &(*w_cond)[(static_cast<size_t>(2 * nc) * i + oc) * kCond];
-          for (int m = 0; m < kCond; ++m) row[3 * nc + m] = f2h(wc[m], e->op_fmt);
-          bias1[li * 2 * nc + np] = (*b_in)[oc] + (*b_cond)[2 * nc * i + oc];
+          double bfold = 0.0;
+          for (int m = 0; m < kCond; ++m) bfold += static_cast<double>(wc[m]) * (*up_bias)[m / kGroup];
+          bias1[li * 2 * nc + np] = static_cast<float>((*b_in)[oc] + (*b_cond)[2 * nc * i + oc] + bfold);
         }
         uint16_t* w2 = &w2h[li * kW2Rows * nc];
         if (i < L - 1) {
@@ -453,10 +480,16 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
     if ((rc = upload(e, &e->d_bias1, bias1))) return rc;
     const CUtensorMapDataType dt = e->op_fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     {
-      const uint64_t dims[2] = {static_cast<uint64_t>(K1), static_cast<uint64_t>(NF) * L * 2 * nc};
-      const uint64_t str[1] = {static_cast<uint64_t>(K1) * 2};
+      const uint64_t dims[2] = {static_cast<uint64_t>(K1x), static_cast<uint64_t>(NF) * L * 2 * nc};
+      const uint64_t str[1] = {static_cast<uint64_t>(K1x) * 2};
       const uint32_t box[2] = {64, 256};
       if ((rc = make_map(e, &e->tm_w1, e->d_w1, 2, dims, str, box, dt))) return rc;
+    }
+    {
+      const uint64_t dims[2] = {static_cast<uint64_t>(kUpKdim), static_cast<uint64_t>(NF) * L * kUpPhases * 2 * nc};
+      const uint64_t str[1] = {static_cast<uint64_t>(kUpKdim) * 2};
+      const uint32_t box[2] = {64, 256};
+      if ((rc = make_map(e, &e->tm_v, e->d_v, 2, dims, str, box, dt))) return rc;
     }
     {
       const uint64_t dims[2] = {static_cast<uint64_t>(nc), static_cast<uint64_t>(NF) * L * kW2Rows};
@@ -503,7 +536,7 @@ int wg_debug_view(const wg_engine* e, const char* name, int32_t batch, int32_t f
   uint8_t* base = static_cast<uint8_t*>(workspace);
   if (!strcmp(name, "cond")) {
     *ptr = base + L.cond;
-    *bytes = npos * kCond * L.elt;
+    *bytes = L.cond_bytes;
   } else if (!strcmp(name, "x0")) {
     *ptr = base + L.x0;
     *bytes = npos * e->cfg.n_channels * L.elt;
@@ -557,9 +590,12 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
     if (tc) {
       LayerTcParams lp{};
       lp.T = T;
+      lp.Fq = (T + kUpPhases - 1) / kUpPhases;
       lp.B = B;
       lp.dilation = 1 << i;
+      lp.reverse = static_cast<int>(li & 1);
       lp.w1_row0 = static_cast<int>(li * 2 * nc);
+      lp.v_row0 = static_cast<int>(li * kUpPhases * 2 * nc);
       lp.w2_row0 = static_cast<int>(li * kW2Rows);
       lp.has_res = has_res;
       lp.accumulate_e = i > 0;
@@ -569,9 +605,9 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
       lp.e = ebuf;
       lp.timeline = e->dbg_timeline;
       lp.dbg_flags = e->dbg_flags;
-      const int n_tiles = ((T + kTileM - 1) / kTileM) * B;
+      const int n_tiles = kPhases * ((lp.Fq + kTileM - 1) / kTileM) * B;
       dim3 grid(n_tiles < e->num_sms ? n_tiles : e->num_sms);
-      wn_layer_tc_kernel<<<grid, kTcThreads, TcSmem::total + 1024, st>>>(tm_x[*cur], tm_x[*cur ^ 1], *tm_cond, e->tm_w1,
+      wn_layer_tc_kernel<<<grid, kTcThreads, TcSmem::total + 1024, st>>>(tm_x[*cur], tm_x[*cur ^ 1], *tm_cond, e->tm_w1, e->tm_v,
                                                                         e->tm_w2a, e->tm_w2b, e->tm_ident, lp);
     } else {
       LayerF32Params lp{};
@@ -609,16 +645,21 @@ int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CU
   const CUtensorMapDataType dt = e->op_fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const int nc = e->cfg.n_channels;
   int rc;
-  const uint32_t box[3] = {64, static_cast<uint32_t>(kTileM), 1};
+  const int Fq = T / kUpPhases;       // caller guarantees T % 32 == 0
   {
-    const uint64_t dims[3] = {static_cast<uint64_t>(nc), static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
-    const uint64_t str[2] = {static_cast<uint64_t>(nc) * 2, static_cast<uint64_t>(nc) * 2 * T};
-    if ((rc = make_map(e, &tm_x[0], ws + L.x0, 3, dims, str, box, dt))) return rc;
-    if ((rc = make_map(e, &tm_x[1], ws + L.x1, 3, dims, str, box, dt))) return rc;
+    // x[B][T][nc] seen as {channel, phase, frame, utterance}: group-step t = 32 * frame + phase
+    const uint64_t dims[4] = {static_cast<uint64_t>(nc), static_cast<uint64_t>(kUpPhases), static_cast<uint64_t>(Fq),
+                              static_cast<uint64_t>(B)};
+    const uint64_t str[3] = {static_cast<uint64_t>(nc) * 2, static_cast<uint64_t>(nc) * 2 * kUpPhases,
+                             static_cast<uint64_t>(nc) * 2 * T};
+    const uint32_t box[4] = {64, 1, static_cast<uint32_t>(kTileM), 1};
+    if ((rc = make_map(e, &tm_x[0], ws + L.x0, 4, dims, str, box, dt))) return rc;
+    if ((rc = make_map(e, &tm_x[1], ws + L.x1, 4, dims, str, box, dt))) return rc;
   }
   {
-    const uint64_t dims[3] = {static_cast<uint64_t>(kCond), static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
-    const uint64_t str[2] = {static_cast<uint64_t>(kCond) * 2, static_cast<uint64_t>(kCond) * 2 * T};
+    const uint64_t dims[3] = {static_cast<uint64_t>(kUpKdim), static_cast<uint64_t>(Fq), static_cast<uint64_t>(B)};
+    const uint64_t str[2] = {static_cast<uint64_t>(kUpKdim) * 2, static_cast<uint64_t>(kUpKdim) * 2 * Fq};
+    const uint32_t box[3] = {64, static_cast<uint32_t>(kTileM), 1};
     if ((rc = make_map(e, tm_cond, ws + L.cond, 3, dims, str, box, dt))) return rc;
   }
   return WG_OK;
@@ -673,12 +714,13 @@ int wg_infer(wg_engine* e, const float* mel, int32_t batch, int32_t frames, cons
     const int Fq = (T + kUpPhases - 1) / kUpPhases;
     dim3 grid(kUpPhases, B * ((Fq + kUpFrames - 1) / kUpFrames));
     if (tc) {
+      // tensor-core mode: the upsampler is composed into the conditioning weights; only the 4-frame mel windows are formed
+      const size_t total = static_cast<size_t>(B) * Fq * kUpKdim;
+      const unsigned g1 = static_cast<unsigned>((total + 255) / 256);
       if (e->op_fmt == 1)
-        upsample_squeeze_kernel<__nv_bfloat16><<<grid, kUpThreads, 0, st>>>(mel, e->d_up_w, e->d_up_b,
-                                                                           reinterpret_cast<__nv_bfloat16*>(ws + L.cond), B, frames, T);
+        mel_window_kernel<__nv_bfloat16><<<g1, 256, 0, st>>>(mel, reinterpret_cast<__nv_bfloat16*>(ws + L.cond), B, frames, Fq);
       else
-        upsample_squeeze_kernel<__half><<<grid, kUpThreads, 0, st>>>(mel, e->d_up_w, e->d_up_b,
-                                                                    reinterpret_cast<__half*>(ws + L.cond), B, frames, T);
+        mel_window_kernel<__half><<<g1, 256, 0, st>>>(mel, reinterpret_cast<__half*>(ws + L.cond), B, frames, Fq);
     } else {
       upsample_squeeze_kernel<float><<<grid, kUpThreads, 0, st>>>(mel, e->d_up_w, e->d_up_b,
                                                                  reinterpret_cast<float*>(ws + L.cond), B, frames, T);

@@ -111,6 +111,73 @@ upsample_squeeze_kernel(const float* __restrict__ mel, const float* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------------------ mel windows
+// MW[b, q, m*80 + ci] = mel[b, ci, q - m] (0 outside [0, F)), the A operand of the phase-composed conditioning.
+template <typename OutT>
+__global__ void mel_window_kernel(const float* __restrict__ mel, OutT* __restrict__ mw, int B, int F, int Fq) {
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t total = static_cast<size_t>(B) * Fq * kUpKdim;
+  if (idx >= total) return;
+  const int k = static_cast<int>(idx % kUpKdim);
+  const int q = static_cast<int>((idx / kUpKdim) % Fq);
+  const int b = static_cast<int>(idx / (static_cast<size_t>(kUpKdim) * Fq));
+  const int m = k / kMel, ci = k % kMel;
+  const int f = q - m;
+  const float v = (f >= 0 && f < F) ? mel[(static_cast<size_t>(b) * kMel + ci) * F + f] : 0.f;
+  mw[idx] = from_float<OutT>(v);
+}
+
+// ------------------------------------------------------------------------------------------ weight composition
+// V[(i*32 + p) * 2nc + np][k] = sum_cj Wc[2nc*i + oc(np)][cj] * Wp[p][k][cj]      (one flow per launch)
+//   Wc = cond_layer weight [2nc*L][640] (model.py:95-96), Wp = phase-packed upsampler weight [32][320][640],
+//   np = packed accumulator row: chunk = np/256, half = (np%256)/128, j = np%128 -> oc = half*nc + chunk*128 + j.
+// Load-time only (0.05 TFLOP per flow); plain 64x64x16 smem-tiled fp32 GEMM, output rounded to the operand type.
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+compose_cond_kernel(const float* __restrict__ wc, const float* __restrict__ wp, OutT* __restrict__ v, int nc) {
+  __shared__ float As[16][64 + 1];
+  __shared__ float Bs[16][64 + 1];
+  const int k0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  const int i = blockIdx.z / kUpPhases, p = blockIdx.z % kUpPhases;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  for (int c0 = 0; c0 < kCond; c0 += 16) {
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      const int r = e >> 4, c = e & 15;
+      const int np = n0 + r;
+      const int oc = ((np % 256) / 128) * nc + (np / 256) * 128 + (np % 128);
+      As[c][r] = wc[(static_cast<size_t>(2 * nc) * i + oc) * kCond + c0 + c];
+      Bs[c][r] = wp[(static_cast<size_t>(p) * kUpKdim + k0 + r) * kCond + c0 + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      float a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a[u] = As[c][ty * 4 + u];
+        b[u] = Bs[c][tx * 4 + u];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int w = 0; w < 4; ++w) acc[u][w] = fmaf(a[u], b[w], acc[u][w]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int np = n0 + ty * 4 + u, k = k0 + tx * 4 + w;
+      v[((static_cast<size_t>(i) * kUpPhases + p) * 2 * nc + np) * kUpKdim + k] = from_float<OutT>(acc[u][w]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ flow step
 struct FlowStepParams {
   // "finish" part: flow k

@@ -4,13 +4,17 @@
 // (reference src/waveglow/model.py:123-135) plus this layer's share of cond_layer (model.py:121)
 // and of the skip->end path (model.py:130-137):
 //
-//   GEMM1  pre[128 x 512] = [x(t-d) | x(t) | x(t+d) | S(t)] [128 x 1408] . W1^T      (tcgen05, K-major SW128, TMA-fed)
+//   GEMM1  pre[128 x 512] = [mel(q..q-3) | x(t-d) | x(t) | x(t+d)] [128 x 1088] . [V_p | W_in]^T   (tcgen05, K-major SW128, TMA-fed)
+//          where a tile is 128 consecutive mel frames q of ONE phase p (group-step t = 32 q + p): the mel
+//          upsampler (model.py:145-150, 225) is pre-composed into the conditioning weights, V_p = W_cond . Wup_p
 //   gate   acts = tanh(pre[:, tanh half] + b) * sigmoid(pre[:, sigmoid half] + b)      (TMEM -> registers -> smem fp16)
 //   GEMM2  x'   [128 x 256] = acts . W_res^T + x . I        (residual carried on the tensor core)
 //          e'   [128 x  16] = acts . (W_end W_skip)^T       (skip->end fold, fp32 accumulator in global)
 //
-// Data layout: x, S are time-major fp16 [B, T', C]; the dilation halo comes from three TMA boxes at
-// t-d, t, t+d (out-of-range rows are zero-filled by TMA == the conv's zero padding, model.py:100-102).
+// Data layout: x is time-major fp16 [B, T', C] viewed by TMA as 4-D {C, phase 32, frame, B}; the dilation halo
+// comes from three TMA boxes at t-d, t, t+d (a shift by d moves (phase, frame) to ((p+d) mod 32, q + (p+d) div 32));
+// out-of-range rows are zero-filled by TMA == the conv's zero padding, model.py:100-102.  The mel windows
+// MW[B, frame, 4*80] (fp16) are tiny and L2-resident.
 // W1 rows are pre-permuted so that accumulator chunk c (256 TMEM columns) holds
 // [tanh ch 128c..128c+127 | sigmoid ch 128c..128c+127]; the gate therefore reads column j and j+128 of
 // the same TMEM lane.
@@ -33,9 +37,11 @@ constexpr int kTileM = 128;      // group-steps per CTA
 constexpr int kBlockK = 64;      // 16-bit elements per 128-byte swizzle row
 constexpr int kStages = 3;
 constexpr int kNC = 256;         // WN channels this kernel is built for
-constexpr int kCondC = 640;      // n_mel_channels * n_group
-constexpr int kK1 = 3 * kNC + kCondC;          // 1408
-constexpr int kKB1 = kK1 / kBlockK;            // 22
+constexpr int kMwK = 320;        // mel window: 4 frames x n_mel_channels
+constexpr int kMwKB = kMwK / kBlockK;          // 5
+constexpr int kPhases = 32;      // group-steps per mel frame (256 / n_group)
+constexpr int kK1 = 3 * kNC + kMwK;            // 1088
+constexpr int kKB1 = kK1 / kBlockK;            // 17
 constexpr int kW2Rows = 272;                   // 256 residual rows + 16 skip-end rows
 constexpr int kStageABytes = kTileM * 128;     // 16 KB
 constexpr int kStageBBytes = 256 * 128 + 16 * 128;  // 34 KB (W1 uses the first 32 KB)
@@ -56,10 +62,13 @@ struct TcSmem {
 static_assert(TcSmem::total + 1024 <= 232448, "shared memory budget exceeded");
 
 struct LayerTcParams {
-  int T;              // group-steps per utterance
+  int T;              // group-steps per utterance (= 32 * Fq here)
+  int Fq;             // mel frame slots per utterance
   int B;              // utterances
   int dilation;
-  int w1_row0;        // first packed-W1 row of this (flow, layer)
+  int reverse;        // walk the tiles backwards (alternate per layer: the tail of the previous layer's x' is still in L2)
+  int w1_row0;        // first packed-W1x row of this (flow, layer)
+  int v_row0;         // first packed-V row of this (flow, layer): + phase * 512
   int w2_row0;        // first packed-W2 row of this (flow, layer)
   int has_res;        // 0 for the last layer (no residual output, model.py:107-110)
   int accumulate_e;   // 0 for the first layer (e' = ...), 1 afterwards (e' = e + ...)
@@ -81,10 +90,11 @@ __device__ __forceinline__ float gate_one(float a, float b) {
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
-wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, T, B} box {64,128,1} SW128
+wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, 32, Fq, B} box {64,1,128,1} SW128
                    const __grid_constant__ CUtensorMap tm_x_out,  // same geometry, other buffer
-                   const __grid_constant__ CUtensorMap tm_cond,   // {640, T, B} box {64,128,1}
-                   const __grid_constant__ CUtensorMap tm_w1,     // {1408, rows} box {64,256}
+                   const __grid_constant__ CUtensorMap tm_mw,     // {320, Fq, B} box {64,128,1}
+                   const __grid_constant__ CUtensorMap tm_w1,     // {768, rows} box {64,256}
+                   const __grid_constant__ CUtensorMap tm_v,      // {320, rows} box {64,256}
                    const __grid_constant__ CUtensorMap tm_w2a,    // {256, rows} box {64,256}
                    const __grid_constant__ CUtensorMap tm_w2b,    // {256, rows} box {64,16}
                    const __grid_constant__ CUtensorMap tm_ident,  // {64, 64} box {64,64}
@@ -106,7 +116,7 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, T, B}
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tiles_per_utt = (p.T + kTileM - 1) / kTileM;
+  const int tiles_per_utt = kPhases * ((p.Fq + kTileM - 1) / kTileM);   // tile = (utterance, 128-frame block, phase); phase fastest
   const int n_tiles = tiles_per_utt * p.B;
   // persistent: this CTA processes tiles blockIdx.x, blockIdx.x + gridDim.x, ...  Concurrently running
   // tiles are therefore neighbours in time, so the dilation halos are served from L2.
@@ -144,17 +154,20 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, T, B}
     // =============================== TMA producer ===============================
     if (lane == 0) {
       ptx::prefetch_tmap(&tm_x_in);
-      ptx::prefetch_tmap(&tm_cond);
+      ptx::prefetch_tmap(&tm_mw);
       ptx::prefetch_tmap(&tm_w1);
+      ptx::prefetch_tmap(&tm_v);
       if (p.has_res) {
         ptx::mbar_arrive_expect_tx(ident_full, kIdentBytes);
         ptx::tma_load_2d(smem + TcSmem::ident, &tm_ident, ident_full, 0, 0);
       }
       int use = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        const int tile = blockIdx.x + it * gridDim.x;
+        int tile = blockIdx.x + it * gridDim.x;
+        if (p.reverse) tile = n_tiles - 1 - tile;
         const int b = tile / tiles_per_utt;
-        const int t0 = (tile % tiles_per_utt) * kTileM;
+        const int ph_ = (tile % tiles_per_utt) % kPhases;
+        const int q0 = ((tile % tiles_per_utt) / kPhases) * kTileM;
         for (int chunk = 0; chunk < 2; ++chunk) {
           for (int kb = 0; kb < kKB1; ++kb, ++use) {
             const int s = use % kStages;
@@ -168,15 +181,17 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, T, B}
               continue;
             }
             ptx::mbar_arrive_expect_tx(&full[s], (skip_a ? 0 : kStageABytes) + (skip_b ? 0 : 256 * 128));
-            if (!skip_a) {
-              if (kb < 12) {
-                const int tap = kb >> 2;   // 0: t-d, 1: t, 2: t+d
-                ptx::tma_load_3d(sa, &tm_x_in, &full[s], (kb & 3) * kBlockK, t0 + (tap - 1) * p.dilation, b);
-              } else {
-                ptx::tma_load_3d(sa, &tm_cond, &full[s], (kb - 12) * kBlockK, t0, b);
-              }
+            if (kb < kMwKB) {
+              // conditioning: mel windows (L2-resident) x phase-composed weights V_p
+              if (!skip_a) ptx::tma_load_3d(sa, &tm_mw, &full[s], kb * kBlockK, q0, b);
+              if (!skip_b) ptx::tma_load_2d(sb, &tm_v, &full[s], kb * kBlockK, p.v_row0 + ph_ * 512 + chunk * 256);
+            } else {
+              const int j = kb - kMwKB;          // 0..11: tap (j >> 2) in {t-d, t, t+d}, channel block (j & 3)
+              const int pp = ph_ + ((j >> 2) - 1) * p.dilation;
+              const int dq = pp >> 5;            // floor division by 32 (arithmetic shift)
+              if (!skip_a) ptx::tma_load_4d(sa, &tm_x_in, &full[s], (j & 3) * kBlockK, pp - (dq << 5), q0 + dq, b);
+              if (!skip_b) ptx::tma_load_2d(sb, &tm_w1, &full[s], j * kBlockK, p.w1_row0 + chunk * 256);
             }
-            if (!skip_b) ptx::tma_load_2d(sb, &tm_w1, &full[s], kb * kBlockK, p.w1_row0 + chunk * 256);
           }
         }
         // GEMM2: stage j = W2 K-block j (B region) + x(t) K-block j for the identity term (A region)
@@ -189,7 +204,7 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, T, B}
           ptx::mbar_arrive_expect_tx(&full[s], kStageBBytes + (p.has_res ? kStageABytes : 0));
           ptx::tma_load_2d(sb, &tm_w2a, &full[s], j * kBlockK, p.w2_row0);
           ptx::tma_load_2d(sb + 256 * 128, &tm_w2b, &full[s], j * kBlockK, p.w2_row0 + 256);
-          if (p.has_res) ptx::tma_load_3d(sa, &tm_x_in, &full[s], j * kBlockK, t0, b);
+          if (p.has_res) ptx::tma_load_4d(sa, &tm_x_in, &full[s], j * kBlockK, ph_, q0, b);
         }
       }
     }
@@ -281,9 +296,11 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, T, B}
 
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t par = it & 1;
-      const int tile = blockIdx.x + it * gridDim.x;
+      int tile = blockIdx.x + it * gridDim.x;
+      if (p.reverse) tile = n_tiles - 1 - tile;
       const int b = tile / tiles_per_utt;
-      const int t0 = (tile % tiles_per_utt) * kTileM;
+      const int ph_ = (tile % tiles_per_utt) % kPhases;
+      const int q0 = ((tile % tiles_per_utt) / kPhases) * kTileM;
       const uint32_t ra = lane_base + par * 256;
       const uint32_t rb = lane_base + (par ^ 1) * 256;
       const bool tl = (it == 1) && threadIdx.x == 64;
@@ -340,14 +357,14 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, T, B}
       ptx::mbar_wait(d2_full, par);
       ptx::tc_fence_after_sync();
       if (tl) stamp(p, 11);
-      const int t = t0 + row;
+      const int t = (q0 + row) * kPhases + ph_;     // group-step of this TMEM lane
       if (hh == 0) {
         uint32_t ve[8];
         ptx::tmem_ld8(rb, ve);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before_sync();
         ptx::mbar_arrive(e_drained);
-        if (t < p.T) {
+        if (q0 + row < p.Fq && t < p.T) {
           float4* ep = reinterpret_cast<float4*>(p.e + (static_cast<size_t>(b) * p.T + t) * 8);
           float4 lo = make_float4(__uint_as_float(ve[0]), __uint_as_float(ve[1]), __uint_as_float(ve[2]), __uint_as_float(ve[3]));
           float4 hi = make_float4(__uint_as_float(ve[4]), __uint_as_float(ve[5]), __uint_as_float(ve[6]), __uint_as_float(ve[7]));
@@ -394,7 +411,7 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, T, B}
         asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps only
         if (warp == 2 && lane == 0) {
 #pragma unroll
-          for (int s4 = 0; s4 < 4; ++s4) ptx::tma_store_3d(&tm_x_out, acts + s4 * (kTileM * 128), s4 * kBlockK, t0, b);
+          for (int s4 = 0; s4 < 4; ++s4) ptx::tma_store_4d(&tm_x_out, acts + s4 * (kTileM * 128), s4 * kBlockK, ph_, q0, b);
           ptx::tma_store_commit();
         }
         store_pending = true;
