@@ -472,8 +472,9 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
     d16 = static_cast<uint16_t*>(e->d_w2);
     if ((rc = upload(e, &d16, w2h))) return rc;
     e->d_w2 = d16;
-    std::vector<uint16_t> ident(64 * 64, 0);
-    for (int i = 0; i < 64; ++i) ident[i * 64 + i] = f2h(1.0f, e->op_fmt);
+    // [I32 | 0]: 32 rows x 64 K; K-step (k & 1) of a 64-channel block selects columns 0..15 or 16..31 of the identity
+    std::vector<uint16_t> ident(kIdentN * 64, 0);
+    for (int i = 0; i < kIdentN; ++i) ident[i * 64 + i] = f2h(1.0f, e->op_fmt);
     d16 = static_cast<uint16_t*>(e->d_ident);
     if ((rc = upload(e, &d16, ident))) return rc;
     e->d_ident = d16;
@@ -499,9 +500,9 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
       if ((rc = make_map(e, &e->tm_w2b, e->d_w2, 2, dims, str, boxb, dt))) return rc;
     }
     {
-      const uint64_t dims[2] = {64, 64};
+      const uint64_t dims[2] = {64, static_cast<uint64_t>(kIdentN)};
       const uint64_t str[1] = {128};
-      const uint32_t box[2] = {64, 64};
+      const uint32_t box[2] = {64, static_cast<uint32_t>(kIdentN)};
       if ((rc = make_map(e, &e->tm_ident, e->d_ident, 2, dims, str, box, dt))) return rc;
     }
   } else {

@@ -8,7 +8,8 @@
 //          where a tile is 128 consecutive mel frames q of ONE phase p (group-step t = 32 q + p): the mel
 //          upsampler (model.py:145-150, 225) is pre-composed into the conditioning weights, V_p = W_cond . Wup_p
 //   gate   acts = tanh(pre[:, tanh half] + b) * sigmoid(pre[:, sigmoid half] + b)      (TMEM -> registers -> smem fp16)
-//   GEMM2  x'   [128 x 256] = acts . W_res^T + x . I        (residual carried on the tensor core)
+//   GEMM2  x'   [128 x 256] = acts . W_res^T + x . I        (residual carried on the tensor core; its first
+//                                                            half runs while the chunk-b gate is still busy)
 //          e'   [128 x  16] = acts . (W_end W_skip)^T       (skip->end fold, fp32 accumulator in global)
 //
 // Data layout: x is time-major fp16 [B, T', C] viewed by TMA as 4-D {C, phase 32, frame, B}; the dilation halo
@@ -44,17 +45,20 @@ constexpr int kK1 = 3 * kNC + kMwK;            // 1088
 constexpr int kKB1 = kK1 / kBlockK;            // 17
 constexpr int kW2Rows = 272;                   // 256 residual rows + 16 skip-end rows
 constexpr int kStageABytes = kTileM * 128;     // 16 KB
-constexpr int kStageBBytes = 256 * 128 + 16 * 128;  // 34 KB (W1 uses the first 32 KB)
-constexpr int kStageBytes = kStageABytes + kStageBBytes;   // 51200 (multiple of 1024)
+constexpr int kStageBBytes = 256 * 128;        // 32 KB
+constexpr int kStageBytes = kStageABytes + kStageBBytes;   // 49152
 constexpr int kActsBytes = kTileM * kNC * 2;   // 64 KB, 4 slabs of [128 x 64]
-constexpr int kIdentBytes = 64 * 128;          // 8 KB
+constexpr int kIdentN = 32;                    // identity block width of the residual carry
+constexpr int kIdentBytes = kIdentN * 128;     // 4 KB
+constexpr int kW2bBytes = 4 * 16 * 128;        // 8 KB: skip-end weights [16 x 256], 4 K-blocks, resident for the whole launch
 
 struct TcSmem {
   // offsets inside dynamic smem (after 1024-byte alignment)
   static constexpr int stage0 = 0;
   static constexpr int acts = kStages * kStageBytes;                    // 153600
-  static constexpr int ident = acts + kActsBytes;                       // 219136
-  static constexpr int bias1 = ident + kIdentBytes;                     // 227328
+  static constexpr int ident = acts + kActsBytes;
+  static constexpr int w2b = ident + kIdentBytes;
+  static constexpr int bias1 = w2b + kW2bBytes;
   static constexpr int bias_res = bias1 + 2 * kNC * 4;                  // +2048
   static constexpr int bars = bias_res + kNC * 4;                       // +1024
   static constexpr int total = bars + 128;
@@ -97,7 +101,7 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, 32, F
                    const __grid_constant__ CUtensorMap tm_v,      // {320, rows} box {64,256}
                    const __grid_constant__ CUtensorMap tm_w2a,    // {256, rows} box {64,256}
                    const __grid_constant__ CUtensorMap tm_w2b,    // {256, rows} box {64,16}
-                   const __grid_constant__ CUtensorMap tm_ident,  // {64, 64} box {64,64}
+                   const __grid_constant__ CUtensorMap tm_ident,  // {64, 32} box {64,32}: [I32 | 0]
                    const LayerTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -157,10 +161,10 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, 32, F
       ptx::prefetch_tmap(&tm_mw);
       ptx::prefetch_tmap(&tm_w1);
       ptx::prefetch_tmap(&tm_v);
-      if (p.has_res) {
-        ptx::mbar_arrive_expect_tx(ident_full, kIdentBytes);
-        ptx::tma_load_2d(smem + TcSmem::ident, &tm_ident, ident_full, 0, 0);
-      }
+      // launch-constant operands: identity block and this layer's skip-end weights
+      ptx::mbar_arrive_expect_tx(ident_full, kW2bBytes + (p.has_res ? kIdentBytes : 0));
+      if (p.has_res) ptx::tma_load_2d(smem + TcSmem::ident, &tm_ident, ident_full, 0, 0);
+      for (int j = 0; j < 4; ++j) ptx::tma_load_2d(smem + TcSmem::w2b + j * 2048, &tm_w2b, ident_full, j * kBlockK, p.w2_row0 + 256);
       int use = 0;
       for (int it = 0; it < my_tiles; ++it) {
         int tile = blockIdx.x + it * gridDim.x;
@@ -194,17 +198,18 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, 32, F
             }
           }
         }
-        // GEMM2: stage j = W2 K-block j (B region) + x(t) K-block j for the identity term (A region)
-        for (int j = 0; j < 4; ++j, ++use) {
-          const int s = use % kStages;
-          const uint32_t ph = (use / kStages) & 1;
-          ptx::mbar_wait(&empty[s], ph ^ 1);
-          uint8_t* sa = smem + TcSmem::stage0 + s * kStageBytes;
-          uint8_t* sb = sa + kStageABytes;
-          ptx::mbar_arrive_expect_tx(&full[s], kStageBBytes + (p.has_res ? kStageABytes : 0));
-          ptx::tma_load_2d(sb, &tm_w2a, &full[s], j * kBlockK, p.w2_row0);
-          ptx::tma_load_2d(sb + 256 * 128, &tm_w2b, &full[s], j * kBlockK, p.w2_row0 + 256);
-          if (p.has_res) ptx::tma_load_4d(sa, &tm_x_in, &full[s], j * kBlockK, ph_, q0, b);
+        // GEMM2 (residual part): stage j = W_res K-block j (B region) + x(t) K-block j for the identity carry (A region)
+        if (p.has_res) {
+          for (int j = 0; j < 4; ++j, ++use) {
+            const int s = use % kStages;
+            const uint32_t ph = (use / kStages) & 1;
+            ptx::mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* sa = smem + TcSmem::stage0 + s * kStageBytes;
+            uint8_t* sb = sa + kStageABytes;
+            ptx::mbar_arrive_expect_tx(&full[s], kStageBBytes + kStageABytes);
+            ptx::tma_load_2d(sb, &tm_w2a, &full[s], j * kBlockK, p.w2_row0);
+            ptx::tma_load_4d(sa, &tm_x_in, &full[s], j * kBlockK, ph_, q0, b);
+          }
         }
       }
     }
@@ -212,11 +217,12 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, 32, F
     // =============================== MMA issuer ===============================
     if (lane == 0) {
       const uint32_t idesc256 = ptx::make_idesc_f16(128, 256, p.fmt);
-      const uint32_t idesc64 = ptx::make_idesc_f16(128, 64, p.fmt);
+      const uint32_t idesc32 = ptx::make_idesc_f16(128, kIdentN, p.fmt);
       const uint32_t idesc16 = ptx::make_idesc_f16(128, 16, p.fmt);
       const uint32_t stage_addr0 = ptx::smem_u32(smem + TcSmem::stage0);
       const uint32_t acts_addr = ptx::smem_u32(smem + TcSmem::acts);
       const uint32_t ident_addr = ptx::smem_u32(smem + TcSmem::ident);
+      const uint32_t w2b_addr = ptx::smem_u32(smem + TcSmem::w2b);
       int use = 0;
       stamp(p, 1);
       for (int it = 0; it < my_tiles; ++it) {
@@ -251,35 +257,44 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, 32, F
           ptx::mma_commit(&acc_full[chunk]);
           if (tl) stamp(p, 3 + chunk);
         }
-        // GEMM2 needs all of acts (K = 256) and both accumulator regions drained by the gate.
+        // GEMM2, split so that its first half overlaps the chunk-b gate:
+        //   phase 1 (needs acts slabs 0,1 = gate a, and region A drained): residual K-blocks 0,1 + identity carry
+        //   phase 2 (needs gate b): residual K-blocks 2,3 + identity carry, then all skip-end MMAs into region B
+        if (it == 0) ptx::mbar_wait(ident_full, 0);
         ptx::mbar_wait(&acts_ready[0], par);
-        ptx::mbar_wait(&acts_ready[1], par);
         ptx::tc_fence_after_sync();
-        if (tl) stamp(p, 9);
-        if (p.has_res && it == 0) ptx::mbar_wait(ident_full, 0);
-        for (int j = 0; j < 4; ++j, ++use) {
+        for (int j = 0; j < 4; ++j) {
+          if (j == 2) {
+            ptx::mbar_wait(&acts_ready[1], par);
+            ptx::tc_fence_after_sync();
+            if (tl) stamp(p, 9);
+          }
+          if (!p.has_res) continue;
           const int s = use % kStages;
           const uint32_t ph = (use / kStages) & 1;
+          ++use;
           ptx::mbar_wait(&full[s], ph);
           ptx::tc_fence_after_sync();
           const uint32_t x_addr = stage_addr0 + s * kStageBytes;
           const uint32_t b_addr = x_addr + kStageABytes;
           const uint32_t a_addr = acts_addr + j * (kTileM * 128);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = ptx::make_desc_sw128(a_addr + k * 32);
-            if (p.has_res) ptx::mma_f16_ss(ra, ad, ptx::make_desc_sw128(b_addr + k * 32), idesc256, (j | k) != 0);
-            ptx::mma_f16_ss(rb, ad, ptx::make_desc_sw128(b_addr + 256 * 128 + k * 32), idesc16, (j | k) != 0);
-          }
-          if (p.has_res) {
-            // x' += x . I : carries the residual stream on the tensor core (columns 64j .. 64j+63)
+          for (int k = 0; k < 4; ++k)
+            ptx::mma_f16_ss(ra, ptx::make_desc_sw128(a_addr + k * 32), ptx::make_desc_sw128(b_addr + k * 32), idesc256, (j | k) != 0);
+          // x' += x . I : carries the residual stream on the tensor core.  K-step k of this block covers channels
+          // 64j + 16k .. +15; the [I32 | 0] block maps them onto 32 output columns starting at 64j + 32 (k >> 1).
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              ptx::mma_f16_ss(ra + j * 64, ptx::make_desc_sw128(x_addr + k * 32), ptx::make_desc_sw128(ident_addr + k * 32),
-                              idesc64, 1);
-            }
-          }
+          for (int k = 0; k < 4; ++k)
+            ptx::mma_f16_ss(ra + j * 64 + (k >> 1) * 32, ptx::make_desc_sw128(x_addr + k * 32),
+                            ptx::make_desc_sw128(ident_addr + (k & 1) * 32), idesc32, 1);
           ptx::mma_commit(&empty[s]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::mma_f16_ss(rb, ptx::make_desc_sw128(acts_addr + j * (kTileM * 128) + k * 32),
+                            ptx::make_desc_sw128(w2b_addr + j * 2048 + k * 32), idesc16, (j | k) != 0);
         }
         ptx::mma_commit(d2_full);
         if (tl) stamp(p, 10);
