@@ -188,6 +188,54 @@ def test_batch_independence_and_locality_full_length():
   assert not torch.equal(full[:, f0 * 256:], full2[:, f0 * 256:])
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("name", ["forward_c256_b2_t2048", "forward_c256_b1_t4000"])
+def test_forward_direction_matches_reference_golden(name, precision):
+  """WaveGlow.forward (model.py:178-221) + WaveGlowLoss (train.py:31-45): z, log_s, sums, log-dets, loss.
+  t4000 has T' = 500 (not a multiple of 32 nor 128): exercises the padded phase view of the tensor-core path."""
+  from waveglow_b200.model import WaveGlowLoss
+  g = load_golden(name)
+  model = get_model(256, precision)
+  z, log_s_list, log_det_list = model((torch.from_numpy(g["mel"]).cuda(), torch.from_numpy(g["audio_in"]).cuda()))
+  torch.cuda.synchronize()
+  z_ref = torch.from_numpy(g["z"])
+  tol = 1e-5 if precision == "fp32" else 2e-3
+  ez = max_abs(z_ref, z.cpu())
+  print(f"forward {precision} {name}: z max-abs {ez:.3e} (ref absmax {float(z_ref.abs().max()):.2f})")
+  assert z.shape == z_ref.shape and ez <= tol
+  # sums: fp32 mode 1e-6 of sum|log_s|; fp16 mode 5e-4 (per-element gate is 2e-3 max-abs; observed 1.2e-4)
+  rel = 1e-6 if precision == "fp32" else 5e-4
+  n = z.size(0) * z.size(2)
+  for k, ls in enumerate(log_s_list):
+    ls_ref = torch.from_numpy(g[f"log_s{k}"])
+    assert ls.shape == ls_ref.shape and max_abs(ls_ref, ls.cpu()) <= tol
+    s_ref = float(g["log_s_sum"][k])
+    s_got = float(model.last_forward_stats["log_s_sum"][k])
+    # tolerance relative to the scale of the summands (the sum itself may cancel to ~0)
+    scale = float(ls_ref.double().abs().sum())
+    assert abs(s_got - s_ref) <= rel * scale + 1e-6, (k, s_got, s_ref)
+    # the reference's own fp32 LU log-det carries ~2e-6 * B * T' of noise (tools/make_golden.py)
+    assert abs(float(log_det_list[k]) - float(g["log_det_w"][k])) <= 2e-6 * n + 1e-5 * abs(float(g["log_det_w"][k]))
+  loss = float(WaveGlowLoss(1.0)((z, log_s_list, log_det_list)))
+  print(f"forward {precision} {name}: loss {loss:.6f} ref {float(g['loss']):.6f}")
+  assert abs(loss - float(g["loss"])) <= (1e-5 if precision == "fp32" else 5e-4) * max(1.0, abs(float(g["loss"])))
+
+
+def test_forward_then_infer_round_trip_on_gpu():
+  """Size-independent property: infer(forward(audio) as noise, sigma=1) reproduces the audio (both fused paths)."""
+  hp, sd, w, dims = synthetic_weights(256)
+  model = get_model(256, "fp16")
+  B, F = 2, 64
+  mel = synthetic_mel(B, F, 90).cuda()
+  audio = (torch.rand(B, F * 256, generator=torch.Generator().manual_seed(3)) * 2 - 1).cuda()
+  z, _, _ = model((mel, audio))
+  back = model.infer_with_noise(mel, [z[:, 4:].contiguous(), z[:, 2:4].contiguous(), z[:, :2].contiguous()], 1.0)
+  torch.cuda.synchronize()
+  err = max_abs(audio.cpu(), back.cpu())
+  print(f"forward->infer round trip: max-abs {err:.3e}")
+  assert err <= 4e-3
+
+
 def test_errors_are_loud():
   from waveglow_b200.engine import WgError
   model = get_model(256, "fp16")

@@ -62,6 +62,7 @@ struct wg_engine {
   float* d_wresf = nullptr;           // [flows*layers][nc][nc]
   float* d_wsef = nullptr;            // [flows*layers][nc][8]
   PFN_encodeTiled encode = nullptr;
+  double* d_logdet = nullptr;         // [flows] log|det W_k|
   std::vector<cudaEvent_t> ev;        // 2 per flow: around the WN layer launches of the last call
   int ev_flows = 0;                   // flows recorded by the last call
   long long* dbg_timeline = nullptr;  // device buffer for clock64 stamps of layer launches (tests/diagnostics)
@@ -170,6 +171,8 @@ int make_map(wg_engine* e, CUtensorMap* m, void* base, int rank, const uint64_t*
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
+  int Tpad;                        // x rows per utterance: T rounded up to a multiple of 32 (phase view of the TMA maps)
+  size_t state, sums;              // forward only: time-major state [B,T,8] fp32; double accumulators [n_flows]
   size_t cond, x0, x1, e, total;   // cond: fp32 mode = upsampled conditioning S [B,T,640]; fp16 mode = mel windows MW [B,Fq,320]
   size_t cond_bytes;
   size_t elt;   // operand element size
@@ -179,6 +182,8 @@ WsLayout ws_layout(const wg_engine* e, int B, int T) {
   WsLayout L{};
   L.elt = e->cfg.precision == WG_PRECISION_FP32 ? 4 : 2;
   const size_t npos = static_cast<size_t>(B) * T;
+  L.Tpad = (T + kUpPhases - 1) / kUpPhases * kUpPhases;
+  const size_t nppos = static_cast<size_t>(B) * L.Tpad;
   size_t off = 0;
   L.cond = off;
   L.cond_bytes = e->cfg.precision == WG_PRECISION_FP32
@@ -186,11 +191,15 @@ WsLayout ws_layout(const wg_engine* e, int B, int T) {
                      : static_cast<size_t>(B) * ((T + kUpPhases - 1) / kUpPhases) * kUpKdim * L.elt;
   off = align_up(off + L.cond_bytes, 1024);
   L.x0 = off;
-  off = align_up(off + npos * e->cfg.n_channels * L.elt, 1024);
+  off = align_up(off + nppos * e->cfg.n_channels * L.elt, 1024);
   L.x1 = off;
-  off = align_up(off + npos * e->cfg.n_channels * L.elt, 1024);
+  off = align_up(off + nppos * e->cfg.n_channels * L.elt, 1024);
   L.e = off;
   off = align_up(off + npos * kGroup * sizeof(float), 1024);
+  L.state = off;
+  off = align_up(off + npos * kGroup * sizeof(float), 1024);
+  L.sums = off;
+  off = align_up(off + static_cast<size_t>(e->cfg.n_flows) * sizeof(double), 1024);
   L.total = off;
   return L;
 }
@@ -268,6 +277,7 @@ void wg_destroy(wg_engine* e) {
     cudaFree(f.d_b_start);
   }
   for (auto ev : e->ev) cudaEventDestroy(ev);
+  cudaFree(e->d_logdet);
   cudaFree(e->d_up_w);
   cudaFree(e->d_up_b);
   cudaFree(e->d_w1);
@@ -462,6 +472,11 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
     }
     for (int r = 0; r < 2 * h; ++r) fp.e_bias[r] = static_cast<float>(ebias[r]);
   }
+  {
+    std::vector<double> ld(NF);
+    for (int k = 0; k < NF; ++k) ld[k] = e->flows[k].logdet;
+    if ((rc = upload(e, &e->d_logdet, ld))) return rc;
+  }
   if (bias_res.empty()) bias_res.assign(static_cast<size_t>(NF) * L * nc, 0.f);
   if ((rc = upload(e, &e->d_bias_res, bias_res))) return rc;
   if (tc) {
@@ -540,10 +555,10 @@ int wg_debug_view(const wg_engine* e, const char* name, int32_t batch, int32_t f
     *bytes = L.cond_bytes;
   } else if (!strcmp(name, "x0")) {
     *ptr = base + L.x0;
-    *bytes = npos * e->cfg.n_channels * L.elt;
+    *bytes = static_cast<size_t>(batch) * L.Tpad * e->cfg.n_channels * L.elt;
   } else if (!strcmp(name, "x1")) {
     *ptr = base + L.x1;
-    *bytes = npos * e->cfg.n_channels * L.elt;
+    *bytes = static_cast<size_t>(batch) * L.Tpad * e->cfg.n_channels * L.elt;
   } else if (!strcmp(name, "e")) {
     *ptr = base + L.e;
     *bytes = npos * kGroup * sizeof(float);
@@ -558,9 +573,22 @@ int wg_debug_view(const wg_engine* e, const char* name, int32_t batch, int32_t f
 namespace {
 
 template <typename XT>
-void launch_flow_step(const FlowStepParams& fs, float* state, const float* ebuf, void* x, size_t npos, cudaStream_t st) {
-  const unsigned grid = static_cast<unsigned>((npos + kFsPos - 1) / kFsPos);
-  flow_step_kernel<XT><<<grid, kFsThreads, 0, st>>>(fs, state, ebuf, static_cast<XT*>(x), npos);
+void launch_flow_step(const FlowStepParams& fs, float* state, const float* ebuf, void* x, int B, int T, int Tpad,
+                      cudaStream_t st) {
+  const size_t nppos = static_cast<size_t>(B) * Tpad;
+  const unsigned grid = static_cast<unsigned>((nppos + kFsPos - 1) / kFsPos);
+  flow_step_kernel<XT><<<grid, kFsThreads, 0, st>>>(fs, state, ebuf, static_cast<XT*>(x), B, T, Tpad);
+}
+
+void flow_step_any(wg_engine* e, const FlowStepParams& fs, float* state, const float* ebuf, void* x, int B, int T, int Tpad,
+                   cudaStream_t st) {
+  if (e->cfg.precision == WG_PRECISION_FP32)
+    launch_flow_step<float>(fs, state, ebuf, x, B, T, Tpad, st);
+  else if (e->op_fmt == 1)
+    launch_flow_step<__nv_bfloat16>(fs, state, ebuf, x, B, T, Tpad, st);
+  else
+    launch_flow_step<__half>(fs, state, ebuf, x, B, T, Tpad, st);
+  e->launches++;
 }
 
 // Runs the WN layers of flow k.  x buffers alternate; returns the index of the buffer holding the
@@ -591,7 +619,7 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
     if (tc) {
       LayerTcParams lp{};
       lp.T = T;
-      lp.Fq = (T + kUpPhases - 1) / kUpPhases;
+      lp.Fq = L.Tpad / kUpPhases;
       lp.B = B;
       lp.dilation = 1 << i;
       lp.reverse = static_cast<int>(li & 1);
@@ -613,6 +641,7 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
     } else {
       LayerF32Params lp{};
       lp.T = T;
+      lp.Tpad = L.Tpad;
       lp.dilation = 1 << i;
       lp.has_res = has_res;
       lp.accumulate_e = i > 0;
@@ -642,17 +671,37 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
   return WG_OK;
 }
 
+// Conditioning operand of the WN layers, written to ws + L.cond.
+void launch_conditioning(wg_engine* e, const float* mel, int B, int frames, int T, uint8_t* ws, const WsLayout& L, cudaStream_t st) {
+  const int Fq = L.Tpad / kUpPhases;
+  if (e->cfg.precision == WG_PRECISION_FP16) {
+    // tensor-core mode: the upsampler is composed into the conditioning weights; only the 4-frame mel windows are formed
+    const size_t total = static_cast<size_t>(B) * Fq * kUpKdim;
+    const unsigned g1 = static_cast<unsigned>((total + 255) / 256);
+    if (e->op_fmt == 1)
+      mel_window_kernel<__nv_bfloat16><<<g1, 256, 0, st>>>(mel, reinterpret_cast<__nv_bfloat16*>(ws + L.cond), B, frames, Fq);
+    else
+      mel_window_kernel<__half><<<g1, 256, 0, st>>>(mel, reinterpret_cast<__half*>(ws + L.cond), B, frames, Fq);
+  } else {
+    // ConvTranspose1d + squeeze (model.py:225-232 / 186-193); keeps the first T group-steps (T = 32 F for infer)
+    dim3 grid(kUpPhases, B * ((Fq + kUpFrames - 1) / kUpFrames));
+    upsample_squeeze_kernel<float><<<grid, kUpThreads, 0, st>>>(mel, e->d_up_w, e->d_up_b, reinterpret_cast<float*>(ws + L.cond), B,
+                                                               frames, T);
+  }
+  e->launches++;
+}
+
 int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CUtensorMap* tm_x, CUtensorMap* tm_cond) {
   const CUtensorMapDataType dt = e->op_fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const int nc = e->cfg.n_channels;
   int rc;
-  const int Fq = T / kUpPhases;       // caller guarantees T % 32 == 0
+  const int Fq = L.Tpad / kUpPhases;
   {
     // x[B][T][nc] seen as {channel, phase, frame, utterance}: group-step t = 32 * frame + phase
     const uint64_t dims[4] = {static_cast<uint64_t>(nc), static_cast<uint64_t>(kUpPhases), static_cast<uint64_t>(Fq),
                               static_cast<uint64_t>(B)};
     const uint64_t str[3] = {static_cast<uint64_t>(nc) * 2, static_cast<uint64_t>(nc) * 2 * kUpPhases,
-                             static_cast<uint64_t>(nc) * 2 * T};
+                             static_cast<uint64_t>(nc) * 2 * L.Tpad};
     const uint32_t box[4] = {64, 1, static_cast<uint32_t>(kTileM), 1};
     if ((rc = make_map(e, &tm_x[0], ws + L.x0, 4, dims, str, box, dt))) return rc;
     if ((rc = make_map(e, &tm_x[1], ws + L.x1, 4, dims, str, box, dt))) return rc;
@@ -710,24 +759,8 @@ int wg_infer(wg_engine* e, const float* mel, int32_t batch, int32_t frames, cons
     pack_noise_kernel<<<static_cast<unsigned>((npos + 255) / 256), 256, 0, st>>>(np, sigma, audio, B, T);
     e->launches++;
   }
-  // 2. mel upsampler + squeeze -> conditioning, time-major
-  {
-    const int Fq = (T + kUpPhases - 1) / kUpPhases;
-    dim3 grid(kUpPhases, B * ((Fq + kUpFrames - 1) / kUpFrames));
-    if (tc) {
-      // tensor-core mode: the upsampler is composed into the conditioning weights; only the 4-frame mel windows are formed
-      const size_t total = static_cast<size_t>(B) * Fq * kUpKdim;
-      const unsigned g1 = static_cast<unsigned>((total + 255) / 256);
-      if (e->op_fmt == 1)
-        mel_window_kernel<__nv_bfloat16><<<g1, 256, 0, st>>>(mel, reinterpret_cast<__nv_bfloat16*>(ws + L.cond), B, frames, Fq);
-      else
-        mel_window_kernel<__half><<<g1, 256, 0, st>>>(mel, reinterpret_cast<__half*>(ws + L.cond), B, frames, Fq);
-    } else {
-      upsample_squeeze_kernel<float><<<grid, kUpThreads, 0, st>>>(mel, e->d_up_w, e->d_up_b,
-                                                                 reinterpret_cast<float*>(ws + L.cond), B, frames, T);
-    }
-    e->launches++;
-  }
+  // 2. conditioning operand (mel windows in tensor-core mode, upsampled + squeezed mel in fp32 mode)
+  launch_conditioning(e, mel, B, frames, T, ws, L, st);
   CUtensorMap tm_x[2], tm_cond;
   if (tc) {
     int rc = make_act_maps(e, ws, L, B, T, tm_x, &tm_cond);
@@ -735,15 +768,7 @@ int wg_infer(wg_engine* e, const float* mel, int32_t batch, int32_t frames, cons
   }
   float* ebuf = reinterpret_cast<float*>(ws + L.e);
   int cur = 0;
-  auto flow_step = [&](const FlowStepParams& fs, void* xdst) {
-    if (!tc)
-      launch_flow_step<float>(fs, audio, ebuf, xdst, npos, st);
-    else if (e->op_fmt == 1)
-      launch_flow_step<__nv_bfloat16>(fs, audio, ebuf, xdst, npos, st);
-    else
-      launch_flow_step<__half>(fs, audio, ebuf, xdst, npos, st);
-    e->launches++;
-  };
+  auto flow_step = [&](const FlowStepParams& fs, void* xdst) { flow_step_any(e, fs, audio, ebuf, xdst, B, T, L.Tpad, st); };
   void* xb[2] = {ws + L.x0, ws + L.x1};
   // 3. start conv of the first (last-indexed) flow
   {
@@ -807,9 +832,76 @@ int wg_profile_layers(wg_engine* e, float* total_ms, int32_t* n_launches) {
   return WG_OK;
 }
 
-int wg_forward(wg_engine* e, const float*, int32_t, int32_t, const float*, int32_t, float*, float* const*, float*, float*,
-               void*, size_t, void*) {
-  return fail(e, WG_ERR_UNSUPPORTED, "wg_forward: training-direction flow is not implemented yet in this build");
+int wg_forward(wg_engine* e, const float* mel, int32_t batch, int32_t frames, const float* audio_in, int32_t n_samples,
+               float* z_out, float* const* log_s_out, float* log_s_sum, float* log_det_w, void* workspace, size_t ws_bytes,
+               void* stream) {
+  if (!e) return WG_ERR_INVALID_ARGUMENT;
+  if (!e->loaded) return fail(e, WG_ERR_WEIGHTS, "wg_load_weights has not been called");
+  if (!mel || !audio_in || !z_out || !log_s_sum || !log_det_w || !workspace || batch <= 0 || frames <= 0 || n_samples <= 0)
+    return fail(e, WG_ERR_INVALID_ARGUMENT, "null pointer or non-positive size");
+  if (n_samples % kGroup) return fail(e, WG_ERR_INVALID_ARGUMENT, "n_samples must be a multiple of n_group");
+  // model.py:186-187: the upsampled mel ((frames-1)*256 + 1024 samples) must cover the audio
+  if (n_samples > (frames - 1) * kUpStride + kUpK) return fail(e, WG_ERR_INVALID_ARGUMENT, "audio longer than the upsampled mel");
+  const int NF = e->cfg.n_flows;
+  const int B = batch, T = n_samples / kGroup;
+  const WsLayout L = ws_layout(e, B, T);
+  if (ws_bytes < L.total) return fail(e, WG_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, L.total);
+  if (reinterpret_cast<uintptr_t>(workspace) % 1024) return fail(e, WG_ERR_WORKSPACE, "workspace must be 1024-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  WG_CUDA(e, cudaSetDevice(e->cfg.device));
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const size_t npos = static_cast<size_t>(B) * T;
+  const bool tc = e->cfg.precision == WG_PRECISION_FP16;
+  e->launches = 0;
+  e->ev_flows = 0;
+  // audio[B, 8 T'] viewed as [B, T', 8] IS the squeezed audio (model.py:194-195): copy it into the working state
+  float* state = reinterpret_cast<float*>(ws + L.state);
+  double* sums = reinterpret_cast<double*>(ws + L.sums);
+  WG_CUDA(e, cudaMemcpyAsync(state, audio_in, npos * kGroup * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  WG_CUDA(e, cudaMemsetAsync(sums, 0, NF * sizeof(double), st));
+  launch_conditioning(e, mel, B, frames, T, ws, L, st);
+  CUtensorMap tm_x[2], tm_cond;
+  if (tc) {
+    int rc = make_act_maps(e, ws, L, B, T, tm_x, &tm_cond);
+    if (rc) return rc;
+  }
+  float* ebuf = reinterpret_cast<float*>(ws + L.e);
+  void* xb[2] = {ws + L.x0, ws + L.x1};
+  int cur = 0;
+  // flows run k = 0 .. NF-1; early outputs (model.py:201-203) simply stop being "live": the state keeps them in place
+  for (int k = 0; k <= NF; ++k) {
+    FlowStepParams fs{};
+    fs.forward = 1;
+    if (k > 0) {
+      const FlowPack& f = e->flows[k - 1];
+      fs.do_finish = 1;
+      fs.C = f.C;
+      fs.h = f.h;
+      memcpy(fs.e_bias, f.e_bias, sizeof(fs.e_bias));
+      fs.log_s_sum = sums + (k - 1);
+      fs.log_s_out = log_s_out ? log_s_out[k - 1] : nullptr;
+    }
+    if (k < NF) {
+      const FlowPack& g = e->flows[k];
+      fs.do_start = 1;
+      fs.C2 = g.C;
+      fs.h2 = g.h;
+      memcpy(fs.w_fwd, g.w_fwd, sizeof(fs.w_fwd));
+      fs.nc = e->cfg.n_channels;
+      fs.w_start = g.d_w_start;
+      fs.b_start = g.d_b_start;
+    }
+    flow_step_any(e, fs, state, ebuf, xb[cur], B, T, L.Tpad, st);
+    if (k == NF) break;
+    bool stopped = false;
+    int rc = run_wn_layers(e, k, B, T, ws, L, tm_x, &tm_cond, &cur, st, &stopped);
+    if (rc) return rc;
+  }
+  state_to_channel_major_kernel<<<static_cast<unsigned>((npos + 255) / 256), 256, 0, st>>>(state, z_out, B, T);
+  finalize_forward_stats_kernel<<<1, 64, 0, st>>>(sums, e->d_logdet, log_s_sum, log_det_w, NF, static_cast<double>(B) * T);
+  e->launches += 2;
+  WG_CUDA(e, cudaGetLastError());
+  return WG_OK;
 }
 
 // Diagnostic: D[M x N] fp32 = A[M x K] . B[N x K]^T with 16-bit device operands (fmt 0 fp16 / 1 bf16).

@@ -180,32 +180,49 @@ compose_cond_kernel(const float* __restrict__ wc, const float* __restrict__ wp, 
 
 // ------------------------------------------------------------------------------------------ flow step
 struct FlowStepParams {
-  // "finish" part: flow k
+  int forward;                // 0: inverse flow (infer, model.py:246-271)   1: forward flow (model.py:197-218)
+  // "finish" part: flow k (its WN just produced e)
   int do_finish;
   int C, h;                   // live channels of flow k, C/2
   float e_bias[kGroup];       // folded end bias: [:h] -> b, [h:2h] -> s
-  float w_inv[kGroup * kGroup];   // [C x C] row-major inverse 1x1 weight (model.py:51-59)
-  // "start" part: next flow (k-1), or the first flow
+  float w_inv[kGroup * kGroup];   // inverse: [C x C] row-major W^-1 (model.py:51-59) applied after the coupling
+  // "start" part: the flow whose WN runs next
   int do_start;
   int C2, h2;
+  float w_fwd[kGroup * kGroup];   // forward: [C2 x C2] row-major W applied before the coupling (model.py:205)
   int nc;
   const float* w_start;       // [nc, h2]
   const float* b_start;       // [nc]
+  // forward-only outputs of the finish part
+  double* log_s_sum;          // one accumulator: sum of log_s over all elements of flow k
+  float* log_s_out;           // optional [B, h, T] (reference layout, model.py:216)
 };
 
 constexpr int kFsPos = 64;      // group-steps per block
 constexpr int kFsThreads = 256;
 
+// One block = 64 consecutive PADDED group-steps (utterance stride Tpad >= T for the x stream, T for state / e).
+// Thread < 64: the per-position coupling / 1x1 algebra on the 8-float state row.  Then all 256 threads write the
+// next WN's start conv (model.py:117) coalesced along channels; padded rows of x are written as zeros because the
+// dilated convs must see zero padding beyond the true sequence end (model.py:100-102).
 template <typename XT>
 __global__ void __launch_bounds__(kFsThreads)
 flow_step_kernel(FlowStepParams p, float* __restrict__ state, const float* __restrict__ e, XT* __restrict__ x,
-                 size_t n_pos /* B*T */) {
+                 int B, int T, int Tpad) {
   __shared__ float a0s[kFsPos][4];
-  const size_t pos0 = static_cast<size_t>(blockIdx.x) * kFsPos;
+  __shared__ int valid_s[kFsPos];
+  const size_t n_ppos = static_cast<size_t>(B) * Tpad;
+  const size_t ppos0 = static_cast<size_t>(blockIdx.x) * kFsPos;
   if (threadIdx.x < kFsPos) {
-    const size_t pos = pos0 + threadIdx.x;
+    const size_t ppos = ppos0 + threadIdx.x;
+    const int b = static_cast<int>(ppos / Tpad), t = static_cast<int>(ppos % Tpad);
+    const bool valid = ppos < n_ppos && t < T;
     float row[kGroup];
-    if (pos < n_pos) {
+    float ls_sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kGroup; ++i) row[i] = 0.f;
+    if (valid) {
+      const size_t pos = static_cast<size_t>(b) * T + t;
       const float4* sp = reinterpret_cast<const float4*>(state + pos * kGroup);
       const float4 s0 = sp[0], s1 = sp[1];
       row[0] = s0.x; row[1] = s0.y; row[2] = s0.z; row[3] = s0.w;
@@ -215,32 +232,58 @@ flow_step_kernel(FlowStepParams p, float* __restrict__ state, const float* __res
         const float4 e0 = ep[0], e1 = ep[1];
         const float ev[kGroup] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
         const int base = kGroup - p.C;
-        float v[kGroup];
+        if (!p.forward) {
+          float v[kGroup];
 #pragma unroll
-        for (int i = 0; i < kGroup; ++i) v[i] = 0.f;
-        for (int i = 0; i < p.h; ++i) {
-          v[i] = row[base + i];
-          const float bb = ev[i] + p.e_bias[i];
-          const float ss = ev[p.h + i] + p.e_bias[p.h + i];
-          v[p.h + i] = (row[base + p.h + i] - bb) / expf(ss);      // model.py:255
+          for (int i = 0; i < kGroup; ++i) v[i] = 0.f;
+          for (int i = 0; i < p.h; ++i) {
+            v[i] = row[base + i];
+            const float bb = ev[i] + p.e_bias[i];
+            const float ss = ev[p.h + i] + p.e_bias[p.h + i];
+            v[p.h + i] = (row[base + p.h + i] - bb) / expf(ss);      // model.py:255
+          }
+          for (int i = 0; i < p.C; ++i) {
+            float acc = 0.f;
+            for (int j = 0; j < p.C; ++j) acc = fmaf(p.w_inv[i * p.C + j], v[j], acc);   // model.py:59
+            row[base + i] = acc;
+          }
+        } else {
+          for (int i = 0; i < p.h; ++i) {
+            const float bb = ev[i] + p.e_bias[i];
+            const float ls = ev[p.h + i] + p.e_bias[p.h + i];
+            row[base + p.h + i] = expf(ls) * row[base + p.h + i] + bb;   // model.py:215
+            ls_sum += ls;
+            if (p.log_s_out) p.log_s_out[(static_cast<size_t>(b) * p.h + i) * T + t] = ls;
+          }
         }
-        for (int i = 0; i < p.C; ++i) {
+      }
+      if (p.do_start && p.forward) {
+        const int base2 = kGroup - p.C2;
+        float v[kGroup];
+        for (int i = 0; i < p.C2; ++i) {
           float acc = 0.f;
-          for (int j = 0; j < p.C; ++j) acc = fmaf(p.w_inv[i * p.C + j], v[j], acc);   // model.py:59
-          row[base + i] = acc;
+          for (int j = 0; j < p.C2; ++j) acc = fmaf(p.w_fwd[i * p.C2 + j], row[base2 + j], acc);   // model.py:205
+          v[i] = acc;
         }
+        for (int i = 0; i < p.C2; ++i) row[base2 + i] = v[i];
+      }
+      if (p.do_finish || (p.do_start && p.forward)) {
         float4* dp = reinterpret_cast<float4*>(state + pos * kGroup);
         dp[0] = make_float4(row[0], row[1], row[2], row[3]);
         dp[1] = make_float4(row[4], row[5], row[6], row[7]);
       }
-    } else {
+    }
+    if (p.do_finish && p.forward) {
+      // warp-level sum, then one double atomic per warp (deterministic enough: double accumulation)
 #pragma unroll
-      for (int i = 0; i < kGroup; ++i) row[i] = 0.f;
+      for (int o = 16; o > 0; o >>= 1) ls_sum += __shfl_xor_sync(0xffffffffu, ls_sum, o);
+      if ((threadIdx.x & 31) == 0 && ls_sum != 0.f) atomicAdd(p.log_s_sum, static_cast<double>(ls_sum));
     }
     if (p.do_start) {
       const int base2 = kGroup - p.C2;
 #pragma unroll
       for (int j = 0; j < 4; ++j) a0s[threadIdx.x][j] = (j < p.h2) ? row[base2 + j] : 0.f;
+      valid_s[threadIdx.x] = valid ? 1 : 0;
     }
   }
   if (!p.do_start) return;
@@ -251,13 +294,35 @@ flow_step_kernel(FlowStepParams p, float* __restrict__ state, const float* __res
     for (int j = 0; j < 4; ++j) w[j] = (j < p.h2) ? p.w_start[c * p.h2 + j] : 0.f;
     const float bs = p.b_start[c];
     for (int i = 0; i < kFsPos; ++i) {
-      const size_t pos = pos0 + i;
-      if (pos >= n_pos) break;
+      const size_t ppos = ppos0 + i;
+      if (ppos >= n_ppos) break;
       float acc = bs;
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc = fmaf(w[j], a0s[i][j], acc);              // model.py:117
-      x[pos * p.nc + c] = from_float<XT>(acc);
+      x[ppos * p.nc + c] = from_float<XT>(valid_s[i] ? acc : 0.f);
     }
+  }
+}
+
+// z_out[b, c, t] = state[b, t, c]  (forward returns the reference's channel-major layout, model.py:220-221)
+__global__ void state_to_channel_major_kernel(const float* __restrict__ state, float* __restrict__ z, int B, int T) {
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<size_t>(B) * T) return;
+  const int b = static_cast<int>(idx / T), t = static_cast<int>(idx % T);
+  const float4* sp = reinterpret_cast<const float4*>(state + idx * kGroup);
+  const float4 s0 = sp[0], s1 = sp[1];
+  const float row[kGroup] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+  for (int c = 0; c < kGroup; ++c) z[(static_cast<size_t>(b) * kGroup + c) * T + t] = row[c];
+}
+
+// out_sum[k] = (float) acc[k];  out_det[k] = logdet[k] * B * T   (model.py:63)
+__global__ void finalize_forward_stats_kernel(const double* __restrict__ acc, const double* __restrict__ logdet,
+                                              float* __restrict__ out_sum, float* __restrict__ out_det, int n, double bt) {
+  const int k = threadIdx.x;
+  if (k < n) {
+    out_sum[k] = static_cast<float>(acc[k]);
+    out_det[k] = static_cast<float>(logdet[k] * bt);
   }
 }
 
@@ -266,9 +331,9 @@ flow_step_kernel(FlowStepParams p, float* __restrict__ state, const float* __res
 //   W1  [K1 = 3 NC + 640][2 NC]  (k-major rows, natural channel order: tanh half | sigmoid half)
 //   Wres [NC][NC] (k-major), Wse [NC][8]
 struct LayerF32Params {
-  int T, dilation, has_res, accumulate_e;
-  const float* x_in;    // [B,T,NC]
-  float* x_out;         // [B,T,NC]
+  int T, Tpad, dilation, has_res, accumulate_e;
+  const float* x_in;    // [B,Tpad,NC]
+  float* x_out;         // [B,Tpad,NC]
   const float* cond;    // [B,T,640]
   const float* w1;
   const float* bias1;   // [2 NC]
@@ -291,7 +356,8 @@ __global__ void __launch_bounds__(256, 1) wn_layer_fp32_kernel(const LayerF32Par
   float* acts_s = Ws + kF32KC * 2 * NC;     // [32][NC]
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
   const int t0 = blockIdx.x * kF32Pos, b = blockIdx.y;
-  const size_t ubase = static_cast<size_t>(b) * p.T;
+  const size_t ubase = static_cast<size_t>(b) * p.T;       // cond / e rows
+  const size_t xbase = static_cast<size_t>(b) * p.Tpad;    // residual stream rows
 
   float acc[8][2 * CPT];
 #pragma unroll
@@ -308,7 +374,7 @@ __global__ void __launch_bounds__(256, 1) wn_layer_fp32_kernel(const LayerF32Par
       if (k < 3 * NC) {
         const int tap = k / NC, ch = k % NC;
         const int t = t0 + pos + (tap - 1) * p.dilation;
-        if (t >= 0 && t < p.T) v = p.x_in[(ubase + t) * NC + ch];
+        if (t >= 0 && t < p.T) v = p.x_in[(xbase + t) * NC + ch];
       } else {
         const int t = t0 + pos;
         if (t < p.T) v = p.cond[(ubase + t) * kCond + (k - 3 * NC)];
@@ -396,7 +462,7 @@ __global__ void __launch_bounds__(256, 1) wn_layer_fp32_kernel(const LayerF32Par
     if (t < p.T) {
 #pragma unroll
       for (int j = 0; j < CPT; ++j) {
-        const size_t o = (ubase + t) * NC + tx * CPT + j;
+        const size_t o = (xbase + t) * NC + tx * CPT + j;
         p.x_out[o] = p.x_in[o] + r[i][j] + p.bias_res[tx * CPT + j];      // model.py:131-132
       }
     }

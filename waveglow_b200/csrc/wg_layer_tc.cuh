@@ -66,8 +66,8 @@ struct TcSmem {
 static_assert(TcSmem::total + 1024 <= 232448, "shared memory budget exceeded");
 
 struct LayerTcParams {
-  int T;              // group-steps per utterance (= 32 * Fq here)
-  int Fq;             // mel frame slots per utterance
+  int T;              // valid group-steps per utterance
+  int Fq;             // mel frame slots per utterance = ceil(T / 32); the x buffers have 32 * Fq rows per utterance
   int B;              // utterances
   int dilation;
   int reverse;        // walk the tiles backwards (alternate per layer: the tail of the previous layer's x' is still in L2)
@@ -402,8 +402,9 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, 32, F
           uint32_t pk[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float a0 = __uint_as_float(v[2 * i]) + s_bias_res[ch0 + 2 * i];
-            const float a1 = __uint_as_float(v[2 * i + 1]) + s_bias_res[ch0 + 2 * i + 1];
+            // rows beyond the true sequence end stay exactly zero: they are the conv's zero padding for later layers
+            const float a0 = t < p.T ? __uint_as_float(v[2 * i]) + s_bias_res[ch0 + 2 * i] : 0.f;
+            const float a1 = t < p.T ? __uint_as_float(v[2 * i + 1]) + s_bias_res[ch0 + 2 * i + 1] : 0.f;
             if (p.fmt == 0) {
               pk[i] = ptx::pack_half2(a0, a1);
             } else {

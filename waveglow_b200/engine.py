@@ -170,6 +170,31 @@ class Engine:
     self._check(rc, "wg_infer")
     return audio
 
+  def forward(self, mel: torch.Tensor, audio: torch.Tensor, flow_halves: Sequence[int], want_log_s: bool = True):
+    """Training-direction flow.  mel [B,80,F], audio [B, n_samples] fp32 cuda.
+    Returns (z [B,8,T'], [log_s_k [B,h_k,T']] or None, log_s_sum [n_flows], log_det_w [n_flows])."""
+    if mel.device != self.device or audio.device != self.device:
+      raise WgError(f"inputs must be on {self.device}")
+    mel = mel.to(torch.float32).contiguous()
+    audio = audio.to(torch.float32).contiguous()
+    B, _, F = mel.shape
+    n_samples = audio.shape[1]
+    if audio.shape[0] != B or n_samples % self.n_group:
+      raise WgError("audio must be [B, n_samples] with n_samples a multiple of n_group")
+    T = n_samples // self.n_group
+    n_flows = len(flow_halves)
+    z = torch.empty((B, self.n_group, T), dtype=torch.float32, device=self.device)
+    log_s = [torch.empty((B, h, T), dtype=torch.float32, device=self.device) for h in flow_halves] if want_log_s else None
+    sums = torch.empty((n_flows,), dtype=torch.float32, device=self.device)
+    dets = torch.empty((n_flows,), dtype=torch.float32, device=self.device)
+    ws = self.workspace(B, F)
+    lsp = (ctypes.c_void_p * n_flows)(*[t.data_ptr() for t in log_s]) if want_log_s else None
+    stream = torch.cuda.current_stream(self.device).cuda_stream
+    rc = self.lib.wg_forward(self._h, mel.data_ptr(), B, F, audio.data_ptr(), n_samples, z.data_ptr(), lsp, sums.data_ptr(),
+                             dets.data_ptr(), self._aligned_ptr(ws), ws.numel() - 1024, stream)
+    self._check(rc, "wg_forward")
+    return z, log_s, sums, dets
+
   def launch_count(self) -> int:
     return self.lib.wg_last_launch_count(self._h)
 

@@ -175,7 +175,22 @@ class WaveGlow(torch.nn.Module):
     return self.infer_with_noise(spect, zs, sigma)
 
   def forward(self, forward_input: Tuple[torch.Tensor, torch.Tensor]):
-    raise NotImplementedError("training-direction flow (model.py:178-221) is not wired to the engine yet")
+    """(spect[B,80,F], audio[B,T]) -> (z[B,8,T/8], log_s_list, log_det_W_list) like model.py:178-221.
+
+    Inference-only (no autograd graph: the reference's optimiser/backward are out of scope).
+    The engine also returns the reductions WaveGlowLoss needs; they are kept in `self.last_forward_stats`
+    (`log_s_sum[k]`, `log_det_w[k]`) so `waveglow_b200.model.WaveGlowLoss` does not re-reduce."""
+    spect, audio = forward_input
+    if spect.dim() != 3 or spect.size(1) != self.hparams.n_mel_channels or audio.dim() != 2:
+      raise ValueError("forward_input must be (spect[B, n_mel, frames], audio[B, samples])")
+    # model.py:187: assert(spect.size(2) >= audio.size(1)) on the upsampled mel
+    assert (spect.size(2) - 1) * 256 + 1024 >= audio.size(1)
+    eng = self.engine()
+    halves = [c // 2 for c in flow_channels(self.hparams)]
+    with torch.no_grad():
+      z, log_s_list, sums, dets = eng.forward(spect, audio, halves, want_log_s=True)
+    self.last_forward_stats = {"log_s_sum": sums, "log_det_w": dets}
+    return z, log_s_list, [dets[k] for k in range(self.n_flows)]
 
   @staticmethod
   def remove_weightnorm(model: "WaveGlow") -> "WaveGlow":
@@ -188,6 +203,24 @@ class WaveGlow(torch.nn.Module):
         wnet.res_skip_layers = _remove(wnet.res_skip_layers)
     model.invalidate_packed_weights()
     return model
+
+
+class WaveGlowLoss(torch.nn.Module):
+  """Mirror of train.py:26-45: (sum z^2 / (2 sigma^2) - sum log_s - sum log_det_W) / (B * 8 * T')."""
+
+  def __init__(self, sigma: float = 1.0):
+    super().__init__()
+    self.sigma = sigma
+
+  def forward(self, model_output):
+    z, log_s_list, log_det_W_list = model_output
+    log_s_total = 0
+    log_det_W_total = 0
+    for i, log_s in enumerate(log_s_list):
+      log_s_total = log_s_total + torch.sum(log_s)
+      log_det_W_total = log_det_W_total + log_det_W_list[i]
+    loss = torch.sum(z * z) / (2 * self.sigma * self.sigma) - log_s_total - log_det_W_total
+    return loss / (z.size(0) * z.size(1) * z.size(2))
 
 
 def load_model(hparams: HParams, state_dict: Optional[dict], device: torch.device, precision: str = "fp16") -> WaveGlow:
