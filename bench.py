@@ -161,7 +161,7 @@ def main():
                         f"sigma {SIGMA} (BASELINE.json configs[1])",
             "n_channels": 256, "batch_per_gpu": args.batch, "frames": args.frames, "sigma": SIGMA,
             "sharding": "by utterance, one process per GPU, no data-path collective; NCCL all_gather of the audio at the end of each step",
-            "l2": "working set per step (conditioning 564 MB + residual streams 452 MB) >> 126 MB L2, no flush needed"}
+            "l2": "working set per step (residual streams 2 x 226 MB + packed weights 1.2 GB) >> 126 MB L2, no flush needed"}
 
   if args.impl == "reference":
     if rank != 0:
@@ -287,7 +287,11 @@ def main():
     per_launch_ms = layer_ms / layer_launches
     achieved = per_launch_flops / (per_launch_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": "wn_layer_tc_kernel" if args.precision == "fp16" else "wn_layer_fp32_kernel",
-                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel on this workload, from
+                # profiles/r01/ncu_full_layer_v4_summary.csv (ncu --set full, kernel v4); only valid for the default workload
+                "traffic": 461e6 if (args.batch == 16 and args.frames == 861 and args.precision == "fp16") else None,
+                "traffic_unit": "bytes per launch (ncu)",
                 "peak_source": peak_src, "launch_ms": per_launch_ms, "launches_per_step": layer_launches,
                 "algorithmic_flop_per_launch": per_launch_flops,
                 "executed_tensor_tflops": exec_per_step_layer * (B * T / 8) / (per_launch_ms * 1e-3) / 1e12,

@@ -75,6 +75,13 @@ def test_stagewise_first_flow(precision):
   x0_ref = E.rnd(state0[..., 4:6] @ pf.w_start.t() + pf.b_start, op_dtype)
   failures = []
 
+  def x_view(buf):
+    """engine x buffer -> time-major [B, T, 256] (tensor-core mode keeps it phase-major [B][32][T/32][256])"""
+    raw = eng.debug_view(buf, B, F).float().cpu()
+    if precision == "fp16":
+      return raw.view(B, 32, T // 32, 256).permute(0, 2, 1, 3).reshape(B, T, 256)
+    return raw.view(B, T, 256)
+
   def check(name, got, ref, t=tol):
     err = float((got.double() - ref.double()).abs().max())
     scale = float(ref.abs().max())
@@ -89,7 +96,7 @@ def test_stagewise_first_flow(precision):
       check("mel windows", eng.debug_view("cond", B, F).float().view(B, F, 320).cpu(), E.rnd(E.mel_windows(mel, F), op_dtype))
     else:
       check("cond", eng.debug_view("cond", B, F).float().view(B, T, 640).cpu(), S_ref)
-    check("x after start", eng.debug_view("x0", B, F).float().view(B, T, 256).cpu(), x0_ref)
+    check("x after start", x_view("x0"), x0_ref)
     for i in range(dims.n_layers):
       eng.debug_stop_after(k, i)
       run(model, mel, zs, sigma)
@@ -97,7 +104,7 @@ def test_stagewise_first_flow(precision):
       check(f"e after layer {i}", eng.debug_view("e", B, F).view(B, T, 8).cpu()[..., : 2 * pf.h], lt["e"])
       if i < dims.n_layers - 1:
         buf = "x1" if (i + 1) % 2 == 1 else "x0"
-        check(f"x after layer {i}", eng.debug_view(buf, B, F).float().view(B, T, 256).cpu(), lt["x"])
+        check(f"x after layer {i}", x_view(buf), lt["x"])
     eng.debug_stop_after(k, dims.n_layers)
     state = run(model, mel, zs, sigma).view(B, T, 8)
     check("state after first flow", state, flow_tr["state"], t=tol)

@@ -580,8 +580,10 @@ void launch_flow_step(const FlowStepParams& fs, float* state, const float* ebuf,
   flow_step_kernel<XT><<<grid, kFsThreads, 0, st>>>(fs, state, ebuf, static_cast<XT*>(x), B, T, Tpad);
 }
 
-void flow_step_any(wg_engine* e, const FlowStepParams& fs, float* state, const float* ebuf, void* x, int B, int T, int Tpad,
+void flow_step_any(wg_engine* e, const FlowStepParams& fs_in, float* state, const float* ebuf, void* x, int B, int T, int Tpad,
                    cudaStream_t st) {
+  FlowStepParams fs = fs_in;
+  fs.x_phase_major = e->cfg.precision == WG_PRECISION_FP16 ? 1 : 0;
   if (e->cfg.precision == WG_PRECISION_FP32)
     launch_flow_step<float>(fs, state, ebuf, x, B, T, Tpad, st);
   else if (e->op_fmt == 1)
@@ -697,14 +699,12 @@ int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CU
   int rc;
   const int Fq = L.Tpad / kUpPhases;
   {
-    // x[B][T][nc] seen as {channel, phase, frame, utterance}: group-step t = 32 * frame + phase
-    const uint64_t dims[4] = {static_cast<uint64_t>(nc), static_cast<uint64_t>(kUpPhases), static_cast<uint64_t>(Fq),
-                              static_cast<uint64_t>(B)};
-    const uint64_t str[3] = {static_cast<uint64_t>(nc) * 2, static_cast<uint64_t>(nc) * 2 * kUpPhases,
-                             static_cast<uint64_t>(nc) * 2 * L.Tpad};
-    const uint32_t box[4] = {64, 1, static_cast<uint32_t>(kTileM), 1};
-    if ((rc = make_map(e, &tm_x[0], ws + L.x0, 4, dims, str, box, dt))) return rc;
-    if ((rc = make_map(e, &tm_x[1], ws + L.x1, 4, dims, str, box, dt))) return rc;
+    // phase-major residual stream x[B][phase][frame][nc]: group-step t = 32 * frame + phase; frames outside [0, Fq) read as zero
+    const uint64_t dims[3] = {static_cast<uint64_t>(nc), static_cast<uint64_t>(Fq), static_cast<uint64_t>(B) * kUpPhases};
+    const uint64_t str[2] = {static_cast<uint64_t>(nc) * 2, static_cast<uint64_t>(nc) * 2 * Fq};
+    const uint32_t box[3] = {64, static_cast<uint32_t>(kTileM), 1};
+    if ((rc = make_map(e, &tm_x[0], ws + L.x0, 3, dims, str, box, dt))) return rc;
+    if ((rc = make_map(e, &tm_x[1], ws + L.x1, 3, dims, str, box, dt))) return rc;
   }
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(kUpKdim), static_cast<uint64_t>(Fq), static_cast<uint64_t>(B)};

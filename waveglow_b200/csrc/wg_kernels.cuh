@@ -193,6 +193,7 @@ struct FlowStepParams {
   int nc;
   const float* w_start;       // [nc, h2]
   const float* b_start;       // [nc]
+  int x_phase_major;          // 1: x is [B][phase 32][frame][nc] (tensor-core mode), 0: time-major [B][Tpad][nc]
   // forward-only outputs of the finish part
   double* log_s_sum;          // one accumulator: sum of log_s over all elements of flow k
   float* log_s_out;           // optional [B, h, T] (reference layout, model.py:216)
@@ -299,7 +300,14 @@ flow_step_kernel(FlowStepParams p, float* __restrict__ state, const float* __res
       float acc = bs;
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc = fmaf(w[j], a0s[i][j], acc);              // model.py:117
-      x[ppos * p.nc + c] = from_float<XT>(valid_s[i] ? acc : 0.f);
+      size_t row = ppos;
+      if (p.x_phase_major) {
+        // group-step t = 32 q + phase of utterance b lives at row ((b * 32 + phase) * Fq + q): each (phase, 128-frame) tile
+        // of the layer kernel is then one dense block for TMA
+        const size_t b = ppos / Tpad, t = ppos % Tpad;
+        row = (b * kUpPhases + (t % kUpPhases)) * (Tpad / kUpPhases) + t / kUpPhases;
+      }
+      x[row * p.nc + c] = from_float<XT>(valid_s[i] ? acc : 0.f);
     }
   }
 }

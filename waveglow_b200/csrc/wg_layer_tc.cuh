@@ -12,10 +12,10 @@
 //                                                            half runs while the chunk-b gate is still busy)
 //          e'   [128 x  16] = acts . (W_end W_skip)^T       (skip->end fold, fp32 accumulator in global)
 //
-// Data layout: x is time-major fp16 [B, T', C] viewed by TMA as 4-D {C, phase 32, frame, B}; the dilation halo
-// comes from three TMA boxes at t-d, t, t+d (a shift by d moves (phase, frame) to ((p+d) mod 32, q + (p+d) div 32));
-// out-of-range rows are zero-filled by TMA == the conv's zero padding, model.py:100-102.  The mel windows
-// MW[B, frame, 4*80] (fp16) are tiny and L2-resident.
+// Data layout: x is PHASE-major fp16 [B][phase 32][frame][C] (TMA view {C, frame, 32 B}), so a tile and each of its
+// dilation taps is one dense 128 x 512 B block; the halo comes from three TMA boxes at t-d, t, t+d (a shift by d moves
+// (phase, frame) to ((p+d) mod 32, q + (p+d) div 32)); out-of-range frames are zero-filled by TMA == the conv's zero
+// padding, model.py:100-102.  The mel windows MW[B, frame, 4*80] (fp16) are tiny and L2-resident.
 // W1 rows are pre-permuted so that accumulator chunk c (256 TMEM columns) holds
 // [tanh ch 128c..128c+127 | sigmoid ch 128c..128c+127]; the gate therefore reads column j and j+128 of
 // the same TMEM lane.
@@ -94,7 +94,7 @@ __device__ __forceinline__ float gate_one(float a, float b) {
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
-wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, 32, Fq, B} box {64,1,128,1} SW128
+wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, Fq, 32 B} box {64,128,1} SW128
                    const __grid_constant__ CUtensorMap tm_x_out,  // same geometry, other buffer
                    const __grid_constant__ CUtensorMap tm_mw,     // {320, Fq, B} box {64,128,1}
                    const __grid_constant__ CUtensorMap tm_w1,     // {768, rows} box {64,256}
@@ -193,7 +193,7 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, 32, F
               const int j = kb - kMwKB;          // 0..11: tap (j >> 2) in {t-d, t, t+d}, channel block (j & 3)
               const int pp = ph_ + ((j >> 2) - 1) * p.dilation;
               const int dq = pp >> 5;            // floor division by 32 (arithmetic shift)
-              if (!skip_a) ptx::tma_load_4d(sa, &tm_x_in, &full[s], (j & 3) * kBlockK, pp - (dq << 5), q0 + dq, b);
+              if (!skip_a) ptx::tma_load_3d(sa, &tm_x_in, &full[s], (j & 3) * kBlockK, q0 + dq, b * kPhases + pp - (dq << 5));
               if (!skip_b) ptx::tma_load_2d(sb, &tm_w1, &full[s], j * kBlockK, p.w1_row0 + chunk * 256);
             }
           }
@@ -208,7 +208,7 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, 32, F
             uint8_t* sb = sa + kStageABytes;
             ptx::mbar_arrive_expect_tx(&full[s], kStageBBytes + kStageABytes);
             ptx::tma_load_2d(sb, &tm_w2a, &full[s], j * kBlockK, p.w2_row0);
-            ptx::tma_load_4d(sa, &tm_x_in, &full[s], j * kBlockK, ph_, q0, b);
+            ptx::tma_load_3d(sa, &tm_x_in, &full[s], j * kBlockK, q0, b * kPhases + ph_);
           }
         }
       }
@@ -427,7 +427,7 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, 32, F
         asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps only
         if (warp == 2 && lane == 0) {
 #pragma unroll
-          for (int s4 = 0; s4 < 4; ++s4) ptx::tma_store_4d(&tm_x_out, acts + s4 * (kTileM * 128), s4 * kBlockK, ph_, q0, b);
+          for (int s4 = 0; s4 < 4; ++s4) ptx::tma_store_3d(&tm_x_out, acts + s4 * (kTileM * 128), s4 * kBlockK, q0, b * kPhases + ph_);
           ptx::tma_store_commit();
         }
         store_pending = true;
