@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 from oracle import waveglow_oracle as O  # noqa: E402
-from ref_loader import load_reference  # noqa: E402
+from ref_loader import load_reference, load_reference_module  # noqa: E402
 from waveglow_b200.hparams import HParams  # noqa: E402
 from waveglow_b200.synthetic import synthetic_mel, synthetic_state_dict  # noqa: E402
 
@@ -95,5 +95,43 @@ def main():
     print(f"{name}: z {tuple(z.shape)}  (oracle bit-identical)")
 
 
+def make_denoiser_golden():
+  """Runs the reference's own STFT and Denoiser classes (stft.py, denoiser.py) on CPU."""
+  from oracle.denoiser_oracle import StftOracle, denoise
+  ref_stft = load_reference_module("stft")
+  ref_den = load_reference_module("denoiser")
+  _, RefHParams = load_reference()
+  hp = RefHParams()
+  g = torch.Generator().manual_seed(31)
+  bias_audio = torch.randn((1, 88 * 256), generator=g) * 0.01
+  audio = torch.randn((2, 256 * 24), generator=g) * 0.3
+
+  class FakeWaveglow:          # Denoiser only touches .upsample.weight.{dtype,device} and .infer (denoiser.py:29-47)
+    upsample = torch.nn.ConvTranspose1d(1, 1, 4)
+
+    def infer(self, mel, sigma=1.0):
+      assert tuple(mel.shape) == (1, 80, 88) and float(mel.abs().sum()) == 0.0 and sigma == 0.0
+      return bias_audio.clone()
+
+  dev = torch.device("cpu")
+  den = ref_den.Denoiser(waveglow=FakeWaveglow(), hparams=hp, mode="zeros", device=dev)
+  stft = ref_stft.STFT(filter_length=hp.filter_length, hop_length=hp.hop_length, win_length=hp.win_length, device=dev)
+  mag, phase = stft.transform(audio)
+  recon = stft.inverse(mag, phase)
+  outs = {f"denoised_{i}": den(audio, strength=s) for i, s in enumerate((0.0005, 0.1, 1.0))}
+  so = StftOracle(hp.filter_length, hp.hop_length, hp.win_length)
+  m2, p2 = so.transform(audio)
+  assert torch.equal(mag, m2) and torch.equal(phase, p2), "denoiser oracle STFT is not bit-identical to the reference"
+  for i, s in enumerate((0.0005, 0.1, 1.0)):
+    assert torch.equal(outs[f"denoised_{i}"], denoise(so, audio, den.bias_spec, s)), "denoiser oracle mismatch"
+  np.savez_compressed(os.path.join(ROOT, "tests", "golden", "denoiser_b2_n6144.npz"), audio=audio.numpy(),
+                      bias_audio=bias_audio.numpy(), bias_spec=den.bias_spec.numpy(), magnitude=mag.numpy(),
+                      recon=recon.numpy(), strengths=np.array([0.0005, 0.1, 1.0], dtype=np.float32),
+                      **{k: v.numpy() for k, v in outs.items()})
+  print(f"denoiser_b2_n6144: bias_spec {tuple(den.bias_spec.shape)}, denoised {tuple(outs['denoised_0'].shape)} (oracle bit-identical)")
+
+
 if __name__ == "__main__":
-  main()
+  if "--denoiser-only" not in sys.argv:
+    main()
+  make_denoiser_golden()

@@ -37,6 +37,31 @@ def available() -> bool:
   return os.path.isdir(os.path.join(REF_SRC, "waveglow"))
 
 
+def _install_librosa_util_shims():
+  """librosa is not installed; the reference's STFT needs three helpers from librosa.util (stft.py:36).  For the only
+  case the reference uses (win_length == filter_length, norm=None) they are trivial."""
+  import numpy as np
+  util = sys.modules["librosa.util"]
+
+  def pad_center(data, size, axis=-1, **kwargs):
+    n = data.shape[axis]
+    assert size >= n
+    lpad = (size - n) // 2
+    widths = [(0, 0)] * data.ndim
+    widths[axis] = (lpad, size - n - lpad)
+    return np.pad(data, widths, mode="constant")
+
+  util.pad_center = pad_center
+  util.tiny = lambda x: np.finfo(np.asarray(x).dtype if np.issubdtype(np.asarray(x).dtype, np.floating) else np.float32).tiny
+  util.normalize = lambda S, norm=None, **kw: S
+
+
+def load_reference_module(name: str):
+  """Imports `waveglow.<name>` of the reference (after load_reference() has prepared the stubs)."""
+  load_reference()
+  return importlib.import_module("waveglow." + name)
+
+
 def load_reference():
   """Returns (WaveGlow, HParams) classes of the reference, unmodified."""
   if not available():
@@ -50,6 +75,8 @@ def load_reference():
       stub = _Anything(name)
       stub.__path__ = []  # let "from pkg.sub import x" resolve through sys.modules
       sys.modules[name] = stub
+  if "librosa.util" in sys.modules and isinstance(sys.modules["librosa.util"], _Anything):
+    _install_librosa_util_shims()      # must precede the first import of waveglow.stft (binds the names at import time)
   if "waveglow" not in sys.modules or not hasattr(sys.modules["waveglow"], "__path__"):
     shell = types.ModuleType("waveglow")
     shell.__path__ = [os.path.join(REF_SRC, "waveglow")]
