@@ -151,15 +151,16 @@ def main():
   ap.add_argument("--batch", type=int, default=16, help="utterances per GPU")
   ap.add_argument("--frames", type=int, default=861, help="mel frames per utterance (861 = 10 s)")
   ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
+  ap.add_argument("--channels", type=int, default=256, choices=[256, 512], help="WN channels (512 = BASELINE config 3 architecture)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   args = ap.parse_args()
 
   rank = int(os.environ.get("RANK", "0"))
   world = int(os.environ.get("WORLD_SIZE", "1"))
   local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-  config = {"workload": f"WaveGlow-256 infer, batch {args.batch} x {args.frames} frames ({args.frames * 256 / SAMPLING_RATE:.1f} s) per GPU, "
+  config = {"workload": f"WaveGlow-{args.channels} infer, batch {args.batch} x {args.frames} frames ({args.frames * 256 / SAMPLING_RATE:.1f} s) per GPU, "
                         f"sigma {SIGMA} (BASELINE.json configs[1])",
-            "n_channels": 256, "batch_per_gpu": args.batch, "frames": args.frames, "sigma": SIGMA,
+            "n_channels": args.channels, "batch_per_gpu": args.batch, "frames": args.frames, "sigma": SIGMA,
             "sharding": "by utterance, one process per GPU, no data-path collective; NCCL all_gather of the audio at the end of each step",
             "l2": "working set per step (residual streams 2 x 226 MB + packed weights 1.2 GB) >> 126 MB L2, no flush needed"}
 
@@ -197,7 +198,7 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     dist.barrier()
 
-  hp = HParams()
+  hp = HParams(n_channels=args.channels)
   model = WaveGlow(hp, precision=args.precision).to(dev)
   model.load_state_dict(synthetic_state_dict(hp, WEIGHT_SEED))
   model = WaveGlow.remove_weightnorm(model).eval()
@@ -269,7 +270,7 @@ def main():
   total_samples = world * B * T * args.steps
   value = total_samples / (elapsed_ms * 1e-3)
   e2e_value = total_samples / (e2e_ms * 1e-3)
-  flops_sample, layer_flops_sample = algorithmic_flops_per_sample(256)
+  flops_sample, layer_flops_sample = algorithmic_flops_per_sample(args.channels)
   peaks = {}
   try:
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -280,24 +281,26 @@ def main():
       if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
   # tensor FLOPs the fused kernel actually issues per group-step and layer: GEMM1 K = 3*256 + 320
   # (upsampler composed into the conditioning), GEMM2 N = 256 residual + 16 skip-end (skip->end fold), identity carry
-  exec_per_step_layer = 2 * 1088 * 512 + (7 / 8) * (2 * 256 * 256 + 2 * 256 * 32) + 2 * 256 * 16
+  nc = args.channels
+  exec_per_step_layer = 2 * (3 * nc + 320) * 2 * nc + (7 / 8) * (2 * nc * nc + 2 * nc * 32) + 2 * nc * 16
   roofline = None
   if layer_launches:
     per_launch_flops = layer_flops_sample * B * T / layer_launches
     per_launch_ms = layer_ms / layer_launches
     achieved = per_launch_flops / (per_launch_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "wn_layer_tc_kernel" if args.precision == "fp16" else "wn_layer_fp32_kernel",
+    roofline = {"bound": "tensor", "kernel": ("wn_layer_fp32_kernel" if args.precision == "fp32" else
+                           "wn_layer_tc_kernel" if args.channels == 256 else "wn_gate_wide_kernel + wn_res_wide_kernel"),
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel on this workload, from
                 # profiles/r01/ncu_full_layer_v4_summary.csv (ncu --set full, kernel v4); only valid for the default workload
-                "traffic": 461e6 if (args.batch == 16 and args.frames == 861 and args.precision == "fp16") else None,
+                "traffic": 461e6 if (args.batch == 16 and args.frames == 861 and args.precision == "fp16" and args.channels == 256) else None,
                 "traffic_unit": "bytes per launch (ncu)",
                 "peak_source": peak_src, "launch_ms": per_launch_ms, "launches_per_step": layer_launches,
                 "algorithmic_flop_per_launch": per_launch_flops,
                 "executed_tensor_tflops": exec_per_step_layer * (B * T / 8) / (per_launch_ms * 1e-3) / 1e12,
                 "executed_over_algorithmic": exec_per_step_layer * (B * T / 8) / per_launch_flops,
                 "layer_kernels_share_of_step": layer_ms / (elapsed_ms / args.steps)}
-  line = {"metric": "audio samples/sec, WaveGlow-256 infer", "value": value, "unit": "samples/s", "n_gpus": world,
+  line = {"metric": f"audio samples/sec, WaveGlow-{args.channels} infer", "value": value, "unit": "samples/s", "n_gpus": world,
           "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
           "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
           "dtype": "fp16 operands, fp32 accumulate (tcgen05 kind::f16)" if args.precision == "fp16" else "fp32",

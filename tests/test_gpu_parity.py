@@ -19,12 +19,22 @@ _MODELS = {}
 
 
 def get_model(n_channels: int, precision: str, style: str = "parametrized") -> WaveGlow:
+  """precision: "fp32", "fp16" or "fp16-wide" (the two-kernel tensor-core layer of 512-channel models, forced through
+  WG_WIDE=1 so that it can also be checked on the 256-channel model against the same references)."""
+  import os
   key = (n_channels, precision, style)
   if key not in _MODELS:
     hp, sd, w, dims = synthetic_weights(n_channels, style)
-    m = WaveGlow(hp, precision=precision).to("cuda:0")
+    m = WaveGlow(hp, precision="fp16" if precision == "fp16-wide" else precision).to("cuda:0")
     m.load_state_dict(sd)
-    _MODELS[key] = WaveGlow.remove_weightnorm(m).eval()
+    m = WaveGlow.remove_weightnorm(m).eval()
+    if precision == "fp16-wide":
+      os.environ["WG_WIDE"] = "1"
+    try:
+      m.engine()          # the engine reads WG_WIDE when it is created
+    finally:
+      os.environ.pop("WG_WIDE", None)
+    _MODELS[key] = m
   return _MODELS[key]
 
 
@@ -49,7 +59,7 @@ def test_tcgen05_descriptor_gemm():
     assert err <= 2e-3, f"tcgen05 GEMM mismatch for {dt}: {err}"
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "fp16-wide"])
 def test_stagewise_first_flow(precision):
   """cond (upsample+squeeze), start conv, then every WN layer of the first flow, then the coupling step."""
   op_dtype = torch.float32 if precision == "fp32" else torch.float16
@@ -63,7 +73,7 @@ def test_stagewise_first_flow(precision):
   zs = synthetic_noise(hp, B, T, 32)
   sigma = 0.8
   trace = []
-  phase_cond = precision == "fp16"     # tensor-core mode composes the upsampler into the conditioning weights
+  phase_cond = precision != "fp32"     # tensor-core mode composes the upsampler into the conditioning weights
   with torch.no_grad():
     ref_audio = E.infer(w, dims, mel, sigma, zs, op_dtype, trace, phase_cond=phase_cond)
   k = dims.n_flows - 1
@@ -78,7 +88,7 @@ def test_stagewise_first_flow(precision):
   def x_view(buf):
     """engine x buffer -> time-major [B, T, 256] (tensor-core mode keeps it phase-major [B][32][T/32][256])"""
     raw = eng.debug_view(buf, B, F).float().cpu()
-    if precision == "fp16":
+    if precision != "fp32":
       return raw.view(B, 32, T // 32, 256).permute(0, 2, 1, 3).reshape(B, T, 256)
     return raw.view(B, T, 256)
 
@@ -112,6 +122,12 @@ def test_stagewise_first_flow(precision):
     eng.debug_stop_after(-1, 0)
   out = run(model, mel, zs, sigma)
   check("final audio vs engine model", out, ref_audio, t=(2e-5 if precision == "fp32" else 2e-3))
+  if precision == "fp16-wide":
+    # both tensor-core layer implementations use the same rounded operands but sum in a different order (fp32), and the
+    # fp16 re-rounding of x amplifies that: they agree to about the fp16 noise floor, each within the gate of the reference
+    same = run(get_model(256, "fp16"), mel, zs, sigma)
+    print(f"[fp16-wide] vs fused fp16 kernel: max-abs {max_abs(same, out):.3e}")
+    assert max_abs(same, out) <= 1e-3
   assert not failures, "; ".join(failures)
 
 
@@ -138,6 +154,20 @@ def test_fp16_tensor_core_mode_matches_reference_golden(name):
   print(f"fp16 {name}: max-abs {err:.3e}  snr {snr:.1f} dB")
   assert out.shape == ref.shape
   assert err <= FP16_MAX_ABS and snr >= FP16_MIN_SNR_DB
+
+
+@pytest.mark.parametrize("name,nc,mode", [("infer_c512_b1_f10", 512, "fp16"), ("infer_c256_b1_f40", 256, "fp16-wide"),
+                                          ("infer_c256_b3_f7_ragged", 256, "fp16-wide")])
+def test_wide_tensor_core_path_matches_reference_golden(name, nc, mode):
+  """The two-kernel tensor-core layer (wg_layer_wide_tc.cuh): 512-channel model (BASELINE config 3 architecture) and,
+  forced with WG_WIDE=1, the 256-channel model."""
+  g = load_golden(name)
+  model = get_model(nc, mode, str(g["weight_style"]))
+  out = run(model, torch.from_numpy(g["mel"]), golden_noise(g), float(g["sigma"]))
+  ref = torch.from_numpy(g["audio"])
+  err, snr = max_abs(ref, out), snr_db(ref, out)
+  print(f"{mode} {name}: max-abs {err:.3e}  snr {snr:.1f} dB")
+  assert out.shape == ref.shape and err <= FP16_MAX_ABS and snr >= FP16_MIN_SNR_DB
 
 
 def test_fp16_vs_oracle_medium_size():

@@ -16,6 +16,7 @@
 #include "../../include/waveglow_b200.h"
 #include "wg_kernels.cuh"
 #include "wg_layer_tc.cuh"
+#include "wg_layer_wide_tc.cuh"
 
 namespace {
 
@@ -66,6 +67,7 @@ struct wg_engine {
   std::vector<cudaEvent_t> ev;        // 2 per flow: around the WN layer launches of the last call
   int ev_flows = 0;                   // flows recorded by the last call
   long long* dbg_timeline = nullptr;  // device buffer for clock64 stamps of layer launches (tests/diagnostics)
+  bool wide = false;                  // two-kernel tensor-core layer (n_channels = 512; WG_WIDE=1 forces it for 256)
   int num_sms = 148;
   int dbg_flags = 0;                  // WG_DBG_FLAGS env (diagnostics; see LayerTcParams::dbg_flags)
   int op_fmt = 0;                     // 0 = fp16 operands, 1 = bf16 (WG_B200_OPERAND=bf16; fails the max-abs gate, kept for study)
@@ -172,6 +174,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
   int Tpad;                        // x rows per utterance: T rounded up to a multiple of 32 (phase view of the TMA maps)
+  size_t acts;                     // wide tensor-core path only: gated activations [B][32][Fq][nc] 16-bit
   size_t state, sums;              // forward only: time-major state [B,T,8] fp32; double accumulators [n_flows]
   size_t cond, x0, x1, e, total;   // cond: fp32 mode = upsampled conditioning S [B,T,640]; fp16 mode = mel windows MW [B,Fq,320]
   size_t cond_bytes;
@@ -196,6 +199,8 @@ WsLayout ws_layout(const wg_engine* e, int B, int T) {
   off = align_up(off + nppos * e->cfg.n_channels * L.elt, 1024);
   L.e = off;
   off = align_up(off + npos * kGroup * sizeof(float), 1024);
+  L.acts = off;
+  if (e->wide) off = align_up(off + nppos * e->cfg.n_channels * L.elt, 1024);
   L.state = off;
   off = align_up(off + npos * kGroup * sizeof(float), 1024);
   L.sums = off;
@@ -229,7 +234,8 @@ int wg_create(const wg_config* cfg, wg_engine** out) {
       cfg->n_early_size < 0 || (cfg->n_early_size & 1))
     return fail(e, WG_ERR_INVALID_ARGUMENT, "bad n_flows/n_layers/n_early_every/n_early_size");
   if (cfg->precision == WG_PRECISION_FP16) {
-    if (cfg->n_channels != kNC) return fail(e, WG_ERR_UNSUPPORTED, "fp16 tensor-core path is built for n_channels=256 (got %d)", cfg->n_channels);
+    if (cfg->n_channels != 256 && cfg->n_channels != 512)
+      return fail(e, WG_ERR_UNSUPPORTED, "fp16 tensor-core path is built for n_channels in {256, 512} (got %d)", cfg->n_channels);
   } else if (cfg->precision == WG_PRECISION_FP32) {
     if (cfg->n_channels != 256 && cfg->n_channels != 512)
       return fail(e, WG_ERR_UNSUPPORTED, "fp32 path is built for n_channels in {256, 512} (got %d)", cfg->n_channels);
@@ -259,9 +265,15 @@ int wg_create(const wg_config* cfg, wg_engine** out) {
   e->encode = reinterpret_cast<PFN_encodeTiled>(fn);
   const char* fmt_env = getenv("WG_B200_OPERAND");
   e->op_fmt = (fmt_env && strcmp(fmt_env, "bf16") == 0) ? 1 : 0;
+  const char* wide_env = getenv("WG_WIDE");
+  e->wide = cfg->precision == WG_PRECISION_FP16 && (cfg->n_channels == 512 || (wide_env && atoi(wide_env) != 0));
   const char* dbg_env = getenv("WG_DBG_FLAGS");
   e->dbg_flags = dbg_env ? atoi(dbg_env) : 0;
   WG_CUDA(e, cudaFuncSetAttribute(wn_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total + 1024));
+  WG_CUDA(e, cudaFuncSetAttribute(wn_gate_wide_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideCfg<256>::a_total + 1024));
+  WG_CUDA(e, cudaFuncSetAttribute(wn_gate_wide_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideCfg<512>::a_total + 1024));
+  WG_CUDA(e, cudaFuncSetAttribute(wn_res_wide_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideCfg<256>::b_total + 1024));
+  WG_CUDA(e, cudaFuncSetAttribute(wn_res_wide_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideCfg<512>::b_total + 1024));
   WG_CUDA(e, cudaFuncSetAttribute(debug_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 49152 + 1024 + 128));
   WG_CUDA(e, cudaFuncSetAttribute(wn_layer_fp32_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (kF32KC * kF32Pos + kF32KC * 512 + kF32Pos * 256) * 4));
@@ -344,6 +356,7 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
   const bool tc = e->cfg.precision == WG_PRECISION_FP16;
   const int K1 = 3 * nc + kCond;     // fp32 mode: taps | upsampled conditioning
   const int K1x = 3 * nc;            // fp16 mode: taps only (conditioning goes through V)
+  const int w2rows = nc + 16;        // fp16 mode: W_res rows then 16 skip-end rows per layer (272 for 256 channels == kW2Rows)
   std::vector<uint16_t> w1h, w2h;
   const std::vector<float>* up_bias = nullptr;
   if ((rc = need("upsample.bias", {kMel}, &up_bias))) return rc;
@@ -353,7 +366,7 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
     cudaFree(e->d_v);
     e->d_v = nullptr;
     WG_CUDA(e, cudaMalloc(&e->d_v, static_cast<size_t>(NF) * L * kUpPhases * 2 * nc * kUpKdim * 2));
-    w2h.assign(static_cast<size_t>(NF) * L * kW2Rows * nc, 0);
+    w2h.assign(static_cast<size_t>(NF) * L * w2rows * nc, 0);
     bias1.assign(static_cast<size_t>(NF) * L * 2 * nc, 0.f);
     bias_res.assign(static_cast<size_t>(NF) * L * nc, 0.f);
   } else {
@@ -440,7 +453,7 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
           for (int m = 0; m < kCond; ++m) bfold += static_cast<double>(wc[m]) * (*up_bias)[m / kGroup];
           bias1[li * 2 * nc + np] = static_cast<float>((*b_in)[oc] + (*b_cond)[2 * nc * i + oc] + bfold);
         }
-        uint16_t* w2 = &w2h[li * kW2Rows * nc];
+        uint16_t* w2 = &w2h[li * w2rows * nc];
         if (i < L - 1) {
           for (int n = 0; n < nc; ++n) {
             for (int c = 0; c < nc; ++c) w2[static_cast<size_t>(n) * nc + c] = f2h((*w_rs)[static_cast<size_t>(n) * nc + c], e->op_fmt);
@@ -448,7 +461,7 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
           }
         }
         for (int r = 0; r < 2 * h; ++r)
-          for (int c = 0; c < nc; ++c) w2[static_cast<size_t>(256 + r) * nc + c] = f2h(static_cast<float>(wse[static_cast<size_t>(r) * nc + c]), e->op_fmt);
+          for (int c = 0; c < nc; ++c) w2[static_cast<size_t>(nc + r) * nc + c] = f2h(static_cast<float>(wse[static_cast<size_t>(r) * nc + c]), e->op_fmt);
       } else {
         float* w1 = &w1f[li * K1 * 2 * nc];
         for (int oc = 0; oc < 2 * nc; ++oc) {
@@ -508,7 +521,7 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
       if ((rc = make_map(e, &e->tm_v, e->d_v, 2, dims, str, box, dt))) return rc;
     }
     {
-      const uint64_t dims[2] = {static_cast<uint64_t>(nc), static_cast<uint64_t>(NF) * L * kW2Rows};
+      const uint64_t dims[2] = {static_cast<uint64_t>(nc), static_cast<uint64_t>(NF) * L * w2rows};
       const uint64_t str[1] = {static_cast<uint64_t>(nc) * 2};
       const uint32_t boxa[2] = {64, 256}, boxb[2] = {64, 16};
       if ((rc = make_map(e, &e->tm_w2a, e->d_w2, 2, dims, str, boxa, dt))) return rc;
@@ -618,7 +631,39 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
   for (int i = 0; i < NL; ++i) {
     const size_t li = static_cast<size_t>(k) * NL + i;
     const int has_res = i < NL - 1;
-    if (tc) {
+    if (tc && e->wide) {
+      WideParams wp{};
+      wp.T = T;
+      wp.Fq = L.Tpad / kUpPhases;
+      wp.B = B;
+      wp.dilation = 1 << i;
+      wp.reverse = static_cast<int>(li & 1);
+      wp.w1_row0 = static_cast<int>(li * 2 * nc);
+      wp.v_row0 = static_cast<int>(li * kUpPhases * 2 * nc);
+      wp.wres_row0 = static_cast<int>(li * (nc + 16));
+      wp.se_row0 = wp.wres_row0 + nc;
+      wp.accumulate_e = i > 0;
+      wp.fmt = e->op_fmt;
+      wp.bias1 = e->d_bias1 + li * 2 * nc;
+      wp.bias_res = e->d_bias_res + li * nc;
+      wp.e = ebuf;
+      const int n_tiles = kPhases * ((wp.Fq + kTileM - 1) / kTileM) * B;
+      dim3 grid(n_tiles < e->num_sms ? n_tiles : e->num_sms);
+      if (nc == 512) {
+        wn_gate_wide_kernel<512><<<grid, kTcThreads, WideCfg<512>::a_total + 1024, st>>>(tm_x[*cur], *tm_cond, e->tm_w1, e->tm_v,
+                                                                                      e->tm_w2b, tm_x[2], wp);
+        if (has_res)
+          wn_res_wide_kernel<512><<<grid, kTcThreads, WideCfg<512>::b_total + 1024, st>>>(tm_x[2], tm_x[*cur], tm_x[*cur ^ 1],
+                                                                                       e->tm_w2a, e->tm_ident, wp);
+      } else {
+        wn_gate_wide_kernel<256><<<grid, kTcThreads, WideCfg<256>::a_total + 1024, st>>>(tm_x[*cur], *tm_cond, e->tm_w1, e->tm_v,
+                                                                                      e->tm_w2b, tm_x[2], wp);
+        if (has_res)
+          wn_res_wide_kernel<256><<<grid, kTcThreads, WideCfg<256>::b_total + 1024, st>>>(tm_x[2], tm_x[*cur], tm_x[*cur ^ 1],
+                                                                                       e->tm_w2a, e->tm_ident, wp);
+      }
+      e->launches += has_res ? 1 : 0;
+    } else if (tc) {
       LayerTcParams lp{};
       lp.T = T;
       lp.Fq = L.Tpad / kUpPhases;
@@ -694,6 +739,7 @@ void launch_conditioning(wg_engine* e, const float* mel, int B, int frames, int 
 }
 
 int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CUtensorMap* tm_x, CUtensorMap* tm_cond) {
+  // tm_x[0], tm_x[1]: residual stream ping-pong; tm_x[2]: gated activations of the wide path (same geometry)
   const CUtensorMapDataType dt = e->op_fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const int nc = e->cfg.n_channels;
   int rc;
@@ -705,6 +751,7 @@ int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CU
     const uint32_t box[3] = {64, static_cast<uint32_t>(kTileM), 1};
     if ((rc = make_map(e, &tm_x[0], ws + L.x0, 3, dims, str, box, dt))) return rc;
     if ((rc = make_map(e, &tm_x[1], ws + L.x1, 3, dims, str, box, dt))) return rc;
+    if (e->wide && (rc = make_map(e, &tm_x[2], ws + L.acts, 3, dims, str, box, dt))) return rc;
   }
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(kUpKdim), static_cast<uint64_t>(Fq), static_cast<uint64_t>(B)};
@@ -761,7 +808,7 @@ int wg_infer(wg_engine* e, const float* mel, int32_t batch, int32_t frames, cons
   }
   // 2. conditioning operand (mel windows in tensor-core mode, upsampled + squeezed mel in fp32 mode)
   launch_conditioning(e, mel, B, frames, T, ws, L, st);
-  CUtensorMap tm_x[2], tm_cond;
+  CUtensorMap tm_x[3], tm_cond;
   if (tc) {
     int rc = make_act_maps(e, ws, L, B, T, tm_x, &tm_cond);
     if (rc) return rc;
@@ -860,7 +907,7 @@ int wg_forward(wg_engine* e, const float* mel, int32_t batch, int32_t frames, co
   WG_CUDA(e, cudaMemcpyAsync(state, audio_in, npos * kGroup * sizeof(float), cudaMemcpyDeviceToDevice, st));
   WG_CUDA(e, cudaMemsetAsync(sums, 0, NF * sizeof(double), st));
   launch_conditioning(e, mel, B, frames, T, ws, L, st);
-  CUtensorMap tm_x[2], tm_cond;
+  CUtensorMap tm_x[3], tm_cond;
   if (tc) {
     int rc = make_act_maps(e, ws, L, B, T, tm_x, &tm_cond);
     if (rc) return rc;

@@ -289,25 +289,46 @@ flow_step_kernel(FlowStepParams p, float* __restrict__ state, const float* __res
   }
   if (!p.do_start) return;
   __syncthreads();
-  for (int c = threadIdx.x; c < p.nc; c += kFsThreads) {
-    float w[4];
+  // start conv (model.py:117): thread = (8-channel group, position slot); one 16/32-byte vector store per position, so a
+  // warp writes whole contiguous rows of x
+  const int groups = p.nc / 8;                       // 32 (256 channels) or 64 (512)
+  const int slots = kFsThreads / groups;             // positions handled concurrently: 8 or 4
+  const int gidx = threadIdx.x % groups, slot = threadIdx.x / groups;
+  float w[8][4], bs[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) w[j] = (j < p.h2) ? p.w_start[c * p.h2 + j] : 0.f;
-    const float bs = p.b_start[c];
-    for (int i = 0; i < kFsPos; ++i) {
-      const size_t ppos = ppos0 + i;
-      if (ppos >= n_ppos) break;
-      float acc = bs;
+  for (int u = 0; u < 8; ++u) {
+    const int c = gidx * 8 + u;
+    bs[u] = p.b_start[c];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc = fmaf(w[j], a0s[i][j], acc);              // model.py:117
-      size_t row = ppos;
-      if (p.x_phase_major) {
-        // group-step t = 32 q + phase of utterance b lives at row ((b * 32 + phase) * Fq + q): each (phase, 128-frame) tile
-        // of the layer kernel is then one dense block for TMA
-        const size_t b = ppos / Tpad, t = ppos % Tpad;
-        row = (b * kUpPhases + (t % kUpPhases)) * (Tpad / kUpPhases) + t / kUpPhases;
-      }
-      x[row * p.nc + c] = from_float<XT>(valid_s[i] ? acc : 0.f);
+    for (int j = 0; j < 4; ++j) w[u][j] = (j < p.h2) ? p.w_start[c * p.h2 + j] : 0.f;
+  }
+  for (int i = slot; i < kFsPos; i += slots) {
+    const size_t ppos = ppos0 + i;
+    if (ppos >= n_ppos) break;
+    size_t row = ppos;
+    if (p.x_phase_major) {
+      // group-step t = 32 q + phase of utterance b lives at row ((b * 32 + phase) * Fq + q): each (phase, 128-frame) tile
+      // of the layer kernel is then one dense block for TMA
+      const size_t b = ppos / Tpad, t = ppos % Tpad;
+      row = (b * kUpPhases + (t % kUpPhases)) * (Tpad / kUpPhases) + t / kUpPhases;
+    }
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      float acc = bs[u];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc = fmaf(w[u][j], a0s[i][j], acc);
+      v[u] = valid_s[i] ? acc : 0.f;
+    }
+    XT* dst = x + row * p.nc + gidx * 8;
+    if constexpr (sizeof(XT) == 2) {
+      XT h[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) h[u] = from_float<XT>(v[u]);
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+    } else {
+      reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
+      reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
     }
   }
 }

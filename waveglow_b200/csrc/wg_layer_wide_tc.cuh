@@ -1,0 +1,519 @@
+// wg_layer_wide_tc.cuh -- tensor-core WN layer for WIDE models (n_channels = 512, BASELINE config 3), sm_100a.
+//
+// With 512 channels a 128-row tile of the residual update needs 512 fp32 TMEM columns by itself, and the gated
+// activations (128 x 512 fp16 = 128 KB) do not fit shared memory next to the operand ring, so the single fused kernel of
+// wg_layer_tc.cuh (256 channels) does not apply.  The layer is split into two persistent tcgen05 kernels:
+//
+//   A  wn_gate_wide_kernel<NC>   per tile (utterance, phase, 128 frames), for each half h of the gate pairs:
+//        GEMM1  pre[128 x 512] = [mel window | x(t-d) | x(t) | x(t+d)] [128 x (320 + 3 NC)] . [V_p | W_in]^T   (2 chunks of 256 columns)
+//        gate   acts_h = tanh(.) * sigmoid(.)  -> fp16, swizzled smem -> TMA store to the global acts buffer
+//        skip-end  e' += acts_h . (W_end W_skip)^T  (N = 16 MMAs, weights resident in smem; partial sums of the halves are
+//                  added in registers, one fp32 RMW of `e` per tile)
+//      The two accumulator regions are freed by the gate itself, so GEMM1 of the next chunk/half/tile is always queued
+//      behind the current one: the MMA pipe never waits for the epilogue.
+//   B  wn_res_wide_kernel<NC>    per tile and half o of the output channels:
+//        x'[128 x 256] = acts[128 x NC] . W_res[256 o.., :]^T + x[:, 256 o..] . I + b_res   (ping-pong TMEM regions, TMA store)
+//
+// Same data layouts as the 256-channel kernel (phase-major x / acts, mel windows, packed row order per 512-row block:
+// [tanh 128 | sigmoid 128] x 2 chunks per half).  Replaces reference model.py:121-137 for one layer.
+#pragma once
+#include "wg_layer_tc.cuh"
+
+namespace wg {
+
+template <int NC>
+struct WideCfg {
+  static constexpr int kHalves = NC / 256;          // halves of the gate pairs / of the residual output channels
+  static constexpr int kCB = NC / 64;               // 64-channel K-blocks per tap
+  static constexpr int kKB = kMwKB + 3 * kCB;       // K-blocks of GEMM1 (mel window first, then taps)
+  static constexpr int kSeBytes = kCB * 16 * 128;   // resident skip-end weights [16 x NC] as kCB K-blocks
+  // kernel A smem
+  static constexpr int a_acts = kStages * kStageBytes;
+  static constexpr int a_se = a_acts + kActsBytes;
+  static constexpr int a_bars = a_se + kSeBytes;
+  static constexpr int a_total = a_bars + 128;
+  // kernel B smem
+  static constexpr int b_stage_out = kStages * kStageBytes;
+  static constexpr int b_ident = b_stage_out + kActsBytes;
+  static constexpr int b_bias = b_ident + kIdentBytes;
+  static constexpr int b_bars = b_bias + 256 * 4;
+  static constexpr int b_total = b_bars + 128;
+};
+static_assert(WideCfg<512>::a_total + 1024 <= 232448 && WideCfg<512>::b_total + 1024 <= 232448, "shared memory budget exceeded");
+
+struct WideParams {
+  int T, Fq, B;
+  int dilation;
+  int reverse;
+  int w1_row0;        // first packed W_in row of this (flow, layer): li * 2 NC
+  int v_row0;         // first packed V row of this (flow, layer): li * 32 * 2 NC (+ phase * 2 NC)
+  int se_row0;        // first skip-end row: li * 16
+  int wres_row0;      // first W_res row: li * NC
+  int accumulate_e;
+  int fmt;
+  const float* bias1;     // [2 NC] packed order (global; read through L1)
+  const float* bias_res;  // [NC]
+  float* e;               // [B, T, 8]
+};
+
+struct TileCoord {
+  int b, ph, q0;
+};
+__device__ __forceinline__ TileCoord decode_tile(int tile, int tiles_per_utt) {
+  TileCoord c;
+  c.b = tile / tiles_per_utt;
+  c.ph = (tile % tiles_per_utt) % kPhases;
+  c.q0 = ((tile % tiles_per_utt) / kPhases) * kTileM;
+  return c;
+}
+
+// ================================================================================================ kernel A
+template <int NC>
+__global__ void __launch_bounds__(kTcThreads, 1)
+wn_gate_wide_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC, Fq, 32 B} box {64,128,1}
+                    const __grid_constant__ CUtensorMap tm_mw,      // {320, Fq, B} box {64,128,1}
+                    const __grid_constant__ CUtensorMap tm_w1,      // {3 NC, rows} box {64,256}
+                    const __grid_constant__ CUtensorMap tm_v,       // {320, rows} box {64,256}
+                    const __grid_constant__ CUtensorMap tm_se,      // {NC, rows} box {64,16}
+                    const __grid_constant__ CUtensorMap tm_acts,    // {NC, Fq, 32 B} box {64,128,1} (store)
+                    const WideParams p) {
+  using C = WideCfg<NC>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::a_bars);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* acc_full = bars + 2 * kStages;     // [2]
+  uint64_t* acts_ready = acc_full + 2;         // [2]
+  uint64_t* se_full = acts_ready + 2;
+  uint64_t* e_drained = se_full + 1;
+  uint64_t* res_w = e_drained + 1;             // resident skip-end weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_w + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_utt = kPhases * ((p.Fq + kTileM - 1) / kTileM);
+  const int n_tiles = tiles_per_utt * p.B;
+  const int my_tiles = (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int n_units = my_tiles * C::kHalves;    // unit n = (tile it = n / kHalves, half h = n % kHalves)
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    ptx::mbar_init(&acc_full[0], 1);
+    ptx::mbar_init(&acc_full[1], 1);
+    ptx::mbar_init(&acts_ready[0], 256);
+    ptx::mbar_init(&acts_ready[1], 256);
+    ptx::mbar_init(se_full, 1);
+    ptx::mbar_init(e_drained, 128);
+    ptx::mbar_init(res_w, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_of = [&](int it) {
+    int tile = blockIdx.x + it * gridDim.x;
+    if (p.reverse) tile = n_tiles - 1 - tile;
+    return decode_tile(tile, tiles_per_utt);
+  };
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tm_x_in);
+      ptx::prefetch_tmap(&tm_mw);
+      ptx::prefetch_tmap(&tm_w1);
+      ptx::prefetch_tmap(&tm_v);
+      ptx::mbar_arrive_expect_tx(res_w, C::kSeBytes);
+      for (int j = 0; j < C::kCB; ++j) ptx::tma_load_2d(smem + C::a_se + j * 2048, &tm_se, res_w, j * kBlockK, p.se_row0);
+      int use = 0;
+      auto load_pass = [&](int n, int chunk) {
+        const TileCoord tc = tile_of(n / C::kHalves);
+        const int h = n % C::kHalves;
+        for (int kb = 0; kb < C::kKB; ++kb, ++use) {
+          const int s = use % kStages;
+          const uint32_t ph = (use / kStages) & 1;
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * kStageBytes;
+          uint8_t* sb = sa + kStageABytes;
+          ptx::mbar_arrive_expect_tx(&full[s], kStageBytes);
+          if (kb < kMwKB) {
+            ptx::tma_load_3d(sa, &tm_mw, &full[s], kb * kBlockK, tc.q0, tc.b);
+            ptx::tma_load_2d(sb, &tm_v, &full[s], kb * kBlockK, p.v_row0 + tc.ph * 2 * NC + h * 512 + chunk * 256);
+          } else {
+            const int j = kb - kMwKB;                    // tap (j / kCB), channel block (j % kCB)
+            const int pp = tc.ph + ((j / C::kCB) - 1) * p.dilation;
+            const int dq = pp >> 5;
+            ptx::tma_load_3d(sa, &tm_x_in, &full[s], (j % C::kCB) * kBlockK, tc.q0 + dq, tc.b * kPhases + pp - (dq << 5));
+            ptx::tma_load_2d(sb, &tm_w1, &full[s], j * kBlockK, p.w1_row0 + h * 512 + chunk * 256);
+          }
+        }
+      };
+      // same order as the MMA issuer consumes: G1a(0), then per unit G1b(n), G1a(n+1)
+      if (n_units > 0) load_pass(0, 0);
+      for (int n = 0; n < n_units; ++n) {
+        load_pass(n, 1);
+        if (n + 1 < n_units) load_pass(n + 1, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      const uint32_t idesc256 = ptx::make_idesc_f16(128, 256, p.fmt);
+      const uint32_t idesc16 = ptx::make_idesc_f16(128, 16, p.fmt);
+      const uint32_t stage_addr0 = ptx::smem_u32(smem);
+      const uint32_t acts_addr = ptx::smem_u32(smem + C::a_acts);
+      const uint32_t se_addr = ptx::smem_u32(smem + C::a_se);
+      const uint32_t ra = tmem_base, rb = tmem_base + 256;
+      int use = 0;
+      auto mma_pass = [&](int chunk) {
+        const uint32_t d = chunk == 0 ? ra : rb;
+        for (int kb = 0; kb < C::kKB; ++kb, ++use) {
+          const int s = use % kStages;
+          const uint32_t ph = (use / kStages) & 1;
+          ptx::mbar_wait(&full[s], ph);
+          ptx::tc_fence_after_sync();
+          const uint32_t a_addr = stage_addr0 + s * kStageBytes;
+          const uint32_t b_addr = a_addr + kStageABytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::mma_f16_ss(d, ptx::make_desc_sw128(a_addr + k * 32), ptx::make_desc_sw128(b_addr + k * 32), idesc256, (kb | k) != 0);
+          ptx::mma_commit(&empty[s]);
+        }
+        ptx::mma_commit(&acc_full[chunk]);
+      };
+      ptx::mbar_wait(res_w, 0);
+      if (n_units > 0) mma_pass(0);
+      for (int n = 0; n < n_units; ++n) {
+        const uint32_t par = n & 1;
+        const int h = n % C::kHalves;
+        if (n > 0) {                       // region b still holds the previous unit's 16 skip-end columns
+          ptx::mbar_wait(e_drained, par ^ 1);
+          ptx::tc_fence_after_sync();
+        }
+        mma_pass(1);
+        if (n + 1 < n_units) {             // region a is free once this unit's chunk-a gate has read it
+          ptx::mbar_wait(&acts_ready[0], par);
+          ptx::tc_fence_after_sync();
+          mma_pass(0);
+        }
+        ptx::mbar_wait(&acts_ready[1], par);
+        if (n + 1 >= n_units) ptx::mbar_wait(&acts_ready[0], par);
+        ptx::tc_fence_after_sync();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::mma_f16_ss(rb, ptx::make_desc_sw128(acts_addr + j * (kTileM * 128) + k * 32),
+                            ptx::make_desc_sw128(se_addr + (h * 4 + j) * 2048 + k * 32), idesc16, (j | k) != 0);
+        }
+        ptx::mma_commit(se_full);
+      }
+    }
+  } else {
+    // =============================== gate / epilogue warps ===============================
+    const int q = warp & 3;
+    const int hh = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint8_t* acts = smem + C::a_acts;
+    float e_acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e_acc[i] = 0.f;
+
+    for (int n = 0; n < n_units; ++n) {
+      const uint32_t par = n & 1;
+      const int h = n % C::kHalves;
+      const TileCoord tc = tile_of(n / C::kHalves);
+      for (int chunk = 0; chunk < 2; ++chunk) {
+        ptx::mbar_wait(&acc_full[chunk], par);
+        ptx::tc_fence_after_sync();
+        if (chunk == 0 && n > 0) {
+          // the acts buffer is still being read by the TMA store of the previous unit
+          if (warp == 2 && lane == 0) ptx::tma_store_wait_read();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        const uint32_t rc = lane_base + chunk * 256;
+        const int slab = 2 * chunk + hh;
+        uint8_t* slab_row = acts + slab * (kTileM * 128) + row * 128;
+        const float* bt = p.bias1 + h * 512 + chunk * 256 + hh * 64;
+        const float* bs = bt + 128;
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          uint32_t vt[16], vs[16];
+          const uint32_t col = hh * 64 + g * 16;
+          ptx::tmem_ld16(rc + col, vt);
+          ptx::tmem_ld16(rc + col + 128, vs);
+          ptx::tmem_ld_wait();
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float a0 = gate_one(__uint_as_float(vt[2 * i]) + __ldg(bt + g * 16 + 2 * i),
+                                      __uint_as_float(vs[2 * i]) + __ldg(bs + g * 16 + 2 * i));
+            const float a1 = gate_one(__uint_as_float(vt[2 * i + 1]) + __ldg(bt + g * 16 + 2 * i + 1),
+                                      __uint_as_float(vs[2 * i + 1]) + __ldg(bs + g * 16 + 2 * i + 1));
+            if (p.fmt == 0) {
+              pk[i] = ptx::pack_half2(a0, a1);
+            } else {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
+              pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+          }
+          const int c0 = (2 * g) ^ (row & 7);
+          const int c1 = (2 * g + 1) ^ (row & 7);
+          *reinterpret_cast<uint4*>(slab_row + c0 * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(slab_row + c1 * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        ptx::tc_fence_before_sync();
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&acts_ready[chunk]);
+      }
+      // acts of this half -> global (channels 256 h + 64 s), read by kernel B
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp == 2 && lane == 0) {
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4)
+          ptx::tma_store_3d(&tm_acts, acts + s4 * (kTileM * 128), h * 256 + s4 * kBlockK, tc.q0, tc.b * kPhases + tc.ph);
+        ptx::tma_store_commit();
+      }
+      // skip-end partial of this half
+      ptx::mbar_wait(se_full, par);
+      ptx::tc_fence_after_sync();
+      if (hh == 0) {
+        uint32_t ve[8];
+        ptx::tmem_ld8(lane_base + 256, ve);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before_sync();
+        ptx::mbar_arrive(e_drained);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e_acc[i] = (h == 0 ? 0.f : e_acc[i]) + __uint_as_float(ve[i]);
+        if (h == C::kHalves - 1) {
+          const int t = (tc.q0 + row) * kPhases + tc.ph;
+          if (tc.q0 + row < p.Fq && t < p.T) {
+            float4* ep = reinterpret_cast<float4*>(p.e + (static_cast<size_t>(tc.b) * p.T + t) * 8);
+            float4 lo = make_float4(e_acc[0], e_acc[1], e_acc[2], e_acc[3]);
+            float4 hi = make_float4(e_acc[4], e_acc[5], e_acc[6], e_acc[7]);
+            if (p.accumulate_e) {
+              const float4 o0 = ep[0], o1 = ep[1];
+              lo.x += o0.x; lo.y += o0.y; lo.z += o0.z; lo.w += o0.w;
+              hi.x += o1.x; hi.y += o1.y; hi.z += o1.z; hi.w += o1.w;
+            }
+            ep[0] = lo;
+            ep[1] = hi;
+          }
+        }
+      }
+    }
+    if (warp == 2 && lane == 0) ptx::tma_store_wait_all();
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ================================================================================================ kernel B
+template <int NC>
+__global__ void __launch_bounds__(kTcThreads, 1)
+wn_res_wide_kernel(const __grid_constant__ CUtensorMap tm_acts,    // {NC, Fq, 32 B} box {64,128,1}
+                   const __grid_constant__ CUtensorMap tm_x_in,    // {NC, Fq, 32 B} box {64,128,1}
+                   const __grid_constant__ CUtensorMap tm_x_out,   // same geometry, other buffer (store)
+                   const __grid_constant__ CUtensorMap tm_wres,    // {NC, rows} box {64,256}
+                   const __grid_constant__ CUtensorMap tm_ident,   // {64, 32} box {64,32}
+                   const WideParams p) {
+  using C = WideCfg<NC>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::b_bars);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* d_full = bars + 2 * kStages;       // [2] per TMEM region
+  uint64_t* drained = d_full + 2;              // [2] per TMEM region
+  uint64_t* ident_full = drained + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ident_full + 1);
+  float* s_bias = reinterpret_cast<float*>(smem + C::b_bias);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_utt = kPhases * ((p.Fq + kTileM - 1) / kTileM);
+  const int n_tiles = tiles_per_utt * p.B;
+  const int my_tiles = (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int n_units = my_tiles * C::kHalves;    // unit n = (tile it = n / kHalves, output half o = n % kHalves)
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&d_full[i], 1);
+      ptx::mbar_init(&drained[i], 256);
+    }
+    ptx::mbar_init(ident_full, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_of = [&](int it) {
+    int tile = blockIdx.x + it * gridDim.x;
+    if (p.reverse) tile = n_tiles - 1 - tile;
+    return decode_tile(tile, tiles_per_utt);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tm_acts);
+      ptx::prefetch_tmap(&tm_x_in);
+      ptx::prefetch_tmap(&tm_wres);
+      ptx::mbar_arrive_expect_tx(ident_full, kIdentBytes);
+      ptx::tma_load_2d(smem + C::b_ident, &tm_ident, ident_full, 0, 0);
+      int use = 0;
+      for (int n = 0; n < n_units; ++n) {
+        const TileCoord tc = tile_of(n / C::kHalves);
+        const int o = n % C::kHalves;
+        // K-blocks of acts x W_res; the first 4 stages also carry this half's x(t) blocks for the identity term
+        for (int kb = 0; kb < C::kCB; ++kb, ++use) {
+          const int s = use % kStages;
+          const uint32_t ph = (use / kStages) & 1;
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * kStageBytes;
+          uint8_t* sb = sa + kStageABytes;
+          ptx::mbar_arrive_expect_tx(&full[s], kStageBytes);
+          ptx::tma_load_3d(sa, &tm_acts, &full[s], kb * kBlockK, tc.q0, tc.b * kPhases + tc.ph);
+          ptx::tma_load_2d(sb, &tm_wres, &full[s], kb * kBlockK, p.wres_row0 + o * 256);
+        }
+        for (int j = 0; j < 4; ++j, ++use) {
+          const int s = use % kStages;
+          const uint32_t ph = (use / kStages) & 1;
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[s], kStageABytes);
+          ptx::tma_load_3d(smem + s * kStageBytes, &tm_x_in, &full[s], o * 256 + j * kBlockK, tc.q0, tc.b * kPhases + tc.ph);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc256 = ptx::make_idesc_f16(128, 256, p.fmt);
+      const uint32_t idesc32 = ptx::make_idesc_f16(128, kIdentN, p.fmt);
+      const uint32_t stage_addr0 = ptx::smem_u32(smem);
+      const uint32_t ident_addr = ptx::smem_u32(smem + C::b_ident);
+      int use = 0;
+      ptx::mbar_wait(ident_full, 0);
+      for (int n = 0; n < n_units; ++n) {
+        const int r = n & 1;
+        const uint32_t d = tmem_base + r * 256;
+        if (n >= 2) {                       // this region was drained by the epilogue of unit n - 2
+          ptx::mbar_wait(&drained[r], ((n >> 1) - 1) & 1);
+          ptx::tc_fence_after_sync();
+        }
+        for (int kb = 0; kb < C::kCB; ++kb, ++use) {
+          const int s = use % kStages;
+          const uint32_t ph = (use / kStages) & 1;
+          ptx::mbar_wait(&full[s], ph);
+          ptx::tc_fence_after_sync();
+          const uint32_t a_addr = stage_addr0 + s * kStageBytes;
+          const uint32_t b_addr = a_addr + kStageABytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::mma_f16_ss(d, ptx::make_desc_sw128(a_addr + k * 32), ptx::make_desc_sw128(b_addr + k * 32), idesc256, (kb | k) != 0);
+          ptx::mma_commit(&empty[s]);
+        }
+        for (int j = 0; j < 4; ++j, ++use) {
+          const int s = use % kStages;
+          const uint32_t ph = (use / kStages) & 1;
+          ptx::mbar_wait(&full[s], ph);
+          ptx::tc_fence_after_sync();
+          const uint32_t x_addr = stage_addr0 + s * kStageBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::mma_f16_ss(d + j * 64 + (k >> 1) * 32, ptx::make_desc_sw128(x_addr + k * 32),
+                            ptx::make_desc_sw128(ident_addr + (k & 1) * 32), idesc32, 1);
+          ptx::mma_commit(&empty[s]);
+        }
+        ptx::mma_commit(&d_full[r]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int hh = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint8_t* stage_out = smem + C::b_stage_out;
+    for (int n = 0; n < n_units; ++n) {
+      const int r = n & 1;
+      const int o = n % C::kHalves;
+      const TileCoord tc = tile_of(n / C::kHalves);
+      const int t = (tc.q0 + row) * kPhases + tc.ph;
+      // bias of this output half (all epilogue threads; previous readers are past their last use after the bar below)
+      if (n > 0) {
+        if (warp == 2 && lane == 0) ptx::tma_store_wait_read();      // staging buffer free again
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      s_bias[threadIdx.x - 64] = p.bias_res[o * 256 + threadIdx.x - 64];
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      ptx::mbar_wait(&d_full[r], (n >> 1) & 1);
+      ptx::tc_fence_after_sync();
+#pragma unroll 1
+      for (int g = 0; g < 8; ++g) {
+        uint32_t v[16];
+        const int ch0 = hh * 128 + g * 16;
+        ptx::tmem_ld16(lane_base + r * 256 + ch0, v);
+        ptx::tmem_ld_wait();
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float a0 = t < p.T ? __uint_as_float(v[2 * i]) + s_bias[ch0 + 2 * i] : 0.f;
+          const float a1 = t < p.T ? __uint_as_float(v[2 * i + 1]) + s_bias[ch0 + 2 * i + 1] : 0.f;
+          if (p.fmt == 0) {
+            pk[i] = ptx::pack_half2(a0, a1);
+          } else {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
+            pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+        }
+        const int slab = ch0 >> 6;
+        const int cc = (ch0 & 63) >> 3;
+        uint8_t* slab_row = stage_out + slab * (kTileM * 128) + row * 128;
+        *reinterpret_cast<uint4*>(slab_row + ((cc ^ (row & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(slab_row + (((cc + 1) ^ (row & 7)) * 16)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(&drained[r]);
+      ptx::fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp == 2 && lane == 0) {
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4)
+          ptx::tma_store_3d(&tm_x_out, stage_out + s4 * (kTileM * 128), o * 256 + s4 * kBlockK, tc.q0, tc.b * kPhases + tc.ph);
+        ptx::tma_store_commit();
+      }
+    }
+    if (warp == 2 && lane == 0) ptx::tma_store_wait_all();
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace wg
