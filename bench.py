@@ -190,13 +190,14 @@ def main():
 
   if not torch.cuda.is_available():
     raise SystemExit("bench.py --impl b200 needs a GPU (no CPU fallback)")
-  if rank == 0:
-    graft.build()
   torch.cuda.set_device(local_rank)
   dev = torch.device("cuda", local_rank)
   if world > 1:
     dist.init_process_group("nccl", device_id=dev)
-    dist.barrier()
+  if rank == 0:
+    graft.build()                 # no-op when the in-tree library matches the sources (content hash)
+  if world > 1:
+    dist.barrier()                # nobody loads the library before rank 0 is done with it
 
   hp = HParams(n_channels=args.channels)
   model = WaveGlow(hp, precision=args.precision).to(dev)
