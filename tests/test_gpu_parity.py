@@ -170,6 +170,24 @@ def test_wide_tensor_core_path_matches_reference_golden(name, nc, mode):
   assert out.shape == ref.shape and err <= FP16_MAX_ABS and snr >= FP16_MIN_SNR_DB
 
 
+@pytest.mark.parametrize("B,F", [(1, 1), (5, 3), (2, 129), (1, 257)])
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_edge_shapes_vs_oracle(B, F, precision):
+  """Single frame (shorter than the upsampler's 4-frame support), odd batch, and lengths that cross the 128-frame tile
+  boundary by one frame (the second / third tile of a phase holds a single valid row)."""
+  hp, sd, w, dims = synthetic_weights(256)
+  model = get_model(256, precision)
+  mel = synthetic_mel(B, F, 300 + F)
+  zs = synthetic_noise(hp, B, F * 32, 301 + F)
+  with torch.no_grad():
+    ref = O.infer(w, dims, mel, 0.75, zs)
+  out = run(model, mel, zs, 0.75)
+  err = max_abs(ref, out)
+  print(f"edge {precision} B={B} F={F}: max-abs {err:.3e}")
+  assert out.shape == (B, F * 256) and torch.isfinite(out).all()
+  assert err <= (FP32_MAX_ABS if precision == "fp32" else FP16_MAX_ABS)
+
+
 def test_fp16_vs_oracle_medium_size():
   """B=4 x 2.3 s: against the oracle itself (CPU, a few seconds)."""
   hp, sd, w, dims = synthetic_weights(256)
