@@ -120,6 +120,10 @@ int wg_profile_layers(wg_engine* e, float* total_ms, int32_t* n_launches);
 int wg_debug_gemm(wg_engine* e, const void* a, const void* b, float* d, int32_t m, int32_t n, int32_t k,
                   int32_t fmt, void* stream);
 
+/* Same through tcgen05.mma.cta_group::2 on CTA pairs (M % 256 == 0): validates the 2-CTA mechanisms in isolation. */
+int wg_debug_gemm2(wg_engine* e, const void* a, const void* b, float* d, int32_t m, int32_t n, int32_t k,
+                   int32_t fmt, void* stream);
+
 /* Diagnostics: when set (device pointer to [n_ctas][16] int64), every fused layer launch writes clock64
  * stamps of its pipeline phases per CTA (slot meaning: tools/timeline.py).  NULL disables (default). */
 int wg_debug_timeline(wg_engine* e, long long* device_buffer);

@@ -59,6 +59,21 @@ def test_tcgen05_descriptor_gemm():
     assert err <= 2e-3, f"tcgen05 GEMM mismatch for {dt}: {err}"
 
 
+def test_tcgen05_cta_pair_gemm():
+  """cta_group::2 mechanisms in isolation: cluster launch, paired TMEM allocation, TMA loads completing on the leader
+  CTA's barrier, multicast tcgen05.commit, M = 256 across the pair with each CTA staging half of B."""
+  eng = get_model(256, "fp16").engine()
+  g = torch.Generator().manual_seed(1)
+  a = torch.randn((512, 384), generator=g).to(torch.float16)
+  b = torch.randn((512, 384), generator=g).to(torch.float16)
+  d = eng.debug_gemm2(a.cuda(), b.cuda()).cpu()
+  torch.cuda.synchronize()
+  ref = a.double() @ b.double().t()
+  err = float((d.double() - ref).abs().max())
+  print(f"debug gemm2 (cta_group::2): max err {err:.3e} (ref absmax {float(ref.abs().max()):.2f})")
+  assert err <= 2e-3
+
+
 @pytest.mark.parametrize("precision", ["fp32", "fp16", "fp16-wide"])
 def test_stagewise_first_flow(precision):
   """cond (upsample+squeeze), start conv, then every WN layer of the first flow, then the coupling step."""

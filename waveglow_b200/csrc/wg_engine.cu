@@ -978,4 +978,31 @@ int wg_debug_gemm(wg_engine* e, const void* A, const void* Bm, float* D, int32_t
   return WG_OK;
 }
 
+// Diagnostic 2-CTA GEMM (cta_group::2): M % 256 == 0, N % 256 == 0, K % 64 == 0.
+int wg_debug_gemm2(wg_engine* e, const void* A, const void* Bm, float* D, int32_t M, int32_t N, int32_t K, int32_t fmt,
+                   void* stream) {
+  if (!e || !e->encode) return WG_ERR_INVALID_ARGUMENT;
+  if (M % 256 || N % 256 || K % 64) return fail(e, WG_ERR_INVALID_ARGUMENT, "debug gemm2 needs M%%256==0, N%%256==0, K%%64==0");
+  const CUtensorMapDataType dt = fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap ta, tb;
+  int rc;
+  const uint32_t box[2] = {64, 128};
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    const uint64_t str[1] = {static_cast<uint64_t>(K) * 2};
+    if ((rc = make_map(e, &ta, const_cast<void*>(A), 2, dims, str, box, dt))) return rc;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    const uint64_t str[1] = {static_cast<uint64_t>(K) * 2};
+    if ((rc = make_map(e, &tb, const_cast<void*>(Bm), 2, dims, str, box, dt))) return rc;
+  }
+  const int smem = 2 * 32768 + 1024 + 128;
+  WG_CUDA(e, cudaFuncSetAttribute(debug_gemm2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  dim3 grid(2 * (M / 256), N / 256);
+  debug_gemm2_tc_kernel<<<grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(ta, tb, D, M, N, K, fmt);
+  WG_CUDA(e, cudaGetLastError());
+  return WG_OK;
+}
+
 }  // extern "C"

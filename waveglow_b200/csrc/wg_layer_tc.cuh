@@ -530,4 +530,87 @@ debug_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a,   // {K, M} box {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Diagnostic 2-CTA GEMM: D[M x N] = A[M x K] . B[N x K]^T with tcgen05.mma.cta_group::2 (M = 256 per CTA pair, each CTA
+// stages its own 128 rows of A and HALF of the 256 B rows).  Cluster (2,1,1); tests only (wg_debug_gemm2).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+debug_gemm2_tc_kernel(const __grid_constant__ CUtensorMap tm_a,   // {K, M} box {64,128}
+                      const __grid_constant__ CUtensorMap tm_b,   // {K, N} box {64,128}
+                      float* __restrict__ D, int M, int N, int K, int fmt) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int stage_bytes = 16384 + 16384;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
+  uint64_t* full = bars;        // used in the leader CTA only: bytes of BOTH CTAs' loads land here
+  uint64_t* empty = bars + 2;   // per CTA, released by the leader's multicast commit
+  uint64_t* done = bars + 4;    // per CTA, multicast commit
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int m0 = pair * 256 + rank * 128, n0 = blockIdx.y * 256;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    ptx::mbar_init(done, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_slot, 256);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nkb = K / 64;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb & 1;
+        ptx::mbar_wait(&empty[s], ((kb >> 1) & 1) ^ 1);
+        if (rank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2 * stage_bytes);
+        const uint32_t leader_full = ptx::map_to_cta(&full[s], 0);
+        ptx::tma_load_2d_pair(smem + s * stage_bytes, &tm_a, leader_full, kb * 64, m0);
+        ptx::tma_load_2d_pair(smem + s * stage_bytes + 16384, &tm_b, leader_full, kb * 64, n0 + rank * 128);
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_f16(256, 256, fmt);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb & 1;
+        ptx::mbar_wait(&full[s], (kb >> 1) & 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t a_addr = ptx::smem_u32(smem + s * stage_bytes);
+        for (int k = 0; k < 4; ++k)
+          ptx::mma_f16_ss_pair(tmem_base, ptx::make_desc_sw128(a_addr + k * 32), ptx::make_desc_sw128(a_addr + 16384 + k * 32),
+                               idesc, (kb | k) != 0);
+        ptx::mma_commit_pair(&empty[s], 3);
+      }
+      ptx::mma_commit_pair(done, 3);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    ptx::mbar_wait(done, 0);
+    ptx::tc_fence_after_sync();
+    for (int g = 0; g < 16; ++g) {
+      uint32_t v[16];
+      ptx::tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 16, v);
+      ptx::tmem_ld_wait();
+      if (m0 + row < M)
+        for (int i = 0; i < 16; ++i) D[static_cast<size_t>(m0 + row) * N + n0 + g * 16 + i] = __uint_as_float(v[i]);
+    }
+  }
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync_all();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc_pair(tmem_base, 256);
+  }
+}
+
 }  // namespace wg

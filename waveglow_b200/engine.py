@@ -18,7 +18,7 @@ PRECISION_FP16 = 1
 
 EXPORTED_SYMBOLS = [
   "wg_create", "wg_load_weights", "wg_workspace_bytes", "wg_infer", "wg_forward", "wg_last_launch_count",
-  "wg_debug_stop_after", "wg_debug_view", "wg_debug_gemm", "wg_debug_timeline", "wg_profile_layers", "wg_last_error", "wg_version",
+  "wg_debug_stop_after", "wg_debug_view", "wg_debug_gemm", "wg_debug_gemm2", "wg_debug_timeline", "wg_profile_layers", "wg_last_error", "wg_version",
   "wg_destroy",
 ]
 
@@ -70,6 +70,8 @@ def load_library() -> ctypes.CDLL:
   lib.wg_debug_view.restype = ctypes.c_int
   lib.wg_debug_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
   lib.wg_debug_gemm.restype = ctypes.c_int
+  lib.wg_debug_gemm2.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
+  lib.wg_debug_gemm2.restype = ctypes.c_int
   lib.wg_debug_timeline.argtypes = [vp, vp]
   lib.wg_debug_timeline.restype = ctypes.c_int
   lib.wg_profile_layers.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
@@ -224,6 +226,17 @@ class Engine:
     if name == "e" or self.precision == PRECISION_FP32:
       return raw.view(torch.float32)
     return raw.view(torch.float16)
+
+  def debug_gemm2(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """D = A @ B^T through the cta_group::2 (CTA pair) diagnostic kernel."""
+    assert a.dtype == b.dtype and a.dtype in (torch.float16, torch.bfloat16)
+    a = a.contiguous()
+    b = b.contiguous()
+    d = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=self.device)
+    stream = torch.cuda.current_stream(self.device).cuda_stream
+    self._check(self.lib.wg_debug_gemm2(self._h, a.data_ptr(), b.data_ptr(), d.data_ptr(), a.shape[0], b.shape[0], a.shape[1],
+                                        0 if a.dtype == torch.float16 else 1, stream), "wg_debug_gemm2")
+    return d
 
   def debug_gemm(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """D = A @ B^T through the TMA -> tcgen05.mma -> tcgen05.ld diagnostic kernel (fp16/bf16 inputs)."""
