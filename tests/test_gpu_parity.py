@@ -19,21 +19,25 @@ _MODELS = {}
 
 
 def get_model(n_channels: int, precision: str, style: str = "parametrized") -> WaveGlow:
-  """precision: "fp32", "fp16" or "fp16-wide" (the two-kernel tensor-core layer of 512-channel models, forced through
-  WG_WIDE=1 so that it can also be checked on the 256-channel model against the same references)."""
+  """precision: "fp32", "fp16" (default tensor-core path: fused layer on CTA pairs), "fp16-single" (WG_PAIR=0: the same
+  fused layer on single CTAs) or "fp16-wide" (WG_WIDE=1: the two-kernel layer of 512-channel models, forced onto the
+  256-channel model so that it can be checked against the same references)."""
   import os
   key = (n_channels, precision, style)
   if key not in _MODELS:
     hp, sd, w, dims = synthetic_weights(n_channels, style)
-    m = WaveGlow(hp, precision="fp16" if precision == "fp16-wide" else precision).to("cuda:0")
+    m = WaveGlow(hp, precision="fp16" if precision.startswith("fp16") else precision).to("cuda:0")
     m.load_state_dict(sd)
     m = WaveGlow.remove_weightnorm(m).eval()
     if precision == "fp16-wide":
       os.environ["WG_WIDE"] = "1"
+    if precision == "fp16-single":
+      os.environ["WG_PAIR"] = "0"
     try:
-      m.engine()          # the engine reads WG_WIDE when it is created
+      m.engine()          # the engine reads WG_WIDE / WG_PAIR when it is created
     finally:
       os.environ.pop("WG_WIDE", None)
+      os.environ.pop("WG_PAIR", None)
     _MODELS[key] = m
   return _MODELS[key]
 
@@ -74,7 +78,7 @@ def test_tcgen05_cta_pair_gemm():
   assert err <= 2e-3
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16", "fp16-wide"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "fp16-wide", "fp16-single"])
 def test_stagewise_first_flow(precision):
   """cond (upsample+squeeze), start conv, then every WN layer of the first flow, then the coupling step."""
   op_dtype = torch.float32 if precision == "fp32" else torch.float16
@@ -137,6 +141,10 @@ def test_stagewise_first_flow(precision):
     eng.debug_stop_after(-1, 0)
   out = run(model, mel, zs, sigma)
   check("final audio vs engine model", out, ref_audio, t=(2e-5 if precision == "fp32" else 2e-3))
+  if precision == "fp16-single":
+    same = run(get_model(256, "fp16"), mel, zs, sigma)
+    print(f"[fp16-single] vs CTA-pair kernel: max-abs {max_abs(same, out):.3e}")
+    assert torch.equal(same, out)      # same operands, same accumulation order: bit-identical
   if precision == "fp16-wide":
     # both tensor-core layer implementations use the same rounded operands but sum in a different order (fp32), and the
     # fp16 re-rounding of x amplifies that: they agree to about the fp16 noise floor, each within the gate of the reference
@@ -172,7 +180,8 @@ def test_fp16_tensor_core_mode_matches_reference_golden(name):
 
 
 @pytest.mark.parametrize("name,nc,mode", [("infer_c512_b1_f10", 512, "fp16"), ("infer_c256_b1_f40", 256, "fp16-wide"),
-                                          ("infer_c256_b3_f7_ragged", 256, "fp16-wide")])
+                                          ("infer_c256_b3_f7_ragged", 256, "fp16-wide"), ("infer_c256_b1_f40", 256, "fp16-single"),
+                                          ("infer_c256_b3_f7_ragged", 256, "fp16-single"), ("infer_c256_b2_f12", 256, "fp16-single")])
 def test_wide_tensor_core_path_matches_reference_golden(name, nc, mode):
   """The two-kernel tensor-core layer (wg_layer_wide_tc.cuh): 512-channel model (BASELINE config 3 architecture) and,
   forced with WG_WIDE=1, the 256-channel model."""

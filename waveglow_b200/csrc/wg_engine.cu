@@ -16,6 +16,7 @@
 #include "../../include/waveglow_b200.h"
 #include "wg_kernels.cuh"
 #include "wg_layer_tc.cuh"
+#include "wg_layer_pair_tc.cuh"
 #include "wg_layer_wide_tc.cuh"
 
 namespace {
@@ -57,6 +58,8 @@ struct wg_engine {
   float* d_bias1 = nullptr;           // [flows*layers][512] packed order
   float* d_bias_res = nullptr;        // [flows*layers][256]
   CUtensorMap tm_w1{}, tm_v{}, tm_w2a{}, tm_w2b{}, tm_ident{};
+  CUtensorMap tm_w1h{}, tm_vh{}, tm_w2h{}, tm_se8{}, tm_ident16{};   // half-height boxes for the CTA-pair kernel
+  bool pair = false;                  // fused layer on CTA pairs (cta_group::2); default for 256 channels, WG_PAIR=0 disables
   // fp32 path
   float* d_w1f = nullptr;             // [flows*layers][K1][2nc]
   float* d_bias1f = nullptr;          // [flows*layers][2nc]
@@ -267,6 +270,11 @@ int wg_create(const wg_config* cfg, wg_engine** out) {
   e->op_fmt = (fmt_env && strcmp(fmt_env, "bf16") == 0) ? 1 : 0;
   const char* wide_env = getenv("WG_WIDE");
   e->wide = cfg->precision == WG_PRECISION_FP16 && (cfg->n_channels == 512 || (wide_env && atoi(wide_env) != 0));
+  const char* pair_env = getenv("WG_PAIR");
+  // default for 256 channels: the fused layer on CTA pairs (bit-identical to the single-CTA kernel, ~3 % faster); WG_PAIR=0 disables
+  e->pair = cfg->precision == WG_PRECISION_FP16 && cfg->n_channels == 256 && !e->wide && !(pair_env && atoi(pair_env) == 0) &&
+            prop.multiProcessorCount >= 2;
+  WG_CUDA(e, cudaFuncSetAttribute(wn_layer_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem::total + 1024));
   const char* dbg_env = getenv("WG_DBG_FLAGS");
   e->dbg_flags = dbg_env ? atoi(dbg_env) : 0;
   WG_CUDA(e, cudaFuncSetAttribute(wn_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total + 1024));
@@ -513,12 +521,16 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
       const uint64_t str[1] = {static_cast<uint64_t>(K1x) * 2};
       const uint32_t box[2] = {64, 256};
       if ((rc = make_map(e, &e->tm_w1, e->d_w1, 2, dims, str, box, dt))) return rc;
+      const uint32_t boxh[2] = {64, 128};
+      if ((rc = make_map(e, &e->tm_w1h, e->d_w1, 2, dims, str, boxh, dt))) return rc;
     }
     {
       const uint64_t dims[2] = {static_cast<uint64_t>(kUpKdim), static_cast<uint64_t>(NF) * L * kUpPhases * 2 * nc};
       const uint64_t str[1] = {static_cast<uint64_t>(kUpKdim) * 2};
       const uint32_t box[2] = {64, 256};
       if ((rc = make_map(e, &e->tm_v, e->d_v, 2, dims, str, box, dt))) return rc;
+      const uint32_t boxh[2] = {64, 128};
+      if ((rc = make_map(e, &e->tm_vh, e->d_v, 2, dims, str, boxh, dt))) return rc;
     }
     {
       const uint64_t dims[2] = {static_cast<uint64_t>(nc), static_cast<uint64_t>(NF) * L * w2rows};
@@ -526,12 +538,17 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
       const uint32_t boxa[2] = {64, 256}, boxb[2] = {64, 16};
       if ((rc = make_map(e, &e->tm_w2a, e->d_w2, 2, dims, str, boxa, dt))) return rc;
       if ((rc = make_map(e, &e->tm_w2b, e->d_w2, 2, dims, str, boxb, dt))) return rc;
+      const uint32_t boxh[2] = {64, 128}, box8[2] = {64, 8};
+      if ((rc = make_map(e, &e->tm_w2h, e->d_w2, 2, dims, str, boxh, dt))) return rc;
+      if ((rc = make_map(e, &e->tm_se8, e->d_w2, 2, dims, str, box8, dt))) return rc;
     }
     {
       const uint64_t dims[2] = {64, static_cast<uint64_t>(kIdentN)};
       const uint64_t str[1] = {128};
       const uint32_t box[2] = {64, static_cast<uint32_t>(kIdentN)};
       if ((rc = make_map(e, &e->tm_ident, e->d_ident, 2, dims, str, box, dt))) return rc;
+      const uint32_t box16[2] = {64, static_cast<uint32_t>(kIdentN / 2)};
+      if ((rc = make_map(e, &e->tm_ident16, e->d_ident, 2, dims, str, box16, dt))) return rc;
     }
   } else {
     if ((rc = upload(e, &e->d_w1f, w1f))) return rc;
@@ -682,6 +699,19 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
       lp.timeline = e->dbg_timeline;
       lp.dbg_flags = e->dbg_flags;
       const int n_tiles = kPhases * ((lp.Fq + kTileM - 1) / kTileM) * B;
+      if (e->pair) {
+        const int n_ptiles = kPhases * ((((lp.Fq + kTileM - 1) / kTileM) * B + 1) / 2);
+        const int n_pairs = n_ptiles < e->num_sms / 2 ? n_ptiles : e->num_sms / 2;
+        wn_layer_pair_kernel<<<dim3(2 * n_pairs), kTcThreads, PairSmem::total + 1024, st>>>(
+            tm_x[*cur], tm_x[*cur ^ 1], *tm_cond, e->tm_w1h, e->tm_vh, e->tm_w2h, e->tm_se8, e->tm_ident16, lp);
+        e->launches++;
+        if (has_res) *cur ^= 1;
+        if (e->dbg_flow == k && e->dbg_layer == i) {
+          *stopped = true;
+          return WG_OK;
+        }
+        continue;
+      }
       dim3 grid(n_tiles < e->num_sms ? n_tiles : e->num_sms);
       wn_layer_tc_kernel<<<grid, kTcThreads, TcSmem::total + 1024, st>>>(tm_x[*cur], tm_x[*cur ^ 1], *tm_cond, e->tm_w1, e->tm_v,
                                                                         e->tm_w2a, e->tm_w2b, e->tm_ident, lp);
