@@ -199,13 +199,15 @@ struct FlowStepParams {
   float* log_s_out;           // optional [B, h, T] (reference layout, model.py:216)
 };
 
-constexpr int kFsPos = 64;      // group-steps per block
+constexpr int kFsPos = 256;     // group-steps per block = 8 mel frames x 32 phases
 constexpr int kFsThreads = 256;
 
-// One block = 64 consecutive PADDED group-steps (utterance stride Tpad >= T for the x stream, T for state / e).
-// Thread < 64: the per-position coupling / 1x1 algebra on the 8-float state row.  Then all 256 threads write the
-// next WN's start conv (model.py:117) coalesced along channels; padded rows of x are written as zeros because the
-// dilated convs must see zero padding beyond the true sequence end (model.py:100-102).
+// One block = 256 consecutive PADDED group-steps (utterance stride Tpad >= T for the x stream, T for state / e).
+// Phase 1: every thread does the per-position coupling / 1x1 algebra on one 8-float state row (coalesced 32-byte rows).
+// Phase 2: the next WN's start conv (model.py:117); thread = (8-channel group, row slot), 16-byte stores.  In tensor-core
+// mode x is phase-major, so the 256 rows are visited in (phase, frame) order: the 8 row slots of an iteration write 8
+// consecutive frames of one phase = one 4 KB contiguous run.  Padded rows of x are written as zeros because the dilated
+// convs must see zero padding beyond the true sequence end (model.py:100-102).
 template <typename XT>
 __global__ void __launch_bounds__(kFsThreads)
 flow_step_kernel(FlowStepParams p, float* __restrict__ state, const float* __restrict__ e, XT* __restrict__ x,
@@ -214,7 +216,7 @@ flow_step_kernel(FlowStepParams p, float* __restrict__ state, const float* __res
   __shared__ int valid_s[kFsPos];
   const size_t n_ppos = static_cast<size_t>(B) * Tpad;
   const size_t ppos0 = static_cast<size_t>(blockIdx.x) * kFsPos;
-  if (threadIdx.x < kFsPos) {
+  {
     const size_t ppos = ppos0 + threadIdx.x;
     const int b = static_cast<int>(ppos / Tpad), t = static_cast<int>(ppos % Tpad);
     const bool valid = ppos < n_ppos && t < T;
@@ -275,7 +277,7 @@ flow_step_kernel(FlowStepParams p, float* __restrict__ state, const float* __res
       }
     }
     if (p.do_finish && p.forward) {
-      // warp-level sum, then one double atomic per warp (deterministic enough: double accumulation)
+      // warp-level sum, then one double atomic per warp
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) ls_sum += __shfl_xor_sync(0xffffffffu, ls_sum, o);
       if ((threadIdx.x & 31) == 0 && ls_sum != 0.f) atomicAdd(p.log_s_sum, static_cast<double>(ls_sum));
@@ -289,10 +291,8 @@ flow_step_kernel(FlowStepParams p, float* __restrict__ state, const float* __res
   }
   if (!p.do_start) return;
   __syncthreads();
-  // start conv (model.py:117): thread = (8-channel group, position slot); one 16/32-byte vector store per position, so a
-  // warp writes whole contiguous rows of x
   const int groups = p.nc / 8;                       // 32 (256 channels) or 64 (512)
-  const int slots = kFsThreads / groups;             // positions handled concurrently: 8 or 4
+  const int slots = kFsThreads / groups;             // rows handled concurrently: 8 or 4
   const int gidx = threadIdx.x % groups, slot = threadIdx.x / groups;
   float w[8][4], bs[8];
 #pragma unroll
@@ -302,15 +302,17 @@ flow_step_kernel(FlowStepParams p, float* __restrict__ state, const float* __res
 #pragma unroll
     for (int j = 0; j < 4; ++j) w[u][j] = (j < p.h2) ? p.w_start[c * p.h2 + j] : 0.f;
   }
-  for (int i = slot; i < kFsPos; i += slots) {
+  const int Fq = Tpad / kUpPhases;
+  for (int r = slot; r < kFsPos; r += slots) {
+    // visit order: phase-major layout -> (phase, frame) so that concurrent slots hit consecutive rows of one plane
+    const int i = p.x_phase_major ? (r % 8) * kUpPhases + r / 8 : r;
     const size_t ppos = ppos0 + i;
-    if (ppos >= n_ppos) break;
+    if (ppos >= n_ppos) continue;
     size_t row = ppos;
     if (p.x_phase_major) {
-      // group-step t = 32 q + phase of utterance b lives at row ((b * 32 + phase) * Fq + q): each (phase, 128-frame) tile
-      // of the layer kernel is then one dense block for TMA
-      const size_t b = ppos / Tpad, t = ppos % Tpad;
-      row = (b * kUpPhases + (t % kUpPhases)) * (Tpad / kUpPhases) + t / kUpPhases;
+      // group-step t = 32 q + phase of utterance b lives at row ((b * 32 + phase) * Fq + q)
+      const int b = static_cast<int>(ppos / Tpad), t = static_cast<int>(ppos % Tpad);
+      row = (static_cast<size_t>(b) * kUpPhases + (t % kUpPhases)) * Fq + t / kUpPhases;
     }
     float v[8];
 #pragma unroll
