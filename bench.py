@@ -290,11 +290,11 @@ def main():
     per_launch_ms = layer_ms / layer_launches
     achieved = per_launch_flops / (per_launch_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": ("wn_layer_fp32_kernel" if args.precision == "fp32" else
-                           "wn_layer_tc_kernel" if args.channels == 256 else "wn_gate_wide_kernel + wn_res_wide_kernel"),
+                           "wn_layer_pair_kernel" if args.channels == 256 else "wn_gate_wide_kernel + wn_res_wide_kernel"),
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel on this workload, from
-                # profiles/r01/ncu_full_layer_v4_summary.csv (ncu --set full, kernel v4); only valid for the default workload
-                "traffic": 461e6 if (args.batch == 16 and args.frames == 861 and args.precision == "fp16" and args.channels == 256) else None,
+                # profiles/r01/ncu_full_layer_v5_pair_summary.csv (ncu --set full, kernel v5); only valid for the default workload
+                "traffic": 472e6 if (args.batch == 16 and args.frames == 861 and args.precision == "fp16" and args.channels == 256) else None,
                 "traffic_unit": "bytes per launch (ncu)",
                 "peak_source": peak_src, "launch_ms": per_launch_ms, "launches_per_step": layer_launches,
                 "algorithmic_flop_per_launch": per_launch_flops,
