@@ -272,36 +272,7 @@ wn_layer_pair_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {256, Fq
           asm volatile("bar.sync 1, 256;" ::: "memory");
           store_pending = false;
         }
-        const uint32_t rc = chunk == 0 ? ra : rb;
-        const int slab = 2 * chunk + hh;
-        uint8_t* slab_row = acts + slab * (kTileM * 128) + row * 128;
-        const float* bt = s_bias1 + chunk * 256 + hh * 64;
-        const float* bs = bt + 128;
-#pragma unroll 1
-        for (int g = 0; g < 4; ++g) {
-          uint32_t vt[16], vs[16];
-          const uint32_t col = hh * 64 + g * 16;
-          ptx::tmem_ld16(rc + col, vt);
-          ptx::tmem_ld16(rc + col + 128, vs);
-          ptx::tmem_ld_wait();
-          uint32_t pk[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float a0 = gate_one(__uint_as_float(vt[2 * i]) + bt[g * 16 + 2 * i], __uint_as_float(vs[2 * i]) + bs[g * 16 + 2 * i]);
-            const float a1 = gate_one(__uint_as_float(vt[2 * i + 1]) + bt[g * 16 + 2 * i + 1],
-                                      __uint_as_float(vs[2 * i + 1]) + bs[g * 16 + 2 * i + 1]);
-            if (p.fmt == 0) {
-              pk[i] = ptx::pack_half2(a0, a1);
-            } else {
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
-              pk[i] = *reinterpret_cast<uint32_t*>(&h2);
-            }
-          }
-          const int c0 = (2 * g) ^ (row & 7);
-          const int c1 = (2 * g + 1) ^ (row & 7);
-          *reinterpret_cast<uint4*>(slab_row + c0 * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(slab_row + c1 * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
+        gate_chunk<false>(chunk == 0 ? ra : rb, acts, chunk, hh, row, s_bias1 + chunk * 256, p.fmt);
         ptx::tc_fence_before_sync();
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive_cluster(l_acts_ready[chunk]);
@@ -319,44 +290,12 @@ wn_layer_pair_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {256, Fq
         ptx::tc_fence_before_sync();
         ptx::mbar_arrive_cluster(l_e_drained);
         if (tc.q0 + row < p.Fq && t < p.T) {
-          float4* ep = reinterpret_cast<float4*>(p.e + (static_cast<size_t>(tc.b) * p.T + t) * 8);
-          float4 lo = make_float4(__uint_as_float(ve[0]), __uint_as_float(ve[1]), __uint_as_float(ve[2]), __uint_as_float(ve[3]));
-          float4 hi = make_float4(__uint_as_float(ve[4]), __uint_as_float(ve[5]), __uint_as_float(ve[6]), __uint_as_float(ve[7]));
-          if (p.accumulate_e) {
-            const float4 o0 = ep[0], o1 = ep[1];
-            lo.x += o0.x; lo.y += o0.y; lo.z += o0.z; lo.w += o0.w;
-            hi.x += o1.x; hi.y += o1.y; hi.z += o1.z; hi.w += o1.w;
-          }
-          ep[0] = lo;
-          ep[1] = hi;
+          const float v[8] = {__uint_as_float(ve[0]), __uint_as_float(ve[1]), __uint_as_float(ve[2]), __uint_as_float(ve[3]),
+                              __uint_as_float(ve[4]), __uint_as_float(ve[5]), __uint_as_float(ve[6]), __uint_as_float(ve[7])};
+          update_e_row(p.e + (static_cast<size_t>(tc.b) * p.T + t) * 8, v, p.accumulate_e != 0);
         }
       }
-      if (p.has_res) {
-#pragma unroll 1
-        for (int g = 0; g < 8; ++g) {
-          uint32_t v[16];
-          const int ch0 = hh * 128 + g * 16;
-          ptx::tmem_ld16(ra + ch0, v);
-          ptx::tmem_ld_wait();
-          uint32_t pk[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float a0 = t < p.T ? __uint_as_float(v[2 * i]) + s_bias_res[ch0 + 2 * i] : 0.f;
-            const float a1 = t < p.T ? __uint_as_float(v[2 * i + 1]) + s_bias_res[ch0 + 2 * i + 1] : 0.f;
-            if (p.fmt == 0) {
-              pk[i] = ptx::pack_half2(a0, a1);
-            } else {
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
-              pk[i] = *reinterpret_cast<uint32_t*>(&h2);
-            }
-          }
-          const int slab = ch0 >> 6;
-          const int cc = (ch0 & 63) >> 3;
-          uint8_t* slab_row = acts + slab * (kTileM * 128) + row * 128;
-          *reinterpret_cast<uint4*>(slab_row + ((cc ^ (row & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(slab_row + (((cc + 1) ^ (row & 7)) * 16)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
-      }
+      if (p.has_res) stage_residual(ra, s_bias_res, acts, hh, row, t < p.T, p.fmt);
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive_cluster(l_res_drained);
       if (p.has_res) {

@@ -93,6 +93,84 @@ __device__ __forceinline__ float gate_one(float a, float b) {
   return ptx::tanh_approx(a) * fmaf(0.5f, ptx::tanh_approx(0.5f * b), 0.5f);
 }
 
+__device__ __forceinline__ uint32_t pack_pair(float a0, float a1, int fmt) {
+  if (fmt == 0) return ptx::pack_half2(a0, a1);
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
+  return *reinterpret_cast<uint32_t*>(&h2);
+}
+
+// Gate of one 256-column accumulator chunk ([tanh 128 | sigmoid 128], model.py:13-20) for one TMEM lane (= group-step
+// `row` of the tile) and one column half `hh`: 64 activations -> fp16/bf16 -> the 128-byte-swizzled K-major acts slab
+// (2 * chunk + hh) that GEMM2 / the skip-end MMAs read as their A operand.  `bt` points at the chunk's packed bias
+// (tanh half at [0,128), sigmoid half at [128,256)); kGlobalBias selects the read-only global path.
+template <bool kGlobalBias>
+__device__ __forceinline__ void gate_chunk(uint32_t rc, uint8_t* acts, int chunk, int hh, int row, const float* bt, int fmt) {
+  uint8_t* slab_row = acts + (2 * chunk + hh) * (kTileM * 128) + row * 128;
+  bt += hh * 64;
+  const float* bs = bt + 128;
+#pragma unroll 1
+  for (int g = 0; g < 4; ++g) {
+    uint32_t vt[16], vs[16];
+    const uint32_t col = hh * 64 + g * 16;
+    ptx::tmem_ld16(rc + col, vt);
+    ptx::tmem_ld16(rc + col + 128, vs);
+    ptx::tmem_ld_wait();
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = g * 16 + 2 * i;
+      const float bt0 = kGlobalBias ? __ldg(bt + j) : bt[j], bt1 = kGlobalBias ? __ldg(bt + j + 1) : bt[j + 1];
+      const float bs0 = kGlobalBias ? __ldg(bs + j) : bs[j], bs1 = kGlobalBias ? __ldg(bs + j + 1) : bs[j + 1];
+      pk[i] = pack_pair(gate_one(__uint_as_float(vt[2 * i]) + bt0, __uint_as_float(vs[2 * i]) + bs0),
+                        gate_one(__uint_as_float(vt[2 * i + 1]) + bt1, __uint_as_float(vs[2 * i + 1]) + bs1), fmt);
+    }
+    // 128-byte swizzle: 16-byte chunk index XOR (row mod 8)
+    const int c0 = (2 * g) ^ (row & 7);
+    const int c1 = (2 * g + 1) ^ (row & 7);
+    *reinterpret_cast<uint4*>(slab_row + c0 * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(slab_row + c1 * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+}
+
+// e[row] (+)= v : the fp32 skip-end accumulator row of one group-step (8 floats, two 16-byte accesses)
+__device__ __forceinline__ void update_e_row(float* e_row, const float (&v)[8], bool accumulate) {
+  float4* ep = reinterpret_cast<float4*>(e_row);
+  float4 lo = make_float4(v[0], v[1], v[2], v[3]);
+  float4 hi = make_float4(v[4], v[5], v[6], v[7]);
+  if (accumulate) {
+    const float4 o0 = ep[0], o1 = ep[1];
+    lo.x += o0.x; lo.y += o0.y; lo.z += o0.z; lo.w += o0.w;
+    hi.x += o1.x; hi.y += o1.y; hi.z += o1.z; hi.w += o1.w;
+  }
+  ep[0] = lo;
+  ep[1] = hi;
+}
+
+// Residual accumulator (256 columns at `ra`) -> + bias -> 16-bit -> swizzled staging tile (4 slabs of [128 x 64]) for the
+// TMA store of x'.  Thread = lane `row`, column half hh.  Rows beyond the true sequence end are written as exact zeros:
+// they are the zero padding later layers read (model.py:100-102).
+__device__ __forceinline__ void stage_residual(uint32_t ra, const float* s_bias, uint8_t* stage, int hh, int row, bool valid, int fmt) {
+#pragma unroll 1
+  for (int g = 0; g < 8; ++g) {
+    uint32_t v[16];
+    const int ch0 = hh * 128 + g * 16;          // first residual channel of this group
+    ptx::tmem_ld16(ra + ch0, v);
+    ptx::tmem_ld_wait();
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float a0 = valid ? __uint_as_float(v[2 * i]) + s_bias[ch0 + 2 * i] : 0.f;
+      const float a1 = valid ? __uint_as_float(v[2 * i + 1]) + s_bias[ch0 + 2 * i + 1] : 0.f;
+      pk[i] = pack_pair(a0, a1, fmt);
+    }
+    const int slab = ch0 >> 6;
+    const int cc = (ch0 & 63) >> 3;             // 16-byte chunk inside the 128-byte row
+    uint8_t* slab_row = stage + slab * (kTileM * 128) + row * 128;
+    *reinterpret_cast<uint4*>(slab_row + ((cc ^ (row & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(slab_row + (((cc + 1) ^ (row & 7)) * 16)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1)
 wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, Fq, 32 B} box {64,128,1} SW128
                    const __grid_constant__ CUtensorMap tm_x_out,  // same geometry, other buffer
@@ -330,38 +408,7 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, Fq, 3
           asm volatile("bar.sync 1, 256;" ::: "memory");
           store_pending = false;
         }
-        const uint32_t rc = chunk == 0 ? ra : rb;
-        const int slab = 2 * chunk + hh;                 // acts channels [64*slab, 64*slab+64)
-        uint8_t* slab_row = acts + slab * (kTileM * 128) + row * 128;
-        const float* bt = s_bias1 + chunk * 256 + hh * 64;
-        const float* bs = bt + 128;
-#pragma unroll 1
-        for (int g = 0; g < 4; ++g) {
-          uint32_t vt[16], vs[16];
-          const uint32_t col = hh * 64 + g * 16;
-          ptx::tmem_ld16(rc + col, vt);
-          ptx::tmem_ld16(rc + col + 128, vs);
-          ptx::tmem_ld_wait();
-          uint32_t pk[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float a0 = gate_one(__uint_as_float(vt[2 * i]) + bt[g * 16 + 2 * i],
-                                      __uint_as_float(vs[2 * i]) + bs[g * 16 + 2 * i]);
-            const float a1 = gate_one(__uint_as_float(vt[2 * i + 1]) + bt[g * 16 + 2 * i + 1],
-                                      __uint_as_float(vs[2 * i + 1]) + bs[g * 16 + 2 * i + 1]);
-            if (p.fmt == 0) {
-              pk[i] = ptx::pack_half2(a0, a1);
-            } else {
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
-              pk[i] = *reinterpret_cast<uint32_t*>(&h2);
-            }
-          }
-          // 128-byte swizzle: 16-byte chunk index XOR (row mod 8)
-          const int c0 = (2 * g) ^ (row & 7);
-          const int c1 = (2 * g + 1) ^ (row & 7);
-          *reinterpret_cast<uint4*>(slab_row + c0 * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(slab_row + c1 * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
+        gate_chunk<false>(chunk == 0 ? ra : rb, acts, chunk, hh, row, s_bias1 + chunk * 256, p.fmt);
         ptx::tc_fence_before_sync();
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&acts_ready[chunk]);
@@ -380,45 +427,12 @@ wn_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_x_in,   // {256, Fq, 3
         ptx::tc_fence_before_sync();
         ptx::mbar_arrive(e_drained);
         if (q0 + row < p.Fq && t < p.T) {
-          float4* ep = reinterpret_cast<float4*>(p.e + (static_cast<size_t>(b) * p.T + t) * 8);
-          float4 lo = make_float4(__uint_as_float(ve[0]), __uint_as_float(ve[1]), __uint_as_float(ve[2]), __uint_as_float(ve[3]));
-          float4 hi = make_float4(__uint_as_float(ve[4]), __uint_as_float(ve[5]), __uint_as_float(ve[6]), __uint_as_float(ve[7]));
-          if (p.accumulate_e) {
-            const float4 o0 = ep[0], o1 = ep[1];
-            lo.x += o0.x; lo.y += o0.y; lo.z += o0.z; lo.w += o0.w;
-            hi.x += o1.x; hi.y += o1.y; hi.z += o1.z; hi.w += o1.w;
-          }
-          ep[0] = lo;
-          ep[1] = hi;
+          const float v[8] = {__uint_as_float(ve[0]), __uint_as_float(ve[1]), __uint_as_float(ve[2]), __uint_as_float(ve[3]),
+                              __uint_as_float(ve[4]), __uint_as_float(ve[5]), __uint_as_float(ve[6]), __uint_as_float(ve[7])};
+          update_e_row(p.e + (static_cast<size_t>(b) * p.T + t) * 8, v, p.accumulate_e != 0);
         }
       }
-      if (p.has_res) {
-#pragma unroll 1
-        for (int g = 0; g < 8; ++g) {
-          uint32_t v[16];
-          const int ch0 = hh * 128 + g * 16;          // first residual channel of this group
-          ptx::tmem_ld16(ra + ch0, v);
-          ptx::tmem_ld_wait();
-          uint32_t pk[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            // rows beyond the true sequence end stay exactly zero: they are the conv's zero padding for later layers
-            const float a0 = t < p.T ? __uint_as_float(v[2 * i]) + s_bias_res[ch0 + 2 * i] : 0.f;
-            const float a1 = t < p.T ? __uint_as_float(v[2 * i + 1]) + s_bias_res[ch0 + 2 * i + 1] : 0.f;
-            if (p.fmt == 0) {
-              pk[i] = ptx::pack_half2(a0, a1);
-            } else {
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
-              pk[i] = *reinterpret_cast<uint32_t*>(&h2);
-            }
-          }
-          const int slab = ch0 >> 6;
-          const int cc = (ch0 & 63) >> 3;             // 16-byte chunk inside the 128-byte row
-          uint8_t* slab_row = acts + slab * (kTileM * 128) + row * 128;
-          *reinterpret_cast<uint4*>(slab_row + ((cc ^ (row & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(slab_row + (((cc + 1) ^ (row & 7)) * 16)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
-      }
+      if (p.has_res) stage_residual(ra, s_bias_res, acts, hh, row, t < p.T, p.fmt);
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(res_drained);
       if (p.has_res) {

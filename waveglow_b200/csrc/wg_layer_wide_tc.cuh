@@ -241,37 +241,7 @@ wn_gate_wide_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC, Fq, 
           if (warp == 2 && lane == 0) ptx::tma_store_wait_read();
           asm volatile("bar.sync 1, 256;" ::: "memory");
         }
-        const uint32_t rc = lane_base + chunk * 256;
-        const int slab = 2 * chunk + hh;
-        uint8_t* slab_row = acts + slab * (kTileM * 128) + row * 128;
-        const float* bt = p.bias1 + h * 512 + chunk * 256 + hh * 64;
-        const float* bs = bt + 128;
-#pragma unroll 1
-        for (int g = 0; g < 4; ++g) {
-          uint32_t vt[16], vs[16];
-          const uint32_t col = hh * 64 + g * 16;
-          ptx::tmem_ld16(rc + col, vt);
-          ptx::tmem_ld16(rc + col + 128, vs);
-          ptx::tmem_ld_wait();
-          uint32_t pk[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float a0 = gate_one(__uint_as_float(vt[2 * i]) + __ldg(bt + g * 16 + 2 * i),
-                                      __uint_as_float(vs[2 * i]) + __ldg(bs + g * 16 + 2 * i));
-            const float a1 = gate_one(__uint_as_float(vt[2 * i + 1]) + __ldg(bt + g * 16 + 2 * i + 1),
-                                      __uint_as_float(vs[2 * i + 1]) + __ldg(bs + g * 16 + 2 * i + 1));
-            if (p.fmt == 0) {
-              pk[i] = ptx::pack_half2(a0, a1);
-            } else {
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
-              pk[i] = *reinterpret_cast<uint32_t*>(&h2);
-            }
-          }
-          const int c0 = (2 * g) ^ (row & 7);
-          const int c1 = (2 * g + 1) ^ (row & 7);
-          *reinterpret_cast<uint4*>(slab_row + c0 * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(slab_row + c1 * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
+        gate_chunk<true>(lane_base + chunk * 256, acts, chunk, hh, row, p.bias1 + h * 512 + chunk * 256, p.fmt);
         ptx::tc_fence_before_sync();
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&acts_ready[chunk]);
@@ -297,18 +267,8 @@ wn_gate_wide_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC, Fq, 
         for (int i = 0; i < 8; ++i) e_acc[i] = (h == 0 ? 0.f : e_acc[i]) + __uint_as_float(ve[i]);
         if (h == C::kHalves - 1) {
           const int t = (tc.q0 + row) * kPhases + tc.ph;
-          if (tc.q0 + row < p.Fq && t < p.T) {
-            float4* ep = reinterpret_cast<float4*>(p.e + (static_cast<size_t>(tc.b) * p.T + t) * 8);
-            float4 lo = make_float4(e_acc[0], e_acc[1], e_acc[2], e_acc[3]);
-            float4 hi = make_float4(e_acc[4], e_acc[5], e_acc[6], e_acc[7]);
-            if (p.accumulate_e) {
-              const float4 o0 = ep[0], o1 = ep[1];
-              lo.x += o0.x; lo.y += o0.y; lo.z += o0.z; lo.w += o0.w;
-              hi.x += o1.x; hi.y += o1.y; hi.z += o1.z; hi.w += o1.w;
-            }
-            ep[0] = lo;
-            ep[1] = hi;
-          }
+          if (tc.q0 + row < p.Fq && t < p.T)
+            update_e_row(p.e + (static_cast<size_t>(tc.b) * p.T + t) * 8, e_acc, p.accumulate_e != 0);
         }
       }
     }
@@ -470,30 +430,7 @@ wn_res_wide_kernel(const __grid_constant__ CUtensorMap tm_acts,    // {NC, Fq, 3
       asm volatile("bar.sync 1, 256;" ::: "memory");
       ptx::mbar_wait(&d_full[r], (n >> 1) & 1);
       ptx::tc_fence_after_sync();
-#pragma unroll 1
-      for (int g = 0; g < 8; ++g) {
-        uint32_t v[16];
-        const int ch0 = hh * 128 + g * 16;
-        ptx::tmem_ld16(lane_base + r * 256 + ch0, v);
-        ptx::tmem_ld_wait();
-        uint32_t pk[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float a0 = t < p.T ? __uint_as_float(v[2 * i]) + s_bias[ch0 + 2 * i] : 0.f;
-          const float a1 = t < p.T ? __uint_as_float(v[2 * i + 1]) + s_bias[ch0 + 2 * i + 1] : 0.f;
-          if (p.fmt == 0) {
-            pk[i] = ptx::pack_half2(a0, a1);
-          } else {
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
-            pk[i] = *reinterpret_cast<uint32_t*>(&h2);
-          }
-        }
-        const int slab = ch0 >> 6;
-        const int cc = (ch0 & 63) >> 3;
-        uint8_t* slab_row = stage_out + slab * (kTileM * 128) + row * 128;
-        *reinterpret_cast<uint4*>(slab_row + ((cc ^ (row & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(slab_row + (((cc + 1) ^ (row & 7)) * 16)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      }
+      stage_residual(lane_base + r * 256, s_bias, stage_out, hh, row, t < p.T, p.fmt);
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(&drained[r]);
       ptx::fence_proxy_async_smem();
