@@ -115,6 +115,10 @@ int wg_last_launch_count(const wg_engine* e);
  * bench.py divides the kernels' algorithmic FLOPs by this for the live roofline figure. */
 int wg_profile_layers(wg_engine* e, float* total_ms, int32_t* n_launches);
 
+/* The per-flow timing events behind wg_profile_layers are recorded by default; switch them off (0) while the caller captures
+ * wg_infer into a CUDA graph (cudaStreamBeginCapture on `stream`), on again (1) afterwards. */
+int wg_set_profiling(wg_engine* e, int32_t enabled);
+
 /* Diagnostic GEMM D[M,N] fp32 = A[M,K] . B[N,K]^T on 16-bit device operands (fmt 0 = fp16, 1 = bf16)
  * through the same TMA / tcgen05 building blocks as the layer kernel (tests only). */
 int wg_debug_gemm(wg_engine* e, const void* a, const void* b, float* d, int32_t m, int32_t n, int32_t k,

@@ -357,6 +357,26 @@ def test_wide_512_properties():
   assert err <= 4e-3
 
 
+def test_cuda_graph_replay_is_bit_identical():
+  """Opt-in CUDA-graph replay of the whole infer call (launch-bound single short utterances)."""
+  hp, sd, w, dims = synthetic_weights(256)
+  model = get_model(256, "fp16")
+  mel = synthetic_mel(1, 40, 81)
+  outs = []
+  for seed in (1, 2):
+    zs = synthetic_noise(hp, 1, 40 * 32, seed)
+    plain = run(model, mel, zs, 0.7)
+    model.use_cuda_graphs = True
+    try:
+      graphed = run(model, mel, zs, 0.7)      # first call captures, second replays
+      graphed2 = run(model, mel, zs, 0.7)
+    finally:
+      model.use_cuda_graphs = False
+    assert torch.equal(plain, graphed) and torch.equal(plain, graphed2)
+    outs.append(plain)
+  assert not torch.equal(outs[0], outs[1])
+
+
 def test_errors_are_loud():
   from waveglow_b200.engine import WgError
   model = get_model(256, "fp16")

@@ -45,6 +45,16 @@ def main():
     print(json.dumps({"config": name, "direction": "infer", "batch": B, "frames": F, "samples": n, "median_ms": med, "best_ms": best,
                       "samples_per_s": n / (med * 1e-3), "x_realtime": n / (med * 1e-3) / 22050,
                       "finite": bool(torch.isfinite(out).all()), "launches": model.engine().launch_count()}), flush=True)
+  # config 1 again through the CUDA-graph replay path
+  B, F = 1, 200
+  mel = synthetic_mel(B, F, 1).to(dev)
+  zs = [z.to(dev) for z in synthetic_noise(hp, B, F * 32, 2)]
+  model.use_cuda_graphs = True
+  med, best = timed(lambda: model.infer_with_noise(mel, zs, 0.666), 10)
+  model.use_cuda_graphs = False
+  n = B * F * 256
+  print(json.dumps({"config": "config1_b1_f200_cuda_graph", "direction": "infer", "batch": B, "frames": F, "samples": n,
+                    "median_ms": med, "best_ms": best, "samples_per_s": n / (med * 1e-3), "x_realtime": n / (med * 1e-3) / 22050}), flush=True)
   B, T, F = 24, 16000, 63
   mel = synthetic_mel(B, F, 3).to(dev)
   audio = (torch.rand(B, T, generator=torch.Generator().manual_seed(4)) * 2 - 1).to(dev)

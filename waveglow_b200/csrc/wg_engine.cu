@@ -69,6 +69,7 @@ struct wg_engine {
   double* d_logdet = nullptr;         // [flows] log|det W_k|
   std::vector<cudaEvent_t> ev;        // 2 per flow: around the WN layer launches of the last call
   int ev_flows = 0;                   // flows recorded by the last call
+  bool profiling = true;              // record the per-flow events (switched off while a CUDA graph is being captured)
   long long* dbg_timeline = nullptr;  // device buffer for clock64 stamps of layer launches (tests/diagnostics)
   bool wide = false;                  // two-kernel tensor-core layer (n_channels = 512; WG_WIDE=1 forces it for 256)
   int num_sms = 148;
@@ -636,11 +637,12 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
     e->ev.resize(2 * e->cfg.n_flows);
     for (auto& ev : e->ev) cudaEventCreate(&ev);
   }
-  cudaEventRecord(e->ev[2 * e->ev_flows], st);
+  if (e->profiling) cudaEventRecord(e->ev[2 * e->ev_flows], st);
   struct RecordEnd {
     wg_engine* e;
     cudaStream_t st;
     ~RecordEnd() {
+      if (!e->profiling) return;
       cudaEventRecord(e->ev[2 * e->ev_flows + 1], st);
       e->ev_flows++;
     }
@@ -886,6 +888,13 @@ int wg_infer(wg_engine* e, const float* mel, int32_t batch, int32_t frames, cons
     if (k > 0 && e->dbg_flow == k - 1 && e->dbg_layer == -1) stopped = true;
   }
   WG_CUDA(e, cudaGetLastError());
+  return WG_OK;
+}
+
+int wg_set_profiling(wg_engine* e, int32_t enabled) {
+  if (!e) return WG_ERR_INVALID_ARGUMENT;
+  e->profiling = enabled != 0;
+  if (!e->profiling) e->ev_flows = 0;
   return WG_OK;
 }
 

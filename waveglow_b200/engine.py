@@ -18,7 +18,7 @@ PRECISION_FP16 = 1
 
 EXPORTED_SYMBOLS = [
   "wg_create", "wg_load_weights", "wg_workspace_bytes", "wg_infer", "wg_forward", "wg_last_launch_count",
-  "wg_debug_stop_after", "wg_debug_view", "wg_debug_gemm", "wg_debug_gemm2", "wg_debug_timeline", "wg_profile_layers", "wg_last_error", "wg_version",
+  "wg_debug_stop_after", "wg_debug_view", "wg_debug_gemm", "wg_debug_gemm2", "wg_debug_timeline", "wg_set_profiling", "wg_profile_layers", "wg_last_error", "wg_version",
   "wg_destroy",
 ]
 
@@ -72,6 +72,8 @@ def load_library() -> ctypes.CDLL:
   lib.wg_debug_gemm.restype = ctypes.c_int
   lib.wg_debug_gemm2.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
   lib.wg_debug_gemm2.restype = ctypes.c_int
+  lib.wg_set_profiling.argtypes = [vp, i32]
+  lib.wg_set_profiling.restype = ctypes.c_int
   lib.wg_debug_timeline.argtypes = [vp, vp]
   lib.wg_debug_timeline.restype = ctypes.c_int
   lib.wg_profile_layers.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
@@ -156,14 +158,14 @@ class Engine:
   def _aligned_ptr(t: torch.Tensor) -> int:
     return (t.data_ptr() + 1023) // 1024 * 1024
 
-  def infer(self, mel: torch.Tensor, zs: Sequence[torch.Tensor], sigma: float) -> torch.Tensor:
+  def infer(self, mel: torch.Tensor, zs: Sequence[torch.Tensor], sigma: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """mel [B,80,F] fp32 cuda; zs pre-drawn N(0,1) in the reference order.  Returns audio [B, 256 F]."""
     if mel.device != self.device:
       raise WgError(f"mel is on {mel.device}, engine on {self.device}")
     mel = mel.to(torch.float32).contiguous()
     B, _, F = mel.shape
     zs = [z.to(torch.float32).contiguous() for z in zs]
-    audio = torch.empty((B, F * 256), dtype=torch.float32, device=self.device)
+    audio = out if out is not None else torch.empty((B, F * 256), dtype=torch.float32, device=self.device)
     ws = self.workspace(B, F)
     zp = (ctypes.c_void_p * len(zs))(*[z.data_ptr() for z in zs])
     stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -196,6 +198,43 @@ class Engine:
                              dets.data_ptr(), self._aligned_ptr(ws), ws.numel() - 1024, stream)
     self._check(rc, "wg_forward")
     return z, log_s, sums, dets
+
+  def infer_graphed(self, mel: torch.Tensor, zs: Sequence[torch.Tensor], sigma: float) -> torch.Tensor:
+    """Same result as `infer`, replayed from a CUDA graph (one graph per (batch, frames, sigma)): the ~110 kernel launches of
+    a call collapse into one graph launch, which matters when a single short utterance is launch-bound (config 1)."""
+    B, _, F = mel.shape
+    key = (B, F, float(sigma))
+    if not hasattr(self, "_graphs"):
+      self._graphs = {}
+    ent = self._graphs.get(key)
+    if ent is None:
+      s_mel = torch.empty((B, mel.shape[1], F), dtype=torch.float32, device=self.device)
+      s_zs = [torch.empty(tuple(z.shape), dtype=torch.float32, device=self.device) for z in zs]
+      s_out = torch.empty((B, F * 256), dtype=torch.float32, device=self.device)
+      s_mel.copy_(mel)
+      for d, z in zip(s_zs, zs):
+        d.copy_(z)
+      self.workspace(B, F)                        # allocate outside the capture
+      self.infer(s_mel, s_zs, sigma, out=s_out)   # warm-up (weights resident, tensor maps exercised)
+      torch.cuda.synchronize(self.device)
+      g = torch.cuda.CUDAGraph()
+      self._check(self.lib.wg_set_profiling(self._h, 0), "wg_set_profiling")
+      try:
+        with torch.cuda.graph(g):
+          self.infer(s_mel, s_zs, sigma, out=s_out)
+      finally:
+        self._check(self.lib.wg_set_profiling(self._h, 1), "wg_set_profiling")
+      ent = (g, s_mel, s_zs, s_out, self._ws)
+      self._graphs[key] = ent
+    g, s_mel, s_zs, s_out, ws_ref = ent
+    if ws_ref is not self._ws:                    # the workspace grew for a larger shape: this graph's pointers are stale
+      del self._graphs[key]
+      return self.infer_graphed(mel, zs, sigma)
+    s_mel.copy_(mel)
+    for d, z in zip(s_zs, zs):
+      d.copy_(z)
+    g.replay()
+    return s_out.clone()
 
   def launch_count(self) -> int:
     return self.lib.wg_last_launch_count(self._h)

@@ -90,6 +90,8 @@ class WaveGlow(torch.nn.Module):
     self._precision = precision
     self._engine: Optional[_engine.Engine] = None
     self._packed = False
+    # opt-in: replay each (batch, frames, sigma) shape from a CUDA graph (latency of short single utterances)
+    self.use_cuda_graphs = False
 
   # ------------------------------------------------------------------ engine plumbing
   def set_precision(self, precision: str) -> "WaveGlow":
@@ -166,6 +168,8 @@ class WaveGlow(torch.nn.Module):
       raise ValueError(f"spect must be [B, {self.hparams.n_mel_channels}, frames], got {tuple(spect.shape)}")
     eng = self.engine()
     with torch.no_grad():
+      if self.use_cuda_graphs:
+        return eng.infer_graphed(spect, zs, sigma)
       return eng.infer(spect, zs, sigma)
 
   def infer(self, spect: torch.Tensor, sigma: float = 1.0) -> torch.Tensor:
