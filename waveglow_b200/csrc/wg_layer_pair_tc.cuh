@@ -42,6 +42,9 @@ wn_layer_pair_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {256, Fq
                      const __grid_constant__ CUtensorMap tm_w2h,     // {256, rows} box {64,128}
                      const __grid_constant__ CUtensorMap tm_se8,     // {256, rows} box {64,8}
                      const __grid_constant__ CUtensorMap tm_ident16, // {64, 32} box {64,16}
+                     const __grid_constant__ CUtensorMap tm_x_in64,  // as tm_x_in, box {64,64,1}   (two short utterances per tile)
+                     const __grid_constant__ CUtensorMap tm_x_out64, // as tm_x_out, box {64,64,1}
+                     const __grid_constant__ CUtensorMap tm_mw64,    // as tm_mw, box {64,64,1}
                      const LayerTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -62,8 +65,11 @@ wn_layer_pair_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {256, Fq
   const uint32_t rank = ptx::cluster_ctarank();
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   // pair-tile = (pair of consecutive (utterance, 128-frame block) entries, phase); phase fastest.  CTA `rank` owns entry 2 pe + rank.
+  // Short utterances (Fq <= 64, seg_rows == 64): a tile holds TWO whole utterances (rows 0..63 and 64..127), loaded / stored
+  // as two 64-row TMA boxes, so 63-frame training segments (config 5) do not waste half of every tile.
+  const bool half = p.seg_rows == 64;
   const int nqb = (p.Fq + kTileM - 1) / kTileM;
-  const int n_entries = p.B * nqb;
+  const int n_entries = half ? (p.B + 1) / 2 : p.B * nqb;
   const int n_pe = (n_entries + 1) / 2;
   const int n_ptiles = n_pe * kPhases;
   const int my_tiles = (n_ptiles - pair + n_pairs - 1) / n_pairs;
@@ -79,8 +85,13 @@ wn_layer_pair_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {256, Fq
     Coord c;
     c.ph = pt % kPhases;
     c.valid = entry < n_entries;
-    c.b = c.valid ? entry / nqb : 0;
-    c.q0 = c.valid ? (entry % nqb) * kTileM : p.Fq;      // an odd entry count leaves one dummy tile: every row out of range
+    if (half) {
+      c.b = c.valid ? 2 * entry : p.B;                   // utterances b, b + 1 (b + 1 may not exist: its rows read zeros, store nothing)
+      c.q0 = 0;
+    } else {
+      c.b = c.valid ? entry / nqb : 0;
+      c.q0 = c.valid ? (entry % nqb) * kTileM : p.Fq;    // an odd entry count leaves one dummy tile: every row out of range
+    }
     return c;
   };
 
@@ -139,13 +150,23 @@ wn_layer_pair_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {256, Fq
             if (rank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2 * kPairStageBytes);
             const uint32_t lb = ptx::map_to_cta(&full[s], 0);
             if (kb < kMwKB) {
-              ptx::tma_load_3d_pair(sa, &tm_mw, lb, kb * kBlockK, tc.q0, tc.b);
+              if (half) {
+                ptx::tma_load_3d_pair(sa, &tm_mw64, lb, kb * kBlockK, 0, tc.b);
+                ptx::tma_load_3d_pair(sa + kPairStageA / 2, &tm_mw64, lb, kb * kBlockK, 0, tc.b + 1);
+              } else {
+                ptx::tma_load_3d_pair(sa, &tm_mw, lb, kb * kBlockK, tc.q0, tc.b);
+              }
               ptx::tma_load_2d_pair(sb, &tm_vh, lb, kb * kBlockK, p.v_row0 + tc.ph * 512 + chunk * 256 + static_cast<int>(rank) * 128);
             } else {
               const int j = kb - kMwKB;
               const int pp = tc.ph + ((j >> 2) - 1) * p.dilation;
               const int dq = pp >> 5;
-              ptx::tma_load_3d_pair(sa, &tm_x_in, lb, (j & 3) * kBlockK, tc.q0 + dq, tc.b * kPhases + pp - (dq << 5));
+              if (half) {
+                ptx::tma_load_3d_pair(sa, &tm_x_in64, lb, (j & 3) * kBlockK, dq, tc.b * kPhases + pp - (dq << 5));
+                ptx::tma_load_3d_pair(sa + kPairStageA / 2, &tm_x_in64, lb, (j & 3) * kBlockK, dq, (tc.b + 1) * kPhases + pp - (dq << 5));
+              } else {
+                ptx::tma_load_3d_pair(sa, &tm_x_in, lb, (j & 3) * kBlockK, tc.q0 + dq, tc.b * kPhases + pp - (dq << 5));
+              }
               ptx::tma_load_2d_pair(sb, &tm_w1h, lb, j * kBlockK, p.w1_row0 + chunk * 256 + static_cast<int>(rank) * 128);
             }
           }
@@ -160,7 +181,12 @@ wn_layer_pair_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {256, Fq
             if (rank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2 * kPairStageBytes);
             const uint32_t lb = ptx::map_to_cta(&full[s], 0);
             ptx::tma_load_2d_pair(sb, &tm_w2h, lb, j * kBlockK, p.w2_row0 + static_cast<int>(rank) * 128);
-            ptx::tma_load_3d_pair(sa, &tm_x_in, lb, j * kBlockK, tc.q0, tc.b * kPhases + tc.ph);
+            if (half) {
+              ptx::tma_load_3d_pair(sa, &tm_x_in64, lb, j * kBlockK, 0, tc.b * kPhases + tc.ph);
+              ptx::tma_load_3d_pair(sa + kPairStageA / 2, &tm_x_in64, lb, j * kBlockK, 0, (tc.b + 1) * kPhases + tc.ph);
+            } else {
+              ptx::tma_load_3d_pair(sa, &tm_x_in, lb, j * kBlockK, tc.q0, tc.b * kPhases + tc.ph);
+            }
           }
         }
       }
@@ -282,20 +308,24 @@ wn_layer_pair_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {256, Fq
       ptx::mbar_wait(d2_full, par);
       ptx::tc_fence_after_sync();
       if (tl) stamp(p, 11);
-      const int t = (tc.q0 + row) * kPhases + tc.ph;
+      // which utterance / frame this TMEM lane is
+      const int row_b = half ? tc.b + (row >> 6) : tc.b;
+      const int row_q = half ? (row & 63) : tc.q0 + row;
+      const bool row_ok = row_b < p.B && row_q < p.Fq;
+      const int t = row_q * kPhases + tc.ph;
       if (hh == 0) {
         uint32_t ve[8];
         ptx::tmem_ld8(rb, ve);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before_sync();
         ptx::mbar_arrive_cluster(l_e_drained);
-        if (tc.q0 + row < p.Fq && t < p.T) {
+        if (row_ok && t < p.T) {
           const float v[8] = {__uint_as_float(ve[0]), __uint_as_float(ve[1]), __uint_as_float(ve[2]), __uint_as_float(ve[3]),
                               __uint_as_float(ve[4]), __uint_as_float(ve[5]), __uint_as_float(ve[6]), __uint_as_float(ve[7])};
-          update_e_row(p.e + (static_cast<size_t>(tc.b) * p.T + t) * 8, v, p.accumulate_e != 0);
+          update_e_row(p.e + (static_cast<size_t>(row_b) * p.T + t) * 8, v, p.accumulate_e != 0);
         }
       }
-      if (p.has_res) stage_residual(ra, s_bias_res, acts, hh, row, t < p.T, p.fmt);
+      if (p.has_res) stage_residual(ra, s_bias_res, acts, hh, row, row_ok && t < p.T, p.fmt);
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive_cluster(l_res_drained);
       if (p.has_res) {
@@ -304,8 +334,15 @@ wn_layer_pair_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {256, Fq
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (warp == 2 && lane == 0) {
 #pragma unroll
-          for (int s4 = 0; s4 < 4; ++s4)
-            ptx::tma_store_3d(&tm_x_out, acts + s4 * (kTileM * 128), s4 * kBlockK, tc.q0, tc.b * kPhases + tc.ph);
+          for (int s4 = 0; s4 < 4; ++s4) {
+            if (half) {
+              if (tc.b < p.B) ptx::tma_store_3d(&tm_x_out64, acts + s4 * (kTileM * 128), s4 * kBlockK, 0, tc.b * kPhases + tc.ph);
+              if (tc.b + 1 < p.B)
+                ptx::tma_store_3d(&tm_x_out64, acts + s4 * (kTileM * 128) + 64 * 128, s4 * kBlockK, 0, (tc.b + 1) * kPhases + tc.ph);
+            } else {
+              ptx::tma_store_3d(&tm_x_out, acts + s4 * (kTileM * 128), s4 * kBlockK, tc.q0, tc.b * kPhases + tc.ph);
+            }
+          }
           ptx::tma_store_commit();
         }
         store_pending = true;

@@ -70,6 +70,7 @@ struct LayerTcParams {
   int Fq;             // mel frame slots per utterance = ceil(T / 32); the x buffers have 32 * Fq rows per utterance
   int B;              // utterances
   int dilation;
+  int seg_rows;       // pair kernel: 128 = a tile is 128 frames of one utterance; 64 = a tile is two whole utterances of <= 64 frames
   int reverse;        // walk the tiles backwards (alternate per layer: the tail of the previous layer's x' is still in L2)
   int w1_row0;        // first packed-W1x row of this (flow, layer)
   int v_row0;         // first packed-V row of this (flow, layer): + phase * 512
