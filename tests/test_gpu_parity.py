@@ -19,8 +19,9 @@ _MODELS = {}
 
 
 def get_model(n_channels: int, precision: str, style: str = "parametrized") -> WaveGlow:
-  """precision: "fp32", "fp16" (default tensor-core path: fused layer on CTA pairs), "fp16-single" (WG_PAIR=0: the same
-  fused layer on single CTAs) or "fp16-wide" (WG_WIDE=1: the two-kernel layer of 512-channel models, forced onto the
+  """precision: "fp32", "fp16" (default tensor-core path: fused layer on CTA pairs, continuous-issue schedule),
+  "fp16-pair1" (WG_PAIR=1: the older CTA-pair schedule with the skip-end outputs on tcgen05), "fp16-single" (WG_PAIR=0: the
+  same fused layer on single CTAs) or "fp16-wide" (WG_WIDE=1: the two-kernel layer of 512-channel models, forced onto the
   256-channel model so that it can be checked against the same references)."""
   import os
   key = (n_channels, precision, style)
@@ -33,6 +34,8 @@ def get_model(n_channels: int, precision: str, style: str = "parametrized") -> W
       os.environ["WG_WIDE"] = "1"
     if precision == "fp16-single":
       os.environ["WG_PAIR"] = "0"
+    if precision == "fp16-pair1":
+      os.environ["WG_PAIR"] = "1"
     try:
       m.engine()          # the engine reads WG_WIDE / WG_PAIR when it is created
     finally:
@@ -78,7 +81,7 @@ def test_tcgen05_cta_pair_gemm():
   assert err <= 2e-3
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16", "fp16-wide", "fp16-single"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "fp16-wide", "fp16-single", "fp16-pair1"])
 def test_stagewise_first_flow(precision):
   """cond (upsample+squeeze), start conv, then every WN layer of the first flow, then the coupling step."""
   op_dtype = torch.float32 if precision == "fp32" else torch.float16
@@ -142,9 +145,14 @@ def test_stagewise_first_flow(precision):
   out = run(model, mel, zs, sigma)
   check("final audio vs engine model", out, ref_audio, t=(2e-5 if precision == "fp32" else 2e-3))
   if precision == "fp16-single":
-    same = run(get_model(256, "fp16"), mel, zs, sigma)
-    print(f"[fp16-single] vs CTA-pair kernel: max-abs {max_abs(same, out):.3e}")
+    same = run(get_model(256, "fp16-pair1"), mel, zs, sigma)
+    print(f"[fp16-single] vs CTA-pair kernel (WG_PAIR=1): max-abs {max_abs(same, out):.3e}")
     assert torch.equal(same, out)      # same operands, same accumulation order: bit-identical
+  if precision == "fp16-pair1":
+    # the default kernel sums the 8 skip-end outputs with mma.sync instead of tcgen05 (another fp32 summation order)
+    same = run(get_model(256, "fp16"), mel, zs, sigma)
+    print(f"[fp16-pair1] vs continuous-issue pair kernel: max-abs {max_abs(same, out):.3e}")
+    assert max_abs(same, out) <= 1e-3
   if precision == "fp16-wide":
     # both tensor-core layer implementations use the same rounded operands but sum in a different order (fp32), and the
     # fp16 re-rounding of x amplifies that: they agree to about the fp16 noise floor, each within the gate of the reference

@@ -3,7 +3,8 @@
   python tools/timeline.py [--batch 16] [--frames 861]
 
 Slots: 0 entry | 1 MMA thread ready | 2 first operands landed | 3 G1a issued | 4 G1b issued | 5 acc a done (epilogue sees it)
-| 6 gate a done | 7 acc b done | 8 gate b done | 9 MMA sees acts | 10 G2 issued | 11 D2 done | 12 x' staged | 13 x' stored | 14 exit
+| 6 gate a done | 7 acc b done | 8 gate b done | 9 MMA sees acts | 10 G2 issued | 11 D2 done | 12 x' staged | 13 x' stored | 14 exit | 15 first operands of tile 2 (continuous
+pair kernel only: there GEMM2 of tile 1 is issued inside tile 2's chunk a, so 9..12 lie after 15)
 """
 import argparse
 import os
@@ -58,6 +59,9 @@ def main():
   print(f"CTA lifetime cycles: median {dur.median():.0f}  p10 {dur.quantile(0.1):.0f}  p90 {dur.quantile(0.9):.0f}")
   span = t[:, 11] - t[:, 2]
   print(f"steady-state tile: first operands of G1a -> D2 done: median {span.median():.0f} cycles")
+  if (t[:, 15] > 0).any():
+    per = (t[:, 15] - t[:, 2])[t[:, 15] > 0]
+    print(f"tile period (first operands of tile 1 -> first operands of tile 2): median {per.median():.0f} cycles")
   g1a = t[:, 5] - t[:, 2]
   g1b = t[:, 7] - t[:, 5]
   print(f"G1a (first operands -> acc a done): median {g1a.median():.0f} cycles = {g1a.median() / 68:.1f} per UTCHMMA (ideal 128)")

@@ -17,6 +17,7 @@
 #include "wg_kernels.cuh"
 #include "wg_layer_tc.cuh"
 #include "wg_layer_pair_tc.cuh"
+#include "wg_layer_pair_cont_tc.cuh"
 #include "wg_layer_wide_tc.cuh"
 
 namespace {
@@ -60,6 +61,7 @@ struct wg_engine {
   CUtensorMap tm_w1{}, tm_v{}, tm_w2a{}, tm_w2b{}, tm_ident{};
   CUtensorMap tm_w1h{}, tm_vh{}, tm_w2h{}, tm_se8{}, tm_ident16{};   // half-height boxes for the CTA-pair kernel
   bool pair = false;                  // fused layer on CTA pairs (cta_group::2); default for 256 channels, WG_PAIR=0 disables
+  bool pair_cont = false;             // ... with the continuous-issue schedule (wg_layer_pair_cont_tc.cuh); WG_PAIR=1 selects the older pair kernel
   // fp32 path
   float* d_w1f = nullptr;             // [flows*layers][K1][2nc]
   float* d_bias1f = nullptr;          // [flows*layers][2nc]
@@ -275,7 +277,9 @@ int wg_create(const wg_config* cfg, wg_engine** out) {
   // default for 256 channels: the fused layer on CTA pairs (bit-identical to the single-CTA kernel, ~3 % faster); WG_PAIR=0 disables
   e->pair = cfg->precision == WG_PRECISION_FP16 && cfg->n_channels == 256 && !e->wide && !(pair_env && atoi(pair_env) == 0) &&
             prop.multiProcessorCount >= 2;
+  e->pair_cont = e->pair && !(pair_env && atoi(pair_env) == 1);
   WG_CUDA(e, cudaFuncSetAttribute(wn_layer_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem::total + 1024));
+  WG_CUDA(e, cudaFuncSetAttribute(wn_layer_pair_cont_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ContSmem::total + 1024));
   const char* dbg_env = getenv("WG_DBG_FLAGS");
   e->dbg_flags = dbg_env ? atoi(dbg_env) : 0;
   WG_CUDA(e, cudaFuncSetAttribute(wn_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total + 1024));
@@ -707,9 +711,16 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
         const int n_tile_entries = lp.seg_rows == 64 ? (B + 1) / 2 : ((lp.Fq + kTileM - 1) / kTileM) * B;
         const int n_ptiles = kPhases * ((n_tile_entries + 1) / 2);
         const int n_pairs = n_ptiles < e->num_sms / 2 ? n_ptiles : e->num_sms / 2;
-        wn_layer_pair_kernel<<<dim3(2 * n_pairs), kTcThreads, PairSmem::total + 1024, st>>>(
-            tm_x[*cur], tm_x[*cur ^ 1], *tm_cond, e->tm_w1h, e->tm_vh, e->tm_w2h, e->tm_se8, e->tm_ident16, tm_x[3 + *cur],
-            tm_x[3 + (*cur ^ 1)], tm_x[5], lp);
+        if (e->pair_cont) {
+          lp.wse = static_cast<const uint16_t*>(e->d_w2) + (li * kW2Rows + 256) * 256;
+          wn_layer_pair_cont_kernel<<<dim3(2 * n_pairs), kTcThreads, ContSmem::total + 1024, st>>>(
+              tm_x[*cur], tm_x[*cur ^ 1], *tm_cond, e->tm_w1h, e->tm_vh, e->tm_w2h, e->tm_ident16, tm_x[3 + *cur], tm_x[3 + (*cur ^ 1)],
+              tm_x[5], lp);
+        } else {
+          wn_layer_pair_kernel<<<dim3(2 * n_pairs), kTcThreads, PairSmem::total + 1024, st>>>(
+              tm_x[*cur], tm_x[*cur ^ 1], *tm_cond, e->tm_w1h, e->tm_vh, e->tm_w2h, e->tm_se8, e->tm_ident16, tm_x[3 + *cur],
+              tm_x[3 + (*cur ^ 1)], tm_x[5], lp);
+        }
         e->launches++;
         if (has_res) *cur ^= 1;
         if (e->dbg_flow == k && e->dbg_layer == i) {

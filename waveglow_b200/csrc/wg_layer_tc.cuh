@@ -81,6 +81,7 @@ struct LayerTcParams {
   const float* bias1;     // [512] packed order, b_in + b_cond
   const float* bias_res;  // [256]
   float* e;               // [B, T, 8] fp32
+  const void* wse;        // continuous pair kernel: this layer's skip-end weights, 16-bit [8][256] (rows 256.. of its packed W2)
   int dbg_flags;          // diagnostics only: bit0 skip GEMM1 B loads, bit1 skip GEMM1 A loads (results invalid)
   long long* timeline;    // optional [n_ctas][16] clock64 stamps (diagnostics; nullptr in production)
 };

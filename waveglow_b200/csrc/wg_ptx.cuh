@@ -222,6 +222,26 @@ __device__ __forceinline__ void mma_commit_pair(uint64_t* bar, uint16_t cta_mask
                : "memory");
 }
 
+// ------------------------------------------------------------------ warp-level mma.sync (small side GEMMs in epilogue warps)
+// four 8x8 16-bit matrices; lane l supplies the row address of row (l & 7) of matrix (l >> 3)
+__device__ __forceinline__ void ldmatrix_x4(uint32_t smem_addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_addr)
+               : "memory");
+}
+// D[16x8] += A[16x16] . B[16x8], fp32 accumulate; fmt 0 = fp16 operands, 1 = bf16
+__device__ __forceinline__ void mma_m16n8k16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, int fmt) {
+  if (fmt == 0)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 // ------------------------------------------------------------------ math
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
