@@ -705,18 +705,45 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
       lp.timeline = e->dbg_timeline;
       lp.dbg_flags = e->dbg_flags;
       const int n_tiles = kPhases * ((lp.Fq + kTileM - 1) / kTileM) * B;
+      if (e->pair && e->pair_cont) {
+        // tiles are built from 128-, 64- or 32-frame segments (one TMA box each).  Smaller boxes cost tile time (measured on
+        // config 2: 4 x 32-row boxes per operand load = +5.4 % per tile, so 861 frames as 27 x 32 instead of 7 x 128 is a wash),
+        // so a smaller segment is taken only when it saves clearly more pair-tiles than that (two whole 63-frame training
+        // segments per tile: -50 %; 40-frame utterances as 2 x 32: -20 %)
+        static const double kBoxCost[3] = {1.0, 1.02, 1.06};
+        int best_pe = 0, best_idx = 0;
+        for (int idx = 0; idx < 3; ++idx) {
+          const int seg = kTileM >> idx;
+          const int n_entries = (B * ((lp.Fq + seg - 1) / seg) + (1 << idx) - 1) >> idx;
+          const int n_pe = (n_entries + 1) / 2;
+          if (idx == 0 || n_pe * kBoxCost[idx] < best_pe * kBoxCost[best_idx]) {
+            best_pe = n_pe;
+            best_idx = idx;
+          }
+        }
+        lp.seg_rows = kTileM >> best_idx;
+        const int n_ptiles = kPhases * best_pe;
+        const int n_pairs = n_ptiles < e->num_sms / 2 ? n_ptiles : e->num_sms / 2;
+        lp.wse = static_cast<const uint16_t*>(e->d_w2) + (li * kW2Rows + 256) * 256;
+        const CUtensorMap* seg_maps = tm_x + (best_idx == 0 ? 0 : (best_idx == 1 ? 3 : 6));      // {x0, x1, .., mel windows}
+        const CUtensorMap& tm_mw_seg = best_idx == 0 ? *tm_cond : seg_maps[2];
+        wn_layer_pair_cont_kernel<<<dim3(2 * n_pairs), kTcThreads, ContSmem::total + 1024, st>>>(
+            seg_maps[*cur], seg_maps[*cur ^ 1], tm_mw_seg, e->tm_w1h, e->tm_vh, e->tm_w2h, e->tm_ident16, lp);
+        e->launches++;
+        if (has_res) *cur ^= 1;
+        if (e->dbg_flow == k && e->dbg_layer == i) {
+          *stopped = true;
+          return WG_OK;
+        }
+        continue;
+      }
       if (e->pair) {
         // two whole utterances per tile when they are short (config 5's 63-frame training segments)
         lp.seg_rows = (lp.Fq <= 64 && B >= 2) ? 64 : 128;
         const int n_tile_entries = lp.seg_rows == 64 ? (B + 1) / 2 : ((lp.Fq + kTileM - 1) / kTileM) * B;
         const int n_ptiles = kPhases * ((n_tile_entries + 1) / 2);
         const int n_pairs = n_ptiles < e->num_sms / 2 ? n_ptiles : e->num_sms / 2;
-        if (e->pair_cont) {
-          lp.wse = static_cast<const uint16_t*>(e->d_w2) + (li * kW2Rows + 256) * 256;
-          wn_layer_pair_cont_kernel<<<dim3(2 * n_pairs), kTcThreads, ContSmem::total + 1024, st>>>(
-              tm_x[*cur], tm_x[*cur ^ 1], *tm_cond, e->tm_w1h, e->tm_vh, e->tm_w2h, e->tm_ident16, tm_x[3 + *cur], tm_x[3 + (*cur ^ 1)],
-              tm_x[5], lp);
-        } else {
+        {
           wn_layer_pair_kernel<<<dim3(2 * n_pairs), kTcThreads, PairSmem::total + 1024, st>>>(
               tm_x[*cur], tm_x[*cur ^ 1], *tm_cond, e->tm_w1h, e->tm_vh, e->tm_w2h, e->tm_se8, e->tm_ident16, tm_x[3 + *cur],
               tm_x[3 + (*cur ^ 1)], tm_x[5], lp);
@@ -787,7 +814,8 @@ void launch_conditioning(wg_engine* e, const float* mel, int B, int frames, int 
 
 int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CUtensorMap* tm_x, CUtensorMap* tm_cond) {
   // tm_x[0], tm_x[1]: residual stream ping-pong; tm_x[2]: gated activations of the wide path (same geometry);
-  // tm_x[3], tm_x[4]: the ping-pong buffers again with 64-row boxes, tm_x[5]: mel windows with 64-row boxes (short utterances)
+  // tm_x[3], tm_x[4]: the ping-pong buffers again with 64-row boxes, tm_x[5]: mel windows with 64-row boxes;
+  // tm_x[6], tm_x[7], tm_x[8]: the same three with 32-row boxes (segment tiles of the CTA-pair kernels)
   const CUtensorMapDataType dt = e->op_fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const int nc = e->cfg.n_channels;
   int rc;
@@ -800,17 +828,20 @@ int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CU
     if ((rc = make_map(e, &tm_x[0], ws + L.x0, 3, dims, str, box, dt))) return rc;
     if ((rc = make_map(e, &tm_x[1], ws + L.x1, 3, dims, str, box, dt))) return rc;
     if (e->wide && (rc = make_map(e, &tm_x[2], ws + L.acts, 3, dims, str, box, dt))) return rc;
-    const uint32_t box64[3] = {64, 64, 1};
+    const uint32_t box64[3] = {64, 64, 1}, box32[3] = {64, 32, 1};
     if ((rc = make_map(e, &tm_x[3], ws + L.x0, 3, dims, str, box64, dt))) return rc;
     if ((rc = make_map(e, &tm_x[4], ws + L.x1, 3, dims, str, box64, dt))) return rc;
+    if ((rc = make_map(e, &tm_x[6], ws + L.x0, 3, dims, str, box32, dt))) return rc;
+    if ((rc = make_map(e, &tm_x[7], ws + L.x1, 3, dims, str, box32, dt))) return rc;
   }
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(kUpKdim), static_cast<uint64_t>(Fq), static_cast<uint64_t>(B)};
     const uint64_t str[2] = {static_cast<uint64_t>(kUpKdim) * 2, static_cast<uint64_t>(kUpKdim) * 2 * Fq};
     const uint32_t box[3] = {64, static_cast<uint32_t>(kTileM), 1};
     if ((rc = make_map(e, tm_cond, ws + L.cond, 3, dims, str, box, dt))) return rc;
-    const uint32_t box64[3] = {64, 64, 1};
+    const uint32_t box64[3] = {64, 64, 1}, box32[3] = {64, 32, 1};
     if ((rc = make_map(e, &tm_x[5], ws + L.cond, 3, dims, str, box64, dt))) return rc;
+    if ((rc = make_map(e, &tm_x[8], ws + L.cond, 3, dims, str, box32, dt))) return rc;
   }
   return WG_OK;
 }
@@ -861,7 +892,7 @@ int wg_infer(wg_engine* e, const float* mel, int32_t batch, int32_t frames, cons
   }
   // 2. conditioning operand (mel windows in tensor-core mode, upsampled + squeezed mel in fp32 mode)
   launch_conditioning(e, mel, B, frames, T, ws, L, st);
-  CUtensorMap tm_x[6], tm_cond;
+  CUtensorMap tm_x[9], tm_cond;
   if (tc) {
     int rc = make_act_maps(e, ws, L, B, T, tm_x, &tm_cond);
     if (rc) return rc;
@@ -967,7 +998,7 @@ int wg_forward(wg_engine* e, const float* mel, int32_t batch, int32_t frames, co
   WG_CUDA(e, cudaMemcpyAsync(state, audio_in, npos * kGroup * sizeof(float), cudaMemcpyDeviceToDevice, st));
   WG_CUDA(e, cudaMemsetAsync(sums, 0, NF * sizeof(double), st));
   launch_conditioning(e, mel, B, frames, T, ws, L, st);
-  CUtensorMap tm_x[6], tm_cond;
+  CUtensorMap tm_x[9], tm_cond;
   if (tc) {
     int rc = make_act_maps(e, ws, L, B, T, tm_x, &tm_cond);
     if (rc) return rc;

@@ -30,16 +30,13 @@ struct ContSmem {
 static_assert(ContSmem::total + 1024 <= 232448, "shared memory budget exceeded");
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
-wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {256, Fq, 32 B} box {64,128,1}
+wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {256, Fq, 32 B} box {64, seg_rows, 1}
                           const __grid_constant__ CUtensorMap tm_x_out,   // same geometry, other buffer
-                          const __grid_constant__ CUtensorMap tm_mw,      // {320, Fq, B} box {64,128,1}
+                          const __grid_constant__ CUtensorMap tm_mw,      // {320, Fq, B} box {64, seg_rows, 1}
                           const __grid_constant__ CUtensorMap tm_w1h,     // {768, rows} box {64,128}
                           const __grid_constant__ CUtensorMap tm_vh,      // {320, rows} box {64,128}
                           const __grid_constant__ CUtensorMap tm_w2h,     // {256, rows} box {64,128}
                           const __grid_constant__ CUtensorMap tm_ident16, // {64, 32} box {64,16}
-                          const __grid_constant__ CUtensorMap tm_x_in64,  // as tm_x_in, box {64,64,1}   (two short utterances per tile)
-                          const __grid_constant__ CUtensorMap tm_x_out64, // as tm_x_out, box {64,64,1}
-                          const __grid_constant__ CUtensorMap tm_mw64,    // as tm_mw, box {64,64,1}
                           const LayerTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -58,33 +55,36 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  // pair-tile = (pair of consecutive (utterance, 128-frame block) entries, phase); phase fastest.  CTA `rank` owns entry 2 pe + rank.
-  // Short utterances (seg_rows == 64): a tile holds TWO whole utterances (rows 0..63 and 64..127) as two 64-row TMA boxes.
-  const bool half = p.seg_rows == 64;
-  const int nqb = (p.Fq + kTileM - 1) / kTileM;
-  const int n_entries = half ? (p.B + 1) / 2 : p.B * nqb;
+  // A tile is 128 / seg_rows SEGMENTS of seg_rows (128, 64 or 32) consecutive frames, all of one phase; segments are numbered
+  // utterance-major, so a tile may span utterances: the host picks the segment size that wastes the fewest rows (861 frames =
+  // 27 segments of 32 instead of 7 blocks of 128; two whole 63-frame training segments per tile).  Each segment is one TMA box.
+  // pair-tile = (pair of consecutive tiles, phase), phase fastest; CTA `rank` owns tile 2 pe + rank.
+  const int seg = p.seg_rows;
+  const int seg_shift = seg == 128 ? 7 : (seg == 64 ? 6 : 5);
+  const int n_sub = kTileM >> seg_shift;
+  const int nseg = (p.Fq + seg - 1) >> seg_shift;          // segments per utterance
+  const int total_segs = p.B * nseg;
+  const int n_entries = (total_segs + n_sub - 1) / n_sub;
   const int n_pe = (n_entries + 1) / 2;
   const int n_ptiles = n_pe * kPhases;
   const int my_tiles = (n_ptiles - pair + n_pairs - 1) / n_pairs;
 
   struct Coord {
-    int b, ph, q0;
+    int ph, seg0;      // phase; first segment of the tile (>= total_segs: dummy tile, every row out of range)
   };
   auto tile_of = [&](int it) {
     int pt = pair + it * n_pairs;
     if (p.reverse) pt = n_ptiles - 1 - pt;
-    const int entry = 2 * (pt / kPhases) + static_cast<int>(rank);
-    const bool valid = entry < n_entries;
     Coord c;
     c.ph = pt % kPhases;
-    if (half) {
-      c.b = valid ? 2 * entry : p.B;                   // utterances b, b + 1 (b + 1 may not exist: its rows read zeros, store nothing)
-      c.q0 = 0;
-    } else {
-      c.b = valid ? entry / nqb : 0;
-      c.q0 = valid ? (entry % nqb) * kTileM : p.Fq;    // an odd entry count leaves one dummy tile: every row out of range
-    }
+    c.seg0 = (2 * (pt / kPhases) + static_cast<int>(rank)) * n_sub;
     return c;
+  };
+  // segment -> (utterance, first frame); a segment past the end maps to utterance B: TMA reads zeros there and nothing is stored
+  auto seg_coord = [&](int sg, int& b, int& q0) {
+    const bool valid = sg < total_segs;
+    b = valid ? sg / nseg : p.B;
+    q0 = valid ? (sg - b * nseg) << seg_shift : 0;
   };
 
   if (threadIdx.x == 0 && rank == 0) stamp(p, 0);
@@ -138,42 +138,46 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
         if (rank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2 * kPairStageBytes);
         lb = ptx::map_to_cta(&full[s], 0);
       };
-      // rows [q0 + dq, +128) of x at (utterance, phase pp) for channel block cb -- or two 64-row boxes of two utterances
-      auto load_x = [&](const Coord& tc, int cb, int dq, int pp) {
-        if (half) {
-          ptx::tma_load_3d_pair(sa, &tm_x_in64, lb, cb * kBlockK, dq, tc.b * kPhases + pp);
-          ptx::tma_load_3d_pair(sa + kPairStageA / 2, &tm_x_in64, lb, cb * kBlockK, dq, (tc.b + 1) * kPhases + pp);
-        } else {
-          ptx::tma_load_3d_pair(sa, &tm_x_in, lb, cb * kBlockK, tc.q0 + dq, tc.b * kPhases + pp);
-        }
+      int sb_[4], sq_[4];            // (utterance, first frame) of the segments of the tile being loaded
+      auto set_tile = [&](const Coord& tc) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) seg_coord(tc.seg0 + i, sb_[i], sq_[i]);
+      };
+      // x rows of the current tile shifted by dq frames, phase pp, channel block cb: one box per segment
+      auto load_x = [&](int cb, int dq, int pp) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < n_sub) ptx::tma_load_3d_pair(sa + ((i << seg_shift) * 128), &tm_x_in, lb, cb * kBlockK, sq_[i] + dq, sb_[i] * kPhases + pp);
       };
       // GEMM2 operands of a tile: W_res K-block j (own 128 rows) + x(t) K-block j for the identity carry
       auto load_gemm2 = [&](const Coord& tc) {
+        set_tile(tc);
         for (int j = 0; j < 4; ++j) {
           next_stage();
           ptx::tma_load_2d_pair(sb, &tm_w2h, lb, j * kBlockK, p.w2_row0 + static_cast<int>(rank) * 128);
-          load_x(tc, j, 0, tc.ph);
+          load_x(j, 0, tc.ph);
         }
       };
       for (int it = 0; it < my_tiles; ++it) {
         const Coord tc = tile_of(it);
+        set_tile(tc);
         for (int chunk = 0; chunk < 2; ++chunk) {
           for (int kb = 0; kb < kKB1; ++kb) {
-            if (chunk == 0 && kb == kG2At && it > 0 && p.has_res) load_gemm2(tile_of(it - 1));
+            if (chunk == 0 && kb == kG2At && it > 0 && p.has_res) {
+              load_gemm2(tile_of(it - 1));
+              set_tile(tc);
+            }
             next_stage();
             if (kb < kMwKB) {
-              if (half) {
-                ptx::tma_load_3d_pair(sa, &tm_mw64, lb, kb * kBlockK, 0, tc.b);
-                ptx::tma_load_3d_pair(sa + kPairStageA / 2, &tm_mw64, lb, kb * kBlockK, 0, tc.b + 1);
-              } else {
-                ptx::tma_load_3d_pair(sa, &tm_mw, lb, kb * kBlockK, tc.q0, tc.b);
-              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (i < n_sub) ptx::tma_load_3d_pair(sa + ((i << seg_shift) * 128), &tm_mw, lb, kb * kBlockK, sq_[i], sb_[i]);
               ptx::tma_load_2d_pair(sb, &tm_vh, lb, kb * kBlockK, p.v_row0 + tc.ph * 512 + chunk * 256 + static_cast<int>(rank) * 128);
             } else {
               const int j = kb - kMwKB;          // 0..11: tap (j >> 2) in {t-d, t, t+d}, channel block (j & 3)
               const int pp = tc.ph + ((j >> 2) - 1) * p.dilation;
               const int dq = pp >> 5;            // floor division by 32
-              load_x(tc, j & 3, dq, pp - (dq << 5));
+              load_x(j & 3, dq, pp - (dq << 5));
               ptx::tma_load_2d_pair(sb, &tm_w1h, lb, j * kBlockK, p.w1_row0 + chunk * 256 + static_cast<int>(rank) * 128);
             }
           }
@@ -336,8 +340,9 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
 #pragma unroll
         for (int hr = 0; hr < 2; ++hr) {
           const int r = 16 * ew + (lane >> 2) + 8 * hr;
-          const int r_b = half ? tc.b + (r >> 6) : tc.b;
-          const int r_q = half ? (r & 63) : tc.q0 + r;
+          int r_b, r_q;
+          seg_coord(tc.seg0 + (r >> seg_shift), r_b, r_q);
+          r_q += r & (seg - 1);
           const int t = r_q * kPhases + tc.ph;
           if (r_b < p.B && r_q < p.Fq && t < p.T) {
             float2* ep = reinterpret_cast<float2*>(p.e + (static_cast<size_t>(r_b) * p.T + t) * 8 + 2 * (lane & 3));
@@ -358,8 +363,9 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
         ptx::tc_fence_after_sync();
         if (tl) stamp(p, 11);
         asm volatile("bar.sync 1, 256;" ::: "memory");    // every warp has finished its ldmatrix reads of acts
-        const int row_b = half ? tc.b + (row >> 6) : tc.b;
-        const int row_q = half ? (row & 63) : tc.q0 + row;
+        int row_b, row_q;
+        seg_coord(tc.seg0 + (row >> seg_shift), row_b, row_q);
+        row_q += row & (seg - 1);
         const bool row_ok = row_b < p.B && row_q < p.Fq && row_q * kPhases + tc.ph < p.T;
         stage_residual(lane_base + 256, s_bias_res, acts, hh, row, row_ok, p.fmt);
         ptx::tc_fence_before_sync();
@@ -368,15 +374,13 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
         if (tl) stamp(p, 12);
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (warp == 2 && lane == 0) {
+          for (int i = 0; i < n_sub; ++i) {
+            int sb2, sq2;
+            seg_coord(tc.seg0 + i, sb2, sq2);
+            if (sb2 >= p.B) continue;
 #pragma unroll
-          for (int s4 = 0; s4 < 4; ++s4) {
-            if (half) {
-              if (tc.b < p.B) ptx::tma_store_3d(&tm_x_out64, acts + s4 * (kTileM * 128), s4 * kBlockK, 0, tc.b * kPhases + tc.ph);
-              if (tc.b + 1 < p.B)
-                ptx::tma_store_3d(&tm_x_out64, acts + s4 * (kTileM * 128) + 64 * 128, s4 * kBlockK, 0, (tc.b + 1) * kPhases + tc.ph);
-            } else {
-              ptx::tma_store_3d(&tm_x_out, acts + s4 * (kTileM * 128), s4 * kBlockK, tc.q0, tc.b * kPhases + tc.ph);
-            }
+            for (int s4 = 0; s4 < 4; ++s4)
+              ptx::tma_store_3d(&tm_x_out, acts + s4 * (kTileM * 128) + ((i << seg_shift) * 128), s4 * kBlockK, sq2, sb2 * kPhases + tc.ph);
           }
           ptx::tma_store_commit();
         }
