@@ -22,7 +22,8 @@ def get_model(n_channels: int, precision: str, style: str = "parametrized") -> W
   """precision: "fp32", "fp16" (default tensor-core path: fused layer on CTA pairs, continuous-issue schedule),
   "fp16-pair1" (WG_PAIR=1: the older CTA-pair schedule with the skip-end outputs on tcgen05), "fp16-single" (WG_PAIR=0: the
   same fused layer on single CTAs) or "fp16-wide" (WG_WIDE=1: the two-kernel layer of 512-channel models, forced onto the
-  256-channel model so that it can be checked against the same references)."""
+  256-channel model so that it can be checked against the same references); "fp16-seg32" / "fp16-seg64" (WG_SEG) force
+  the segment size of the default kernel's tiles."""
   import os
   key = (n_channels, precision, style)
   if key not in _MODELS:
@@ -36,11 +37,14 @@ def get_model(n_channels: int, precision: str, style: str = "parametrized") -> W
       os.environ["WG_PAIR"] = "0"
     if precision == "fp16-pair1":
       os.environ["WG_PAIR"] = "1"
+    if precision.startswith("fp16-seg"):
+      os.environ["WG_SEG"] = precision[len("fp16-seg"):]
     try:
       m.engine()          # the engine reads WG_WIDE / WG_PAIR when it is created
     finally:
       os.environ.pop("WG_WIDE", None)
       os.environ.pop("WG_PAIR", None)
+      os.environ.pop("WG_SEG", None)
     _MODELS[key] = m
   return _MODELS[key]
 
@@ -200,6 +204,41 @@ def test_wide_tensor_core_path_matches_reference_golden(name, nc, mode):
   err, snr = max_abs(ref, out), snr_db(ref, out)
   print(f"{mode} {name}: max-abs {err:.3e}  snr {snr:.1f} dB")
   assert out.shape == ref.shape and err <= FP16_MAX_ABS and snr >= FP16_MIN_SNR_DB
+
+
+@pytest.mark.parametrize("mode", ["fp16-seg32", "fp16-seg64"])
+@pytest.mark.parametrize("name", ["infer_c256_b2_f12", "infer_c256_b1_f40", "infer_c256_b3_f7_ragged"])
+def test_segment_tiles_match_reference_golden(name, mode):
+  """Tiles built from 32- or 64-frame segments (several TMA boxes per operand load, tiles spanning utterances), forced with
+  WG_SEG on shapes that would otherwise use one 128-frame box: same golden gates, and bit-identical to the default choice
+  (the segment size only changes which rows share a tile)."""
+  g = load_golden(name)
+  model = get_model(256, mode, str(g["weight_style"]))
+  mel, zs, sigma = torch.from_numpy(g["mel"]), golden_noise(g), float(g["sigma"])
+  out = run(model, mel, zs, sigma)
+  ref = torch.from_numpy(g["audio"])
+  err, snr = max_abs(ref, out), snr_db(ref, out)
+  print(f"{mode} {name}: max-abs {err:.3e}  snr {snr:.1f} dB")
+  assert out.shape == ref.shape and err <= FP16_MAX_ABS and snr >= FP16_MIN_SNR_DB
+  assert torch.equal(out, run(get_model(256, "fp16", str(g["weight_style"])), mel, zs, sigma))
+
+
+def test_segment_choice_short_utterances_vs_oracle():
+  """B=8 x 72 frames: the engine itself picks 32-frame segments here (18 tile entries instead of 32 of 128 frames); a tile
+  then holds the tail of one utterance and the head of the next."""
+  hp, sd, w, dims = synthetic_weights(256)
+  model = get_model(256, "fp16")
+  B, F = 8, 72
+  mel = synthetic_mel(B, F, 411)
+  zs = synthetic_noise(hp, B, F * 32, 412)
+  with torch.no_grad():
+    ref = O.infer(w, dims, mel, 0.666, zs)
+  out = run(model, mel, zs, 0.666)
+  err, snr = max_abs(ref, out), snr_db(ref, out)
+  print(f"fp16 B8 F72 (32-frame segments): max-abs {err:.3e}  snr {snr:.1f} dB")
+  assert err <= FP16_MAX_ABS and snr >= FP16_MIN_SNR_DB
+  alone = run(model, mel[5:6], [z[5:6] for z in zs], 0.666)
+  assert torch.equal(out[5:6], alone)
 
 
 @pytest.mark.parametrize("B,F", [(1, 1), (5, 3), (2, 129), (1, 257)])

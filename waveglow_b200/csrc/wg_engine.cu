@@ -61,6 +61,8 @@ struct wg_engine {
   CUtensorMap tm_w1{}, tm_v{}, tm_w2a{}, tm_w2b{}, tm_ident{};
   CUtensorMap tm_w1h{}, tm_vh{}, tm_w2h{}, tm_se8{}, tm_ident16{};   // half-height boxes for the CTA-pair kernel
   bool pair = false;                  // fused layer on CTA pairs (cta_group::2); default for 256 channels, WG_PAIR=0 disables
+  int g2_at = 9;                      // see LayerTcParams::g2_at (WG_G2AT env overrides, diagnostics)
+  int force_seg = 0;                  // WG_SEG env (tests/diagnostics): force the segment size (128 / 64 / 32) of the continuous pair kernel
   bool pair_cont = false;             // ... with the continuous-issue schedule (wg_layer_pair_cont_tc.cuh); WG_PAIR=1 selects the older pair kernel
   // fp32 path
   float* d_w1f = nullptr;             // [flows*layers][K1][2nc]
@@ -278,6 +280,13 @@ int wg_create(const wg_config* cfg, wg_engine** out) {
   e->pair = cfg->precision == WG_PRECISION_FP16 && cfg->n_channels == 256 && !e->wide && !(pair_env && atoi(pair_env) == 0) &&
             prop.multiProcessorCount >= 2;
   e->pair_cont = e->pair && !(pair_env && atoi(pair_env) == 1);
+  const char* g2_env = getenv("WG_G2AT");
+  if (g2_env) e->g2_at = atoi(g2_env);
+  if (e->g2_at < 0 || e->g2_at >= kKB1) return fail(e, WG_ERR_INVALID_ARGUMENT, "WG_G2AT must be in [0, %d)", kKB1);
+  const char* seg_env = getenv("WG_SEG");
+  e->force_seg = seg_env ? atoi(seg_env) : 0;
+  if (e->force_seg != 0 && e->force_seg != 128 && e->force_seg != 64 && e->force_seg != 32)
+    return fail(e, WG_ERR_INVALID_ARGUMENT, "WG_SEG must be 128, 64 or 32 (got %d)", e->force_seg);
   WG_CUDA(e, cudaFuncSetAttribute(wn_layer_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem::total + 1024));
   WG_CUDA(e, cudaFuncSetAttribute(wn_layer_pair_cont_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ContSmem::total + 1024));
   const char* dbg_env = getenv("WG_DBG_FLAGS");
@@ -716,7 +725,7 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
           const int seg = kTileM >> idx;
           const int n_entries = (B * ((lp.Fq + seg - 1) / seg) + (1 << idx) - 1) >> idx;
           const int n_pe = (n_entries + 1) / 2;
-          if (idx == 0 || n_pe * kBoxCost[idx] < best_pe * kBoxCost[best_idx]) {
+          if (e->force_seg ? seg == e->force_seg : (idx == 0 || n_pe * kBoxCost[idx] < best_pe * kBoxCost[best_idx])) {
             best_pe = n_pe;
             best_idx = idx;
           }
@@ -725,10 +734,12 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
         const int n_ptiles = kPhases * best_pe;
         const int n_pairs = n_ptiles < e->num_sms / 2 ? n_ptiles : e->num_sms / 2;
         lp.wse = static_cast<const uint16_t*>(e->d_w2) + (li * kW2Rows + 256) * 256;
+        lp.g2_at = e->g2_at;
+        lp.x_out = xb[*cur ^ 1];
         const CUtensorMap* seg_maps = tm_x + (best_idx == 0 ? 0 : (best_idx == 1 ? 3 : 6));      // {x0, x1, .., mel windows}
         const CUtensorMap& tm_mw_seg = best_idx == 0 ? *tm_cond : seg_maps[2];
-        wn_layer_pair_cont_kernel<<<dim3(2 * n_pairs), kTcThreads, ContSmem::total + 1024, st>>>(
-            seg_maps[*cur], seg_maps[*cur ^ 1], tm_mw_seg, e->tm_w1h, e->tm_vh, e->tm_w2h, e->tm_ident16, lp);
+        wn_layer_pair_cont_kernel<<<dim3(2 * n_pairs), kContThreads, ContSmem::total + 1024, st>>>(
+            seg_maps[*cur], tm_mw_seg, e->tm_w1h, e->tm_vh, e->tm_w2h, e->tm_ident16, lp);
         e->launches++;
         if (has_res) *cur ^= 1;
         if (e->dbg_flow == k && e->dbg_layer == i) {

@@ -81,8 +81,11 @@ struct LayerTcParams {
   const float* bias1;     // [512] packed order, b_in + b_cond
   const float* bias_res;  // [256]
   float* e;               // [B, T, 8] fp32
+  int g2_at;              // continuous pair kernel: GEMM2 of tile i-1 is issued before this k-block of tile i's chunk a
+  void* x_out;            // continuous pair kernel: the residual stream it writes (phase-major [B][32][Fq][256], 16-bit), plain stores
   const void* wse;        // continuous pair kernel: this layer's skip-end weights, 16-bit [8][256] (rows 256.. of its packed W2)
-  int dbg_flags;          // diagnostics only: bit0 skip GEMM1 B loads, bit1 skip GEMM1 A loads (results invalid)
+  int dbg_flags;          // diagnostics only (results invalid): bit0 skip GEMM1 B loads, bit1 skip GEMM1 A loads; continuous pair
+                          // kernel: 1 skip all operand loads, 4 skip the gate math, 8 skip x' staging + store, 16 skip the skip-end GEMM
   long long* timeline;    // optional [n_ctas][16] clock64 stamps (diagnostics; nullptr in production)
 };
 
@@ -117,18 +120,99 @@ __device__ __forceinline__ void gate_chunk(uint32_t rc, uint8_t* acts, int chunk
     ptx::tmem_ld16(rc + col, vt);
     ptx::tmem_ld16(rc + col + 128, vs);
     ptx::tmem_ld_wait();
+    // 16 + 16 biases as eight 16-byte loads (every lane reads the same address: one shared-memory wavefront per load;
+    // scalar loads would spend 4x the wavefronts of the operand-fed shared-memory port on 4 useful bytes each)
+    float bt_[16], bs_[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t4 = kGlobalBias ? __ldg(reinterpret_cast<const float4*>(bt + g * 16) + i) : reinterpret_cast<const float4*>(bt + g * 16)[i];
+      const float4 s4 = kGlobalBias ? __ldg(reinterpret_cast<const float4*>(bs + g * 16) + i) : reinterpret_cast<const float4*>(bs + g * 16)[i];
+      bt_[4 * i] = t4.x; bt_[4 * i + 1] = t4.y; bt_[4 * i + 2] = t4.z; bt_[4 * i + 3] = t4.w;
+      bs_[4 * i] = s4.x; bs_[4 * i + 1] = s4.y; bs_[4 * i + 2] = s4.z; bs_[4 * i + 3] = s4.w;
+    }
     uint32_t pk[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int j = g * 16 + 2 * i;
-      const float bt0 = kGlobalBias ? __ldg(bt + j) : bt[j], bt1 = kGlobalBias ? __ldg(bt + j + 1) : bt[j + 1];
-      const float bs0 = kGlobalBias ? __ldg(bs + j) : bs[j], bs1 = kGlobalBias ? __ldg(bs + j + 1) : bs[j + 1];
-      pk[i] = pack_pair(gate_one(__uint_as_float(vt[2 * i]) + bt0, __uint_as_float(vs[2 * i]) + bs0),
-                        gate_one(__uint_as_float(vt[2 * i + 1]) + bt1, __uint_as_float(vs[2 * i + 1]) + bs1), fmt);
+      pk[i] = pack_pair(gate_one(__uint_as_float(vt[2 * i]) + bt_[2 * i], __uint_as_float(vs[2 * i]) + bs_[2 * i]),
+                        gate_one(__uint_as_float(vt[2 * i + 1]) + bt_[2 * i + 1], __uint_as_float(vs[2 * i + 1]) + bs_[2 * i + 1]), fmt);
     }
     // 128-byte swizzle: 16-byte chunk index XOR (row mod 8)
     const int c0 = (2 * g) ^ (row & 7);
     const int c1 = (2 * g + 1) ^ (row & 7);
+    *reinterpret_cast<uint4*>(slab_row + c0 * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(slab_row + c1 * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+}
+
+// gate_chunk with the TMEM loads of column group g + 1 in flight while group g is gated (tcgen05.wait::ld waits for all
+// outstanding loads, so the next pair is issued right after the wait and before the math).  Used by the continuous pair
+// kernel, whose gates run while the tensor pipe is busy and see a much longer tcgen05.ld latency than an idle pipe gives.
+__device__ __forceinline__ void gate_chunk_pipelined(uint32_t rc, uint8_t* acts, int chunk, int hh, int row, const float* bt, int fmt) {
+  uint8_t* slab_row = acts + (2 * chunk + hh) * (kTileM * 128) + row * 128;
+  bt += hh * 64;
+  const float* bs = bt + 128;
+  uint32_t vt[2][16], vs[2][16];
+  ptx::tmem_ld16(rc + hh * 64, vt[0]);
+  ptx::tmem_ld16(rc + hh * 64 + 128, vs[0]);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    ptx::tmem_ld_wait();
+    if (g < 3) {
+      ptx::tmem_ld16(rc + hh * 64 + (g + 1) * 16, vt[(g + 1) & 1]);
+      ptx::tmem_ld16(rc + hh * 64 + (g + 1) * 16 + 128, vs[(g + 1) & 1]);
+    }
+    const uint32_t(&t)[16] = vt[g & 1];
+    const uint32_t(&u)[16] = vs[g & 1];
+    float bt_[16], bs_[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t4 = reinterpret_cast<const float4*>(bt + g * 16)[i];
+      const float4 s4 = reinterpret_cast<const float4*>(bs + g * 16)[i];
+      bt_[4 * i] = t4.x; bt_[4 * i + 1] = t4.y; bt_[4 * i + 2] = t4.z; bt_[4 * i + 3] = t4.w;
+      bs_[4 * i] = s4.x; bs_[4 * i + 1] = s4.y; bs_[4 * i + 2] = s4.z; bs_[4 * i + 3] = s4.w;
+    }
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      pk[i] = pack_pair(gate_one(__uint_as_float(t[2 * i]) + bt_[2 * i], __uint_as_float(u[2 * i]) + bs_[2 * i]),
+                        gate_one(__uint_as_float(t[2 * i + 1]) + bt_[2 * i + 1], __uint_as_float(u[2 * i + 1]) + bs_[2 * i + 1]), fmt);
+    }
+    const int c0 = (2 * g) ^ (row & 7);
+    const int c1 = (2 * g + 1) ^ (row & 7);
+    *reinterpret_cast<uint4*>(slab_row + c0 * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(slab_row + c1 * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+}
+
+// Gate of one accumulator chunk for SIXTEEN epilogue warps: column quarter cq (32 of the chunk's 128 activations) of TMEM lane
+// `row`, two 16-column groups; four warps per scheduler hide the TMEM latency.  Same slab layout as gate_chunk.
+__device__ __forceinline__ void gate_chunk_quarter(uint32_t rc, uint8_t* acts, int chunk, int cq, int row, const float* bias, int fmt) {
+  uint8_t* slab_row = acts + (2 * chunk + (cq >> 1)) * (kTileM * 128) + row * 128;
+  const float* bt = bias + cq * 32;
+  const float* bs = bt + 128;
+#pragma unroll 1
+  for (int g = 0; g < 2; ++g) {
+    uint32_t vt[16], vs[16];
+    ptx::tmem_ld16(rc + cq * 32 + g * 16, vt);
+    ptx::tmem_ld16(rc + cq * 32 + g * 16 + 128, vs);
+    ptx::tmem_ld_wait();
+    float bt_[16], bs_[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t4 = reinterpret_cast<const float4*>(bt + g * 16)[i];
+      const float4 s4 = reinterpret_cast<const float4*>(bs + g * 16)[i];
+      bt_[4 * i] = t4.x; bt_[4 * i + 1] = t4.y; bt_[4 * i + 2] = t4.z; bt_[4 * i + 3] = t4.w;
+      bs_[4 * i] = s4.x; bs_[4 * i + 1] = s4.y; bs_[4 * i + 2] = s4.z; bs_[4 * i + 3] = s4.w;
+    }
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      pk[i] = pack_pair(gate_one(__uint_as_float(vt[2 * i]) + bt_[2 * i], __uint_as_float(vs[2 * i]) + bs_[2 * i]),
+                        gate_one(__uint_as_float(vt[2 * i + 1]) + bt_[2 * i + 1], __uint_as_float(vs[2 * i + 1]) + bs_[2 * i + 1]), fmt);
+    }
+    // 16-byte chunk index inside the 128-byte slab row, XOR-swizzled by (row mod 8)
+    const int c0 = ((cq & 1) * 4 + 2 * g) ^ (row & 7);
+    const int c1 = ((cq & 1) * 4 + 2 * g + 1) ^ (row & 7);
     *reinterpret_cast<uint4*>(slab_row + c0 * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     *reinterpret_cast<uint4*>(slab_row + c1 * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
   }
@@ -158,11 +242,17 @@ __device__ __forceinline__ void stage_residual(uint32_t ra, const float* s_bias,
     const int ch0 = hh * 128 + g * 16;          // first residual channel of this group
     ptx::tmem_ld16(ra + ch0, v);
     ptx::tmem_ld_wait();
+    float b_[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b4 = reinterpret_cast<const float4*>(s_bias + ch0)[i];      // 16-byte loads: see gate_chunk
+      b_[4 * i] = b4.x; b_[4 * i + 1] = b4.y; b_[4 * i + 2] = b4.z; b_[4 * i + 3] = b4.w;
+    }
     uint32_t pk[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float a0 = valid ? __uint_as_float(v[2 * i]) + s_bias[ch0 + 2 * i] : 0.f;
-      const float a1 = valid ? __uint_as_float(v[2 * i + 1]) + s_bias[ch0 + 2 * i + 1] : 0.f;
+      const float a0 = valid ? __uint_as_float(v[2 * i]) + b_[2 * i] : 0.f;
+      const float a1 = valid ? __uint_as_float(v[2 * i + 1]) + b_[2 * i + 1] : 0.f;
       pk[i] = pack_pair(a0, a1, fmt);
     }
     const int slab = ch0 >> 6;
