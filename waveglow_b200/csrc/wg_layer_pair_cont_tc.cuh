@@ -1,24 +1,32 @@
 // wg_layer_pair_cont_tc.cuh -- the fused 256-channel WN layer on CTA pairs with the tensor pipe kept CONTINUOUSLY fed.
 //
-// Same algorithm, operands, tiles and CTA-pair mechanics as wg_layer_pair_tc.cuh (reference model.py:121-137 for one layer),
-// but a different TMEM / issue schedule.  In that kernel the next tile's GEMM1 has to wait for the chunk-b gate (the
-// accumulator regions alternate so that 16 skip-end columns fit), which leaves the tensor pipe idle ~15 % of every tile.
-// Here the 8 skip-end outputs per group-step are taken OFF the tcgen05 path: once a tile's gated activations are complete in
-// shared memory, each epilogue warp computes e' = acts[16 rows x 256] . Wse^T[256 x 8] with 16 warp-level mma.sync
-// (m16n8k16, fp32 accumulate; Wse lives in 32 registers per thread for the whole launch).  TMEM then holds exactly two fixed
-// regions and nothing ever waits for a gate:
-//   P = columns [0,256):   GEMM1 chunk a of every tile
-//   Q = columns [256,512): GEMM1 chunk b, then the residual GEMM2 (x') of the same tile
-//   tensor pipe:  a(i) | b(i) | a(i+1) k-blocks 0..5 | GEMM2(i) | a(i+1) k-blocks 6..16 | b(i+1) | ...
-//   epilogue:             gate a(i)    | gate b(i), e'(i)             | x'(i) drain + TMA store    | gate a(i+1) ...
-// Every dependency points backwards by at least one GEMM chunk (~10k cycles), so the MMA issuer only ever blocks on TMA.
+// Same algorithm, operands and CTA-pair mechanics as wg_layer_pair_tc.cuh (reference model.py:121-137 for one layer), but a
+// different TMEM / issue / epilogue schedule.  In that kernel the next tile's GEMM1 waits for the chunk-b gate (the accumulator
+// regions alternate so that 16 skip-end columns fit), every tcgen05.mma is issued through a compiler-generated waterfall, and
+// eight epilogue warps do gates, skip-end and x' drain in series.  Measured bounds that shaped this one (profiles/r01):
+//   * with all loads and all epilogue work off, the `lane == 0` issue loop alone paced the pipe at 159 cycles per MMA
+//     (nominal 128); converged warps + elect.sync issue: 128.7
+//   * with only the epilogue work off the tile takes 20.9k cycles (= the MMA work); with it on, 30k: the tile period was the
+//     length of the epilogue chain, not operand supply
+//   * tcgen05.ld is slow while the pipe is busy (~5k cycles per 128 KB chunk whatever the warp count), and a warp-level
+//     mma.sync takes several hundred cycles, so both are kept off the paths the tensor pipe waits for.
+// Structure:
+//   TMEM   P = columns [0,256): GEMM1 chunk a of every tile;  Q = [256,512): GEMM1 chunk b, then GEMM2 (x') of the same tile.
+//          The 8 skip-end outputs per group-step are NOT in TMEM: skip-end warps compute e' = acts . Wse^T with mma.sync
+//          (m16n8k16, fp32 accumulate) from the acts slabs in shared memory.
+//   pipe   a(i) | b(i) | a(i+1) k-blocks 0..g2_at-1 | GEMM2(i) | a(i+1) rest | b(i+1) | ...      (nothing waits for a gate
+//          except GEMM2(i) for gate b(i), and b(i+1) for the drain of x'(i))
+//   warps  0: TMA producer, 1: MMA issuer (both converged, elect.sync around the issue);
+//          2..17: gate a, gate b, x' drain -- thread = (TMEM lane, column quarter); x' goes to global memory straight from
+//                 registers with 32-byte stores (no staging tile, no TMA store to wait for);
+//          18..21: skip-end GEMM, 32 rows per warp.
+//   tiles  128 / seg_rows segments of seg_rows (128, 64 or 32) frames of one phase; a tile may span utterances.
 #pragma once
 #include "wg_layer_pair_tc.cuh"
 
 namespace wg {
 
-
-constexpr int kContThreads = 576;   // warp 0 TMA, warp 1 MMA, warps 2..17 gates / skip-end GEMM / x' drain
+constexpr int kContThreads = 704;   // warp 0 TMA, warp 1 MMA, warps 2..17 gates + x' drain, warps 18..21 skip-end GEMM
 
 struct ContSmem {
   static constexpr int acts = kPairStages * kPairStageBytes;   // 131072
@@ -49,7 +57,9 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
   uint64_t* d2_full = acts_ready + 2;             // [1] both (multicast commit): x' accumulator complete
   uint64_t* ident_full = d2_full + 1;             // [1] leader
   uint64_t* res_drained = ident_full + 1;         // [1] leader, 1024 arrivals: x' read out of region Q
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_drained + 1);
+  uint64_t* acts_local = res_drained + 1;         // [1] per CTA, 512 arrivals: both chunks gated, acts slabs complete (-> skip-end warps)
+  uint64_t* e_done = acts_local + 1;              // [1] per CTA, 128 arrivals: the skip-end GEMM has read the acts slabs (-> gate warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(e_done + 1);
   float* s_bias1 = reinterpret_cast<float*>(smem + ContSmem::bias1);
   float* s_bias_res = reinterpret_cast<float*>(smem + ContSmem::bias_res);
   uint32_t* s_wse = reinterpret_cast<uint32_t*>(smem + ContSmem::wse);
@@ -113,6 +123,8 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
     ptx::mbar_init(d2_full, 1);
     ptx::mbar_init(ident_full, 1);
     ptx::mbar_init(res_drained, 1024);
+    ptx::mbar_init(acts_local, 512);
+    ptx::mbar_init(e_done, 128);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -336,72 +348,35 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
       }
       if (my_tiles > 0) gemm2(my_tiles - 1);
     }
-  } else {
-    // =============================== 16 epilogue warps (both CTAs): gates, skip-end GEMM, x' -> global ===============================
-    // Thread = (TMEM lane = group-step `row`, column quarter cq).  Everything the tensor pipe waits for (gate b -> GEMM2,
-    // x' drain -> next chunk b) is split 4 ways per row; with 8 warps that chain was longer than the MMA work it hides behind
-    // (measured 30k cycles per tile against 21k of tensor-pipe work).
+  } else if (warp < 18) {
+    // =============================== 16 gate / drain warps (both CTAs): gates, x' -> global ===============================
+    // Thread = (TMEM lane = group-step `row`, column quarter cq).  What the tensor pipe waits for (gate b -> GEMM2, x' drain ->
+    // next chunk b) is split 4 ways per row; with 8 warps doing gates, the skip-end GEMM and the drain in series that chain was
+    // longer than the MMA work it hides behind (measured 30k cycles per tile against 21k of tensor-pipe work).
     const int q = warp & 3;              // TMEM lane quarter this warp may touch
     const int cq = (warp - 2) >> 2;      // column quarter handled by this warp
     const int row = q * 32 + lane;
-    const int ew = warp - 2;             // skip-end GEMM (warps with ew < 8): tile rows 16 ew .. 16 ew + 15
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint8_t* acts = smem + ContSmem::acts;
-    const uint32_t acts_u32 = ptx::smem_u32(acts);
     const uint32_t l_acts_ready[2] = {ptx::map_to_cta(&acts_ready[0], 0), ptx::map_to_cta(&acts_ready[1], 0)};
     const uint32_t l_res_drained = ptx::map_to_cta(res_drained, 0);
-    // ldmatrix source of this lane inside a [128 x 64] swizzled acts slab: row (lane & 7) + 8 * bit 3, 16-byte chunk 2 kk + bit 4
-    const int lm_row = 16 * (ew & 7) + (lane & 7) + ((lane >> 3) & 1) * 8;
-    const uint32_t lm_base = acts_u32 + lm_row * 128;
-    const int lm_sw = lm_row & 7, lm_hi = lane >> 4;
 
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t par = it & 1;
       const Coord tc = tile_of(it);
       const bool tl = (it == 1) && threadIdx.x == 64 && rank == 0;
       for (int chunk = 0; chunk < 2; ++chunk) {
-        // acc_full also says: GEMM2 of the previous tile (issued before it) has finished reading the acts slabs
+        // acc_full also says: GEMM2 of the previous tile (issued before it) has finished reading the acts slabs ...
         ptx::mbar_wait(&acc_full[chunk], par);
         ptx::tc_fence_after_sync();
         if (tl) stamp(p, 5 + 2 * chunk);
+        if (chunk == 0 && it > 0) ptx::mbar_wait(e_done, par ^ 1);      // ... and so has the skip-end GEMM
         if (!(p.dbg_flags & 4)) gate_chunk_quarter(lane_base + chunk * 256, acts, chunk, cq, row, s_bias1 + chunk * 256, p.fmt);
         ptx::tc_fence_before_sync();
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive_cluster(l_acts_ready[chunk]);
+        if (chunk == 1) ptx::mbar_arrive(acts_local);
         if (tl) stamp(p, 6 + 2 * chunk);
-      }
-
-      // ---- skip-end: e'[16 rows x 8] = acts[16 x 256] . Wse^T on the warp-level tensor path, fp32 accumulate (8 of the 16 warps)
-      asm volatile("bar.sync 1, 512;" ::: "memory");      // every warp's acts columns are visible
-      if (ew < 8 && !(p.dbg_flags & 16)) {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) {
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            uint32_t a[4];
-            ptx::ldmatrix_x4(lm_base + s4 * (kTileM * 128) + (((2 * kk + lm_hi) ^ lm_sw) << 4), a);
-            ptx::mma_m16n8k16(c, a, s_wse[(2 * (s4 * 4 + kk)) * 32 + lane], s_wse[(2 * (s4 * 4 + kk) + 1) * 32 + lane], p.fmt);
-          }
-        }
-#pragma unroll
-        for (int hr = 0; hr < 2; ++hr) {
-          const int r = 16 * ew + (lane >> 2) + 8 * hr;
-          int r_b, r_q;
-          seg_coord(tc.seg0 + (r >> seg_shift), r_b, r_q);
-          r_q += r & (seg - 1);
-          const int t = r_q * kPhases + tc.ph;
-          if (r_b < p.B && r_q < p.Fq && t < p.T) {
-            float2* ep = reinterpret_cast<float2*>(p.e + (static_cast<size_t>(r_b) * p.T + t) * 8 + 2 * (lane & 3));
-            float2 v = make_float2(c[2 * hr], c[2 * hr + 1]);
-            if (p.accumulate_e) {
-              const float2 o = *ep;
-              v.x += o.x;
-              v.y += o.y;
-            }
-            *ep = v;
-          }
-        }
       }
 
       if (p.has_res) {
@@ -415,37 +390,86 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
         ptx::mbar_wait(d2_full, par);
         ptx::tc_fence_after_sync();
         if (tl) stamp(p, 11);
-#pragma unroll 1
+        uint32_t pk[32];      // this thread's 64 channels, packed
+#pragma unroll
         for (int g2 = 0; g2 < 2; ++g2) {
           uint32_t v[32];
           ptx::tmem_ld32(lane_base + 256 + cq * 64 + g2 * 32, v);
           ptx::tmem_ld_wait();
-          if (g2 == 1) {
-            // everything is read: chunk b of the next tile may overwrite region Q
-            ptx::tc_fence_before_sync();
-            ptx::mbar_arrive_cluster(l_res_drained);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b4 = reinterpret_cast<const float4*>(s_bias_res + cq * 64 + g2 * 32)[i];
+            pk[g2 * 16 + 2 * i] = live ? pack_pair(__uint_as_float(v[4 * i]) + b4.x, __uint_as_float(v[4 * i + 1]) + b4.y, p.fmt) : 0u;
+            pk[g2 * 16 + 2 * i + 1] = live ? pack_pair(__uint_as_float(v[4 * i + 2]) + b4.z, __uint_as_float(v[4 * i + 3]) + b4.w, p.fmt) : 0u;
           }
-          if (p.dbg_flags & 8) continue;
+        }
+        // region Q is read: chunk b of the next tile may overwrite it.  Signalled BEFORE the global stores: the release at
+        // cluster scope of a remote arrive waits for this thread's outstanding memory operations.
+        ptx::tc_fence_before_sync();
+        ptx::mbar_arrive_cluster(l_res_drained);
+        if (in_buf && !(p.dbg_flags & 8)) {
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            float b_[16];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 b4 = reinterpret_cast<const float4*>(s_bias_res + cq * 64 + g2 * 32 + g * 16)[i];
-              b_[4 * i] = b4.x; b_[4 * i + 1] = b4.y; b_[4 * i + 2] = b4.z; b_[4 * i + 3] = b4.w;
-            }
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              pk[i] = live ? pack_pair(__uint_as_float(v[g * 16 + 2 * i]) + b_[2 * i], __uint_as_float(v[g * 16 + 2 * i + 1]) + b_[2 * i + 1], p.fmt) : 0u;
-            if (in_buf) ptx::st_global_v8(dst + g2 * 64 + g * 32, pk);
-          }
+          for (int k = 0; k < 4; ++k) ptx::st_global_v8(dst + k * 32, *reinterpret_cast<uint32_t(*)[8]>(&pk[8 * k]));
         }
         if (tl) stamp(p, 12);
       }
-      asm volatile("bar.sync 1, 512;" ::: "memory");      // every warp has finished its ldmatrix reads: the slabs may be rewritten
     }
     if (threadIdx.x == 64 && rank == 0) stamp(p, 13);
+  } else {
+    // =============================== skip-end warps 18..21 (both CTAs): e' = acts . Wse^T ===============================
+    // 32 rows per warp on the warp-level tensor path (mma.sync m16n8k16, fp32 accumulate).  While tcgen05.mma owns the tensor
+    // pipe each of these takes several hundred cycles, which is why they have warps of their own: nothing waits for them
+    // except the next tile's gate a (e_done), a whole GEMM chunk later.
+    const int q = warp & 3;
+    const uint32_t acts_u32 = ptx::smem_u32(smem + ContSmem::acts);
+    // ldmatrix source of this lane inside a [128 x 64] swizzled acts slab: row (lane & 7) + 8 * bit 3, 16-byte chunk 2 kk + bit 4
+    const int lm_row = 32 * q + (lane & 7) + ((lane >> 3) & 1) * 8;      // + 16 for the second 16-row block (same swizzle phase)
+    const uint32_t lm_base = acts_u32 + lm_row * 128;
+    const int lm_sw = lm_row & 7, lm_hi = lane >> 4;
+    for (int it = 0; it < my_tiles; ++it) {
+      const uint32_t par = it & 1;
+      const Coord tc = tile_of(it);
+      ptx::mbar_wait(acts_local, par);
+      float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      if (!(p.dbg_flags & 16)) {
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t b0 = s_wse[(2 * (s4 * 4 + kk)) * 32 + lane], b1 = s_wse[(2 * (s4 * 4 + kk) + 1) * 32 + lane];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              uint32_t a[4];
+              ptx::ldmatrix_x4(lm_base + mt * (16 * 128) + s4 * (kTileM * 128) + (((2 * kk + lm_hi) ^ lm_sw) << 4), a);
+              ptx::mma_m16n8k16(c[mt], a, b0, b1, p.fmt);
+            }
+          }
+        }
+      }
+      ptx::mbar_arrive(e_done);
+      if (p.dbg_flags & 16) continue;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+        for (int hr = 0; hr < 2; ++hr) {
+          const int r = 32 * q + 16 * mt + (lane >> 2) + 8 * hr;
+          int r_b, r_q;
+          seg_coord(tc.seg0 + (r >> seg_shift), r_b, r_q);
+          r_q += r & (seg - 1);
+          const int t = r_q * kPhases + tc.ph;
+          if (r_b < p.B && r_q < p.Fq && t < p.T) {
+            float2* ep = reinterpret_cast<float2*>(p.e + (static_cast<size_t>(r_b) * p.T + t) * 8 + 2 * (lane & 3));
+            float2 v = make_float2(c[mt][2 * hr], c[mt][2 * hr + 1]);
+            if (p.accumulate_e) {
+              const float2 o = *ep;
+              v.x += o.x;
+              v.y += o.y;
+            }
+            *ep = v;
+          }
+        }
+      }
+    }
   }
 
   // ---- teardown: both CTAs must be done with TMEM and with each other's shared memory

@@ -144,46 +144,6 @@ __device__ __forceinline__ void gate_chunk(uint32_t rc, uint8_t* acts, int chunk
   }
 }
 
-// gate_chunk with the TMEM loads of column group g + 1 in flight while group g is gated (tcgen05.wait::ld waits for all
-// outstanding loads, so the next pair is issued right after the wait and before the math).  Used by the continuous pair
-// kernel, whose gates run while the tensor pipe is busy and see a much longer tcgen05.ld latency than an idle pipe gives.
-__device__ __forceinline__ void gate_chunk_pipelined(uint32_t rc, uint8_t* acts, int chunk, int hh, int row, const float* bt, int fmt) {
-  uint8_t* slab_row = acts + (2 * chunk + hh) * (kTileM * 128) + row * 128;
-  bt += hh * 64;
-  const float* bs = bt + 128;
-  uint32_t vt[2][16], vs[2][16];
-  ptx::tmem_ld16(rc + hh * 64, vt[0]);
-  ptx::tmem_ld16(rc + hh * 64 + 128, vs[0]);
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    ptx::tmem_ld_wait();
-    if (g < 3) {
-      ptx::tmem_ld16(rc + hh * 64 + (g + 1) * 16, vt[(g + 1) & 1]);
-      ptx::tmem_ld16(rc + hh * 64 + (g + 1) * 16 + 128, vs[(g + 1) & 1]);
-    }
-    const uint32_t(&t)[16] = vt[g & 1];
-    const uint32_t(&u)[16] = vs[g & 1];
-    float bt_[16], bs_[16];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 t4 = reinterpret_cast<const float4*>(bt + g * 16)[i];
-      const float4 s4 = reinterpret_cast<const float4*>(bs + g * 16)[i];
-      bt_[4 * i] = t4.x; bt_[4 * i + 1] = t4.y; bt_[4 * i + 2] = t4.z; bt_[4 * i + 3] = t4.w;
-      bs_[4 * i] = s4.x; bs_[4 * i + 1] = s4.y; bs_[4 * i + 2] = s4.z; bs_[4 * i + 3] = s4.w;
-    }
-    uint32_t pk[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      pk[i] = pack_pair(gate_one(__uint_as_float(t[2 * i]) + bt_[2 * i], __uint_as_float(u[2 * i]) + bs_[2 * i]),
-                        gate_one(__uint_as_float(t[2 * i + 1]) + bt_[2 * i + 1], __uint_as_float(u[2 * i + 1]) + bs_[2 * i + 1]), fmt);
-    }
-    const int c0 = (2 * g) ^ (row & 7);
-    const int c1 = (2 * g + 1) ^ (row & 7);
-    *reinterpret_cast<uint4*>(slab_row + c0 * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    *reinterpret_cast<uint4*>(slab_row + c1 * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-  }
-}
-
 // Gate of one accumulator chunk for SIXTEEN epilogue warps: column quarter cq (32 of the chunk's 128 activations) of TMEM lane
 // `row`, two 16-column groups; four warps per scheduler hide the TMEM latency.  Same slab layout as gate_chunk.
 __device__ __forceinline__ void gate_chunk_quarter(uint32_t rc, uint8_t* acts, int chunk, int cq, int row, const float* bias, int fmt) {
