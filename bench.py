@@ -281,20 +281,22 @@ def main():
   peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step; fp16 and bf16 share the tcgen05 kind::f16 rate)" \
       if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
   # tensor FLOPs the fused kernel actually issues per group-step and layer: GEMM1 K = 3*256 + 320
-  # (upsampler composed into the conditioning), GEMM2 N = 256 residual + 16 skip-end (skip->end fold), identity carry
+  # (upsampler composed into the conditioning), GEMM2 N = 256 residual + identity carry, skip->end fold (8 outputs on mma.sync in
+  # the 256-channel kernel, 16 tcgen05 columns in the wide path)
   nc = args.channels
-  exec_per_step_layer = 2 * (3 * nc + 320) * 2 * nc + (7 / 8) * (2 * nc * nc + 2 * nc * 32) + 2 * nc * 16
+  exec_per_step_layer = 2 * (3 * nc + 320) * 2 * nc + (7 / 8) * (2 * nc * nc + 2 * nc * 32) + 2 * nc * (8 if nc == 256 else 16)
   roofline = None
   if layer_launches:
     per_launch_flops = layer_flops_sample * B * T / layer_launches
     per_launch_ms = layer_ms / layer_launches
     achieved = per_launch_flops / (per_launch_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": ("wn_layer_fp32_kernel" if args.precision == "fp32" else
-                           "wn_layer_pair_kernel" if args.channels == 256 else "wn_gate_wide_kernel + wn_res_wide_kernel"),
+                           "wn_layer_pair_cont_kernel" if args.channels == 256 else "wn_gate_wide_kernel + wn_res_wide_kernel"),
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel on this workload, from
-                # profiles/r01/ncu_full_layer_v5_pair_summary.csv (ncu --set full, kernel v5); only valid for the default workload
-                "traffic": 472e6 if (args.batch == 16 and args.frames == 861 and args.precision == "fp16" and args.channels == 256) else None,
+                # profiles/r01/ncu_full_layer_v7_cont_summary.csv (ncu --set full, kernel v7: 256 + 217 MB); only valid for the
+                # default workload
+                "traffic": 473e6 if (args.batch == 16 and args.frames == 861 and args.precision == "fp16" and args.channels == 256) else None,
                 "traffic_unit": "bytes per launch (ncu)",
                 "peak_source": peak_src, "launch_ms": per_launch_ms, "launches_per_step": layer_launches,
                 "algorithmic_flop_per_launch": per_launch_flops,
