@@ -117,7 +117,7 @@ wn_gate_wide_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC, Fq, 
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);     // provably warp-uniform for ptxas
 
   auto tile_of = [&](int it) {
     int tile = blockIdx.x + it * gridDim.x;
@@ -125,25 +125,30 @@ wn_gate_wide_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC, Fq, 
     return decode_tile(tile, tiles_per_utt);
   };
 
+  // Warps 0 and 1 run their loops converged and predicate only the issue on elect.sync: inside an `if (lane == 0)` loop ptxas
+  // wraps every TMA / tcgen05.mma in an elect + R2UR.BROADCAST waterfall (see wg_layer_pair_cont_tc.cuh for the measurement).
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       ptx::prefetch_tmap(&tm_x_in);
       ptx::prefetch_tmap(&tm_mw);
       ptx::prefetch_tmap(&tm_w1);
       ptx::prefetch_tmap(&tm_v);
       ptx::mbar_arrive_expect_tx(res_w, C::kSeBytes);
       for (int j = 0; j < C::kCB; ++j) ptx::tma_load_2d(smem + C::a_se + j * 2048, &tm_se, res_w, j * kBlockK, p.se_row0);
-      int use = 0;
-      auto load_pass = [&](int n, int chunk) {
-        const TileCoord tc = tile_of(n / C::kHalves);
-        const int h = n % C::kHalves;
-        for (int kb = 0; kb < C::kKB; ++kb, ++use) {
-          const int s = use % kStages;
-          const uint32_t ph = (use / kStages) & 1;
-          ptx::mbar_wait(&empty[s], ph ^ 1);
-          uint8_t* sa = smem + s * kStageBytes;
-          uint8_t* sb = sa + kStageABytes;
+    }
+    __syncwarp();
+    int use = 0;
+    auto load_pass = [&](int n, int chunk) {
+      const TileCoord tc = tile_of(n / C::kHalves);
+      const int h = n % C::kHalves;
+      for (int kb = 0; kb < C::kKB; ++kb, ++use) {
+        const int s = use % kStages;
+        const uint32_t ph = (use / kStages) & 1;
+        ptx::mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* sa = smem + s * kStageBytes;
+        uint8_t* sb = sa + kStageABytes;
+        if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&full[s], kStageBytes);
           if (kb < kMwKB) {
             ptx::tma_load_3d(sa, &tm_mw, &full[s], kb * kBlockK, tc.q0, tc.b);
@@ -156,58 +161,62 @@ wn_gate_wide_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC, Fq, 
             ptx::tma_load_2d(sb, &tm_w1, &full[s], j * kBlockK, p.w1_row0 + h * 512 + chunk * 256);
           }
         }
-      };
-      // same order as the MMA issuer consumes: G1a(0), then per unit G1b(n), G1a(n+1)
-      if (n_units > 0) load_pass(0, 0);
-      for (int n = 0; n < n_units; ++n) {
-        load_pass(n, 1);
-        if (n + 1 < n_units) load_pass(n + 1, 0);
+        __syncwarp();
       }
+    };
+    // same order as the MMA issuer consumes: G1a(0), then per unit G1b(n), G1a(n+1)
+    if (n_units > 0) load_pass(0, 0);
+    for (int n = 0; n < n_units; ++n) {
+      load_pass(n, 1);
+      if (n + 1 < n_units) load_pass(n + 1, 0);
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      const uint32_t idesc256 = ptx::make_idesc_f16(128, 256, p.fmt);
-      const uint32_t idesc16 = ptx::make_idesc_f16(128, 16, p.fmt);
-      const uint32_t stage_addr0 = ptx::smem_u32(smem);
-      const uint32_t acts_addr = ptx::smem_u32(smem + C::a_acts);
-      const uint32_t se_addr = ptx::smem_u32(smem + C::a_se);
-      const uint32_t ra = tmem_base, rb = tmem_base + 256;
-      int use = 0;
-      auto mma_pass = [&](int chunk) {
-        const uint32_t d = chunk == 0 ? ra : rb;
-        for (int kb = 0; kb < C::kKB; ++kb, ++use) {
-          const int s = use % kStages;
-          const uint32_t ph = (use / kStages) & 1;
-          ptx::mbar_wait(&full[s], ph);
-          ptx::tc_fence_after_sync();
-          const uint32_t a_addr = stage_addr0 + s * kStageBytes;
-          const uint32_t b_addr = a_addr + kStageABytes;
+    const uint32_t idesc256 = ptx::make_idesc_f16(128, 256, p.fmt);
+    const uint32_t idesc16 = ptx::make_idesc_f16(128, 16, p.fmt);
+    const uint32_t stage_addr0 = ptx::smem_u32(smem);
+    const uint32_t acts_addr = ptx::smem_u32(smem + C::a_acts);
+    const uint32_t se_addr = ptx::smem_u32(smem + C::a_se);
+    const uint32_t ra = tmem_base, rb = tmem_base + 256;
+    int use = 0;
+    auto mma_pass = [&](int chunk) {
+      const uint32_t d = chunk == 0 ? ra : rb;
+      for (int kb = 0; kb < C::kKB; ++kb, ++use) {
+        const int s = use % kStages;
+        const uint32_t ph = (use / kStages) & 1;
+        ptx::mbar_wait(&full[s], ph);
+        ptx::tc_fence_after_sync();
+        const uint32_t a_addr = stage_addr0 + s * kStageBytes;
+        const uint32_t b_addr = a_addr + kStageABytes;
+        if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             ptx::mma_f16_ss(d, ptx::make_desc_sw128(a_addr + k * 32), ptx::make_desc_sw128(b_addr + k * 32), idesc256, (kb | k) != 0);
           ptx::mma_commit(&empty[s]);
+          if (kb == C::kKB - 1) ptx::mma_commit(&acc_full[chunk]);
         }
-        ptx::mma_commit(&acc_full[chunk]);
-      };
-      ptx::mbar_wait(res_w, 0);
-      if (n_units > 0) mma_pass(0);
-      for (int n = 0; n < n_units; ++n) {
-        const uint32_t par = n & 1;
-        const int h = n % C::kHalves;
-        if (n > 0) {                       // region b still holds the previous unit's 16 skip-end columns
-          ptx::mbar_wait(e_drained, par ^ 1);
-          ptx::tc_fence_after_sync();
-        }
-        mma_pass(1);
-        if (n + 1 < n_units) {             // region a is free once this unit's chunk-a gate has read it
-          ptx::mbar_wait(&acts_ready[0], par);
-          ptx::tc_fence_after_sync();
-          mma_pass(0);
-        }
-        ptx::mbar_wait(&acts_ready[1], par);
-        if (n + 1 >= n_units) ptx::mbar_wait(&acts_ready[0], par);
+        __syncwarp();
+      }
+    };
+    ptx::mbar_wait(res_w, 0);
+    if (n_units > 0) mma_pass(0);
+    for (int n = 0; n < n_units; ++n) {
+      const uint32_t par = n & 1;
+      const int h = n % C::kHalves;
+      if (n > 0) {                       // region b still holds the previous unit's 16 skip-end columns
+        ptx::mbar_wait(e_drained, par ^ 1);
         ptx::tc_fence_after_sync();
+      }
+      mma_pass(1);
+      if (n + 1 < n_units) {             // region a is free once this unit's chunk-a gate has read it
+        ptx::mbar_wait(&acts_ready[0], par);
+        ptx::tc_fence_after_sync();
+        mma_pass(0);
+      }
+      ptx::mbar_wait(&acts_ready[1], par);
+      if (n + 1 >= n_units) ptx::mbar_wait(&acts_ready[0], par);
+      ptx::tc_fence_after_sync();
+      if (ptx::elect_one()) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
 #pragma unroll
@@ -217,6 +226,7 @@ wn_gate_wide_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC, Fq, 
         }
         ptx::mma_commit(se_full);
       }
+      __syncwarp();
     }
   } else {
     // =============================== gate / epilogue warps ===============================
@@ -329,7 +339,7 @@ wn_res_wide_kernel(const __grid_constant__ CUtensorMap tm_acts,    // {NC, Fq, 3
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);     // provably warp-uniform for ptxas
 
   auto tile_of = [&](int it) {
     int tile = blockIdx.x + it * gridDim.x;
@@ -338,76 +348,87 @@ wn_res_wide_kernel(const __grid_constant__ CUtensorMap tm_acts,    // {NC, Fq, 3
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       ptx::prefetch_tmap(&tm_acts);
       ptx::prefetch_tmap(&tm_x_in);
       ptx::prefetch_tmap(&tm_wres);
       ptx::mbar_arrive_expect_tx(ident_full, kIdentBytes);
       ptx::tma_load_2d(smem + C::b_ident, &tm_ident, ident_full, 0, 0);
-      int use = 0;
-      for (int n = 0; n < n_units; ++n) {
-        const TileCoord tc = tile_of(n / C::kHalves);
-        const int o = n % C::kHalves;
-        // K-blocks of acts x W_res; the first 4 stages also carry this half's x(t) blocks for the identity term
-        for (int kb = 0; kb < C::kCB; ++kb, ++use) {
-          const int s = use % kStages;
-          const uint32_t ph = (use / kStages) & 1;
-          ptx::mbar_wait(&empty[s], ph ^ 1);
-          uint8_t* sa = smem + s * kStageBytes;
-          uint8_t* sb = sa + kStageABytes;
+    }
+    __syncwarp();
+    int use = 0;
+    for (int n = 0; n < n_units; ++n) {
+      const TileCoord tc = tile_of(n / C::kHalves);
+      const int o = n % C::kHalves;
+      // K-blocks of acts x W_res; the first 4 stages also carry this half's x(t) blocks for the identity term
+      for (int kb = 0; kb < C::kCB; ++kb, ++use) {
+        const int s = use % kStages;
+        const uint32_t ph = (use / kStages) & 1;
+        ptx::mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* sa = smem + s * kStageBytes;
+        uint8_t* sb = sa + kStageABytes;
+        if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&full[s], kStageBytes);
           ptx::tma_load_3d(sa, &tm_acts, &full[s], kb * kBlockK, tc.q0, tc.b * kPhases + tc.ph);
           ptx::tma_load_2d(sb, &tm_wres, &full[s], kb * kBlockK, p.wres_row0 + o * 256);
         }
-        for (int j = 0; j < 4; ++j, ++use) {
-          const int s = use % kStages;
-          const uint32_t ph = (use / kStages) & 1;
-          ptx::mbar_wait(&empty[s], ph ^ 1);
+        __syncwarp();
+      }
+      for (int j = 0; j < 4; ++j, ++use) {
+        const int s = use % kStages;
+        const uint32_t ph = (use / kStages) & 1;
+        ptx::mbar_wait(&empty[s], ph ^ 1);
+        if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&full[s], kStageABytes);
           ptx::tma_load_3d(smem + s * kStageBytes, &tm_x_in, &full[s], o * 256 + j * kBlockK, tc.q0, tc.b * kPhases + tc.ph);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc256 = ptx::make_idesc_f16(128, 256, p.fmt);
-      const uint32_t idesc32 = ptx::make_idesc_f16(128, kIdentN, p.fmt);
-      const uint32_t stage_addr0 = ptx::smem_u32(smem);
-      const uint32_t ident_addr = ptx::smem_u32(smem + C::b_ident);
-      int use = 0;
-      ptx::mbar_wait(ident_full, 0);
-      for (int n = 0; n < n_units; ++n) {
-        const int r = n & 1;
-        const uint32_t d = tmem_base + r * 256;
-        if (n >= 2) {                       // this region was drained by the epilogue of unit n - 2
-          ptx::mbar_wait(&drained[r], ((n >> 1) - 1) & 1);
-          ptx::tc_fence_after_sync();
-        }
-        for (int kb = 0; kb < C::kCB; ++kb, ++use) {
-          const int s = use % kStages;
-          const uint32_t ph = (use / kStages) & 1;
-          ptx::mbar_wait(&full[s], ph);
-          ptx::tc_fence_after_sync();
-          const uint32_t a_addr = stage_addr0 + s * kStageBytes;
-          const uint32_t b_addr = a_addr + kStageABytes;
+    const uint32_t idesc256 = ptx::make_idesc_f16(128, 256, p.fmt);
+    const uint32_t idesc32 = ptx::make_idesc_f16(128, kIdentN, p.fmt);
+    const uint32_t stage_addr0 = ptx::smem_u32(smem);
+    const uint32_t ident_addr = ptx::smem_u32(smem + C::b_ident);
+    int use = 0;
+    ptx::mbar_wait(ident_full, 0);
+    for (int n = 0; n < n_units; ++n) {
+      const int r = n & 1;
+      const uint32_t d = tmem_base + r * 256;
+      if (n >= 2) {                       // this region was drained by the epilogue of unit n - 2
+        ptx::mbar_wait(&drained[r], ((n >> 1) - 1) & 1);
+        ptx::tc_fence_after_sync();
+      }
+      for (int kb = 0; kb < C::kCB; ++kb, ++use) {
+        const int s = use % kStages;
+        const uint32_t ph = (use / kStages) & 1;
+        ptx::mbar_wait(&full[s], ph);
+        ptx::tc_fence_after_sync();
+        const uint32_t a_addr = stage_addr0 + s * kStageBytes;
+        const uint32_t b_addr = a_addr + kStageABytes;
+        if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             ptx::mma_f16_ss(d, ptx::make_desc_sw128(a_addr + k * 32), ptx::make_desc_sw128(b_addr + k * 32), idesc256, (kb | k) != 0);
           ptx::mma_commit(&empty[s]);
         }
-        for (int j = 0; j < 4; ++j, ++use) {
-          const int s = use % kStages;
-          const uint32_t ph = (use / kStages) & 1;
-          ptx::mbar_wait(&full[s], ph);
-          ptx::tc_fence_after_sync();
-          const uint32_t x_addr = stage_addr0 + s * kStageBytes;
+        __syncwarp();
+      }
+      for (int j = 0; j < 4; ++j, ++use) {
+        const int s = use % kStages;
+        const uint32_t ph = (use / kStages) & 1;
+        ptx::mbar_wait(&full[s], ph);
+        ptx::tc_fence_after_sync();
+        const uint32_t x_addr = stage_addr0 + s * kStageBytes;
+        if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             ptx::mma_f16_ss(d + j * 64 + (k >> 1) * 32, ptx::make_desc_sw128(x_addr + k * 32),
                             ptx::make_desc_sw128(ident_addr + (k & 1) * 32), idesc32, 1);
           ptx::mma_commit(&empty[s]);
+          if (j == 3) ptx::mma_commit(&d_full[r]);
         }
-        ptx::mma_commit(&d_full[r]);
+        __syncwarp();
       }
     }
   } else {
