@@ -158,11 +158,19 @@ def main():
   rank = int(os.environ.get("RANK", "0"))
   world = int(os.environ.get("WORLD_SIZE", "1"))
   local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  if args.channels == 256 and args.batch == 16 and args.frames == 861:
+    which = "BASELINE.json configs[1]"
+  elif args.channels == 512 and args.frames == 861:
+    which = "BASELINE.json configs[2] architecture and utterance length"
+  else:
+    which = "non-headline shape"
+  x_bytes = args.batch * ((args.frames + 127) // 128 * 128) * 32 * args.channels * 2
   config = {"workload": f"WaveGlow-{args.channels} infer, batch {args.batch} x {args.frames} frames ({args.frames * 256 / SAMPLING_RATE:.1f} s) per GPU, "
-                        f"sigma {SIGMA} (BASELINE.json configs[1])",
+                        f"sigma {SIGMA} ({which})",
             "n_channels": args.channels, "batch_per_gpu": args.batch, "frames": args.frames, "sigma": SIGMA,
             "sharding": "by utterance, one process per GPU, no data-path collective; NCCL all_gather of the audio at the end of each step",
-            "l2": "working set per step (residual streams 2 x 226 MB + packed weights 1.2 GB) >> 126 MB L2, no flush needed"}
+            "l2": f"working set per step (residual streams 2 x {x_bytes / 1e6:.0f} MB + packed weights > 1 GB) "
+                  + (">> 126 MB L2, no flush needed" if 2 * x_bytes > 252e6 else "comparable to the 126 MB L2: small-shape run, not a headline number")}
 
   if args.impl == "reference":
     if rank != 0:
