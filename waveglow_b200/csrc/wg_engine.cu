@@ -61,7 +61,7 @@ struct wg_engine {
   CUtensorMap tm_w1{}, tm_v{}, tm_w2a{}, tm_w2b{}, tm_ident{};
   CUtensorMap tm_w1h{}, tm_vh{}, tm_w2h{}, tm_se8{}, tm_ident16{};   // half-height boxes for the CTA-pair kernel
   bool pair = false;                  // fused layer on CTA pairs (cta_group::2); default for 256 channels, WG_PAIR=0 disables
-  int g2_at = 9;                      // see LayerTcParams::g2_at (WG_G2AT env overrides, diagnostics)
+  int g2_at = 6;                      // see LayerTcParams::g2_at (WG_G2AT env overrides, diagnostics)
   int force_seg = 0;                  // WG_SEG env (tests/diagnostics): force the segment size (128 / 64 / 32) of the continuous pair kernel
   bool pair_cont = false;             // ... with the continuous-issue schedule (wg_layer_pair_cont_tc.cuh); WG_PAIR=1 selects the older pair kernel
   // fp32 path

@@ -53,12 +53,12 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
   uint64_t* full = bars;                          // [4] leader: TMA bytes of both CTAs
   uint64_t* empty = bars + kPairStages;           // [4] both (multicast commit)
   uint64_t* acc_full = empty + kPairStages;       // [2] both (multicast commit): GEMM1 chunk a / b complete
-  uint64_t* acts_ready = acc_full + 2;            // [2] leader, 1024 arrivals: chunk gated (acts slabs written, TMEM region read)
+  uint64_t* acts_ready = acc_full + 2;            // [2] leader, 32 arrivals (one per gate warp of both CTAs): chunk gated (acts slabs written, TMEM region read)
   uint64_t* d2_full = acts_ready + 2;             // [1] both (multicast commit): x' accumulator complete
   uint64_t* ident_full = d2_full + 1;             // [1] leader
-  uint64_t* res_drained = ident_full + 1;         // [1] leader, 1024 arrivals: x' read out of region Q
-  uint64_t* acts_local = res_drained + 1;         // [1] per CTA, 512 arrivals: both chunks gated, acts slabs complete (-> skip-end warps)
-  uint64_t* e_done = acts_local + 1;              // [1] per CTA, 128 arrivals: the skip-end GEMM has read the acts slabs (-> gate warps)
+  uint64_t* res_drained = ident_full + 1;         // [1] leader, 32 arrivals: x' read out of region Q
+  uint64_t* acts_local = res_drained + 1;         // [2] per CTA, 16 arrivals: chunk a / b gated, its acts slabs complete (-> skip-end warps)
+  uint64_t* e_done = acts_local + 2;              // [1] per CTA, 4 arrivals: the skip-end GEMM has read the acts slabs (-> gate warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(e_done + 1);
   float* s_bias1 = reinterpret_cast<float*>(smem + ContSmem::bias1);
   float* s_bias_res = reinterpret_cast<float*>(smem + ContSmem::bias_res);
@@ -118,13 +118,15 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
     }
     ptx::mbar_init(&acc_full[0], 1);
     ptx::mbar_init(&acc_full[1], 1);
-    ptx::mbar_init(&acts_ready[0], 1024);
-    ptx::mbar_init(&acts_ready[1], 1024);
+    // cross-warp signals are raised by ONE lane per warp after __syncwarp(): a cluster-scope release costs a MEMBAR.ALL.GPU
+    ptx::mbar_init(&acts_ready[0], 32);
+    ptx::mbar_init(&acts_ready[1], 32);
     ptx::mbar_init(d2_full, 1);
     ptx::mbar_init(ident_full, 1);
-    ptx::mbar_init(res_drained, 1024);
-    ptx::mbar_init(acts_local, 512);
-    ptx::mbar_init(e_done, 128);
+    ptx::mbar_init(res_drained, 32);
+    ptx::mbar_init(&acts_local[0], 16);
+    ptx::mbar_init(&acts_local[1], 16);
+    ptx::mbar_init(e_done, 4);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -374,8 +376,11 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
         if (!(p.dbg_flags & 4)) gate_chunk_quarter(lane_base + chunk * 256, acts, chunk, cq, row, s_bias1 + chunk * 256, p.fmt);
         ptx::tc_fence_before_sync();
         ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive_cluster(l_acts_ready[chunk]);
-        if (chunk == 1) ptx::mbar_arrive(acts_local);
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive_cluster(l_acts_ready[chunk]);
+          ptx::mbar_arrive(&acts_local[chunk]);
+        }
         if (tl) stamp(p, 6 + 2 * chunk);
       }
 
@@ -393,20 +398,25 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
         uint32_t pk[32];      // this thread's 64 channels, packed
 #pragma unroll
         for (int g2 = 0; g2 < 2; ++g2) {
-          uint32_t v[32];
-          ptx::tmem_ld32(lane_base + 256 + cq * 64 + g2 * 32, v);
+          uint32_t v0[16], v1[16];
+          ptx::tmem_ld16(lane_base + 256 + cq * 64 + g2 * 32, v0);
+          ptx::tmem_ld16(lane_base + 256 + cq * 64 + g2 * 32 + 16, v1);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 4; ++i) {
             const float4 b4 = reinterpret_cast<const float4*>(s_bias_res + cq * 64 + g2 * 32)[i];
-            pk[g2 * 16 + 2 * i] = live ? pack_pair(__uint_as_float(v[4 * i]) + b4.x, __uint_as_float(v[4 * i + 1]) + b4.y, p.fmt) : 0u;
-            pk[g2 * 16 + 2 * i + 1] = live ? pack_pair(__uint_as_float(v[4 * i + 2]) + b4.z, __uint_as_float(v[4 * i + 3]) + b4.w, p.fmt) : 0u;
+            const float4 c4 = reinterpret_cast<const float4*>(s_bias_res + cq * 64 + g2 * 32 + 16)[i];
+            pk[g2 * 16 + 2 * i] = live ? pack_pair(__uint_as_float(v0[4 * i]) + b4.x, __uint_as_float(v0[4 * i + 1]) + b4.y, p.fmt) : 0u;
+            pk[g2 * 16 + 2 * i + 1] = live ? pack_pair(__uint_as_float(v0[4 * i + 2]) + b4.z, __uint_as_float(v0[4 * i + 3]) + b4.w, p.fmt) : 0u;
+            pk[g2 * 16 + 8 + 2 * i] = live ? pack_pair(__uint_as_float(v1[4 * i]) + c4.x, __uint_as_float(v1[4 * i + 1]) + c4.y, p.fmt) : 0u;
+            pk[g2 * 16 + 8 + 2 * i + 1] = live ? pack_pair(__uint_as_float(v1[4 * i + 2]) + c4.z, __uint_as_float(v1[4 * i + 3]) + c4.w, p.fmt) : 0u;
           }
         }
         // region Q is read: chunk b of the next tile may overwrite it.  Signalled BEFORE the global stores: the release at
         // cluster scope of a remote arrive waits for this thread's outstanding memory operations.
         ptx::tc_fence_before_sync();
-        ptx::mbar_arrive_cluster(l_res_drained);
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(l_res_drained);
         if (in_buf && !(p.dbg_flags & 8)) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) ptx::st_global_v8(dst + k * 32, *reinterpret_cast<uint32_t(*)[8]>(&pk[8 * k]));
@@ -429,24 +439,27 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t par = it & 1;
       const Coord tc = tile_of(it);
-      ptx::mbar_wait(acts_local, par);
       float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-      if (!(p.dbg_flags & 16)) {
+      // channels 0..127 (gate a) are there a whole GEMM chunk before channels 128..255 (gate b): only half of the work is left
+      // for the time after gate b, when these mma.sync compete with the x' drain
 #pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) {
+      for (int s4 = 0; s4 < 4; ++s4) {
+        if (s4 == 0) ptx::mbar_wait(&acts_local[0], par);
+        if (s4 == 2) ptx::mbar_wait(&acts_local[1], par);
+        if (p.dbg_flags & 16) continue;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint32_t b0 = s_wse[(2 * (s4 * 4 + kk)) * 32 + lane], b1 = s_wse[(2 * (s4 * 4 + kk) + 1) * 32 + lane];
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t b0 = s_wse[(2 * (s4 * 4 + kk)) * 32 + lane], b1 = s_wse[(2 * (s4 * 4 + kk) + 1) * 32 + lane];
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-              uint32_t a[4];
-              ptx::ldmatrix_x4(lm_base + mt * (16 * 128) + s4 * (kTileM * 128) + (((2 * kk + lm_hi) ^ lm_sw) << 4), a);
-              ptx::mma_m16n8k16(c[mt], a, b0, b1, p.fmt);
-            }
+          for (int mt = 0; mt < 2; ++mt) {
+            uint32_t a[4];
+            ptx::ldmatrix_x4(lm_base + mt * (16 * 128) + s4 * (kTileM * 128) + (((2 * kk + lm_hi) ^ lm_sw) << 4), a);
+            ptx::mma_m16n8k16(c[mt], a, b0, b1, p.fmt);
           }
         }
       }
-      ptx::mbar_arrive(e_done);
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(e_done);
       if (p.dbg_flags & 16) continue;
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {

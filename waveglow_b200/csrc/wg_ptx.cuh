@@ -204,8 +204,13 @@ __device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
   return r;
 }
+// Arrive on a barrier of another CTA of the cluster.  Default semantics (release at CTA scope), NOT `.release.cluster`: the
+// cluster-scope release compiles to MEMBAR.ALL.GPU + ERRBAR, an L2 round trip of ~2.5k cycles per arrive (measured: an epilogue
+// step that did nothing but fence + arrive took 2.8k cycles), and nothing in memory has to become visible to the other CTA --
+// the consumer is the tensor pipe reading THIS CTA's shared memory / TMEM, ordered by fence.proxy.async and
+// tcgen05.fence::before_thread_sync before the arrive.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion bytes are signalled on a barrier that may live in the PEER CTA of the pair
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
