@@ -14,6 +14,10 @@ algebraically equivalent form that suits one fused tcgen05 kernel per WN layer:
   * the skip path and the `end` 1x1 conv (model.py:130-137) are folded per layer:
         end(sum_i skip_i) = sum_i (W_end W_skip_i) acts_i + (W_end sum_i b_skip_i + b_end)
     so each layer emits only 2h <= 8 "skip-end" channels accumulated in fp32 (`e`);
+  * (default 256-channel tensor-core kernel, `first_composed=True`) the `start` 1x1 conv (model.py:117) is composed into
+    the first layer: in_0(start(a0))(t) = sum_tau (W_in_0[tau] W_start) a0(t+tau) + (W_in_0[tau] b_start) 1(t+tau), where
+    1(t) is 1 inside the sequence and 0 in the zero padding, and the residual carry of that layer is
+    x(t) = [W_start | b_start] [a0(t); 1]; the 256-channel x of a flow's first layer is never formed;
   * the residual stream x is carried in the MMA operand dtype (fp16 by default) and updated
     on the tensor core:  x <- [W_res_i | I] . [acts; x] + b_res_i;
   * the audio state is time-major [B, T', 8]; live channels are the LAST C slots, so the two
@@ -130,13 +134,31 @@ def shift_time(x: Tensor, s: int) -> Tensor:
 
 
 def wn_layers(pf: PackedFlow, dims: O.ModelDims, x: Tensor, S: Tensor, op_dtype: torch.dtype,
-              trace: Optional[list] = None, mw: Optional[Tensor] = None) -> Tensor:
+              trace: Optional[list] = None, mw: Optional[Tensor] = None, a0: Optional[Tensor] = None) -> Tensor:
   """x: [B,T',nc] (already in op_dtype precision), S: [B,T',640] (or None with mw = mel windows [B,F',320]).
+  a0 [B,T',h] (with mw): the first layer takes the live half of the audio state itself (start conv composed in).
   Returns e [B,T',2h] fp32 (without e_bias)."""
   nc = dims.n_channels
   e = torch.zeros(x.size(0), x.size(1), 2 * pf.h, dtype=torch.float32)
   for i in range(dims.n_layers):
     d = 2 ** i
+    if a0 is not None and i == 0:
+      assert mw is not None and pf.w_res[0] is not None
+      a01 = rnd(torch.cat([a0, torch.ones_like(a0[..., :1])], dim=2), op_dtype)           # [B,T',h+1]
+      ws1 = torch.cat([pf.w_start.double(), pf.b_start.double()[:, None]], dim=1)        # [nc, h+1]
+      pre = pf.b1p[0].clone()
+      for tap in range(3):
+        wc = (pf.w1[0][:, tap * nc:(tap + 1) * nc].double() @ ws1).float()               # [2nc, h+1]
+        pre = pre + shift_time(a01, tap - 1) @ rnd(wc, op_dtype).t()
+      B, T = x.size(0), x.size(1)
+      cond = torch.einsum("bqk,pok->bqpo", mw, rnd(pf.v[0], op_dtype))
+      pre = pre + cond.reshape(B, -1, 2 * nc)[:, :T]
+      acts = rnd(torch.tanh(pre[..., :nc]) * torch.sigmoid(pre[..., nc:]), op_dtype)
+      e = e + acts @ rnd(pf.w_se[0], op_dtype).t()
+      x = rnd(a01 @ rnd(ws1.float(), op_dtype).t() + acts @ rnd(pf.w_res[0], op_dtype).t() + pf.b_res[0], op_dtype)
+      if trace is not None:
+        trace.append({"layer": 0, "acts": acts.clone(), "x": x.clone(), "e": e.clone()})
+      continue
     if mw is None:
       a = torch.cat([shift_time(x, -d), x, shift_time(x, d), S], dim=2)          # [B,T',3nc+640]
       pre = a @ rnd(pf.w1[i], op_dtype).t() + pf.b1[i]                           # fp32 accumulate
@@ -167,7 +189,8 @@ def pack_noise(dims: O.ModelDims, zs: Sequence[Tensor], sigma: float) -> Tensor:
 
 
 def infer(w: Dict[str, Tensor], dims: O.ModelDims, mel: Tensor, sigma: float, zs: Sequence[Tensor],
-          op_dtype: torch.dtype = torch.float16, trace: Optional[list] = None, phase_cond: bool = False) -> Tensor:
+          op_dtype: torch.dtype = torch.float16, trace: Optional[list] = None, phase_cond: bool = False,
+          first_composed: bool = False) -> Tensor:
   state = pack_noise(dims, zs, sigma)                   # [B,T',8] fp32
   G = dims.n_group
   if phase_cond:
@@ -184,7 +207,7 @@ def infer(w: Dict[str, Tensor], dims: O.ModelDims, mel: Tensor, sigma: float, zs
     a1 = state[..., G - c + h:]
     x = rnd(a0 @ pf.w_start.t() + pf.b_start, op_dtype)
     tr = [] if trace is not None else None
-    e = wn_layers(pf, dims, x, S, op_dtype, tr, mw) + pf.e_bias
+    e = wn_layers(pf, dims, x, S, op_dtype, tr, mw, a0 if first_composed else None) + pf.e_bias
     b, s = e[..., :h], e[..., h:]
     a1 = (a1 - b) * torch.exp(-s)
     live = torch.cat([a0, a1], dim=2) @ pf.w_inv.t()

@@ -100,8 +100,9 @@ def test_stagewise_first_flow(precision):
   sigma = 0.8
   trace = []
   phase_cond = precision != "fp32"     # tensor-core mode composes the upsampler into the conditioning weights
+  first_composed = precision == "fp16"  # ... and the default kernel composes the start conv into each flow's first layer
   with torch.no_grad():
-    ref_audio = E.infer(w, dims, mel, sigma, zs, op_dtype, trace, phase_cond=phase_cond)
+    ref_audio = E.infer(w, dims, mel, sigma, zs, op_dtype, trace, phase_cond=phase_cond, first_composed=first_composed)
   k = dims.n_flows - 1
   flow_tr = trace[0]
   assert flow_tr["flow"] == k
@@ -132,7 +133,14 @@ def test_stagewise_first_flow(precision):
       check("mel windows", eng.debug_view("cond", B, F).float().view(B, F, 320).cpu(), E.rnd(E.mel_windows(mel, F), op_dtype))
     else:
       check("cond", eng.debug_view("cond", B, F).float().view(B, T, 640).cpu(), S_ref)
-    check("x after start", x_view("x0"), x0_ref)
+    if first_composed:
+      a0 = eng.debug_view("a0", B, F).float().cpu().view(B, 32, T // 32, 16).permute(0, 2, 1, 3).reshape(B, T, 16)
+      a0_ref = torch.zeros(B, T, 16)
+      a0_ref[..., :2] = E.rnd(state0[..., 4:6], op_dtype)
+      a0_ref[..., 4] = 1.0
+      check("[a0 | 1] rows after start", a0, a0_ref)
+    else:
+      check("x after start", x_view("x0"), x0_ref)
     for i in range(dims.n_layers):
       eng.debug_stop_after(k, i)
       run(model, mel, zs, sigma)

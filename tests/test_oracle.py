@@ -71,6 +71,21 @@ def test_engine_model_fp32_is_exact_restructuring(name):
   assert max_abs(torch.from_numpy(g["audio"]), out) <= FP32_MAX_ABS
 
 
+@pytest.mark.parametrize("name", ["infer_c256_b2_f12", "infer_c256_b3_f7_ragged"])
+def test_engine_model_composed_first_layer_is_exact_and_in_budget(name):
+  """start conv composed into each flow's first layer (and the upsampler into the conditioning): exact in fp32, and
+  inside the tensor-mode gate with fp16 operands."""
+  g = load_golden(name)
+  hp, sd, w, dims = synthetic_weights(256, str(g["weight_style"]))
+  ref = torch.from_numpy(g["audio"])
+  mel, sigma, zs = torch.from_numpy(g["mel"]), float(g["sigma"]), golden_noise(g)
+  with torch.no_grad():
+    out32 = E.infer(w, dims, mel, sigma, zs, torch.float32, phase_cond=True, first_composed=True)
+    out16 = E.infer(w, dims, mel, sigma, zs, torch.float16, phase_cond=True, first_composed=True)
+  assert max_abs(ref, out32) <= FP32_MAX_ABS
+  assert max_abs(ref, out16) <= FP16_MAX_ABS and snr_db(ref, out16) >= FP16_MIN_SNR_DB
+
+
 @pytest.mark.parametrize("name", ["infer_c256_b2_f12", "infer_c256_b1_f40"])
 def test_engine_model_fp16_budget(name):
   """fp16 operands / fp32 accumulate / fp16 residual stream stay inside the BF16-TF32-mode gate; bf16 does not."""

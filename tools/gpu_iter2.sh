@@ -1,0 +1,9 @@
+#!/bin/bash
+# quick loop: the default-kernel tests first, then the whole GPU suite, bench and per-layer timing
+mkdir -p gpurun_out
+run() { name=$1; shift; echo "=== $name" ; timeout 900 "$@" > gpurun_out/$name.log 2>&1; rc=$?; echo "exit $rc"; tail -n ${TAILN:-12} gpurun_out/$name.log | cut -c1-400; return $rc; }
+TAILN=40 run t_stage python -m pytest tests/test_gpu_parity.py -q -m gpu -x -s --timeout 300 -k "stagewise and fp16 and not wide and not single and not pair1" || exit 1
+TAILN=6 run t_all python -m pytest tests -q -m gpu -x --timeout 600 || exit 1
+TAILN=2 run bench_a python bench.py --steps 5 --warmup 3 --no-cpu-baseline
+TAILN=2 run bench_b python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+TAILN=8 run configs python tools/measure_configs.py

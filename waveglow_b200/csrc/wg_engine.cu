@@ -64,6 +64,10 @@ struct wg_engine {
   int g2_at = 6;                      // see LayerTcParams::g2_at (WG_G2AT env overrides, diagnostics)
   int force_seg = 0;                  // WG_SEG env (tests/diagnostics): force the segment size (128 / 64 / 32) of the continuous pair kernel
   bool pair_cont = false;             // ... with the continuous-issue schedule (wg_layer_pair_cont_tc.cuh); WG_PAIR=1 selects the older pair kernel
+  bool first_comp = false;            // continuous pair kernel: start conv composed into the first layer of each flow (WG_FIRST=0 disables)
+  int g2_at_first = 7;                // g2_at of those first layers (8 k-blocks per chunk; WG_G2AT0 overrides)
+  void* d_wc = nullptr;               // [flows][3 taps x 512 packed rows + 256 carry rows][16] 16-bit composed start weights
+  CUtensorMap tm_wc{};
   // fp32 path
   float* d_w1f = nullptr;             // [flows*layers][K1][2nc]
   float* d_bias1f = nullptr;          // [flows*layers][2nc]
@@ -184,6 +188,7 @@ struct WsLayout {
   int Tpad;                        // x rows per utterance: T rounded up to a multiple of 32 (phase view of the TMA maps)
   size_t acts;                     // wide tensor-core path only: gated activations [B][32][Fq][nc] 16-bit
   size_t state, sums;              // forward only: time-major state [B,T,8] fp32; double accumulators [n_flows]
+  size_t a0;                       // start conv composed into the first layer: [B][32][Fq][16] 16-bit rows [a0 | 1]
   size_t cond, x0, x1, e, total;   // cond: fp32 mode = upsampled conditioning S [B,T,640]; fp16 mode = mel windows MW [B,Fq,320]
   size_t cond_bytes;
   size_t elt;   // operand element size
@@ -213,6 +218,8 @@ WsLayout ws_layout(const wg_engine* e, int B, int T) {
   off = align_up(off + npos * kGroup * sizeof(float), 1024);
   L.sums = off;
   off = align_up(off + static_cast<size_t>(e->cfg.n_flows) * sizeof(double), 1024);
+  L.a0 = off;
+  if (e->first_comp) off = align_up(off + nppos * 16 * L.elt, 1024);
   L.total = off;
   return L;
 }
@@ -283,6 +290,11 @@ int wg_create(const wg_config* cfg, wg_engine** out) {
   const char* g2_env = getenv("WG_G2AT");
   if (g2_env) e->g2_at = atoi(g2_env);
   if (e->g2_at < 0 || e->g2_at >= kKB1) return fail(e, WG_ERR_INVALID_ARGUMENT, "WG_G2AT must be in [0, %d)", kKB1);
+  const char* first_env = getenv("WG_FIRST");
+  e->first_comp = e->pair_cont && !(first_env && atoi(first_env) == 0);
+  const char* g20_env = getenv("WG_G2AT0");
+  if (g20_env) e->g2_at_first = atoi(g20_env);
+  if (e->g2_at_first < 0 || e->g2_at_first >= kMwKB + 3) return fail(e, WG_ERR_INVALID_ARGUMENT, "WG_G2AT0 must be in [0, %d)", kMwKB + 3);
   const char* seg_env = getenv("WG_SEG");
   e->force_seg = seg_env ? atoi(seg_env) : 0;
   if (e->force_seg != 0 && e->force_seg != 128 && e->force_seg != 64 && e->force_seg != 32)
@@ -318,6 +330,7 @@ void wg_destroy(wg_engine* e) {
   cudaFree(e->d_v);
   cudaFree(e->d_w2);
   cudaFree(e->d_ident);
+  cudaFree(e->d_wc);
   cudaFree(e->d_bias1);
   cudaFree(e->d_bias_res);
   cudaFree(e->d_w1f);
@@ -379,7 +392,8 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
   const int K1 = 3 * nc + kCond;     // fp32 mode: taps | upsampled conditioning
   const int K1x = 3 * nc;            // fp16 mode: taps only (conditioning goes through V)
   const int w2rows = nc + 16;        // fp16 mode: W_res rows then 16 skip-end rows per layer (272 for 256 channels == kW2Rows)
-  std::vector<uint16_t> w1h, w2h;
+  std::vector<uint16_t> w1h, w2h, wch;
+  constexpr int kWcRows = 3 * 512 + 256;     // per flow: composed taps (packed row order), then the carry rows
   const std::vector<float>* up_bias = nullptr;
   if ((rc = need("upsample.bias", {kMel}, &up_bias))) return rc;
   std::vector<float> bias1, bias_res, w1f, bias1f, wresf, wsef;
@@ -389,6 +403,7 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
     e->d_v = nullptr;
     WG_CUDA(e, cudaMalloc(&e->d_v, static_cast<size_t>(NF) * L * kUpPhases * 2 * nc * kUpKdim * 2));
     w2h.assign(static_cast<size_t>(NF) * L * w2rows * nc, 0);
+    if (e->first_comp) wch.assign(static_cast<size_t>(NF) * kWcRows * 16, 0);
     bias1.assign(static_cast<size_t>(NF) * L * 2 * nc, 0.f);
     bias_res.assign(static_cast<size_t>(NF) * L * nc, 0.f);
   } else {
@@ -474,6 +489,29 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
           double bfold = 0.0;
           for (int m = 0; m < kCond; ++m) bfold += static_cast<double>(wc[m]) * (*up_bias)[m / kGroup];
           bias1[li * 2 * nc + np] = static_cast<float>((*b_in)[oc] + (*b_cond)[2 * nc * i + oc] + bfold);
+          if (i == 0 && e->first_comp) {
+            // in_layers[0](start(a0)) (model.py:117, 125): per tap, W_in[:, :, tap] . W_start (h columns) and
+            // W_in[:, :, tap] . b_start (column 4, multiplied by the operand's `1`, which is 0 in the zero padding)
+            for (int tap = 0; tap < 3; ++tap) {
+              uint16_t* crow = &wch[(static_cast<size_t>(k) * kWcRows + tap * 512 + np) * 16];
+              double acc[5] = {0, 0, 0, 0, 0};
+              for (int ci = 0; ci < nc; ++ci) {
+                const double wi = (*w_in)[(static_cast<size_t>(oc) * nc + ci) * 3 + tap];
+                for (int j = 0; j < h; ++j) acc[j] += wi * (*w_start)[static_cast<size_t>(ci) * h + j];
+                acc[4] += wi * (*b_start)[ci];
+              }
+              for (int j = 0; j < h; ++j) crow[j] = f2h(static_cast<float>(acc[j]), e->op_fmt);
+              crow[4] = f2h(static_cast<float>(acc[4]), e->op_fmt);
+            }
+          }
+        }
+        if (i == 0 && e->first_comp) {
+          // residual carry of the first layer: x(t) = W_start a0(t) + b_start
+          for (int n = 0; n < nc; ++n) {
+            uint16_t* crow = &wch[(static_cast<size_t>(k) * kWcRows + 3 * 512 + n) * 16];
+            for (int j = 0; j < h; ++j) crow[j] = f2h((*w_start)[static_cast<size_t>(n) * h + j], e->op_fmt);
+            crow[4] = f2h((*b_start)[n], e->op_fmt);
+          }
         }
         uint16_t* w2 = &w2h[li * w2rows * nc];
         if (i < L - 1) {
@@ -556,6 +594,16 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
       if ((rc = make_map(e, &e->tm_w2h, e->d_w2, 2, dims, str, boxh, dt))) return rc;
       if ((rc = make_map(e, &e->tm_se8, e->d_w2, 2, dims, str, box8, dt))) return rc;
     }
+    if (e->first_comp) {
+      d16 = static_cast<uint16_t*>(e->d_wc);
+      if ((rc = upload(e, &d16, wch))) return rc;
+      e->d_wc = d16;
+      // 16 real columns; the 64-wide box reads the other 48 as zeros (out-of-bounds fill)
+      const uint64_t dims[2] = {16, static_cast<uint64_t>(NF) * kWcRows};
+      const uint64_t str[1] = {32};
+      const uint32_t boxh[2] = {64, 128};
+      if ((rc = make_map(e, &e->tm_wc, e->d_wc, 2, dims, str, boxh, dt))) return rc;
+    }
     {
       const uint64_t dims[2] = {64, static_cast<uint64_t>(kIdentN)};
       const uint64_t str[1] = {128};
@@ -603,6 +651,9 @@ int wg_debug_view(const wg_engine* e, const char* name, int32_t batch, int32_t f
   } else if (!strcmp(name, "x1")) {
     *ptr = base + L.x1;
     *bytes = static_cast<size_t>(batch) * L.Tpad * e->cfg.n_channels * L.elt;
+  } else if (!strcmp(name, "a0") && e->first_comp) {
+    *ptr = base + L.a0;
+    *bytes = static_cast<size_t>(batch) * L.Tpad * 16 * L.elt;
   } else if (!strcmp(name, "e")) {
     *ptr = base + L.e;
     *bytes = npos * kGroup * sizeof(float);
@@ -628,6 +679,7 @@ void flow_step_any(wg_engine* e, const FlowStepParams& fs_in, float* state, cons
                    cudaStream_t st) {
   FlowStepParams fs = fs_in;
   fs.x_phase_major = e->cfg.precision == WG_PRECISION_FP16 ? 1 : 0;
+  if (!e->first_comp) fs.a0_out = nullptr;
   if (e->cfg.precision == WG_PRECISION_FP32)
     launch_flow_step<float>(fs, state, ebuf, x, B, T, Tpad, st);
   else if (e->op_fmt == 1)
@@ -640,7 +692,7 @@ void flow_step_any(wg_engine* e, const FlowStepParams& fs_in, float* state, cons
 // Runs the WN layers of flow k.  x buffers alternate; returns the index of the buffer holding the
 // current residual stream through *cur.  Returns 1 if the debug stop triggered.
 int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout& L, const CUtensorMap* tm_x,
-                  const CUtensorMap* tm_cond, int* cur, cudaStream_t st, bool* stopped) {
+                  const CUtensorMap* tm_cond, const CUtensorMap* tm_a0, int* cur, cudaStream_t st, bool* stopped) {
   const int nc = e->cfg.n_channels, NL = e->cfg.n_layers;
   const bool tc = e->cfg.precision == WG_PRECISION_FP16;
   void* xb[2] = {ws + L.x0, ws + L.x1};
@@ -734,12 +786,14 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
         const int n_ptiles = kPhases * best_pe;
         const int n_pairs = n_ptiles < e->num_sms / 2 ? n_ptiles : e->num_sms / 2;
         lp.wse = static_cast<const uint16_t*>(e->d_w2) + (li * kW2Rows + 256) * 256;
-        lp.g2_at = e->g2_at;
+        lp.first = e->first_comp && i == 0 && has_res;
+        lp.wc_row0 = k * (3 * 512 + 256);
+        lp.g2_at = lp.first ? e->g2_at_first : e->g2_at;
         lp.x_out = xb[*cur ^ 1];
         const CUtensorMap* seg_maps = tm_x + (best_idx == 0 ? 0 : (best_idx == 1 ? 3 : 6));      // {x0, x1, .., mel windows}
         const CUtensorMap& tm_mw_seg = best_idx == 0 ? *tm_cond : seg_maps[2];
         wn_layer_pair_cont_kernel<<<dim3(2 * n_pairs), kContThreads, ContSmem::total + 1024, st>>>(
-            seg_maps[*cur], tm_mw_seg, e->tm_w1h, e->tm_vh, e->tm_w2h, e->tm_ident16, lp);
+            seg_maps[*cur], tm_mw_seg, e->tm_w1h, e->tm_vh, e->tm_w2h, e->tm_ident16, tm_a0[best_idx], e->tm_wc, lp);
         e->launches++;
         if (has_res) *cur ^= 1;
         if (e->dbg_flow == k && e->dbg_layer == i) {
@@ -823,7 +877,8 @@ void launch_conditioning(wg_engine* e, const float* mel, int B, int frames, int 
   e->launches++;
 }
 
-int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CUtensorMap* tm_x, CUtensorMap* tm_cond) {
+int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CUtensorMap* tm_x, CUtensorMap* tm_cond,
+                  CUtensorMap* tm_a0) {
   // tm_x[0], tm_x[1]: residual stream ping-pong; tm_x[2]: gated activations of the wide path (same geometry);
   // tm_x[3], tm_x[4]: the ping-pong buffers again with 64-row boxes, tm_x[5]: mel windows with 64-row boxes;
   // tm_x[6], tm_x[7], tm_x[8]: the same three with 32-row boxes (segment tiles of the CTA-pair kernels)
@@ -853,6 +908,15 @@ int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CU
     const uint32_t box64[3] = {64, 64, 1}, box32[3] = {64, 32, 1};
     if ((rc = make_map(e, &tm_x[5], ws + L.cond, 3, dims, str, box64, dt))) return rc;
     if ((rc = make_map(e, &tm_x[8], ws + L.cond, 3, dims, str, box32, dt))) return rc;
+  }
+  if (e->first_comp) {
+    // [a0 | 1] rows of the composed first layer, phase-major like x; 16 real channels, the 64-wide boxes zero-fill the rest
+    const uint64_t dims[3] = {16, static_cast<uint64_t>(Fq), static_cast<uint64_t>(B) * kUpPhases};
+    const uint64_t str[2] = {32, static_cast<uint64_t>(32) * Fq};
+    for (int idx = 0; idx < 3; ++idx) {
+      const uint32_t box[3] = {64, static_cast<uint32_t>(kTileM >> idx), 1};
+      if ((rc = make_map(e, &tm_a0[idx], ws + L.a0, 3, dims, str, box, dt))) return rc;
+    }
   }
   return WG_OK;
 }
@@ -903,9 +967,9 @@ int wg_infer(wg_engine* e, const float* mel, int32_t batch, int32_t frames, cons
   }
   // 2. conditioning operand (mel windows in tensor-core mode, upsampled + squeezed mel in fp32 mode)
   launch_conditioning(e, mel, B, frames, T, ws, L, st);
-  CUtensorMap tm_x[9], tm_cond;
+  CUtensorMap tm_x[9], tm_cond, tm_a0[3];
   if (tc) {
-    int rc = make_act_maps(e, ws, L, B, T, tm_x, &tm_cond);
+    int rc = make_act_maps(e, ws, L, B, T, tm_x, &tm_cond, tm_a0);
     if (rc) return rc;
   }
   float* ebuf = reinterpret_cast<float*>(ws + L.e);
@@ -923,11 +987,12 @@ int wg_infer(wg_engine* e, const float* mel, int32_t batch, int32_t frames, cons
     fs.nc = e->cfg.n_channels;
     fs.w_start = f.d_w_start;
     fs.b_start = f.d_b_start;
+    fs.a0_out = ws + L.a0;
     flow_step(fs, xb[cur]);
   }
   bool stopped = (e->dbg_flow == NF - 1 && e->dbg_layer == -1);
   for (int k = NF - 1; k >= 0 && !stopped; --k) {
-    int rc = run_wn_layers(e, k, B, T, ws, L, tm_x, &tm_cond, &cur, st, &stopped);
+    int rc = run_wn_layers(e, k, B, T, ws, L, tm_x, &tm_cond, tm_a0, &cur, st, &stopped);
     if (rc) return rc;
     if (stopped) break;
     FlowStepParams fs{};
@@ -945,6 +1010,7 @@ int wg_infer(wg_engine* e, const float* mel, int32_t batch, int32_t frames, cons
       fs.nc = e->cfg.n_channels;
       fs.w_start = g.d_w_start;
       fs.b_start = g.d_b_start;
+      fs.a0_out = ws + L.a0;
     }
     flow_step(fs, xb[cur]);
     if (e->dbg_flow == k && e->dbg_layer >= e->cfg.n_layers) stopped = true;
@@ -1009,9 +1075,9 @@ int wg_forward(wg_engine* e, const float* mel, int32_t batch, int32_t frames, co
   WG_CUDA(e, cudaMemcpyAsync(state, audio_in, npos * kGroup * sizeof(float), cudaMemcpyDeviceToDevice, st));
   WG_CUDA(e, cudaMemsetAsync(sums, 0, NF * sizeof(double), st));
   launch_conditioning(e, mel, B, frames, T, ws, L, st);
-  CUtensorMap tm_x[9], tm_cond;
+  CUtensorMap tm_x[9], tm_cond, tm_a0[3];
   if (tc) {
-    int rc = make_act_maps(e, ws, L, B, T, tm_x, &tm_cond);
+    int rc = make_act_maps(e, ws, L, B, T, tm_x, &tm_cond, tm_a0);
     if (rc) return rc;
   }
   float* ebuf = reinterpret_cast<float*>(ws + L.e);
@@ -1039,11 +1105,12 @@ int wg_forward(wg_engine* e, const float* mel, int32_t batch, int32_t frames, co
       fs.nc = e->cfg.n_channels;
       fs.w_start = g.d_w_start;
       fs.b_start = g.d_b_start;
+      fs.a0_out = ws + L.a0;
     }
     flow_step_any(e, fs, state, ebuf, xb[cur], B, T, L.Tpad, st);
     if (k == NF) break;
     bool stopped = false;
-    int rc = run_wn_layers(e, k, B, T, ws, L, tm_x, &tm_cond, &cur, st, &stopped);
+    int rc = run_wn_layers(e, k, B, T, ws, L, tm_x, &tm_cond, tm_a0, &cur, st, &stopped);
     if (rc) return rc;
   }
   state_to_channel_major_kernel<<<static_cast<unsigned>((npos + 255) / 256), 256, 0, st>>>(state, z_out, B, T);

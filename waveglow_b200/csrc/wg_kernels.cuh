@@ -194,6 +194,8 @@ struct FlowStepParams {
   const float* w_start;       // [nc, h2]
   const float* b_start;       // [nc]
   int x_phase_major;          // 1: x is [B][phase 32][frame][nc] (tensor-core mode), 0: time-major [B][Tpad][nc]
+  void* a0_out;               // tensor-core mode with the start conv composed into the first WN layer: instead of x, write the
+                              // 16-bit rows [a0 (h2 channels) | 0.. | 1 at index 4 | 0 x 11], phase-major [B][32][Fq][16]
   // forward-only outputs of the finish part
   double* log_s_sum;          // one accumulator: sum of log_s over all elements of flow k
   float* log_s_out;           // optional [B, h, T] (reference layout, model.py:216)
@@ -281,6 +283,30 @@ flow_step_kernel(FlowStepParams p, float* __restrict__ state, const float* __res
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) ls_sum += __shfl_xor_sync(0xffffffffu, ls_sum, o);
       if ((threadIdx.x & 31) == 0 && ls_sum != 0.f) atomicAdd(p.log_s_sum, static_cast<double>(ls_sum));
+    }
+    if (p.do_start && p.a0_out) {
+      // the first WN layer applies the start conv itself (composed weights): it only needs the live first-half channels
+      // and a `1` that carries the start bias; padded rows are exact zeros (the conv's zero padding, model.py:100-102)
+      if constexpr (sizeof(XT) == 2) {
+        if (ppos < n_ppos) {
+          const int base2 = kGroup - p.C2;
+          XT h[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) h[j] = from_float<XT>(0.f);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < p.h2) h[j] = from_float<XT>(row[base2 + j]);
+            h[4] = from_float<XT>(1.f);
+          }
+          const int Fq = Tpad / kUpPhases;
+          const size_t arow = (static_cast<size_t>(b) * kUpPhases + (t % kUpPhases)) * Fq + t / kUpPhases;
+          uint4* dst = reinterpret_cast<uint4*>(static_cast<XT*>(p.a0_out) + arow * 16);
+          dst[0] = reinterpret_cast<const uint4*>(h)[0];
+          dst[1] = reinterpret_cast<const uint4*>(h)[1];
+        }
+      }
+      return;
     }
     if (p.do_start) {
       const int base2 = kGroup - p.C2;

@@ -46,6 +46,8 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
                           const __grid_constant__ CUtensorMap tm_vh,      // {320, rows} box {64,128}
                           const __grid_constant__ CUtensorMap tm_w2h,     // {256, rows} box {64,128}
                           const __grid_constant__ CUtensorMap tm_ident16, // {64, 32} box {64,16}
+                          const __grid_constant__ CUtensorMap tm_a0,      // first layer: {16, Fq, 32 B} box {64, seg_rows, 1}
+                          const __grid_constant__ CUtensorMap tm_wc,      // first layer: {16, rows} box {64,128}
                           const LayerTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -80,6 +82,11 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
   const int n_pe = (n_entries + 1) / 2;
   const int n_ptiles = n_pe * kPhases;
   const int my_tiles = (n_ptiles - pair + n_pairs - 1) / n_pairs;
+  // First layer of a flow (p.first): x = start(a0) is never materialised.  in_layers[0](start(a0)) is a k=3 conv of the
+  // h <= 4 live channels with composed weights, so the three tap K-blocks hold [a0(t + tau) | 1 | 0 ..] (16 channels, the
+  // `1` carries W_in[tau] . b_start and vanishes with the zero padding) and need ONE K=16 MMA each instead of 3 x 16; the
+  // residual carry x(t) = W_start a0(t) + b_start is one more MMA in GEMM2 instead of the identity blocks.
+  const int n_kb = p.first ? kMwKB + 3 : kKB1;
 
   struct Coord {
     int ph, seg0;      // phase; first segment of the tile (>= total_segs: dummy tile, every row out of range)
@@ -150,7 +157,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
       ptx::prefetch_tmap(&tm_mw);
       ptx::prefetch_tmap(&tm_w1h);
       ptx::prefetch_tmap(&tm_vh);
-      if (p.has_res) {
+      if (p.has_res && !p.first) {
         // launch-constant operand (own half): identity rows of the residual carry
         if (rank == 0) ptx::mbar_arrive_expect_tx(ident_full, 2 * kPairIdentBytes);
         ptx::tma_load_2d_pair(smem + ContSmem::ident, &tm_ident16, ptx::map_to_cta(ident_full, 0), 0, static_cast<int>(rank) * (kIdentN / 2));
@@ -173,10 +180,10 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
       skip_loads = (p.dbg_flags & 1) && use > kPairStages;      // diagnostics: stages keep their stale contents
     };
     // elected lane: arm the leader's full barrier with the bytes of both CTAs; returns its cluster address
-    auto arm = [&]() -> uint32_t {
+    auto arm = [&](uint32_t bytes = 2 * kPairStageBytes) -> uint32_t {
       if (rank == 0) {
         if (skip_loads) ptx::mbar_arrive(full_s);
-        else ptx::mbar_arrive_expect_tx(full_s, 2 * kPairStageBytes);
+        else ptx::mbar_arrive_expect_tx(full_s, bytes);
       }
       return ptx::map_to_cta(full_s, 0);
     };
@@ -191,16 +198,34 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
       for (int i = 0; i < 4; ++i)
         if (i < n_sub) ptx::tma_load_3d_pair(sa + ((i << seg_shift) * 128), &tm_x_in, lb, cb * kBlockK, sq_[i] + dq, sb_[i] * kPhases + pp);
     };
+    // first layer: the [a0 | 1] rows of the current tile shifted by dq frames, phase pp (channels 16..63 are zero-filled by TMA)
+    auto load_a0 = [&](uint32_t lb, int dq, int pp) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < n_sub) ptx::tma_load_3d_pair(sa + ((i << seg_shift) * 128), &tm_a0, lb, 0, sq_[i] + dq, sb_[i] * kPhases + pp);
+    };
     // GEMM2 operands of a tile: W_res K-block j (own 128 rows) + x(t) K-block j for the identity carry
+    // (first layer: W_res only, then one stage with [a0 | 1](t) and the carry weights [W_start | b_start])
     auto load_gemm2 = [&](const Coord& tc) {
       set_tile(tc);
       for (int j = 0; j < 4; ++j) {
         next_stage();
         if (ptx::elect_one()) {
-          const uint32_t lb = arm();
+          const uint32_t lb = arm(p.first ? 2 * kPairStageB : 2 * kPairStageBytes);
           if (!skip_loads) {
             ptx::tma_load_2d_pair(sb, &tm_w2h, lb, j * kBlockK, p.w2_row0 + static_cast<int>(rank) * 128);
-            load_x(lb, j, 0, tc.ph);
+            if (!p.first) load_x(lb, j, 0, tc.ph);
+          }
+        }
+        __syncwarp();
+      }
+      if (p.first) {
+        next_stage();
+        if (ptx::elect_one()) {
+          const uint32_t lb = arm();
+          if (!skip_loads) {
+            ptx::tma_load_2d_pair(sb, &tm_wc, lb, 0, p.wc_row0 + 3 * 512 + static_cast<int>(rank) * 128);
+            load_a0(lb, 0, tc.ph);
           }
         }
         __syncwarp();
@@ -210,7 +235,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
       const Coord tc = tile_of(it);
       set_tile(tc);
       for (int chunk = 0; chunk < 2; ++chunk) {
-        for (int kb = 0; kb < kKB1; ++kb) {
+        for (int kb = 0; kb < n_kb; ++kb) {
           if (chunk == 0 && kb == p.g2_at && it > 0 && p.has_res) {
             load_gemm2(tile_of(it - 1));
             set_tile(tc);
@@ -238,6 +263,12 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
                 for (int i = 0; i < 4; ++i)
                   if (i < n_sub) ptx::tma_load_3d_pair(sa + ((i << seg_shift) * 128), &tm_mw, lb, kb * kBlockK, sq_[i], sb_[i]);
                 ptx::tma_load_2d_pair(sb, &tm_vh, lb, kb * kBlockK, p.v_row0 + tc.ph * 512 + chunk * 256 + static_cast<int>(rank) * 128);
+              } else if (p.first) {
+                const int tap = kb - kMwKB;        // 0..2: a0 at t-1, t, t+1 (dilation 1)
+                const int pp = tc.ph + tap - 1;
+                const int dq = pp >> 5;
+                load_a0(lb, dq, pp - (dq << 5));
+                ptx::tma_load_2d_pair(sb, &tm_wc, lb, 0, p.wc_row0 + tap * 512 + chunk * 256 + static_cast<int>(rank) * 128);
               } else {
                 const int j = kb - kMwKB;          // 0..11: tap (j >> 2) in {t-d, t, t+d}, channel block (j & 3)
                 const int pp = tc.ph + ((j >> 2) - 1) * p.dilation;
@@ -273,7 +304,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
         ptx::tc_fence_after_sync();
         if (j == 1 && lane == 0) stamp(p, 9);
         if (!p.has_res) return;
-        if (!ident_seen) {
+        if (!ident_seen && !p.first) {
           ptx::mbar_wait(ident_full, 0);
           ident_seen = true;
         }
@@ -291,12 +322,29 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
             for (int k = 0; k < 4; ++k)
               ptx::mma_f16_ss_pair(rQ, ptx::make_desc_sw128(a_addr + k * 32), ptx::make_desc_sw128(b_addr + k * 32), idesc256, (jj | k) != 0);
             // K-step k of this block covers channels 64 jj + 16 k .. +15; [I32 | 0] maps them onto 32 output columns at 64 jj + 32 (k >> 1)
+            if (!(p.dbg_flags & 128) && !p.first) {      // diagnostics: 128 = no identity carry
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              ptx::mma_f16_ss_pair(rQ + jj * 64 + (k >> 1) * 32, ptx::make_desc_sw128(x_addr + k * 32),
-                                   ptx::make_desc_sw128(ident_addr + (k & 1) * 32), idesc32, 1);
+              for (int k = 0; k < 4; ++k)
+                ptx::mma_f16_ss_pair(rQ + jj * 64 + (k >> 1) * 32, ptx::make_desc_sw128(x_addr + k * 32),
+                                     ptx::make_desc_sw128(ident_addr + (k & 1) * 32), idesc32, 1);
+            }
             ptx::mma_commit_pair(&empty[s], 3);
-            if (jj == 3) ptx::mma_commit_pair(d2_full, 3);
+            if (jj == 3 && !p.first) ptx::mma_commit_pair(d2_full, 3);
+          }
+          __syncwarp();
+        }
+        if (p.first) {
+          // residual carry of the first layer: x(t) = [a0(t) | 1] . [W_start | b_start]^T, one K = 16 step
+          const int s = use % kPairStages;
+          const uint32_t ph = (use / kPairStages) & 1;
+          ++use;
+          ptx::mbar_wait(&full[s], ph);
+          ptx::tc_fence_after_sync();
+          const uint32_t a_addr = stage_addr0 + s * kPairStageBytes;
+          if (ptx::elect_one()) {
+            ptx::mma_f16_ss_pair(rQ, ptx::make_desc_sw128(a_addr), ptx::make_desc_sw128(a_addr + kPairStageA), idesc256, 1);
+            ptx::mma_commit_pair(&empty[s], 3);
+            ptx::mma_commit_pair(d2_full, 3);
           }
           __syncwarp();
         }
@@ -318,7 +366,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
             }
           }
           const uint32_t d = chunk == 0 ? rP : rQ;
-          for (int kb = 0; kb < kKB1; ++kb) {
+          for (int kb = 0; kb < n_kb; ++kb) {
             if (chunk == 0 && kb == p.g2_at && it > 0) gemm2(it - 1);
             const int s = use % kPairStages;
             const uint32_t ph = (use / kPairStages) & 1;
@@ -335,13 +383,15 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
             }
             const uint32_t a_addr = stage_addr0 + s * kPairStageBytes;
             const uint32_t b_addr = a_addr + kPairStageA;
+            const int n_k = (p.first && kb >= kMwKB) ? 1 : 4;      // first layer: a tap block is 16 channels wide
             if (ptx::elect_one()) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                ptx::mma_f16_ss_pair(d, ptx::make_desc_sw128(a_addr + k * 32), ptx::make_desc_sw128(b_addr + k * 32), idesc256,
-                                     (kb | k) != 0);
+                if (k < n_k)
+                  ptx::mma_f16_ss_pair(d, ptx::make_desc_sw128(a_addr + k * 32), ptx::make_desc_sw128(b_addr + k * 32), idesc256,
+                                       (kb | k) != 0);
               ptx::mma_commit_pair(&empty[s], 3);
-              if (kb == kKB1 - 1) ptx::mma_commit_pair(&acc_full[chunk], 3);
+              if (kb == n_kb - 1) ptx::mma_commit_pair(&acc_full[chunk], 3);
             }
             __syncwarp();
           }
