@@ -100,7 +100,7 @@ def test_stagewise_first_flow(precision):
   sigma = 0.8
   trace = []
   phase_cond = precision != "fp32"     # tensor-core mode composes the upsampler into the conditioning weights
-  first_composed = precision == "fp16"  # ... and the default kernel composes the start conv into each flow's first layer
+  first_composed = precision in ("fp16", "fp16-wide")  # ... and the default / wide kernels compose the start conv into each flow's first layer
   with torch.no_grad():
     ref_audio = E.infer(w, dims, mel, sigma, zs, op_dtype, trace, phase_cond=phase_cond, first_composed=first_composed)
   k = dims.n_flows - 1

@@ -67,7 +67,7 @@ struct wg_engine {
   bool first_comp = false;            // continuous pair kernel: start conv composed into the first layer of each flow (WG_FIRST=0 disables)
   int g2_at_first = 7;                // g2_at of those first layers (8 k-blocks per chunk; WG_G2AT0 overrides)
   void* d_wc = nullptr;               // [flows][3 taps x 512 packed rows + 256 carry rows][16] 16-bit composed start weights
-  CUtensorMap tm_wc{};
+  CUtensorMap tm_wc{}, tm_wc256{};    // 128-row boxes (CTA pairs stage half of B each) / 256-row boxes (wide kernels)
   // fp32 path
   float* d_w1f = nullptr;             // [flows*layers][K1][2nc]
   float* d_bias1f = nullptr;          // [flows*layers][2nc]
@@ -291,7 +291,7 @@ int wg_create(const wg_config* cfg, wg_engine** out) {
   if (g2_env) e->g2_at = atoi(g2_env);
   if (e->g2_at < 0 || e->g2_at >= kKB1) return fail(e, WG_ERR_INVALID_ARGUMENT, "WG_G2AT must be in [0, %d)", kKB1);
   const char* first_env = getenv("WG_FIRST");
-  e->first_comp = e->pair_cont && !(first_env && atoi(first_env) == 0);
+  e->first_comp = (e->pair_cont || e->wide) && !(first_env && atoi(first_env) == 0);
   const char* g20_env = getenv("WG_G2AT0");
   if (g20_env) e->g2_at_first = atoi(g20_env);
   if (e->g2_at_first < 0 || e->g2_at_first >= kMwKB + 3) return fail(e, WG_ERR_INVALID_ARGUMENT, "WG_G2AT0 must be in [0, %d)", kMwKB + 3);
@@ -393,7 +393,7 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
   const int K1x = 3 * nc;            // fp16 mode: taps only (conditioning goes through V)
   const int w2rows = nc + 16;        // fp16 mode: W_res rows then 16 skip-end rows per layer (272 for 256 channels == kW2Rows)
   std::vector<uint16_t> w1h, w2h, wch;
-  constexpr int kWcRows = 3 * 512 + 256;     // per flow: composed taps (packed row order), then the carry rows
+  const int kWcRows = 7 * nc;                // per flow: 3 taps x 2 nc composed rows (packed row order), then nc carry rows
   const std::vector<float>* up_bias = nullptr;
   if ((rc = need("upsample.bias", {kMel}, &up_bias))) return rc;
   std::vector<float> bias1, bias_res, w1f, bias1f, wresf, wsef;
@@ -493,7 +493,7 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
             // in_layers[0](start(a0)) (model.py:117, 125): per tap, W_in[:, :, tap] . W_start (h columns) and
             // W_in[:, :, tap] . b_start (column 4, multiplied by the operand's `1`, which is 0 in the zero padding)
             for (int tap = 0; tap < 3; ++tap) {
-              uint16_t* crow = &wch[(static_cast<size_t>(k) * kWcRows + tap * 512 + np) * 16];
+              uint16_t* crow = &wch[(static_cast<size_t>(k) * kWcRows + tap * 2 * nc + np) * 16];
               double acc[5] = {0, 0, 0, 0, 0};
               for (int ci = 0; ci < nc; ++ci) {
                 const double wi = (*w_in)[(static_cast<size_t>(oc) * nc + ci) * 3 + tap];
@@ -508,7 +508,7 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
         if (i == 0 && e->first_comp) {
           // residual carry of the first layer: x(t) = W_start a0(t) + b_start
           for (int n = 0; n < nc; ++n) {
-            uint16_t* crow = &wch[(static_cast<size_t>(k) * kWcRows + 3 * 512 + n) * 16];
+            uint16_t* crow = &wch[(static_cast<size_t>(k) * kWcRows + 6 * nc + n) * 16];
             for (int j = 0; j < h; ++j) crow[j] = f2h((*w_start)[static_cast<size_t>(n) * h + j], e->op_fmt);
             crow[4] = f2h((*b_start)[n], e->op_fmt);
           }
@@ -603,6 +603,8 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
       const uint64_t str[1] = {32};
       const uint32_t boxh[2] = {64, 128};
       if ((rc = make_map(e, &e->tm_wc, e->d_wc, 2, dims, str, boxh, dt))) return rc;
+      const uint32_t box256[2] = {64, 256};
+      if ((rc = make_map(e, &e->tm_wc256, e->d_wc, 2, dims, str, box256, dt))) return rc;
     }
     {
       const uint64_t dims[2] = {64, static_cast<uint64_t>(kIdentN)};
@@ -731,20 +733,22 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
       wp.bias1 = e->d_bias1 + li * 2 * nc;
       wp.bias_res = e->d_bias_res + li * nc;
       wp.e = ebuf;
+      wp.first = e->first_comp && i == 0 && has_res;
+      wp.wc_row0 = k * 7 * nc;
       const int n_tiles = kPhases * ((wp.Fq + kTileM - 1) / kTileM) * B;
       dim3 grid(n_tiles < e->num_sms ? n_tiles : e->num_sms);
       if (nc == 512) {
         wn_gate_wide_kernel<512><<<grid, kTcThreads, WideCfg<512>::a_total + 1024, st>>>(tm_x[*cur], *tm_cond, e->tm_w1, e->tm_v,
-                                                                                      e->tm_w2b, tm_x[2], wp);
+                                                                                      e->tm_w2b, tm_x[2], tm_a0[0], e->tm_wc256, wp);
         if (has_res)
           wn_res_wide_kernel<512><<<grid, kTcThreads, WideCfg<512>::b_total + 1024, st>>>(tm_x[2], tm_x[*cur], tm_x[*cur ^ 1],
-                                                                                       e->tm_w2a, e->tm_ident, wp);
+                                                                                       e->tm_w2a, e->tm_ident, tm_a0[0], e->tm_wc256, wp);
       } else {
         wn_gate_wide_kernel<256><<<grid, kTcThreads, WideCfg<256>::a_total + 1024, st>>>(tm_x[*cur], *tm_cond, e->tm_w1, e->tm_v,
-                                                                                      e->tm_w2b, tm_x[2], wp);
+                                                                                      e->tm_w2b, tm_x[2], tm_a0[0], e->tm_wc256, wp);
         if (has_res)
           wn_res_wide_kernel<256><<<grid, kTcThreads, WideCfg<256>::b_total + 1024, st>>>(tm_x[2], tm_x[*cur], tm_x[*cur ^ 1],
-                                                                                       e->tm_w2a, e->tm_ident, wp);
+                                                                                       e->tm_w2a, e->tm_ident, tm_a0[0], e->tm_wc256, wp);
       }
       e->launches += has_res ? 1 : 0;
     } else if (tc) {
@@ -787,7 +791,7 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
         const int n_pairs = n_ptiles < e->num_sms / 2 ? n_ptiles : e->num_sms / 2;
         lp.wse = static_cast<const uint16_t*>(e->d_w2) + (li * kW2Rows + 256) * 256;
         lp.first = e->first_comp && i == 0 && has_res;
-        lp.wc_row0 = k * (3 * 512 + 256);
+        lp.wc_row0 = k * 7 * nc;
         lp.g2_at = lp.first ? e->g2_at_first : e->g2_at;
         lp.x_out = xb[*cur ^ 1];
         const CUtensorMap* seg_maps = tm_x + (best_idx == 0 ? 0 : (best_idx == 1 ? 3 : 6));      // {x0, x1, .., mel windows}

@@ -54,6 +54,9 @@ struct WideParams {
   const float* bias1;     // [2 NC] packed order (global; read through L1)
   const float* bias_res;  // [NC]
   float* e;               // [B, T, 8]
+  int first;              // first layer of a flow with the start conv composed in (see wg_layer_pair_cont_tc.cuh): the tap K-blocks
+                          // are [a0 | 1] rows (one K = 16 MMA each), the residual carry is one MMA with [W_start | b_start]
+  int wc_row0;            // first row of this flow's composed weights: 3 taps x 2 NC packed rows, then NC carry rows
 };
 
 struct TileCoord {
@@ -76,6 +79,8 @@ wn_gate_wide_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC, Fq, 
                     const __grid_constant__ CUtensorMap tm_v,       // {320, rows} box {64,256}
                     const __grid_constant__ CUtensorMap tm_se,      // {NC, rows} box {64,16}
                     const __grid_constant__ CUtensorMap tm_acts,    // {NC, Fq, 32 B} box {64,128,1} (store)
+                    const __grid_constant__ CUtensorMap tm_a0,      // first layer: {16, Fq, 32 B} box {64,128,1}
+                    const __grid_constant__ CUtensorMap tm_wc,      // first layer: {16, rows} box {64,256}
                     const WideParams p) {
   using C = WideCfg<NC>;
   extern __shared__ uint8_t smem_raw[];
@@ -95,6 +100,7 @@ wn_gate_wide_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC, Fq, 
   const int n_tiles = tiles_per_utt * p.B;
   const int my_tiles = (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const int n_units = my_tiles * C::kHalves;    // unit n = (tile it = n / kHalves, half h = n % kHalves)
+  const int n_kb = p.first ? kMwKB + 3 : C::kKB;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -142,7 +148,7 @@ wn_gate_wide_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC, Fq, 
     auto load_pass = [&](int n, int chunk) {
       const TileCoord tc = tile_of(n / C::kHalves);
       const int h = n % C::kHalves;
-      for (int kb = 0; kb < C::kKB; ++kb, ++use) {
+      for (int kb = 0; kb < n_kb; ++kb, ++use) {
         const int s = use % kStages;
         const uint32_t ph = (use / kStages) & 1;
         ptx::mbar_wait(&empty[s], ph ^ 1);
@@ -153,6 +159,12 @@ wn_gate_wide_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC, Fq, 
           if (kb < kMwKB) {
             ptx::tma_load_3d(sa, &tm_mw, &full[s], kb * kBlockK, tc.q0, tc.b);
             ptx::tma_load_2d(sb, &tm_v, &full[s], kb * kBlockK, p.v_row0 + tc.ph * 2 * NC + h * 512 + chunk * 256);
+          } else if (p.first) {
+            const int tap = kb - kMwKB;                  // [a0 | 1] at t-1, t, t+1
+            const int pp = tc.ph + tap - 1;
+            const int dq = pp >> 5;
+            ptx::tma_load_3d(sa, &tm_a0, &full[s], 0, tc.q0 + dq, tc.b * kPhases + pp - (dq << 5));
+            ptx::tma_load_2d(sb, &tm_wc, &full[s], 0, p.wc_row0 + tap * 2 * NC + h * 512 + chunk * 256);
           } else {
             const int j = kb - kMwKB;                    // tap (j / kCB), channel block (j % kCB)
             const int pp = tc.ph + ((j / C::kCB) - 1) * p.dilation;
@@ -181,19 +193,21 @@ wn_gate_wide_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC, Fq, 
     int use = 0;
     auto mma_pass = [&](int chunk) {
       const uint32_t d = chunk == 0 ? ra : rb;
-      for (int kb = 0; kb < C::kKB; ++kb, ++use) {
+      for (int kb = 0; kb < n_kb; ++kb, ++use) {
         const int s = use % kStages;
         const uint32_t ph = (use / kStages) & 1;
         ptx::mbar_wait(&full[s], ph);
         ptx::tc_fence_after_sync();
         const uint32_t a_addr = stage_addr0 + s * kStageBytes;
         const uint32_t b_addr = a_addr + kStageABytes;
+        const int n_k = (p.first && kb >= kMwKB) ? 1 : 4;
         if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            ptx::mma_f16_ss(d, ptx::make_desc_sw128(a_addr + k * 32), ptx::make_desc_sw128(b_addr + k * 32), idesc256, (kb | k) != 0);
+            if (k < n_k)
+              ptx::mma_f16_ss(d, ptx::make_desc_sw128(a_addr + k * 32), ptx::make_desc_sw128(b_addr + k * 32), idesc256, (kb | k) != 0);
           ptx::mma_commit(&empty[s]);
-          if (kb == C::kKB - 1) ptx::mma_commit(&acc_full[chunk]);
+          if (kb == n_kb - 1) ptx::mma_commit(&acc_full[chunk]);
         }
         __syncwarp();
       }
@@ -301,6 +315,8 @@ wn_res_wide_kernel(const __grid_constant__ CUtensorMap tm_acts,    // {NC, Fq, 3
                    const __grid_constant__ CUtensorMap tm_x_out,   // same geometry, other buffer (store)
                    const __grid_constant__ CUtensorMap tm_wres,    // {NC, rows} box {64,256}
                    const __grid_constant__ CUtensorMap tm_ident,   // {64, 32} box {64,32}
+                   const __grid_constant__ CUtensorMap tm_a0,      // first layer: {16, Fq, 32 B} box {64,128,1}
+                   const __grid_constant__ CUtensorMap tm_wc,      // first layer: {16, rows} box {64,256}
                    const WideParams p) {
   using C = WideCfg<NC>;
   extern __shared__ uint8_t smem_raw[];
@@ -374,6 +390,20 @@ wn_res_wide_kernel(const __grid_constant__ CUtensorMap tm_acts,    // {NC, Fq, 3
         }
         __syncwarp();
       }
+      if (p.first) {
+        // residual carry x(t) = [a0(t) | 1] . [W_start | b_start]^T of this output half: one stage, one K = 16 MMA
+        const int s = use % kStages;
+        const uint32_t ph = (use / kStages) & 1;
+        ++use;
+        ptx::mbar_wait(&empty[s], ph ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(&full[s], kStageBytes);
+          ptx::tma_load_3d(smem + s * kStageBytes, &tm_a0, &full[s], 0, tc.q0, tc.b * kPhases + tc.ph);
+          ptx::tma_load_2d(smem + s * kStageBytes + kStageABytes, &tm_wc, &full[s], 0, p.wc_row0 + 3 * 2 * NC + o * 256);
+        }
+        __syncwarp();
+        continue;
+      }
       for (int j = 0; j < 4; ++j, ++use) {
         const int s = use % kStages;
         const uint32_t ph = (use / kStages) & 1;
@@ -413,6 +443,21 @@ wn_res_wide_kernel(const __grid_constant__ CUtensorMap tm_acts,    // {NC, Fq, 3
           ptx::mma_commit(&empty[s]);
         }
         __syncwarp();
+      }
+      if (p.first) {
+        const int s = use % kStages;
+        const uint32_t ph = (use / kStages) & 1;
+        ++use;
+        ptx::mbar_wait(&full[s], ph);
+        ptx::tc_fence_after_sync();
+        const uint32_t a_addr = stage_addr0 + s * kStageBytes;
+        if (ptx::elect_one()) {
+          ptx::mma_f16_ss(d, ptx::make_desc_sw128(a_addr), ptx::make_desc_sw128(a_addr + kStageABytes), idesc256, 1);
+          ptx::mma_commit(&empty[s]);
+          ptx::mma_commit(&d_full[r]);
+        }
+        __syncwarp();
+        continue;
       }
       for (int j = 0; j < 4; ++j, ++use) {
         const int s = use % kStages;
