@@ -288,11 +288,15 @@ def main():
   peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
   peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step; fp16 and bf16 share the tcgen05 kind::f16 rate)" \
       if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
-  # tensor FLOPs the fused kernel actually issues per group-step and layer: GEMM1 K = 3*256 + 320
-  # (upsampler composed into the conditioning), GEMM2 N = 256 residual + identity carry, skip->end fold (8 outputs on mma.sync in
-  # the 256-channel kernel, 16 tcgen05 columns in the wide path)
+  # tensor FLOPs the layer kernels actually issue per group-step, averaged over the 8 layers of a flow:
+  # GEMM1 K = 3 nc + 320 (upsampler composed into the conditioning), K = 320 + 3 x 16 in a flow's first layer (start conv
+  # composed in); GEMM2 N = nc residual + identity carry (one K = 16 step in the first layer, none in the last);
+  # skip->end fold (8 outputs on mma.sync in the 256-channel kernel, 16 tcgen05 columns in the wide path)
   nc = args.channels
-  exec_per_step_layer = 2 * (3 * nc + 320) * 2 * nc + (7 / 8) * (2 * nc * nc + 2 * nc * 32) + 2 * nc * (8 if nc == 256 else 16)
+  se = 2 * nc * (8 if nc == 256 else 16)
+  g1_full, g1_first = 2 * (3 * nc + 320) * 2 * nc, 2 * (320 + 3 * 16) * 2 * nc
+  g2_mid, g2_first = 2 * nc * nc + 2 * nc * 32, 2 * nc * nc + 2 * 16 * nc
+  exec_per_step_layer = ((g1_first + g2_first + se) + 6 * (g1_full + g2_mid + se) + (g1_full + se)) / 8
   roofline = None
   if layer_launches:
     per_launch_flops = layer_flops_sample * B * T / layer_launches
@@ -301,10 +305,10 @@ def main():
     roofline = {"bound": "tensor", "kernel": ("wn_layer_fp32_kernel" if args.precision == "fp32" else
                            "wn_layer_pair_cont_kernel" if args.channels == 256 else "wn_gate_wide_kernel + wn_res_wide_kernel"),
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel on this workload, from
-                # profiles/r01/ncu_full_layer_v7_cont_summary.csv (ncu --set full, kernel v7: 256 + 217 MB); only valid for the
-                # default workload
-                "traffic": 473e6 if (args.batch == 16 and args.frames == 861 and args.precision == "fp16" and args.channels == 256) else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel on this workload, averaged over the 8
+                # layers of a flow, from profiles/r01/ncu_full_layer_v9_first_and_generic_summary.csv (ncu --set full: generic
+                # layer 268 + 213 MB, first layer 34 + 189 MB); only valid for the default workload
+                "traffic": 449e6 if (args.batch == 16 and args.frames == 861 and args.precision == "fp16" and args.channels == 256) else None,
                 "traffic_unit": "bytes per launch (ncu)",
                 "peak_source": peak_src, "launch_ms": per_launch_ms, "launches_per_step": layer_launches,
                 "algorithmic_flop_per_launch": per_launch_flops,
