@@ -23,7 +23,8 @@ def get_model(n_channels: int, precision: str, style: str = "parametrized") -> W
   "fp16-pair1" (WG_PAIR=1: the older CTA-pair schedule with the skip-end outputs on tcgen05), "fp16-single" (WG_PAIR=0: the
   same fused layer on single CTAs) or "fp16-wide" (WG_WIDE=1: the two-kernel layer of 512-channel models, forced onto the
   256-channel model so that it can be checked against the same references); "fp16-seg32" / "fp16-seg64" (WG_SEG) force
-  the segment size of the default kernel's tiles."""
+  the segment size of the default kernel's tiles; "fp16-nopack" (WG_PACK4=0) switches the packed ragged tails off and
+  "fp16-nofirst" (WG_FIRST=0) the composition of the start conv into each flow's first layer."""
   import os
   key = (n_channels, precision, style)
   if key not in _MODELS:
@@ -39,12 +40,18 @@ def get_model(n_channels: int, precision: str, style: str = "parametrized") -> W
       os.environ["WG_PAIR"] = "1"
     if precision.startswith("fp16-seg"):
       os.environ["WG_SEG"] = precision[len("fp16-seg"):]
+    if precision == "fp16-nopack":
+      os.environ["WG_PACK4"] = "0"
+    if precision == "fp16-nofirst":
+      os.environ["WG_FIRST"] = "0"
     try:
       m.engine()          # the engine reads WG_WIDE / WG_PAIR when it is created
     finally:
       os.environ.pop("WG_WIDE", None)
       os.environ.pop("WG_PAIR", None)
       os.environ.pop("WG_SEG", None)
+      os.environ.pop("WG_PACK4", None)
+      os.environ.pop("WG_FIRST", None)
     _MODELS[key] = m
   return _MODELS[key]
 
@@ -231,9 +238,46 @@ def test_segment_tiles_match_reference_golden(name, mode):
   assert torch.equal(out, run(get_model(256, "fp16", str(g["weight_style"])), mel, zs, sigma))
 
 
+@pytest.mark.parametrize("B,F", [(6, 140), (4, 861), (9, 40)])
+def test_packed_ragged_tails_vs_oracle_and_unpacked(B, F):
+  """The frames past the last whole 128-frame block are tiled as 32 frames x 4 consecutive utterances (one 4-D TMA box):
+  B = 6 leaves a group with two missing utterances, 861 frames is the headline length (6 blocks + 93 frames -> 3 packed
+  tiles per 4 utterances), 40 frames has no whole block at all.  Same gates against the oracle, and bit-identical to the
+  engine with the packing switched off (only the assignment of rows to tiles changes)."""
+  hp, sd, w, dims = synthetic_weights(256)
+  model = get_model(256, "fp16")
+  mel = synthetic_mel(B, F, 511 + F)
+  zs = synthetic_noise(hp, B, F * 32, 512 + F)
+  out = run(model, mel, zs, 0.666)
+  assert torch.equal(out, run(get_model(256, "fp16-nopack"), mel, zs, 0.666))
+  if F <= 200:
+    with torch.no_grad():
+      ref = O.infer(w, dims, mel, 0.666, zs)
+    err, snr = max_abs(ref, out), snr_db(ref, out)
+    print(f"fp16 B{B} F{F} (packed tails): max-abs {err:.3e}  snr {snr:.1f} dB")
+    assert err <= FP16_MAX_ABS and snr >= FP16_MIN_SNR_DB
+  alone = run(model, mel[B - 1:B], [z[B - 1:B] for z in zs], 0.666)
+  assert torch.equal(out[B - 1:B], alone)
+
+
+def test_first_layer_composition_vs_explicit_start_conv():
+  """WG_FIRST=0 keeps the explicit start conv (the flow step writes the 256-channel x): both forms stay inside the gates
+  against the reference golden and differ from each other only by operand rounding."""
+  g = load_golden("infer_c256_b1_f40")
+  mel, zs, sigma = torch.from_numpy(g["mel"]), golden_noise(g), float(g["sigma"])
+  ref = torch.from_numpy(g["audio"])
+  a = run(get_model(256, "fp16"), mel, zs, sigma)
+  b = run(get_model(256, "fp16-nofirst"), mel, zs, sigma)
+  for name, out in (("composed", a), ("explicit", b)):
+    err, snr = max_abs(ref, out), snr_db(ref, out)
+    print(f"first layer {name}: max-abs {err:.3e}  snr {snr:.1f} dB")
+    assert err <= FP16_MAX_ABS and snr >= FP16_MIN_SNR_DB
+  assert max_abs(a, b) <= 2e-3      # each is within 2e-3 of the reference; measured 1.3e-3 between them
+
+
 def test_segment_choice_short_utterances_vs_oracle():
-  """B=8 x 72 frames: the engine itself picks 32-frame segments here (18 tile entries instead of 32 of 128 frames); a tile
-  then holds the tail of one utterance and the head of the next."""
+  """B=8 x 72 frames, no whole 128-frame block: the engine packs 32 frames x 4 utterances per tile (6 tile entries instead
+  of 8 ragged ones; before the packed tails existed it picked 32-frame segments here, which WG_SEG still forces)."""
   hp, sd, w, dims = synthetic_weights(256)
   model = get_model(256, "fp16")
   B, F = 8, 72

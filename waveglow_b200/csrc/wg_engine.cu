@@ -65,6 +65,7 @@ struct wg_engine {
   int force_seg = 0;                  // WG_SEG env (tests/diagnostics): force the segment size (128 / 64 / 32) of the continuous pair kernel
   bool pair_cont = false;             // ... with the continuous-issue schedule (wg_layer_pair_cont_tc.cuh); WG_PAIR=1 selects the older pair kernel
   bool first_comp = false;            // continuous pair kernel: start conv composed into the first layer of each flow (WG_FIRST=0 disables)
+  bool pack4 = true;                  // continuous pair kernel: pack the ragged last frames of 4 utterances into shared tiles (WG_PACK4=0 disables)
   int g2_at_first = 7;                // g2_at of those first layers (8 k-blocks per chunk; WG_G2AT0 overrides)
   void* d_wc = nullptr;               // [flows][3 taps x 512 packed rows + 256 carry rows][16] 16-bit composed start weights
   CUtensorMap tm_wc{}, tm_wc256{};    // 128-row boxes (CTA pairs stage half of B each) / 256-row boxes (wide kernels)
@@ -292,6 +293,8 @@ int wg_create(const wg_config* cfg, wg_engine** out) {
   if (e->g2_at < 0 || e->g2_at >= kKB1) return fail(e, WG_ERR_INVALID_ARGUMENT, "WG_G2AT must be in [0, %d)", kKB1);
   const char* first_env = getenv("WG_FIRST");
   e->first_comp = (e->pair_cont || e->wide) && !(first_env && atoi(first_env) == 0);
+  const char* pack_env = getenv("WG_PACK4");
+  e->pack4 = !(pack_env && atoi(pack_env) == 0);
   const char* g20_env = getenv("WG_G2AT0");
   if (g20_env) e->g2_at_first = atoi(g20_env);
   if (e->g2_at_first < 0 || e->g2_at_first >= kMwKB + 3) return fail(e, WG_ERR_INVALID_ARGUMENT, "WG_G2AT0 must be in [0, %d)", kMwKB + 3);
@@ -694,7 +697,8 @@ void flow_step_any(wg_engine* e, const FlowStepParams& fs_in, float* state, cons
 // Runs the WN layers of flow k.  x buffers alternate; returns the index of the buffer holding the
 // current residual stream through *cur.  Returns 1 if the debug stop triggered.
 int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout& L, const CUtensorMap* tm_x,
-                  const CUtensorMap* tm_cond, const CUtensorMap* tm_a0, int* cur, cudaStream_t st, bool* stopped) {
+                  const CUtensorMap* tm_cond, const CUtensorMap* tm_a0, const CUtensorMap* tm_p4, int* cur, cudaStream_t st,
+                  bool* stopped) {
   const int nc = e->cfg.n_channels, NL = e->cfg.n_layers;
   const bool tc = e->cfg.precision == WG_PRECISION_FP16;
   void* xb[2] = {ws + L.x0, ws + L.x1};
@@ -787,6 +791,20 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
           }
         }
         lp.seg_rows = kTileM >> best_idx;
+        // ragged tail: n_full whole 128-frame blocks per utterance, then the remaining frames of 4 consecutive utterances
+        // share tiles of 32 frames x 4 utterances (one 4-D TMA box per operand load, so no box cost)
+        if (e->pack4 && !e->force_seg) {
+          const int n_full = lp.Fq / kTileM, rem = lp.Fq - n_full * kTileM, n_rem = (rem + 31) / 32;
+          const int n_pe4 = (B * n_full + ((B + 3) / 4) * n_rem + 1) / 2;
+          if (rem > 0 && n_pe4 < best_pe * kBoxCost[best_idx]) {
+            lp.pack4 = 1;
+            lp.n_full = n_full;
+            lp.n_rem = n_rem;
+            lp.seg_rows = kTileM;
+            best_idx = 0;
+            best_pe = n_pe4;
+          }
+        }
         const int n_ptiles = kPhases * best_pe;
         const int n_pairs = n_ptiles < e->num_sms / 2 ? n_ptiles : e->num_sms / 2;
         lp.wse = static_cast<const uint16_t*>(e->d_w2) + (li * kW2Rows + 256) * 256;
@@ -797,7 +815,8 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
         const CUtensorMap* seg_maps = tm_x + (best_idx == 0 ? 0 : (best_idx == 1 ? 3 : 6));      // {x0, x1, .., mel windows}
         const CUtensorMap& tm_mw_seg = best_idx == 0 ? *tm_cond : seg_maps[2];
         wn_layer_pair_cont_kernel<<<dim3(2 * n_pairs), kContThreads, ContSmem::total + 1024, st>>>(
-            seg_maps[*cur], tm_mw_seg, e->tm_w1h, e->tm_vh, e->tm_w2h, e->tm_ident16, tm_a0[best_idx], e->tm_wc, lp);
+            seg_maps[*cur], tm_mw_seg, e->tm_w1h, e->tm_vh, e->tm_w2h, e->tm_ident16, tm_a0[best_idx], e->tm_wc, tm_p4[*cur], tm_p4[2],
+            tm_p4[3], lp);
         e->launches++;
         if (has_res) *cur ^= 1;
         if (e->dbg_flow == k && e->dbg_layer == i) {
@@ -882,7 +901,7 @@ void launch_conditioning(wg_engine* e, const float* mel, int B, int frames, int 
 }
 
 int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CUtensorMap* tm_x, CUtensorMap* tm_cond,
-                  CUtensorMap* tm_a0) {
+                  CUtensorMap* tm_a0, CUtensorMap* tm_p4) {
   // tm_x[0], tm_x[1]: residual stream ping-pong; tm_x[2]: gated activations of the wide path (same geometry);
   // tm_x[3], tm_x[4]: the ping-pong buffers again with 64-row boxes, tm_x[5]: mel windows with 64-row boxes;
   // tm_x[6], tm_x[7], tm_x[8]: the same three with 32-row boxes (segment tiles of the CTA-pair kernels)
@@ -912,6 +931,25 @@ int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CU
     const uint32_t box64[3] = {64, 64, 1}, box32[3] = {64, 32, 1};
     if ((rc = make_map(e, &tm_x[5], ws + L.cond, 3, dims, str, box64, dt))) return rc;
     if ((rc = make_map(e, &tm_x[8], ws + L.cond, 3, dims, str, box32, dt))) return rc;
+  }
+  if (e->pair_cont) {
+    // packed ragged tails (LayerTcParams::pack4): 32 frames x 4 consecutive utterances per box.  tm_p4[0], [1]: x ping-pong
+    // as {nc, Fq, 32 phases, B}; [2]: mel windows; [3]: [a0 | 1] rows
+    const uint64_t dims[4] = {static_cast<uint64_t>(nc), static_cast<uint64_t>(Fq), kUpPhases, static_cast<uint64_t>(B)};
+    const uint64_t str[3] = {static_cast<uint64_t>(nc) * 2, static_cast<uint64_t>(nc) * 2 * Fq, static_cast<uint64_t>(nc) * 2 * Fq * kUpPhases};
+    const uint32_t box[4] = {64, 32, 1, 4};
+    if ((rc = make_map(e, &tm_p4[0], ws + L.x0, 4, dims, str, box, dt))) return rc;
+    if ((rc = make_map(e, &tm_p4[1], ws + L.x1, 4, dims, str, box, dt))) return rc;
+    const uint64_t mdims[3] = {static_cast<uint64_t>(kUpKdim), static_cast<uint64_t>(Fq), static_cast<uint64_t>(B)};
+    const uint64_t mstr[2] = {static_cast<uint64_t>(kUpKdim) * 2, static_cast<uint64_t>(kUpKdim) * 2 * Fq};
+    const uint32_t mbox[3] = {64, 32, 4};
+    if ((rc = make_map(e, &tm_p4[2], ws + L.cond, 3, mdims, mstr, mbox, dt))) return rc;
+    tm_p4[3] = tm_p4[2];
+    if (e->first_comp) {
+      const uint64_t adims[4] = {16, static_cast<uint64_t>(Fq), kUpPhases, static_cast<uint64_t>(B)};
+      const uint64_t astr[3] = {32, static_cast<uint64_t>(32) * Fq, static_cast<uint64_t>(32) * Fq * kUpPhases};
+      if ((rc = make_map(e, &tm_p4[3], ws + L.a0, 4, adims, astr, box, dt))) return rc;
+    }
   }
   if (e->first_comp) {
     // [a0 | 1] rows of the composed first layer, phase-major like x; 16 real channels, the 64-wide boxes zero-fill the rest
@@ -971,9 +1009,9 @@ int wg_infer(wg_engine* e, const float* mel, int32_t batch, int32_t frames, cons
   }
   // 2. conditioning operand (mel windows in tensor-core mode, upsampled + squeezed mel in fp32 mode)
   launch_conditioning(e, mel, B, frames, T, ws, L, st);
-  CUtensorMap tm_x[9], tm_cond, tm_a0[3];
+  CUtensorMap tm_x[9], tm_cond, tm_a0[3], tm_p4[4];
   if (tc) {
-    int rc = make_act_maps(e, ws, L, B, T, tm_x, &tm_cond, tm_a0);
+    int rc = make_act_maps(e, ws, L, B, T, tm_x, &tm_cond, tm_a0, tm_p4);
     if (rc) return rc;
   }
   float* ebuf = reinterpret_cast<float*>(ws + L.e);
@@ -996,7 +1034,7 @@ int wg_infer(wg_engine* e, const float* mel, int32_t batch, int32_t frames, cons
   }
   bool stopped = (e->dbg_flow == NF - 1 && e->dbg_layer == -1);
   for (int k = NF - 1; k >= 0 && !stopped; --k) {
-    int rc = run_wn_layers(e, k, B, T, ws, L, tm_x, &tm_cond, tm_a0, &cur, st, &stopped);
+    int rc = run_wn_layers(e, k, B, T, ws, L, tm_x, &tm_cond, tm_a0, tm_p4, &cur, st, &stopped);
     if (rc) return rc;
     if (stopped) break;
     FlowStepParams fs{};
@@ -1079,9 +1117,9 @@ int wg_forward(wg_engine* e, const float* mel, int32_t batch, int32_t frames, co
   WG_CUDA(e, cudaMemcpyAsync(state, audio_in, npos * kGroup * sizeof(float), cudaMemcpyDeviceToDevice, st));
   WG_CUDA(e, cudaMemsetAsync(sums, 0, NF * sizeof(double), st));
   launch_conditioning(e, mel, B, frames, T, ws, L, st);
-  CUtensorMap tm_x[9], tm_cond, tm_a0[3];
+  CUtensorMap tm_x[9], tm_cond, tm_a0[3], tm_p4[4];
   if (tc) {
-    int rc = make_act_maps(e, ws, L, B, T, tm_x, &tm_cond, tm_a0);
+    int rc = make_act_maps(e, ws, L, B, T, tm_x, &tm_cond, tm_a0, tm_p4);
     if (rc) return rc;
   }
   float* ebuf = reinterpret_cast<float*>(ws + L.e);
@@ -1114,7 +1152,7 @@ int wg_forward(wg_engine* e, const float* mel, int32_t batch, int32_t frames, co
     flow_step_any(e, fs, state, ebuf, xb[cur], B, T, L.Tpad, st);
     if (k == NF) break;
     bool stopped = false;
-    int rc = run_wn_layers(e, k, B, T, ws, L, tm_x, &tm_cond, tm_a0, &cur, st, &stopped);
+    int rc = run_wn_layers(e, k, B, T, ws, L, tm_x, &tm_cond, tm_a0, tm_p4, &cur, st, &stopped);
     if (rc) return rc;
   }
   state_to_channel_major_kernel<<<static_cast<unsigned>((npos + 255) / 256), 256, 0, st>>>(state, z_out, B, T);

@@ -48,6 +48,9 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
                           const __grid_constant__ CUtensorMap tm_ident16, // {64, 32} box {64,16}
                           const __grid_constant__ CUtensorMap tm_a0,      // first layer: {16, Fq, 32 B} box {64, seg_rows, 1}
                           const __grid_constant__ CUtensorMap tm_wc,      // first layer: {16, rows} box {64,128}
+                          const __grid_constant__ CUtensorMap tm_x4,      // pack4: x_in as {256, Fq, 32, B} box {64, 32, 1, 4}
+                          const __grid_constant__ CUtensorMap tm_mw4,     // pack4: {320, Fq, B} box {64, 32, 4}
+                          const __grid_constant__ CUtensorMap tm_a04,     // pack4, first layer: {16, Fq, 32, B} box {64, 32, 1, 4}
                           const LayerTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -78,7 +81,11 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
   const int n_sub = kTileM >> seg_shift;
   const int nseg = (p.Fq + seg - 1) >> seg_shift;          // segments per utterance
   const int total_segs = p.B * nseg;
-  const int n_entries = (total_segs + n_sub - 1) / n_sub;
+  // pack4 (seg_rows == 128 only): entries [0, n_class1) are the whole 128-frame blocks, utterance-major; then, per group of 4
+  // consecutive utterances, n_rem tiles of 32 remaining frames x 4 utterances (row = 32 * utterance + frame): 861 frames are
+  // 6 blocks + 93 frames, i.e. 3 packed tiles per 4 utterances instead of 4 ragged ones.
+  const int n_class1 = p.pack4 ? p.B * p.n_full : 0;
+  const int n_entries = p.pack4 ? n_class1 + ((p.B + 3) >> 2) * p.n_rem : (total_segs + n_sub - 1) / n_sub;
   const int n_pe = (n_entries + 1) / 2;
   const int n_ptiles = n_pe * kPhases;
   const int my_tiles = (n_ptiles - pair + n_pairs - 1) / n_pairs;
@@ -104,6 +111,33 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
     const bool valid = sg < total_segs;
     b = valid ? sg / nseg : p.B;
     q0 = valid ? (sg - b * nseg) << seg_shift : 0;
+  };
+  // pack4: entry -> class (false: whole block, true: packed remainder), first utterance, first frame
+  auto entry_coord = [&](int en, bool& packed, int& b0, int& q0) {
+    packed = en >= n_class1 && en < n_entries;
+    if (packed) {
+      const int e2 = en - n_class1, g = e2 / p.n_rem;
+      b0 = 4 * g;
+      q0 = p.n_full * kTileM + 32 * (e2 - g * p.n_rem);
+    } else if (en < n_class1) {
+      b0 = en / p.n_full;
+      q0 = (en - b0 * p.n_full) * kTileM;
+    } else {
+      b0 = p.B;      // dummy tile: every row out of range
+      q0 = 0;
+    }
+  };
+  // row of a tile -> (utterance, frame)
+  auto row_coord = [&](const Coord& tc, int row, int& b, int& q) {
+    if (p.pack4) {
+      bool packed;
+      entry_coord(tc.seg0, packed, b, q);
+      b += packed ? (row >> 5) : 0;
+      q += packed ? (row & 31) : row;
+    } else {
+      seg_coord(tc.seg0 + (row >> seg_shift), b, q);
+      q += row & (seg - 1);
+    }
   };
 
   if (threadIdx.x == 0 && rank == 0) stamp(p, 0);
@@ -188,18 +222,31 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
       return ptx::map_to_cta(full_s, 0);
     };
     int sb_[4], sq_[4];            // (utterance, first frame) of the segments of the tile being loaded
+    bool packed = false;           // pack4: the tile is 32 frames x 4 utterances starting at (sb_[0], sq_[0])
     auto set_tile = [&](const Coord& tc) {
+      if (p.pack4) {
+        entry_coord(tc.seg0, packed, sb_[0], sq_[0]);
+      } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) seg_coord(tc.seg0 + i, sb_[i], sq_[i]);
+        for (int i = 0; i < 4; ++i) seg_coord(tc.seg0 + i, sb_[i], sq_[i]);
+      }
     };
     // x rows of the current tile shifted by dq frames, phase pp, channel block cb: one box per segment
     auto load_x = [&](uint32_t lb, int cb, int dq, int pp) {
+      if (packed) {
+        ptx::tma_load_4d_pair(sa, &tm_x4, lb, cb * kBlockK, sq_[0] + dq, pp, sb_[0]);
+        return;
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         if (i < n_sub) ptx::tma_load_3d_pair(sa + ((i << seg_shift) * 128), &tm_x_in, lb, cb * kBlockK, sq_[i] + dq, sb_[i] * kPhases + pp);
     };
     // first layer: the [a0 | 1] rows of the current tile shifted by dq frames, phase pp (channels 16..63 are zero-filled by TMA)
     auto load_a0 = [&](uint32_t lb, int dq, int pp) {
+      if (packed) {
+        ptx::tma_load_4d_pair(sa, &tm_a04, lb, 0, sq_[0] + dq, pp, sb_[0]);
+        return;
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         if (i < n_sub) ptx::tma_load_3d_pair(sa + ((i << seg_shift) * 128), &tm_a0, lb, 0, sq_[i] + dq, sb_[i] * kPhases + pp);
@@ -240,28 +287,15 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
             load_gemm2(tile_of(it - 1));
             set_tile(tc);
           }
-          if ((p.dbg_flags & 32) && chunk == 1 && kb == 0 && it + 1 < my_tiles) {
-            // experiment: pull the next tile's own x rows (its centre tap; the +-d taps are other tiles' centre taps) into L2
-            const Coord nt = tile_of(it + 1);
-            int nb[4], nq[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) seg_coord(nt.seg0 + i, nb[i], nq[i]);
-            if (ptx::elect_one()) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (i < n_sub && nb[i] < p.B)
-                  for (int cb = 0; cb < 4; ++cb) ptx::tma_prefetch_3d(&tm_x_in, cb * kBlockK, nq[i], nb[i] * kPhases + nt.ph);
-            }
-            __syncwarp();
-          }
           next_stage();
           if (ptx::elect_one()) {
             const uint32_t lb = arm();
             if (!skip_loads) {
               if (kb < kMwKB) {
+                if (packed) ptx::tma_load_3d_pair(sa, &tm_mw4, lb, kb * kBlockK, sq_[0], sb_[0]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                  if (i < n_sub) ptx::tma_load_3d_pair(sa + ((i << seg_shift) * 128), &tm_mw, lb, kb * kBlockK, sq_[i], sb_[i]);
+                  if (i < n_sub && !packed) ptx::tma_load_3d_pair(sa + ((i << seg_shift) * 128), &tm_mw, lb, kb * kBlockK, sq_[i], sb_[i]);
                 ptx::tma_load_2d_pair(sb, &tm_vh, lb, kb * kBlockK, p.v_row0 + tc.ph * 512 + chunk * 256 + static_cast<int>(rank) * 128);
               } else if (p.first) {
                 const int tap = kb - kMwKB;        // 0..2: a0 at t-1, t, t+1 (dilation 1)
@@ -437,8 +471,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
       if (p.has_res) {
         // ---- x' (16-bit): 64 columns of region Q -> + bias -> this row of the phase-major x buffer, 32-byte stores from registers
         int row_b, row_q;
-        seg_coord(tc.seg0 + (row >> seg_shift), row_b, row_q);
-        row_q += row & (seg - 1);
+        row_coord(tc, row, row_b, row_q);
         const bool in_buf = row_b < p.B && row_q < p.Fq;                      // the row exists in the x buffer
         const bool live = in_buf && row_q * kPhases + tc.ph < p.T;           // ... and is a real group-step (else: exact zeros)
         uint8_t* dst = static_cast<uint8_t*>(p.x_out) + ((static_cast<size_t>(row_b) * kPhases + tc.ph) * p.Fq + row_q) * (kNC * 2) + cq * 128;
@@ -517,8 +550,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
         for (int hr = 0; hr < 2; ++hr) {
           const int r = 32 * q + 16 * mt + (lane >> 2) + 8 * hr;
           int r_b, r_q;
-          seg_coord(tc.seg0 + (r >> seg_shift), r_b, r_q);
-          r_q += r & (seg - 1);
+          row_coord(tc, r, r_b, r_q);
           const int t = r_q * kPhases + tc.ph;
           if (r_b < p.B && r_q < p.Fq && t < p.T) {
             float2* ep = reinterpret_cast<float2*>(p.e + (static_cast<size_t>(r_b) * p.T + t) * 8 + 2 * (lane & 3));

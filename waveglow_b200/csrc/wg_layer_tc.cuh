@@ -84,6 +84,8 @@ struct LayerTcParams {
   int g2_at;              // continuous pair kernel: GEMM2 of tile i-1 is issued before this k-block of tile i's chunk a
   void* x_out;            // continuous pair kernel: the residual stream it writes (phase-major [B][32][Fq][256], 16-bit), plain stores
   const void* wse;        // continuous pair kernel: this layer's skip-end weights, 16-bit [8][256] (rows 256.. of its packed W2)
+  int pack4;              // continuous pair kernel, seg_rows == 128: each utterance is n_full whole 128-frame blocks; the remaining
+  int n_full, n_rem;      // frames are tiled as n_rem blocks of 32 frames x 4 consecutive utterances (one 4-D TMA box per operand)
   int first;              // continuous pair kernel: first layer of a flow with the start conv composed in (x is not materialised)
   int wc_row0;            // ... first row of this flow's composed weights: 3 taps x 512 packed rows, then 256 carry rows
   int dbg_flags;          // diagnostics only (results invalid): bit0 skip GEMM1 B loads, bit1 skip GEMM1 A loads; continuous pair
