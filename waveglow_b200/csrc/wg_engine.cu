@@ -65,6 +65,7 @@ struct wg_engine {
   int force_seg = 0;                  // WG_SEG env (tests/diagnostics): force the segment size (128 / 64 / 32) of the continuous pair kernel
   bool pair_cont = false;             // ... with the continuous-issue schedule (wg_layer_pair_cont_tc.cuh); WG_PAIR=1 selects the older pair kernel
   bool first_comp = false;            // continuous pair kernel: start conv composed into the first layer of each flow (WG_FIRST=0 disables)
+  bool pdl = true;                    // continuous pair kernel: programmatic dependent launch between layer launches (WG_PDL=0 disables)
   bool pack4 = true;                  // continuous pair kernel: pack the ragged last frames of 4 utterances into shared tiles (WG_PACK4=0 disables)
   int g2_at_first = 7;                // g2_at of those first layers (8 k-blocks per chunk; WG_G2AT0 overrides)
   void* d_wc = nullptr;               // [flows][3 taps x 512 packed rows + 256 carry rows][16] 16-bit composed start weights
@@ -293,6 +294,8 @@ int wg_create(const wg_config* cfg, wg_engine** out) {
   if (e->g2_at < 0 || e->g2_at >= kKB1) return fail(e, WG_ERR_INVALID_ARGUMENT, "WG_G2AT must be in [0, %d)", kKB1);
   const char* first_env = getenv("WG_FIRST");
   e->first_comp = (e->pair_cont || e->wide) && !(first_env && atoi(first_env) == 0);
+  const char* pdl_env = getenv("WG_PDL");
+  e->pdl = !(pdl_env && atoi(pdl_env) == 0);
   const char* pack_env = getenv("WG_PACK4");
   e->pack4 = !(pack_env && atoi(pack_env) == 0);
   const char* g20_env = getenv("WG_G2AT0");
@@ -814,9 +817,22 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
         lp.x_out = xb[*cur ^ 1];
         const CUtensorMap* seg_maps = tm_x + (best_idx == 0 ? 0 : (best_idx == 1 ? 3 : 6));      // {x0, x1, .., mel windows}
         const CUtensorMap& tm_mw_seg = best_idx == 0 ? *tm_cond : seg_maps[2];
-        wn_layer_pair_cont_kernel<<<dim3(2 * n_pairs), kContThreads, ContSmem::total + 1024, st>>>(
-            seg_maps[*cur], tm_mw_seg, e->tm_w1h, e->tm_vh, e->tm_w2h, e->tm_ident16, tm_a0[best_idx], e->tm_wc, tm_p4[*cur], tm_p4[2],
-            tm_p4[3], lp);
+        {
+          // programmatic dependent launch: this grid's CTAs may start their prologue and conditioning K-blocks while the
+          // previous layer's last tiles drain (griddepcontrol.wait in the kernel guards every dependent access)
+          cudaLaunchConfig_t cfg{};
+          cfg.gridDim = dim3(2 * n_pairs);
+          cfg.blockDim = dim3(kContThreads);
+          cfg.dynamicSmemBytes = ContSmem::total + 1024;
+          cfg.stream = st;
+          cudaLaunchAttribute attr[1];
+          attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+          attr[0].val.programmaticStreamSerializationAllowed = 1;
+          cfg.attrs = attr;
+          cfg.numAttrs = e->pdl ? 1 : 0;
+          WG_CUDA(e, cudaLaunchKernelEx(&cfg, wn_layer_pair_cont_kernel, seg_maps[*cur], tm_mw_seg, e->tm_w1h, e->tm_vh, e->tm_w2h,
+                                        e->tm_ident16, tm_a0[best_idx], e->tm_wc, tm_p4[*cur], tm_p4[2], tm_p4[3], lp));
+        }
         e->launches++;
         if (has_res) *cur ^= 1;
         if (e->dbg_flow == k && e->dbg_layer == i) {

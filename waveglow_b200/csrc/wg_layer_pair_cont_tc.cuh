@@ -178,6 +178,10 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
   ptx::cluster_sync_all();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);     // provably warp-uniform for ptxas
+  // Programmatic dependent launch (the host sets the launch attribute): the next layer's CTAs may become resident as soon as
+  // CTAs of this grid exit, run this prologue and their conditioning K-blocks (mel windows x V: constant during the call),
+  // and block in griddep_wait() before the first access to anything this grid writes (x, a0, e).
+  if (threadIdx.x == 0) ptx::griddep_launch_dependents();
 
   // Warps 0 and 1 run their loops CONVERGED (all 32 lanes wait on the barriers and compute the same addresses) and only the
   // instruction issue itself is predicated on elect.sync.  With a `lane == 0` branch around the whole loop, ptxas cannot prove
@@ -202,6 +206,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
     uint8_t *sa, *sb;
     uint64_t* full_s;
     bool skip_loads = false;
+    bool dep_ok = false;           // the previous grid (the layer / flow step that wrote x or a0) is known to be complete
     // all lanes: wait until the stage is free
     auto next_stage = [&]() {
       const int s = use % kPairStages;
@@ -286,6 +291,10 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
           if (chunk == 0 && kb == p.g2_at && it > 0 && p.has_res) {
             load_gemm2(tile_of(it - 1));
             set_tile(tc);
+          }
+          if (kb == kMwKB && !dep_ok) {
+            ptx::griddep_wait();
+            dep_ok = true;
           }
           next_stage();
           if (ptx::elect_one()) {
@@ -446,6 +455,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
     uint8_t* acts = smem + ContSmem::acts;
     const uint32_t l_acts_ready[2] = {ptx::map_to_cta(&acts_ready[0], 0), ptx::map_to_cta(&acts_ready[1], 0)};
     const uint32_t l_res_drained = ptx::map_to_cta(res_drained, 0);
+    ptx::griddep_wait();      // these warps write x' over the previous grid's input
 
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t par = it & 1;
@@ -519,6 +529,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
     const int lm_row = 32 * q + (lane & 7) + ((lane >> 3) & 1) * 8;      // + 16 for the second 16-row block (same swizzle phase)
     const uint32_t lm_base = acts_u32 + lm_row * 128;
     const int lm_sw = lm_row & 7, lm_hi = lane >> 4;
+    ptx::griddep_wait();      // e is read-modify-written across the layers of a flow
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t par = it & 1;
       const Coord tc = tile_of(it);
