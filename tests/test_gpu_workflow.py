@@ -91,3 +91,43 @@ def test_cli_synthesize_end_to_end(tmp_path):
   assert cli_main(["synthesize", str(ckpt), str(folder), "-out", str(out), "--custom-seed", "3"]) == 0
   assert (out / "a.wav").stat().st_mtime_ns == before
   assert cli_main(["synthesize", str(tmp_path / "nope.pt"), str(folder)]) == 1
+
+
+def test_mel_front_end_on_device_matches_reference_golden():
+  """taco_stft.TacotronSTFT on cuda:0 (cuFFT + mel matmul + log-clamp) against the reference class's golden mels."""
+  from tests.helpers import load_golden
+  from waveglow_b200.taco_stft import TacotronSTFT, TSTFTHParams
+  g = load_golden("taco_stft_b2_n8192")
+  tstft = TacotronSTFT(TSTFTHParams(), torch.device("cuda:0"))
+  mel = tstft.mel_spectrogram(torch.from_numpy(g["audio"]).cuda())
+  ref = torch.from_numpy(g["mel"])
+  assert mel.is_cuda and mel.shape == ref.shape
+  err = float((mel.cpu() - ref).abs().max())
+  print(f"on-device mel front-end: max-abs (log domain) {err:.3e}")
+  assert err <= 2e-3
+
+
+def test_cli_synthesize_wav_equals_synthesize_of_its_mels(tmp_path):
+  """`synthesize-wav` (inference_wav.py:74-130) = mel front-end + `synthesize`: feeding the mels it computes to
+  `synthesize` as .npy files gives the same wavs."""
+  from scipy.io.wavfile import write as write_wav
+  from waveglow_b200.taco_stft import TacotronSTFT, TSTFTHParams
+  hp, sd, w, dims = synthetic_weights(256)
+  ckpt = tmp_path / "1.pt"
+  CheckpointWaveglow.from_state_dict(sd, hp, iteration=1).save(ckpt)
+  src, mels = tmp_path / "src", tmp_path / "mels"
+  src.mkdir()
+  mels.mkdir()
+  tstft = TacotronSTFT(TSTFTHParams(), torch.device("cuda:0"))
+  g = torch.Generator().manual_seed(77)
+  for name, n in (("x.wav", 256 * 11), ("y.wav", 256 * 11), ("z.wav", 256 * 15 + 100)):
+    pcm = (torch.randn(n, generator=g).clamp(-3, 3) / 3 * 20000).to(torch.int16).numpy()
+    write_wav(str(src / name), 22050, pcm)
+    np.save(mels / name.replace(".wav", ".npy"), tstft.get_mel_tensor_from_file(src / name).cpu().numpy())
+  out_a, out_b = tmp_path / "a", tmp_path / "b"
+  assert cli_main(["synthesize-wav", str(ckpt), str(src), "-out", str(out_a), "--custom-seed", "4", "--sigma", "0.7"]) == 0
+  assert cli_main(["synthesize", str(ckpt), str(mels), "-out", str(out_b), "--custom-seed", "4", "--sigma", "0.7"]) == 0
+  for name, frames in (("x.wav", 12), ("y.wav", 12), ("z.wav", 16)):
+    sr, a = read_wav(out_a / name)
+    _, b = read_wav(out_b / name)
+    assert sr == 22050 and a.shape == (frames * 256,) and np.array_equal(a, b)

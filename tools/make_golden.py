@@ -131,7 +131,36 @@ def make_denoiser_golden():
   print(f"denoiser_b2_n6144: bias_spec {tuple(den.bias_spec.shape)}, denoised {tuple(outs['denoised_0'].shape)} (oracle bit-identical)")
 
 
+def make_taco_stft_golden():
+  """Runs the reference's own TacotronSTFT class (taco_stft.py) on CPU.  Its one third-party ingredient,
+  librosa.filters.mel, is absent from this image: oracle/taco_stft_oracle.py::librosa_mel (a restatement of the published
+  algorithm) is injected in its place (see that file's header: the filterbank is not pinned against librosa proper)."""
+  from oracle import taco_stft_oracle as TO
+  load_reference()                                   # registers the stub modules (incl. librosa.filters)
+  sys.modules["librosa.filters"].mel = TO.librosa_mel
+  sys.modules.pop("waveglow.taco_stft", None)        # re-import so that `from librosa.filters import mel` binds the injection
+  ref_taco = load_reference_module("taco_stft")
+  hp = ref_taco.TSTFTHParams()
+  tstft = ref_taco.TacotronSTFT(hp, torch.device("cpu"))
+  g = torch.Generator().manual_seed(41)
+  n = 8192
+  t = torch.arange(n) / hp.sampling_rate
+  # two "utterances": a chirp-like tone mix with noise, and low-level noise (exercises the 1e-5 clamp)
+  y0 = 0.4 * torch.sin(2 * np.pi * (220.0 + 900.0 * t) * t) + 0.2 * torch.sin(2 * np.pi * 3100.0 * t) + 0.05 * torch.randn(n, generator=g)
+  y1 = 1e-6 * torch.randn(n, generator=g)
+  y = torch.stack([y0, y1]).clamp(-1.0, 1.0)
+  mel = tstft.mel_spectrogram(y)
+  mel_single = tstft.get_mel_tensor(y[0])
+  assert torch.equal(mel, TO.mel_spectrogram(y)), "taco_stft oracle is not bit-identical to the reference class"
+  assert torch.allclose(mel_single, mel[0], atol=1e-4)      # batch 1 vs 2 may take another conv1d path
+  np.savez_compressed(os.path.join(ROOT, "tests", "golden", "taco_stft_b2_n8192.npz"), audio=y.numpy(), mel=mel.numpy(),
+                      mel_basis=tstft.mel_basis.numpy())
+  print(f"taco_stft_b2_n8192: mel {tuple(mel.shape)}, range [{float(mel.min()):.3f}, {float(mel.max()):.3f}] (oracle bit-identical)")
+
+
 if __name__ == "__main__":
-  if "--denoiser-only" not in sys.argv:
+  if "--denoiser-only" not in sys.argv and "--taco-only" not in sys.argv:
     main()
-  make_denoiser_golden()
+  if "--taco-only" not in sys.argv:
+    make_denoiser_golden()
+  make_taco_stft_golden()

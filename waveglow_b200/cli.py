@@ -6,6 +6,10 @@ Mirrors /root/reference/src/waveglow_cli/inference_v2.py:57-130 (arguments, defa
 quantised to int16 on the GPU.  Results are identical to the one-by-one loop because the reference
 re-seeds the RNG for every utterance (synthesizer.py:56), i.e. equal-length utterances share their noise anyway.
 `--include-stats` (MCD / SSIM plots) is reporting-only and not provided.
+
+`python -m waveglow_b200.cli synthesize-wav CHECKPOINT FOLDER` is the reference's `waveglow-cli synthesize-wav`
+(waveglow_cli/inference_wav.py:57-130: same arguments, `.wav` inputs): each wav goes through the on-device mel front-end
+(`taco_stft.TacotronSTFT`) and then through exactly the same batched path as `synthesize`.
 """
 import argparse
 import random
@@ -41,12 +45,8 @@ def split_hparams_string(hparams: Optional[str]) -> Optional[Dict[str, str]]:
   return dict([x.split("=") for x in hparams.split(",")])
 
 
-def build_parser() -> argparse.ArgumentParser:
-  parser = argparse.ArgumentParser(prog="waveglow_b200", description="B200-native WaveGlow synthesis")
-  sub = parser.add_subparsers(dest="command", required=True)
-  p = sub.add_parser("synthesize", description="Synthesize mel-spectrograms to audio files (.wav).")
-  p.add_argument("checkpoint", type=Path, metavar="CHECKPOINT", help="path to checkpoint which should be used for synthesis")
-  p.add_argument("folder", type=Path, metavar="FOLDER", help="path to folder which contains the mel-spectrograms (.npy)")
+def add_common(p: argparse.ArgumentParser) -> None:
+  """Options shared by `synthesize` (inference_v2.py:57-72) and `synthesize-wav` (inference_wav.py:57-72)."""
   p.add_argument("--sigma", type=_unit_interval, default=DEFAULT_SIGMA, help="sigma used for synthesis")
   p.add_argument("--denoiser-strength", type=_unit_interval, default=DEFAULT_DENOISER_STRENGTH,
                  help="strength of denoising to remove model bias after synthesis")
@@ -58,7 +58,21 @@ def build_parser() -> argparse.ArgumentParser:
   p.add_argument("--precision", choices=["fp16", "fp32"], default="fp16")
   p.add_argument("-out", "--output-directory", type=Path, default=None, help="custom output directory if FOLDER should not be used")
   p.add_argument("-o", "--overwrite", action="store_true", help="overwrite already synthesized lines")
-  p.set_defaults(handler=synthesize)
+
+
+def build_parser() -> argparse.ArgumentParser:
+  parser = argparse.ArgumentParser(prog="waveglow_b200", description="B200-native WaveGlow synthesis")
+  sub = parser.add_subparsers(dest="command", required=True)
+  p = sub.add_parser("synthesize", description="Synthesize mel-spectrograms to audio files (.wav).")
+  p.add_argument("checkpoint", type=Path, metavar="CHECKPOINT", help="path to checkpoint which should be used for synthesis")
+  p.add_argument("folder", type=Path, metavar="FOLDER", help="path to folder which contains the mel-spectrograms (.npy)")
+  p.set_defaults(handler=synthesize, source="mel")
+  add_common(p)
+  p = sub.add_parser("synthesize-wav", description="Synthesize audio files to audio files (.wav).")
+  p.add_argument("checkpoint", type=Path, metavar="CHECKPOINT", help="path to checkpoint which should be used for synthesis")
+  p.add_argument("folder", type=Path, metavar="FOLDER", help="path to folder which contains the audio files (.wav) that should be synthesized")
+  p.set_defaults(handler=synthesize, source="wav")
+  add_common(p)
   return parser
 
 
@@ -80,7 +94,8 @@ def synthesize(ns: argparse.Namespace) -> bool:
   except Exception:
     logger.error("Checkpoint couldn't be loaded!")
     return False
-  mel_files = sorted(f for f in ns.folder.rglob("*") if f.is_file() and f.suffix.lower() == ".npy")
+  suffix = ".wav" if ns.source == "wav" else ".npy"
+  mel_files = sorted(f for f in ns.folder.rglob("*") if f.is_file() and f.suffix.lower() == suffix)
   todo = []
   for f in mel_files:
     wav_path = out_dir / f.relative_to(ns.folder).parent / f"{f.stem}.wav"
@@ -90,7 +105,15 @@ def synthesize(ns: argparse.Namespace) -> bool:
   synth = Synthesizer(checkpoint, custom_hparams=split_hparams_string(ns.custom_hparams), device=torch.device(ns.device),
                       precision=ns.precision)
   by_len: Dict[int, List] = defaultdict(list)
+  taco_stft = None
+  if ns.source == "wav":
+    from .taco_stft import TacotronSTFT
+    taco_stft = TacotronSTFT(synth.hparams, torch.device(ns.device))      # inference_wav.py:109
   for f, wav_path in todo:
+    if taco_stft is not None:
+      mel_t = taco_stft.get_mel_tensor_from_file(f)                        # stays on the device (inference_wav.py:114)
+      by_len[mel_t.shape[1]].append((mel_t, wav_path))
+      continue
     mel = np.load(f)
     if mel.ndim != 2 or mel.shape[0] != synth.hparams.n_mel_channels:
       logger.error(f"{f}: expected a [{synth.hparams.n_mel_channels}, frames] array, got {mel.shape}")
