@@ -79,6 +79,16 @@ int wg_create(const wg_config* cfg, wg_engine** out);
  * May be called again after the caller's weights changed. */
 int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs);
 
+/* Packed-weight cache (the reference rebuilds and re-folds the whole module tree on every start,
+ * synthesizer.py:32-52).  wg_save_packed writes the engine's packed arrays (K-major 16-bit weights, folded biases, the
+ * skip->end fold, composed start weights, 1x1 inverses and log-dets, and the fp32 conditioning weights from which the
+ * phase-composed V is rebuilt on the device) to `path`; wg_load_packed restores them instead of wg_load_weights.
+ * `fingerprint` identifies the source weights (e.g. checkpoint size and mtime); a cache written for other weights, another
+ * wg_config, another library version or another kernel selection is rejected with WG_ERR_WEIGHTS and the caller packs
+ * from the state_dict as usual. */
+int wg_save_packed(wg_engine* e, const char* path, uint64_t fingerprint);
+int wg_load_packed(wg_engine* e, const char* path, uint64_t fingerprint);
+
 /* Bytes of scratch wg_infer / wg_forward need for a batch of `batch` mels of `frames` frames. */
 size_t wg_workspace_bytes(const wg_engine* e, int32_t batch, int32_t frames);
 

@@ -131,3 +131,53 @@ def test_cli_synthesize_wav_equals_synthesize_of_its_mels(tmp_path):
     sr, a = read_wav(out_a / name)
     _, b = read_wav(out_b / name)
     assert sr == 22050 and a.shape == (frames * 256,) and np.array_equal(a, b)
+
+
+def test_packed_weight_cache_round_trip(tmp_path):
+  """the engine's packed arrays written by one Synthesizer are restored by the next one (bit-identical
+  audio, no fold / re-pack); other weights, another precision or a damaged file fall back to packing from the state_dict."""
+  import time
+  hp, sd, w, dims = synthetic_weights(256)
+  ck = CheckpointWaveglow.from_state_dict(sd, hp, iteration=1)
+  cache = tmp_path / "1.pt.b200pack"
+  mel = synthetic_mel(2, 9, 91).cuda()
+  dev = torch.device("cuda:0")
+
+  def build(**kw):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    s = Synthesizer(ck, device=dev, **kw)
+    torch.cuda.synchronize()
+    return s, time.perf_counter() - t0
+
+  a, t_a = build(precision="fp16", pack_cache=cache, pack_fingerprint=123)
+  assert a.model.pack_cache_hit is False and cache.is_file()
+  b, t_b = build(precision="fp16", pack_cache=cache, pack_fingerprint=123)
+  assert b.model.pack_cache_hit is True
+  print(f"Synthesizer start: {t_a:.2f} s packing from the state_dict, {t_b:.2f} s from the cache ({cache.stat().st_size / 1e6:.0f} MB)")
+  init_global_seeds(3)
+  out_a = a.model.infer(mel, sigma=0.7)
+  init_global_seeds(3)
+  out_b = b.model.infer(mel, sigma=0.7)
+  assert torch.equal(out_a, out_b)
+  assert torch.equal(a.denoiser.bias_spec, b.denoiser.bias_spec)
+  # forward direction works from the cache too (w_fwd, log-dets)
+  audio_in = torch.rand(2, 2048, device=dev) * 2 - 1
+  za = a.model((mel[:, :, :8], audio_in))
+  zb = b.model((mel[:, :, :8], audio_in))
+  assert torch.equal(za[0], zb[0]) and all(torch.equal(x, y) for x, y in zip(za[2], zb[2]))
+  # other weights (fingerprint), another precision, a truncated file: rejected, packed as usual, cache rewritten
+  c, _ = build(precision="fp16", pack_cache=cache, pack_fingerprint=124)
+  assert c.model.pack_cache_hit is False
+  d, _ = build(precision="fp32", pack_cache=cache, pack_fingerprint=124)
+  assert d.model.pack_cache_hit is False
+  e, _ = build(precision="fp32", pack_cache=cache, pack_fingerprint=124)
+  assert e.model.pack_cache_hit is True
+  init_global_seeds(3)
+  out_d = d.model.infer(mel, sigma=0.7)
+  init_global_seeds(3)
+  assert torch.equal(out_d, e.model.infer(mel, sigma=0.7))
+  data = cache.read_bytes()
+  cache.write_bytes(data[: len(data) // 2])
+  f, _ = build(precision="fp32", pack_cache=cache, pack_fingerprint=124)
+  assert f.model.pack_cache_hit is False and cache.stat().st_size == len(data)

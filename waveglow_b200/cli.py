@@ -25,7 +25,7 @@ import torch
 from scipy.io.wavfile import write as write_wav
 
 from .checkpoint import CheckpointWaveglow
-from .synthesizer import Synthesizer
+from .synthesizer import Synthesizer, checkpoint_fingerprint
 
 DEFAULT_SIGMA = 1.0                   # waveglow_cli/defaults.py:9
 DEFAULT_DENOISER_STRENGTH = 0.0005    # waveglow_cli/defaults.py:10
@@ -56,6 +56,8 @@ def add_common(p: argparse.ArgumentParser) -> None:
   p.add_argument("--custom-seed", type=int, default=None, help="custom seed; if unset a random seed is chosen")
   p.add_argument("--batch-size", type=int, default=64, help="max. utterances of equal length per engine call")
   p.add_argument("--precision", choices=["fp16", "fp32"], default="fp16")
+  p.add_argument("--pack-cache", action="store_true",
+                 help="keep the engine's packed weights in CHECKPOINT.b200pack and reuse them on the next start")
   p.add_argument("-out", "--output-directory", type=Path, default=None, help="custom output directory if FOLDER should not be used")
   p.add_argument("-o", "--overwrite", action="store_true", help="overwrite already synthesized lines")
 
@@ -102,8 +104,10 @@ def synthesize(ns: argparse.Namespace) -> bool:
     if wav_path.exists() and not ns.overwrite:
       continue
     todo.append((f, wav_path))
+  cache = Path(str(ns.checkpoint) + ".b200pack") if ns.pack_cache else None
   synth = Synthesizer(checkpoint, custom_hparams=split_hparams_string(ns.custom_hparams), device=torch.device(ns.device),
-                      precision=ns.precision)
+                      precision=ns.precision, pack_cache=cache,
+                      pack_fingerprint=checkpoint_fingerprint(ns.checkpoint) if ns.pack_cache else 0)
   by_len: Dict[int, List] = defaultdict(list)
   taco_stft = None
   if ns.source == "wav":

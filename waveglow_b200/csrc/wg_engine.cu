@@ -36,6 +36,7 @@ struct FlowPack {
   float w_fwd[kGroup * kGroup] = {0};   // forward 1x1 weight (row-major C x C)
   float* d_w_start = nullptr;   // [nc, h]
   float* d_b_start = nullptr;   // [nc]
+  float* d_w_cond = nullptr;    // tensor-core mode: [2 nc L, 640] fp32, the source of the composed conditioning weights V
 };
 
 }  // namespace
@@ -84,6 +85,8 @@ struct wg_engine {
   bool wide = false;                  // two-kernel tensor-core layer (n_channels = 512; WG_WIDE=1 forces it for 256)
   int num_sms = 148;
   int dbg_flags = 0;                  // WG_DBG_FLAGS env (diagnostics; see LayerTcParams::dbg_flags)
+  // device arrays that make up the packed weights, by tag: what wg_save_packed writes and wg_load_packed restores
+  std::map<std::string, std::pair<void**, size_t>> sections;
   int op_fmt = 0;                     // 0 = fp16 operands, 1 = bf16 (WG_B200_OPERAND=bf16; fails the max-abs gate, kept for study)
 };
 
@@ -156,14 +159,16 @@ struct HostWeights {
   std::map<std::string, std::vector<int64_t>> shape;
 };
 
+// Device copy of a packed array; `tag` registers it as a section of the packed-weight cache (wg_save_packed).
 template <typename T>
-int upload(wg_engine* e, T** dst, const std::vector<T>& src) {
+int upload(wg_engine* e, T** dst, const std::vector<T>& src, const std::string& tag = std::string()) {
   if (*dst) {
     cudaFree(*dst);
     *dst = nullptr;
   }
   WG_CUDA(e, cudaMalloc(reinterpret_cast<void**>(dst), src.size() * sizeof(T)));
   WG_CUDA(e, cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  if (!tag.empty()) e->sections[tag] = {reinterpret_cast<void**>(dst), src.size() * sizeof(T)};
   return WG_OK;
 }
 
@@ -181,6 +186,72 @@ int make_map(wg_engine* e, CUtensorMap* m, void* base, int rank, const uint64_t*
   CUresult r = e->encode(m, dt, rank, base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(e, WG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return WG_OK;
+}
+
+// Second half of loading in tensor-core mode, shared by wg_load_weights and wg_load_packed: everything that is DERIVED from
+// the packed arrays on the device -- V = W_cond . Wup_p for all flows, layers and phases (1 GB for 256 channels, which is why
+// the cache stores W_cond instead) -- and the tensor maps over the packed weights.
+int finish_tensor_core_load(wg_engine* e) {
+  const int nc = e->cfg.n_channels, L = e->cfg.n_layers, NF = e->cfg.n_flows;
+  const int K1x = 3 * nc, w2rows = nc + 16, kWcRows = 7 * nc;
+  int rc;
+  cudaFree(e->d_v);
+  e->d_v = nullptr;
+  WG_CUDA(e, cudaMalloc(&e->d_v, static_cast<size_t>(NF) * L * kUpPhases * 2 * nc * kUpKdim * 2));
+  for (int k = 0; k < NF; ++k) {
+    dim3 grid(kUpKdim / 64, 2 * nc / 64, L * kUpPhases);
+    const size_t v_off = static_cast<size_t>(k) * L * kUpPhases * 2 * nc * kUpKdim;
+    if (e->op_fmt == 1)
+      compose_cond_kernel<__nv_bfloat16><<<grid, 256>>>(e->flows[k].d_w_cond, e->d_up_w, static_cast<__nv_bfloat16*>(e->d_v) + v_off, nc);
+    else
+      compose_cond_kernel<__half><<<grid, 256>>>(e->flows[k].d_w_cond, e->d_up_w, static_cast<__half*>(e->d_v) + v_off, nc);
+  }
+  WG_CUDA(e, cudaDeviceSynchronize());
+  const CUtensorMapDataType dt = e->op_fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K1x), static_cast<uint64_t>(NF) * L * 2 * nc};
+    const uint64_t str[1] = {static_cast<uint64_t>(K1x) * 2};
+    const uint32_t box[2] = {64, 256};
+    if ((rc = make_map(e, &e->tm_w1, e->d_w1, 2, dims, str, box, dt))) return rc;
+    const uint32_t boxh[2] = {64, 128};
+    if ((rc = make_map(e, &e->tm_w1h, e->d_w1, 2, dims, str, boxh, dt))) return rc;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(kUpKdim), static_cast<uint64_t>(NF) * L * kUpPhases * 2 * nc};
+    const uint64_t str[1] = {static_cast<uint64_t>(kUpKdim) * 2};
+    const uint32_t box[2] = {64, 256};
+    if ((rc = make_map(e, &e->tm_v, e->d_v, 2, dims, str, box, dt))) return rc;
+    const uint32_t boxh[2] = {64, 128};
+    if ((rc = make_map(e, &e->tm_vh, e->d_v, 2, dims, str, boxh, dt))) return rc;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(nc), static_cast<uint64_t>(NF) * L * w2rows};
+    const uint64_t str[1] = {static_cast<uint64_t>(nc) * 2};
+    const uint32_t boxa[2] = {64, 256}, boxb[2] = {64, 16};
+    if ((rc = make_map(e, &e->tm_w2a, e->d_w2, 2, dims, str, boxa, dt))) return rc;
+    if ((rc = make_map(e, &e->tm_w2b, e->d_w2, 2, dims, str, boxb, dt))) return rc;
+    const uint32_t boxh[2] = {64, 128}, box8[2] = {64, 8};
+    if ((rc = make_map(e, &e->tm_w2h, e->d_w2, 2, dims, str, boxh, dt))) return rc;
+    if ((rc = make_map(e, &e->tm_se8, e->d_w2, 2, dims, str, box8, dt))) return rc;
+  }
+  if (e->first_comp) {
+    // 16 real columns; the 64-wide box reads the other 48 as zeros (out-of-bounds fill)
+    const uint64_t dims[2] = {16, static_cast<uint64_t>(NF) * kWcRows};
+    const uint64_t str[1] = {32};
+    const uint32_t boxh[2] = {64, 128};
+    if ((rc = make_map(e, &e->tm_wc, e->d_wc, 2, dims, str, boxh, dt))) return rc;
+    const uint32_t box256[2] = {64, 256};
+    if ((rc = make_map(e, &e->tm_wc256, e->d_wc, 2, dims, str, box256, dt))) return rc;
+  }
+  {
+    const uint64_t dims[2] = {64, static_cast<uint64_t>(kIdentN)};
+    const uint64_t str[1] = {128};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(kIdentN)};
+    if ((rc = make_map(e, &e->tm_ident, e->d_ident, 2, dims, str, box, dt))) return rc;
+    const uint32_t box16[2] = {64, static_cast<uint32_t>(kIdentN / 2)};
+    if ((rc = make_map(e, &e->tm_ident16, e->d_ident, 2, dims, str, box16, dt))) return rc;
+  }
   return WG_OK;
 }
 
@@ -327,6 +398,7 @@ void wg_destroy(wg_engine* e) {
   for (auto& f : e->flows) {
     cudaFree(f.d_w_start);
     cudaFree(f.d_b_start);
+    cudaFree(f.d_w_cond);
   }
   for (auto ev : e->ev) cudaEventDestroy(ev);
   cudaFree(e->d_logdet);
@@ -351,6 +423,8 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
   if (!e->encode) return fail(e, WG_ERR_INVALID_ARGUMENT, "engine was not created successfully");
   WG_CUDA(e, cudaSetDevice(e->cfg.device));
   const int nc = e->cfg.n_channels, L = e->cfg.n_layers, NF = e->cfg.n_flows;
+  e->sections.clear();
+  e->loaded = false;
   HostWeights hw;
   for (int i = 0; i < n_descs; ++i) {
     const wg_weight_desc& d = descs[i];
@@ -391,8 +465,8 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
             for (int j = 0; j < kGroup; ++j)
               wp[(static_cast<size_t>(p) * kUpKdim + m * kMel + ci) * kCond + co * kGroup + j] =
                   (*w)[(static_cast<size_t>(ci) * kMel + co) * kUpK + kGroup * p + j + kUpStride * m];
-    if ((rc = upload(e, &e->d_up_w, wp))) return rc;
-    if ((rc = upload(e, &e->d_up_b, *b))) return rc;
+    if ((rc = upload(e, &e->d_up_w, wp, "up_w"))) return rc;
+    if ((rc = upload(e, &e->d_up_b, *b, "up_b"))) return rc;
   }
   const bool tc = e->cfg.precision == WG_PRECISION_FP16;
   const int K1 = 3 * nc + kCond;     // fp32 mode: taps | upsampled conditioning
@@ -405,9 +479,6 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
   std::vector<float> bias1, bias_res, w1f, bias1f, wresf, wsef;
   if (tc) {
     w1h.assign(static_cast<size_t>(NF) * L * 2 * nc * K1x, 0);
-    cudaFree(e->d_v);
-    e->d_v = nullptr;
-    WG_CUDA(e, cudaMalloc(&e->d_v, static_cast<size_t>(NF) * L * kUpPhases * 2 * nc * kUpKdim * 2));
     w2h.assign(static_cast<size_t>(NF) * L * w2rows * nc, 0);
     if (e->first_comp) wch.assign(static_cast<size_t>(NF) * kWcRows * 16, 0);
     bias1.assign(static_cast<size_t>(NF) * L * 2 * nc, 0.f);
@@ -421,6 +492,7 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
   for (auto& f : e->flows) {
     cudaFree(f.d_w_start);
     cudaFree(f.d_b_start);
+    cudaFree(f.d_w_cond);
   }
   e->flows.assign(NF, FlowPack());
   for (int k = 0; k < NF; ++k) {
@@ -437,21 +509,10 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
     if ((rc = need(p + "cond_layer.weight", {2 * nc * L, kCond, 1}, &w_cond))) return rc;
     if ((rc = need(p + "cond_layer.bias", {2 * nc * L}, &b_cond))) return rc;
     if ((rc = need("convinv." + std::to_string(k) + ".conv.weight", {C, C, 1}, &w_ci))) return rc;
-    if ((rc = upload(e, &fp.d_w_start, *w_start))) return rc;
-    if ((rc = upload(e, &fp.d_b_start, *b_start))) return rc;
-    if (tc) {
-      // V = W_cond . Wup_p for all layers and phases of this flow, composed on the device (fp32 accumulate)
-      float* d_wc = nullptr;
-      if ((rc = upload(e, &d_wc, *w_cond))) return rc;
-      dim3 grid(kUpKdim / 64, 2 * nc / 64, L * kUpPhases);
-      const size_t v_off = static_cast<size_t>(k) * L * kUpPhases * 2 * nc * kUpKdim;
-      if (e->op_fmt == 1)
-        compose_cond_kernel<__nv_bfloat16><<<grid, 256>>>(d_wc, e->d_up_w, static_cast<__nv_bfloat16*>(e->d_v) + v_off, nc);
-      else
-        compose_cond_kernel<__half><<<grid, 256>>>(d_wc, e->d_up_w, static_cast<__half*>(e->d_v) + v_off, nc);
-      WG_CUDA(e, cudaDeviceSynchronize());
-      cudaFree(d_wc);
-    }
+    if ((rc = upload(e, &fp.d_w_start, *w_start, "w_start." + std::to_string(k)))) return rc;
+    if ((rc = upload(e, &fp.d_b_start, *b_start, "b_start." + std::to_string(k)))) return rc;
+    // tensor-core mode: W_cond stays on the device (fp32); V = W_cond . Wup_p is composed from it in finish_tensor_core_load
+    if (tc && (rc = upload(e, &fp.d_w_cond, *w_cond, "w_cond." + std::to_string(k)))) return rc;
     {
       double a[kGroup * kGroup], inv[kGroup * kGroup];
       for (int i = 0; i < C * C; ++i) {
@@ -554,77 +615,25 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
   {
     std::vector<double> ld(NF);
     for (int k = 0; k < NF; ++k) ld[k] = e->flows[k].logdet;
-    if ((rc = upload(e, &e->d_logdet, ld))) return rc;
+    if ((rc = upload(e, &e->d_logdet, ld, "logdet"))) return rc;
   }
   if (bias_res.empty()) bias_res.assign(static_cast<size_t>(NF) * L * nc, 0.f);
-  if ((rc = upload(e, &e->d_bias_res, bias_res))) return rc;
+  if ((rc = upload(e, &e->d_bias_res, bias_res, "bias_res"))) return rc;
   if (tc) {
-    uint16_t* d16 = nullptr;
-    d16 = static_cast<uint16_t*>(e->d_w1);
-    if ((rc = upload(e, &d16, w1h))) return rc;
-    e->d_w1 = d16;
-    d16 = static_cast<uint16_t*>(e->d_w2);
-    if ((rc = upload(e, &d16, w2h))) return rc;
-    e->d_w2 = d16;
+    if ((rc = upload(e, reinterpret_cast<uint16_t**>(&e->d_w1), w1h, "w1"))) return rc;
+    if ((rc = upload(e, reinterpret_cast<uint16_t**>(&e->d_w2), w2h, "w2"))) return rc;
     // [I32 | 0]: 32 rows x 64 K; K-step (k & 1) of a 64-channel block selects columns 0..15 or 16..31 of the identity
     std::vector<uint16_t> ident(kIdentN * 64, 0);
     for (int i = 0; i < kIdentN; ++i) ident[i * 64 + i] = f2h(1.0f, e->op_fmt);
-    d16 = static_cast<uint16_t*>(e->d_ident);
-    if ((rc = upload(e, &d16, ident))) return rc;
-    e->d_ident = d16;
-    if ((rc = upload(e, &e->d_bias1, bias1))) return rc;
-    const CUtensorMapDataType dt = e->op_fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    {
-      const uint64_t dims[2] = {static_cast<uint64_t>(K1x), static_cast<uint64_t>(NF) * L * 2 * nc};
-      const uint64_t str[1] = {static_cast<uint64_t>(K1x) * 2};
-      const uint32_t box[2] = {64, 256};
-      if ((rc = make_map(e, &e->tm_w1, e->d_w1, 2, dims, str, box, dt))) return rc;
-      const uint32_t boxh[2] = {64, 128};
-      if ((rc = make_map(e, &e->tm_w1h, e->d_w1, 2, dims, str, boxh, dt))) return rc;
-    }
-    {
-      const uint64_t dims[2] = {static_cast<uint64_t>(kUpKdim), static_cast<uint64_t>(NF) * L * kUpPhases * 2 * nc};
-      const uint64_t str[1] = {static_cast<uint64_t>(kUpKdim) * 2};
-      const uint32_t box[2] = {64, 256};
-      if ((rc = make_map(e, &e->tm_v, e->d_v, 2, dims, str, box, dt))) return rc;
-      const uint32_t boxh[2] = {64, 128};
-      if ((rc = make_map(e, &e->tm_vh, e->d_v, 2, dims, str, boxh, dt))) return rc;
-    }
-    {
-      const uint64_t dims[2] = {static_cast<uint64_t>(nc), static_cast<uint64_t>(NF) * L * w2rows};
-      const uint64_t str[1] = {static_cast<uint64_t>(nc) * 2};
-      const uint32_t boxa[2] = {64, 256}, boxb[2] = {64, 16};
-      if ((rc = make_map(e, &e->tm_w2a, e->d_w2, 2, dims, str, boxa, dt))) return rc;
-      if ((rc = make_map(e, &e->tm_w2b, e->d_w2, 2, dims, str, boxb, dt))) return rc;
-      const uint32_t boxh[2] = {64, 128}, box8[2] = {64, 8};
-      if ((rc = make_map(e, &e->tm_w2h, e->d_w2, 2, dims, str, boxh, dt))) return rc;
-      if ((rc = make_map(e, &e->tm_se8, e->d_w2, 2, dims, str, box8, dt))) return rc;
-    }
-    if (e->first_comp) {
-      d16 = static_cast<uint16_t*>(e->d_wc);
-      if ((rc = upload(e, &d16, wch))) return rc;
-      e->d_wc = d16;
-      // 16 real columns; the 64-wide box reads the other 48 as zeros (out-of-bounds fill)
-      const uint64_t dims[2] = {16, static_cast<uint64_t>(NF) * kWcRows};
-      const uint64_t str[1] = {32};
-      const uint32_t boxh[2] = {64, 128};
-      if ((rc = make_map(e, &e->tm_wc, e->d_wc, 2, dims, str, boxh, dt))) return rc;
-      const uint32_t box256[2] = {64, 256};
-      if ((rc = make_map(e, &e->tm_wc256, e->d_wc, 2, dims, str, box256, dt))) return rc;
-    }
-    {
-      const uint64_t dims[2] = {64, static_cast<uint64_t>(kIdentN)};
-      const uint64_t str[1] = {128};
-      const uint32_t box[2] = {64, static_cast<uint32_t>(kIdentN)};
-      if ((rc = make_map(e, &e->tm_ident, e->d_ident, 2, dims, str, box, dt))) return rc;
-      const uint32_t box16[2] = {64, static_cast<uint32_t>(kIdentN / 2)};
-      if ((rc = make_map(e, &e->tm_ident16, e->d_ident, 2, dims, str, box16, dt))) return rc;
-    }
+    if ((rc = upload(e, reinterpret_cast<uint16_t**>(&e->d_ident), ident, "ident"))) return rc;
+    if ((rc = upload(e, &e->d_bias1, bias1, "bias1"))) return rc;
+    if (e->first_comp && (rc = upload(e, reinterpret_cast<uint16_t**>(&e->d_wc), wch, "wc"))) return rc;
+    if ((rc = finish_tensor_core_load(e))) return rc;
   } else {
-    if ((rc = upload(e, &e->d_w1f, w1f))) return rc;
-    if ((rc = upload(e, &e->d_bias1f, bias1f))) return rc;
-    if ((rc = upload(e, &e->d_wresf, wresf))) return rc;
-    if ((rc = upload(e, &e->d_wsef, wsef))) return rc;
+    if ((rc = upload(e, &e->d_w1f, w1f, "w1f"))) return rc;
+    if ((rc = upload(e, &e->d_bias1f, bias1f, "bias1f"))) return rc;
+    if ((rc = upload(e, &e->d_wresf, wresf, "wresf"))) return rc;
+    if ((rc = upload(e, &e->d_wsef, wsef, "wsef"))) return rc;
   }
   e->loaded = true;
   return WG_OK;
@@ -668,6 +677,197 @@ int wg_debug_view(const wg_engine* e, const char* name, int32_t batch, int32_t f
   } else {
     return WG_ERR_INVALID_ARGUMENT;
   }
+  return WG_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------ packed-weight cache
+namespace {
+
+constexpr uint32_t kPackVersion = 3;
+
+struct PackHeader {
+  char magic[8];             // "WGB200PK"
+  uint32_t version;
+  int32_t cfg[10];           // wg_config without the device ordinal
+  int32_t op_fmt, first_comp, wide;
+  int32_t n_flows, n_sections;
+  uint64_t fingerprint;      // caller's identity of the source weights (e.g. checkpoint size and mtime)
+};
+
+struct FlowPod {
+  int32_t C, h;
+  float e_bias[kGroup];
+  float w_inv[kGroup * kGroup];
+  double logdet;
+  float w_fwd[kGroup * kGroup];
+};
+
+struct SectionHeader {
+  char tag[40];
+  uint64_t bytes;
+};
+
+void fill_cfg(const wg_engine* e, int32_t* c) {
+  const wg_config& g = e->cfg;
+  const int32_t v[10] = {g.n_mel_channels, g.n_flows, g.n_group, g.n_early_every, g.n_early_size, g.n_layers,
+                         g.n_channels, g.kernel_size, g.segment_length, g.precision};
+  memcpy(c, v, sizeof(v));
+}
+
+// where a section of the cache lives in the engine
+void** section_slot(wg_engine* e, const std::string& tag) {
+  static const struct { const char* tag; void* wg_engine::* m; } kVoid[] = {
+      {"w1", &wg_engine::d_w1}, {"w2", &wg_engine::d_w2}, {"ident", &wg_engine::d_ident}, {"wc", &wg_engine::d_wc}};
+  for (const auto& it : kVoid)
+    if (tag == it.tag) return &(e->*(it.m));
+  static const struct { const char* tag; float* wg_engine::* m; } kFloat[] = {
+      {"up_w", &wg_engine::d_up_w}, {"up_b", &wg_engine::d_up_b}, {"bias1", &wg_engine::d_bias1}, {"bias_res", &wg_engine::d_bias_res},
+      {"w1f", &wg_engine::d_w1f}, {"bias1f", &wg_engine::d_bias1f}, {"wresf", &wg_engine::d_wresf}, {"wsef", &wg_engine::d_wsef}};
+  for (const auto& it : kFloat)
+    if (tag == it.tag) return reinterpret_cast<void**>(&(e->*(it.m)));
+  if (tag == "logdet") return reinterpret_cast<void**>(&e->d_logdet);
+  const size_t dot = tag.find('.');
+  if (dot != std::string::npos) {
+    const int k = atoi(tag.c_str() + dot + 1);
+    if (k < 0 || k >= static_cast<int>(e->flows.size())) return nullptr;
+    const std::string base = tag.substr(0, dot);
+    if (base == "w_start") return reinterpret_cast<void**>(&e->flows[k].d_w_start);
+    if (base == "b_start") return reinterpret_cast<void**>(&e->flows[k].d_b_start);
+    if (base == "w_cond") return reinterpret_cast<void**>(&e->flows[k].d_w_cond);
+  }
+  return nullptr;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wg_save_packed(wg_engine* e, const char* path, uint64_t fingerprint) {
+  if (!e || !path) return WG_ERR_INVALID_ARGUMENT;
+  if (!e->loaded) return fail(e, WG_ERR_WEIGHTS, "wg_load_weights has not been called");
+  WG_CUDA(e, cudaSetDevice(e->cfg.device));
+  const std::string tmp = std::string(path) + ".tmp";
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return fail(e, WG_ERR_INVALID_ARGUMENT, "cannot open '%s' for writing", tmp.c_str());
+  PackHeader h{};
+  memcpy(h.magic, "WGB200PK", 8);
+  h.version = kPackVersion;
+  fill_cfg(e, h.cfg);
+  h.op_fmt = e->op_fmt;
+  h.first_comp = e->first_comp ? 1 : 0;
+  h.wide = e->wide ? 1 : 0;
+  h.n_flows = static_cast<int32_t>(e->flows.size());
+  h.n_sections = static_cast<int32_t>(e->sections.size());
+  h.fingerprint = fingerprint;
+  bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+  for (const FlowPack& fp : e->flows) {
+    FlowPod p{};
+    p.C = fp.C;
+    p.h = fp.h;
+    memcpy(p.e_bias, fp.e_bias, sizeof(p.e_bias));
+    memcpy(p.w_inv, fp.w_inv, sizeof(p.w_inv));
+    p.logdet = fp.logdet;
+    memcpy(p.w_fwd, fp.w_fwd, sizeof(p.w_fwd));
+    ok = ok && fwrite(&p, sizeof(p), 1, f) == 1;
+  }
+  std::vector<uint8_t> host;
+  for (const auto& kv : e->sections) {
+    SectionHeader sh{};
+    snprintf(sh.tag, sizeof(sh.tag), "%s", kv.first.c_str());
+    sh.bytes = kv.second.second;
+    host.resize(sh.bytes);
+    if (cudaMemcpy(host.data(), *kv.second.first, sh.bytes, cudaMemcpyDeviceToHost) != cudaSuccess) {
+      fclose(f);
+      remove(tmp.c_str());
+      return fail(e, WG_ERR_CUDA, "reading section '%s' back from the device failed", sh.tag);
+    }
+    ok = ok && fwrite(&sh, sizeof(sh), 1, f) == 1 && fwrite(host.data(), 1, sh.bytes, f) == sh.bytes;
+  }
+  ok = (fclose(f) == 0) && ok;
+  if (!ok || rename(tmp.c_str(), path) != 0) {
+    remove(tmp.c_str());
+    return fail(e, WG_ERR_INVALID_ARGUMENT, "writing '%s' failed", path);
+  }
+  return WG_OK;
+}
+
+int wg_load_packed(wg_engine* e, const char* path, uint64_t fingerprint) {
+  if (!e || !path) return WG_ERR_INVALID_ARGUMENT;
+  if (!e->encode) return fail(e, WG_ERR_INVALID_ARGUMENT, "engine was not created successfully");
+  WG_CUDA(e, cudaSetDevice(e->cfg.device));
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(e, WG_ERR_WEIGHTS, "packed-weight cache '%s' not found", path);
+  struct Closer {
+    FILE* f;
+    ~Closer() { fclose(f); }
+  } closer{f};
+  PackHeader h{};
+  int32_t want[10];
+  fill_cfg(e, want);
+  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "WGB200PK", 8) != 0 || h.version != kPackVersion)
+    return fail(e, WG_ERR_WEIGHTS, "'%s' is not a packed-weight cache of this library version", path);
+  if (memcmp(h.cfg, want, sizeof(want)) != 0 || h.op_fmt != e->op_fmt || h.first_comp != (e->first_comp ? 1 : 0) ||
+      h.wide != (e->wide ? 1 : 0) || h.n_flows != e->cfg.n_flows)
+    return fail(e, WG_ERR_WEIGHTS, "'%s' was packed for another engine configuration", path);
+  if (h.fingerprint != fingerprint) return fail(e, WG_ERR_WEIGHTS, "'%s' was packed from other weights (fingerprint mismatch)", path);
+  e->loaded = false;
+  e->sections.clear();
+  for (auto& fp : e->flows) {
+    cudaFree(fp.d_w_start);
+    cudaFree(fp.d_b_start);
+    cudaFree(fp.d_w_cond);
+  }
+  e->flows.assign(h.n_flows, FlowPack());
+  for (int k = 0; k < h.n_flows; ++k) {
+    FlowPod p{};
+    if (fread(&p, sizeof(p), 1, f) != 1) return fail(e, WG_ERR_WEIGHTS, "'%s' is truncated", path);
+    FlowPack& fp = e->flows[k];
+    if (p.C != e->flowC[k]) return fail(e, WG_ERR_WEIGHTS, "'%s': flow %d has %d channels, expected %d", path, k, p.C, e->flowC[k]);
+    fp.C = p.C;
+    fp.h = p.h;
+    memcpy(fp.e_bias, p.e_bias, sizeof(p.e_bias));
+    memcpy(fp.w_inv, p.w_inv, sizeof(p.w_inv));
+    fp.logdet = p.logdet;
+    memcpy(fp.w_fwd, p.w_fwd, sizeof(p.w_fwd));
+  }
+  std::vector<uint8_t> host;
+  for (int i = 0; i < h.n_sections; ++i) {
+    SectionHeader sh{};
+    if (fread(&sh, sizeof(sh), 1, f) != 1) return fail(e, WG_ERR_WEIGHTS, "'%s' is truncated", path);
+    sh.tag[sizeof(sh.tag) - 1] = 0;
+    void** slot = section_slot(e, sh.tag);
+    if (!slot || sh.bytes == 0 || sh.bytes > (size_t(1) << 34)) return fail(e, WG_ERR_WEIGHTS, "'%s': bad section '%s'", path, sh.tag);
+    host.resize(sh.bytes);
+    if (fread(host.data(), 1, sh.bytes, f) != sh.bytes) return fail(e, WG_ERR_WEIGHTS, "'%s' is truncated", path);
+    if (*slot) cudaFree(*slot);
+    *slot = nullptr;
+    WG_CUDA(e, cudaMalloc(slot, sh.bytes));
+    WG_CUDA(e, cudaMemcpy(*slot, host.data(), sh.bytes, cudaMemcpyHostToDevice));
+    e->sections[sh.tag] = {slot, sh.bytes};
+  }
+  // every array the configured path reads must have been in the file
+  const bool tc = e->cfg.precision == WG_PRECISION_FP16;
+  std::vector<std::string> need = {"up_w", "up_b", "bias_res", "logdet"};
+  if (tc) {
+    need.insert(need.end(), {"w1", "w2", "ident", "bias1"});
+    if (e->first_comp) need.push_back("wc");
+  } else {
+    need.insert(need.end(), {"w1f", "bias1f", "wresf", "wsef"});
+  }
+  for (int k = 0; k < h.n_flows; ++k) {
+    need.push_back("w_start." + std::to_string(k));
+    need.push_back("b_start." + std::to_string(k));
+    if (tc) need.push_back("w_cond." + std::to_string(k));
+  }
+  for (const auto& t : need)
+    if (!e->sections.count(t)) return fail(e, WG_ERR_WEIGHTS, "'%s' lacks section '%s'", path, t.c_str());
+  if (tc) {
+    int rc = finish_tensor_core_load(e);
+    if (rc) return rc;
+  }
+  e->loaded = true;
   return WG_OK;
 }
 

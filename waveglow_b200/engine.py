@@ -17,7 +17,7 @@ PRECISION_FP32 = 0
 PRECISION_FP16 = 1
 
 EXPORTED_SYMBOLS = [
-  "wg_create", "wg_load_weights", "wg_workspace_bytes", "wg_infer", "wg_forward", "wg_last_launch_count",
+  "wg_create", "wg_load_weights", "wg_save_packed", "wg_load_packed", "wg_workspace_bytes", "wg_infer", "wg_forward", "wg_last_launch_count",
   "wg_debug_stop_after", "wg_debug_view", "wg_debug_gemm", "wg_debug_gemm2", "wg_debug_timeline", "wg_set_profiling", "wg_profile_layers", "wg_last_error", "wg_version",
   "wg_destroy",
 ]
@@ -63,6 +63,10 @@ def load_library() -> ctypes.CDLL:
   lib.wg_forward.argtypes = [vp, vp, i32, i32, vp, i32, vp, ctypes.POINTER(vp), vp, vp, vp, ctypes.c_size_t, vp]
   lib.wg_forward.restype = ctypes.c_int
   lib.wg_last_launch_count.argtypes = [vp]
+  lib.wg_save_packed.argtypes = [vp, ctypes.c_char_p, ctypes.c_uint64]
+  lib.wg_save_packed.restype = ctypes.c_int
+  lib.wg_load_packed.argtypes = [vp, ctypes.c_char_p, ctypes.c_uint64]
+  lib.wg_load_packed.restype = ctypes.c_int
   lib.wg_last_launch_count.restype = ctypes.c_int
   lib.wg_debug_stop_after.argtypes = [vp, i32, i32]
   lib.wg_debug_stop_after.restype = ctypes.c_int
@@ -146,6 +150,22 @@ class Engine:
         descs[i].shape[j] = t.size(j)
     torch.cuda.synchronize(self.device)
     self._check(self.lib.wg_load_weights(self._h, descs, len(folded)), "wg_load_weights")
+
+  def save_packed(self, path, fingerprint: int) -> None:
+    """Write the engine's packed weights next to the checkpoint."""
+    self._check(self.lib.wg_save_packed(self._h, os.fsencode(str(path)), ctypes.c_uint64(fingerprint & (2 ** 64 - 1))),
+                "wg_save_packed")
+
+  def load_packed(self, path, fingerprint: int) -> bool:
+    """Restore packed weights written by `save_packed`.  False (with the reason in `last_cache_miss`) if the file is missing,
+    stale, or was packed for another configuration -- the caller then packs from the state_dict as usual."""
+    rc = self.lib.wg_load_packed(self._h, os.fsencode(str(path)), ctypes.c_uint64(fingerprint & (2 ** 64 - 1)))
+    if rc == 0:
+      return True
+    self.last_cache_miss = self._err()
+    if rc != -5:       # WG_ERR_WEIGHTS is the "not usable" answer; anything else is a real failure
+      raise WgError(f"wg_load_packed failed ({rc}): {self.last_cache_miss}")
+    return False
 
   def workspace(self, batch: int, frames: int) -> torch.Tensor:
     need = self.lib.wg_workspace_bytes(self._h, batch, frames)

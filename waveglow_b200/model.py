@@ -8,6 +8,8 @@ of `infer` (model.py:223-274) is done by hand-written sm_100a kernels behind the
 (waveglow_b200/engine.py).  There is no torch/CPU fallback: calling `infer` without a CUDA device or
 without the built library raises.
 """
+import os
+from logging import getLogger
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -148,8 +150,18 @@ class WaveGlow(torch.nn.Module):
       self._engine = _engine.Engine(self.hparams, prec, device)
       self._packed = False
     if not self._packed:
-      with torch.no_grad():
-        self._engine.load_weights(self.folded_weights())
+      cache = getattr(self, "pack_cache", None)          # (path, fingerprint) set by Synthesizer(pack_cache=...)
+      if cache is not None and os.path.isfile(cache[0]) and self._engine.load_packed(cache[0], cache[1]):
+        self.pack_cache_hit = True
+      else:
+        with torch.no_grad():
+          self._engine.load_weights(self.folded_weights())
+        self.pack_cache_hit = False
+        if cache is not None:
+          try:
+            self._engine.save_packed(cache[0], cache[1])
+          except _engine.WgError as ex:                    # a read-only checkpoint folder must not break synthesis
+            getLogger(__name__).warning(f"packed-weight cache not written: {ex}")
       self._packed = True
     return self._engine
 

@@ -25,6 +25,12 @@ from .hparams import overwrite_custom_hparams
 from .model import WaveGlow, load_model
 
 
+def checkpoint_fingerprint(path) -> int:
+  """Cheap identity of a checkpoint file for the packed-weight cache: size and modification time."""
+  st = os.stat(path)
+  return (st.st_size * 1000003 + st.st_mtime_ns) & (2 ** 64 - 1)
+
+
 def init_global_seeds(seed: int) -> None:
   """utils.py:221-231."""
   os.environ["PYTHONHASHSEED"] = str(seed)
@@ -49,7 +55,11 @@ class InferenceResult():
 
 class Synthesizer():
   def __init__(self, checkpoint: CheckpointWaveglow, *, custom_hparams: Optional[Dict[str, str]] = None,
-               device: torch.device = None, precision: str = "fp16"):
+               device: torch.device = None, precision: str = "fp16", pack_cache=None, pack_fingerprint: int = 0):
+    """pack_cache: optional path of a packed-weight cache.  If it exists and was written for these weights
+    (`pack_fingerprint`, e.g. `checkpoint_fingerprint(path)`), this engine configuration and this library version, the
+    engine restores its packed arrays from it instead of folding and re-packing the state_dict; otherwise it packs as usual
+    and writes the file for the next start."""
     if device is None:
       device = torch.device("cuda:0")
     device = torch.device(device)
@@ -58,6 +68,8 @@ class Synthesizer():
     model = load_model(hparams, checkpoint.state_dict, device, precision=precision)
     model = WaveGlow.remove_weightnorm(model)
     model = model.eval()
+    if pack_cache is not None:
+      model.pack_cache = (str(pack_cache), int(pack_fingerprint))
     denoiser = Denoiser(waveglow=model, hparams=hparams, mode="zeros", device=device).to(device)
     self.device = device
     self.hparams = hparams
