@@ -144,18 +144,29 @@ def wn_layers(pf: PackedFlow, dims: O.ModelDims, x: Tensor, S: Tensor, op_dtype:
     d = 2 ** i
     if a0 is not None and i == 0:
       assert mw is not None and pf.w_res[0] is not None
-      a01 = rnd(torch.cat([a0, torch.ones_like(a0[..., :1])], dim=2), op_dtype)           # [B,T',h+1]
+      # operand rows [a_hi | a_lo | a_hi | 1 | 1] against weight columns [W_hi | W_hi | W_lo | b_hi | b_lo]: two-term splits in
+      # the operand dtype, so the start conv enters at nearly fp32 accuracy
+      a_hi = rnd(a0, op_dtype)
+      a_lo = rnd(a0 - a_hi, op_dtype)
+      one = torch.ones_like(a0[..., :1])
+      a01 = torch.cat([a_hi, a_lo, a_hi, one, one], dim=2)                                # [B,T',3h+2]
+
+      def split_cols(wb):                                                                 # wb [rows, h+1] float64
+        hi = rnd(wb.float(), op_dtype)
+        lo = rnd((wb - hi.double()).float(), op_dtype)
+        return torch.cat([hi[:, :-1], hi[:, :-1], lo[:, :-1], hi[:, -1:], lo[:, -1:]], dim=1)
+
       ws1 = torch.cat([pf.w_start.double(), pf.b_start.double()[:, None]], dim=1)        # [nc, h+1]
       pre = pf.b1p[0].clone()
       for tap in range(3):
-        wc = (pf.w1[0][:, tap * nc:(tap + 1) * nc].double() @ ws1).float()               # [2nc, h+1]
-        pre = pre + shift_time(a01, tap - 1) @ rnd(wc, op_dtype).t()
+        wc = pf.w1[0][:, tap * nc:(tap + 1) * nc].double() @ ws1                         # [2nc, h+1]
+        pre = pre + shift_time(a01, tap - 1) @ split_cols(wc).t()
       B, T = x.size(0), x.size(1)
       cond = torch.einsum("bqk,pok->bqpo", mw, rnd(pf.v[0], op_dtype))
       pre = pre + cond.reshape(B, -1, 2 * nc)[:, :T]
       acts = rnd(torch.tanh(pre[..., :nc]) * torch.sigmoid(pre[..., nc:]), op_dtype)
       e = e + acts @ rnd(pf.w_se[0], op_dtype).t()
-      x = rnd(a01 @ rnd(ws1.float(), op_dtype).t() + acts @ rnd(pf.w_res[0], op_dtype).t() + pf.b_res[0], op_dtype)
+      x = rnd(a01 @ split_cols(ws1).t() + acts @ rnd(pf.w_res[0], op_dtype).t() + pf.b_res[0], op_dtype)
       if trace is not None:
         trace.append({"layer": 0, "acts": acts.clone(), "x": x.clone(), "e": e.clone()})
       continue

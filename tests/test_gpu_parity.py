@@ -143,9 +143,12 @@ def test_stagewise_first_flow(precision):
     if first_composed:
       a0 = eng.debug_view("a0", B, F).float().cpu().view(B, 32, T // 32, 16).permute(0, 2, 1, 3).reshape(B, T, 16)
       a0_ref = torch.zeros(B, T, 16)
-      a0_ref[..., :2] = E.rnd(state0[..., 4:6], op_dtype)
-      a0_ref[..., 4] = 1.0
-      check("[a0 | 1] rows after start", a0, a0_ref)
+      hi = E.rnd(state0[..., 4:6], op_dtype)
+      a0_ref[..., 0:2] = hi
+      a0_ref[..., 4:6] = E.rnd(state0[..., 4:6] - hi, op_dtype)
+      a0_ref[..., 8:10] = hi
+      a0_ref[..., 12:14] = 1.0
+      check("[a_hi | a_lo | a_hi | 1 | 1] rows after start", a0, a0_ref)
     else:
       check("x after start", x_view("x0"), x0_ref)
     for i in range(dims.n_layers):

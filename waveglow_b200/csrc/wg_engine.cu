@@ -108,6 +108,11 @@ int fail(wg_engine* e, int code, const char* fmt, ...) {
     if (_st != cudaSuccess) return fail((e), WG_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_st)); \
   } while (0)
 
+float h2f(uint16_t v, int fmt);
+
+// two-term 16-bit split of a value: hi = round(v), lo = round(v - hi)
+void split16(double v, int fmt, uint16_t* hi, uint16_t* lo);
+
 uint16_t f2h(float f, int fmt) {
   if (fmt == 1) {  // bf16 round-to-nearest-even
     uint32_t u;
@@ -120,6 +125,23 @@ uint16_t f2h(float f, int fmt) {
   uint16_t r;
   memcpy(&r, &h, 2);
   return r;
+}
+
+float h2f(uint16_t v, int fmt) {
+  if (fmt == 1) {
+    const uint32_t u = static_cast<uint32_t>(v) << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+  }
+  __half h;
+  memcpy(&h, &v, 2);
+  return __half2float(h);
+}
+
+void split16(double v, int fmt, uint16_t* hi, uint16_t* lo) {
+  *hi = f2h(static_cast<float>(v), fmt);
+  *lo = f2h(static_cast<float>(v - static_cast<double>(h2f(*hi, fmt))), fmt);
 }
 
 // Gauss-Jordan inverse + log|det| in double.  Returns false if singular.
@@ -567,8 +589,12 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
                 for (int j = 0; j < h; ++j) acc[j] += wi * (*w_start)[static_cast<size_t>(ci) * h + j];
                 acc[4] += wi * (*b_start)[ci];
               }
-              for (int j = 0; j < h; ++j) crow[j] = f2h(static_cast<float>(acc[j]), e->op_fmt);
-              crow[4] = f2h(static_cast<float>(acc[4]), e->op_fmt);
+              // columns match the operand rows [a_hi | a_lo | a_hi | 1 | 1]: [W_hi | W_hi | W_lo | b_hi | b_lo]
+              for (int j = 0; j < h; ++j) {
+                split16(acc[j], e->op_fmt, &crow[j], &crow[8 + j]);
+                crow[4 + j] = crow[j];
+              }
+              split16(acc[4], e->op_fmt, &crow[12], &crow[13]);
             }
           }
         }
@@ -576,8 +602,11 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
           // residual carry of the first layer: x(t) = W_start a0(t) + b_start
           for (int n = 0; n < nc; ++n) {
             uint16_t* crow = &wch[(static_cast<size_t>(k) * kWcRows + 6 * nc + n) * 16];
-            for (int j = 0; j < h; ++j) crow[j] = f2h((*w_start)[static_cast<size_t>(n) * h + j], e->op_fmt);
-            crow[4] = f2h((*b_start)[n], e->op_fmt);
+            for (int j = 0; j < h; ++j) {
+              split16((*w_start)[static_cast<size_t>(n) * h + j], e->op_fmt, &crow[j], &crow[8 + j]);
+              crow[4 + j] = crow[j];
+            }
+            split16((*b_start)[n], e->op_fmt, &crow[12], &crow[13]);
           }
         }
         uint16_t* w2 = &w2h[li * w2rows * nc];
@@ -685,7 +714,7 @@ int wg_debug_view(const wg_engine* e, const char* name, int32_t batch, int32_t f
 // ------------------------------------------------------------------------------------------ packed-weight cache
 namespace {
 
-constexpr uint32_t kPackVersion = 3;
+constexpr uint32_t kPackVersion = 4;
 
 struct PackHeader {
   char magic[8];             // "WGB200PK"

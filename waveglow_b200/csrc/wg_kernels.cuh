@@ -195,7 +195,8 @@ struct FlowStepParams {
   const float* b_start;       // [nc]
   int x_phase_major;          // 1: x is [B][phase 32][frame][nc] (tensor-core mode), 0: time-major [B][Tpad][nc]
   void* a0_out;               // tensor-core mode with the start conv composed into the first WN layer: instead of x, write the
-                              // 16-bit rows [a0 (h2 channels) | 0.. | 1 at index 4 | 0 x 11], phase-major [B][32][Fq][16]
+                              // 16-bit rows [a_hi (4) | a_lo (4) | a_hi (4) | 1 | 1 | 0 | 0], phase-major [B][32][Fq][16], where
+                              // a_hi + a_lo is the two-term 16-bit split of the live first-half channels a0 (h2 <= 4 of them)
   // forward-only outputs of the finish part
   double* log_s_sum;          // one accumulator: sum of log_s over all elements of flow k
   float* log_s_out;           // optional [B, h, T] (reference layout, model.py:216)
@@ -294,10 +295,19 @@ flow_step_kernel(FlowStepParams p, float* __restrict__ state, const float* __res
 #pragma unroll
           for (int j = 0; j < 16; ++j) h[j] = from_float<XT>(0.f);
           if (valid) {
+            // a0 = a_hi + a_lo to ~2^-22: the composed weights are split the same way (W_hi + W_lo), and the K = 16 step
+            // computes W_hi a_hi + W_hi a_lo + W_lo a_hi + (b_hi + b_lo) . 1 -- the start conv at nearly fp32 accuracy
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (j < p.h2) h[j] = from_float<XT>(row[base2 + j]);
-            h[4] = from_float<XT>(1.f);
+              if (j < p.h2) {
+                const float a = row[base2 + j];
+                const XT hi = from_float<XT>(a);
+                h[j] = hi;
+                h[4 + j] = from_float<XT>(a - to_float<XT>(hi));
+                h[8 + j] = hi;
+              }
+            h[12] = from_float<XT>(1.f);
+            h[13] = from_float<XT>(1.f);
           }
           const int Fq = Tpad / kUpPhases;
           const size_t arow = (static_cast<size_t>(b) * kUpPhases + (t % kUpPhases)) * Fq + t / kUpPhases;

@@ -90,9 +90,10 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {25
   const int n_ptiles = n_pe * kPhases;
   const int my_tiles = (n_ptiles - pair + n_pairs - 1) / n_pairs;
   // First layer of a flow (p.first): x = start(a0) is never materialised.  in_layers[0](start(a0)) is a k=3 conv of the
-  // h <= 4 live channels with composed weights, so the three tap K-blocks hold [a0(t + tau) | 1 | 0 ..] (16 channels, the
-  // `1` carries W_in[tau] . b_start and vanishes with the zero padding) and need ONE K=16 MMA each instead of 3 x 16; the
-  // residual carry x(t) = W_start a0(t) + b_start is one more MMA in GEMM2 instead of the identity blocks.
+  // h <= 4 live channels with composed weights, so the three tap K-blocks hold [a_hi | a_lo | a_hi | 1 | 1 | 0 0](t + tau)
+  // (16 channels: a0 = a_hi + a_lo and the weights W = W_hi + W_lo as two-term 16-bit splits, columns [W_hi | W_hi | W_lo |
+  // b_hi | b_lo]; the `1`s carry W_in[tau] . b_start and vanish with the zero padding) and need ONE K=16 MMA each instead of
+  // 3 x 16; the residual carry x(t) = W_start a0(t) + b_start is one more MMA in GEMM2 instead of the identity blocks.
   const int n_kb = p.first ? kMwKB + 3 : kKB1;
 
   struct Coord {
