@@ -32,7 +32,7 @@ def get_model(n_channels: int, precision: str, style: str = "parametrized") -> W
     m = WaveGlow(hp, precision="fp16" if precision.startswith("fp16") else precision).to("cuda:0")
     m.load_state_dict(sd)
     m = WaveGlow.remove_weightnorm(m).eval()
-    if precision == "fp16-wide":
+    if precision in ("fp16-wide", "fp16-wide-nopack"):
       os.environ["WG_WIDE"] = "1"
     if precision == "fp16-single":
       os.environ["WG_PAIR"] = "0"
@@ -40,7 +40,7 @@ def get_model(n_channels: int, precision: str, style: str = "parametrized") -> W
       os.environ["WG_PAIR"] = "1"
     if precision.startswith("fp16-seg"):
       os.environ["WG_SEG"] = precision[len("fp16-seg"):]
-    if precision == "fp16-nopack":
+    if precision in ("fp16-nopack", "fp16-wide-nopack"):
       os.environ["WG_PACK4"] = "0"
     if precision == "fp16-nofirst":
       os.environ["WG_FIRST"] = "0"
@@ -261,6 +261,25 @@ def test_packed_ragged_tails_vs_oracle_and_unpacked(B, F):
     assert err <= FP16_MAX_ABS and snr >= FP16_MIN_SNR_DB
   alone = run(model, mel[B - 1:B], [z[B - 1:B] for z in zs], 0.666)
   assert torch.equal(out[B - 1:B], alone)
+
+
+@pytest.mark.parametrize("nc,mode", [(256, "fp16-wide"), (512, "fp16")])
+def test_packed_ragged_tails_on_the_wide_kernels(nc, mode):
+  """The two-kernel wide layer with packed tails (4-D TMA loads and stores of acts / x): bit-identical to the same kernels
+  without the packing; the forced-wide 256-channel model is also checked against the oracle."""
+  hp, sd, w, dims = synthetic_weights(nc)
+  B, F = 6, 140
+  mel = synthetic_mel(B, F, 611)
+  zs = synthetic_noise(hp, B, F * 32, 612)
+  out = run(get_model(nc, mode), mel, zs, 0.666)
+  assert torch.isfinite(out).all()
+  assert torch.equal(out, run(get_model(nc, mode + "-nopack" if mode != "fp16" else "fp16-nopack"), mel, zs, 0.666))
+  if nc == 256:
+    with torch.no_grad():
+      ref = O.infer(w, dims, mel, 0.666, zs)
+    err, snr = max_abs(ref, out), snr_db(ref, out)
+    print(f"wide kernels, packed tails, B{B} F{F}: max-abs {err:.3e}  snr {snr:.1f} dB")
+    assert err <= FP16_MAX_ABS and snr >= FP16_MIN_SNR_DB
 
 
 def test_first_layer_composition_vs_explicit_start_conv():

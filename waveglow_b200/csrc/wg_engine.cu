@@ -971,20 +971,31 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
       wp.e = ebuf;
       wp.first = e->first_comp && i == 0 && has_res;
       wp.wc_row0 = k * 7 * nc;
-      const int n_tiles = kPhases * ((wp.Fq + kTileM - 1) / kTileM) * B;
+      int n_tiles = kPhases * ((wp.Fq + kTileM - 1) / kTileM) * B;
+      if (e->pack4) {
+        // packed ragged tails, as in the continuous pair kernel
+        const int n_full = wp.Fq / kTileM, rem = wp.Fq - n_full * kTileM, n_rem = (rem + 31) / 32;
+        const int n4 = kPhases * (B * n_full + ((B + 3) / 4) * n_rem);
+        if (rem > 0 && n4 < n_tiles) {
+          wp.pack4 = 1;
+          wp.n_full = n_full;
+          wp.n_rem = n_rem;
+          n_tiles = n4;
+        }
+      }
       dim3 grid(n_tiles < e->num_sms ? n_tiles : e->num_sms);
       if (nc == 512) {
         wn_gate_wide_kernel<512><<<grid, kTcThreads, WideCfg<512>::a_total + 1024, st>>>(tm_x[*cur], *tm_cond, e->tm_w1, e->tm_v,
-                                                                                      e->tm_w2b, tm_x[2], tm_a0[0], e->tm_wc256, wp);
+                                                                                      e->tm_w2b, tm_x[2], tm_a0[0], e->tm_wc256, tm_p4[*cur], tm_p4[2], tm_p4[3], tm_p4[4], wp);
         if (has_res)
           wn_res_wide_kernel<512><<<grid, kTcThreads, WideCfg<512>::b_total + 1024, st>>>(tm_x[2], tm_x[*cur], tm_x[*cur ^ 1],
-                                                                                       e->tm_w2a, e->tm_ident, tm_a0[0], e->tm_wc256, wp);
+                                                                                       e->tm_w2a, e->tm_ident, tm_a0[0], e->tm_wc256, tm_p4[4], tm_p4[*cur], tm_p4[*cur ^ 1], tm_p4[3], wp);
       } else {
         wn_gate_wide_kernel<256><<<grid, kTcThreads, WideCfg<256>::a_total + 1024, st>>>(tm_x[*cur], *tm_cond, e->tm_w1, e->tm_v,
-                                                                                      e->tm_w2b, tm_x[2], tm_a0[0], e->tm_wc256, wp);
+                                                                                      e->tm_w2b, tm_x[2], tm_a0[0], e->tm_wc256, tm_p4[*cur], tm_p4[2], tm_p4[3], tm_p4[4], wp);
         if (has_res)
           wn_res_wide_kernel<256><<<grid, kTcThreads, WideCfg<256>::b_total + 1024, st>>>(tm_x[2], tm_x[*cur], tm_x[*cur ^ 1],
-                                                                                       e->tm_w2a, e->tm_ident, tm_a0[0], e->tm_wc256, wp);
+                                                                                       e->tm_w2a, e->tm_ident, tm_a0[0], e->tm_wc256, tm_p4[4], tm_p4[*cur], tm_p4[*cur ^ 1], tm_p4[3], wp);
       }
       e->launches += has_res ? 1 : 0;
     } else if (tc) {
@@ -1177,9 +1188,9 @@ int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CU
     if ((rc = make_map(e, &tm_x[5], ws + L.cond, 3, dims, str, box64, dt))) return rc;
     if ((rc = make_map(e, &tm_x[8], ws + L.cond, 3, dims, str, box32, dt))) return rc;
   }
-  if (e->pair_cont) {
+  if (e->pair_cont || e->wide) {
     // packed ragged tails (LayerTcParams::pack4): 32 frames x 4 consecutive utterances per box.  tm_p4[0], [1]: x ping-pong
-    // as {nc, Fq, 32 phases, B}; [2]: mel windows; [3]: [a0 | 1] rows
+    // as {nc, Fq, 32 phases, B}; [2]: mel windows; [3]: [a0 | 1] rows; [4]: gated activations of the wide path
     const uint64_t dims[4] = {static_cast<uint64_t>(nc), static_cast<uint64_t>(Fq), kUpPhases, static_cast<uint64_t>(B)};
     const uint64_t str[3] = {static_cast<uint64_t>(nc) * 2, static_cast<uint64_t>(nc) * 2 * Fq, static_cast<uint64_t>(nc) * 2 * Fq * kUpPhases};
     const uint32_t box[4] = {64, 32, 1, 4};
@@ -1190,6 +1201,8 @@ int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CU
     const uint32_t mbox[3] = {64, 32, 4};
     if ((rc = make_map(e, &tm_p4[2], ws + L.cond, 3, mdims, mstr, mbox, dt))) return rc;
     tm_p4[3] = tm_p4[2];
+    tm_p4[4] = tm_p4[0];
+    if (e->wide && (rc = make_map(e, &tm_p4[4], ws + L.acts, 4, dims, str, box, dt))) return rc;
     if (e->first_comp) {
       const uint64_t adims[4] = {16, static_cast<uint64_t>(Fq), kUpPhases, static_cast<uint64_t>(B)};
       const uint64_t astr[3] = {32, static_cast<uint64_t>(32) * Fq, static_cast<uint64_t>(32) * Fq * kUpPhases};
@@ -1254,7 +1267,7 @@ int wg_infer(wg_engine* e, const float* mel, int32_t batch, int32_t frames, cons
   }
   // 2. conditioning operand (mel windows in tensor-core mode, upsampled + squeezed mel in fp32 mode)
   launch_conditioning(e, mel, B, frames, T, ws, L, st);
-  CUtensorMap tm_x[9], tm_cond, tm_a0[3], tm_p4[4];
+  CUtensorMap tm_x[9], tm_cond, tm_a0[3], tm_p4[5];
   if (tc) {
     int rc = make_act_maps(e, ws, L, B, T, tm_x, &tm_cond, tm_a0, tm_p4);
     if (rc) return rc;
@@ -1362,7 +1375,7 @@ int wg_forward(wg_engine* e, const float* mel, int32_t batch, int32_t frames, co
   WG_CUDA(e, cudaMemcpyAsync(state, audio_in, npos * kGroup * sizeof(float), cudaMemcpyDeviceToDevice, st));
   WG_CUDA(e, cudaMemsetAsync(sums, 0, NF * sizeof(double), st));
   launch_conditioning(e, mel, B, frames, T, ws, L, st);
-  CUtensorMap tm_x[9], tm_cond, tm_a0[3], tm_p4[4];
+  CUtensorMap tm_x[9], tm_cond, tm_a0[3], tm_p4[5];
   if (tc) {
     int rc = make_act_maps(e, ws, L, B, T, tm_x, &tm_cond, tm_a0, tm_p4);
     if (rc) return rc;

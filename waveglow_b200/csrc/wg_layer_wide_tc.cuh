@@ -57,17 +57,45 @@ struct WideParams {
   int first;              // first layer of a flow with the start conv composed in (see wg_layer_pair_cont_tc.cuh): the tap K-blocks
                           // are [a0 | 1] rows (one K = 16 MMA each), the residual carry is one MMA with [W_start | b_start]
   int wc_row0;            // first row of this flow's composed weights: 3 taps x 2 NC packed rows, then NC carry rows
+  int pack4;              // packed ragged tails (see LayerTcParams::pack4): n_full whole 128-frame tiles per utterance, then
+  int n_full, n_rem;      // n_rem tiles of 32 frames x 4 consecutive utterances per group of 4 (4-D TMA boxes)
 };
 
 struct TileCoord {
   int b, ph, q0;
+  bool packed;      // rows are 32 frames (from q0) x 4 utterances (from b): row = 32 * utterance + frame
 };
-__device__ __forceinline__ TileCoord decode_tile(int tile, int tiles_per_utt) {
+__device__ __forceinline__ int wide_tile_count(const WideParams& p) {
+  if (p.pack4) return kPhases * (p.B * p.n_full + ((p.B + 3) >> 2) * p.n_rem);
+  return kPhases * ((p.Fq + kTileM - 1) / kTileM) * p.B;
+}
+__device__ __forceinline__ TileCoord decode_tile(int tile, const WideParams& p) {
   TileCoord c;
+  c.packed = false;
+  if (p.pack4) {
+    c.ph = tile % kPhases;
+    const int en = tile / kPhases, n_class1 = p.B * p.n_full;
+    if (en < n_class1) {
+      c.b = en / p.n_full;
+      c.q0 = (en - c.b * p.n_full) * kTileM;
+    } else {
+      const int e2 = en - n_class1, g = e2 / p.n_rem;
+      c.b = 4 * g;
+      c.q0 = p.n_full * kTileM + 32 * (e2 - g * p.n_rem);
+      c.packed = true;
+    }
+    return c;
+  }
+  const int tiles_per_utt = kPhases * ((p.Fq + kTileM - 1) / kTileM);
   c.b = tile / tiles_per_utt;
   c.ph = (tile % tiles_per_utt) % kPhases;
   c.q0 = ((tile % tiles_per_utt) / kPhases) * kTileM;
   return c;
+}
+// row of a tile -> (utterance, frame)
+__device__ __forceinline__ void wide_row_coord(const TileCoord& tc, int row, int& b, int& q) {
+  b = tc.b + (tc.packed ? (row >> 5) : 0);
+  q = tc.q0 + (tc.packed ? (row & 31) : row);
 }
 
 // ================================================================================================ kernel A
@@ -81,6 +109,10 @@ wn_gate_wide_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC, Fq, 
                     const __grid_constant__ CUtensorMap tm_acts,    // {NC, Fq, 32 B} box {64,128,1} (store)
                     const __grid_constant__ CUtensorMap tm_a0,      // first layer: {16, Fq, 32 B} box {64,128,1}
                     const __grid_constant__ CUtensorMap tm_wc,      // first layer: {16, rows} box {64,256}
+                    const __grid_constant__ CUtensorMap tm_x4,      // pack4: x_in as {NC, Fq, 32, B} box {64,32,1,4}
+                    const __grid_constant__ CUtensorMap tm_mw4,     // pack4: {320, Fq, B} box {64,32,4}
+                    const __grid_constant__ CUtensorMap tm_a04,     // pack4, first layer: {16, Fq, 32, B} box {64,32,1,4}
+                    const __grid_constant__ CUtensorMap tm_acts4,   // pack4: acts as {NC, Fq, 32, B} box {64,32,1,4} (store)
                     const WideParams p) {
   using C = WideCfg<NC>;
   extern __shared__ uint8_t smem_raw[];
@@ -96,8 +128,7 @@ wn_gate_wide_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC, Fq, 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_w + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_per_utt = kPhases * ((p.Fq + kTileM - 1) / kTileM);
-  const int n_tiles = tiles_per_utt * p.B;
+  const int n_tiles = wide_tile_count(p);
   const int my_tiles = (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const int n_units = my_tiles * C::kHalves;    // unit n = (tile it = n / kHalves, half h = n % kHalves)
   const int n_kb = p.first ? kMwKB + 3 : C::kKB;
@@ -128,7 +159,7 @@ wn_gate_wide_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC, Fq, 
   auto tile_of = [&](int it) {
     int tile = blockIdx.x + it * gridDim.x;
     if (p.reverse) tile = n_tiles - 1 - tile;
-    return decode_tile(tile, tiles_per_utt);
+    return decode_tile(tile, p);
   };
 
   // Warps 0 and 1 run their loops converged and predicate only the issue on elect.sync: inside an `if (lane == 0)` loop ptxas
@@ -157,19 +188,22 @@ wn_gate_wide_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC, Fq, 
         if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&full[s], kStageBytes);
           if (kb < kMwKB) {
-            ptx::tma_load_3d(sa, &tm_mw, &full[s], kb * kBlockK, tc.q0, tc.b);
+            if (tc.packed) ptx::tma_load_3d(sa, &tm_mw4, &full[s], kb * kBlockK, tc.q0, tc.b);
+            else ptx::tma_load_3d(sa, &tm_mw, &full[s], kb * kBlockK, tc.q0, tc.b);
             ptx::tma_load_2d(sb, &tm_v, &full[s], kb * kBlockK, p.v_row0 + tc.ph * 2 * NC + h * 512 + chunk * 256);
           } else if (p.first) {
             const int tap = kb - kMwKB;                  // [a0 | 1] at t-1, t, t+1
             const int pp = tc.ph + tap - 1;
             const int dq = pp >> 5;
-            ptx::tma_load_3d(sa, &tm_a0, &full[s], 0, tc.q0 + dq, tc.b * kPhases + pp - (dq << 5));
+            if (tc.packed) ptx::tma_load_4d(sa, &tm_a04, &full[s], 0, tc.q0 + dq, pp - (dq << 5), tc.b);
+            else ptx::tma_load_3d(sa, &tm_a0, &full[s], 0, tc.q0 + dq, tc.b * kPhases + pp - (dq << 5));
             ptx::tma_load_2d(sb, &tm_wc, &full[s], 0, p.wc_row0 + tap * 2 * NC + h * 512 + chunk * 256);
           } else {
             const int j = kb - kMwKB;                    // tap (j / kCB), channel block (j % kCB)
             const int pp = tc.ph + ((j / C::kCB) - 1) * p.dilation;
             const int dq = pp >> 5;
-            ptx::tma_load_3d(sa, &tm_x_in, &full[s], (j % C::kCB) * kBlockK, tc.q0 + dq, tc.b * kPhases + pp - (dq << 5));
+            if (tc.packed) ptx::tma_load_4d(sa, &tm_x4, &full[s], (j % C::kCB) * kBlockK, tc.q0 + dq, pp - (dq << 5), tc.b);
+            else ptx::tma_load_3d(sa, &tm_x_in, &full[s], (j % C::kCB) * kBlockK, tc.q0 + dq, tc.b * kPhases + pp - (dq << 5));
             ptx::tma_load_2d(sb, &tm_w1, &full[s], j * kBlockK, p.w1_row0 + h * 512 + chunk * 256);
           }
         }
@@ -274,8 +308,10 @@ wn_gate_wide_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC, Fq, 
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (warp == 2 && lane == 0) {
 #pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4)
-          ptx::tma_store_3d(&tm_acts, acts + s4 * (kTileM * 128), h * 256 + s4 * kBlockK, tc.q0, tc.b * kPhases + tc.ph);
+        for (int s4 = 0; s4 < 4; ++s4) {
+          if (tc.packed) ptx::tma_store_4d(&tm_acts4, acts + s4 * (kTileM * 128), h * 256 + s4 * kBlockK, tc.q0, tc.ph, tc.b);
+          else ptx::tma_store_3d(&tm_acts, acts + s4 * (kTileM * 128), h * 256 + s4 * kBlockK, tc.q0, tc.b * kPhases + tc.ph);
+        }
         ptx::tma_store_commit();
       }
       // skip-end partial of this half
@@ -290,9 +326,11 @@ wn_gate_wide_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC, Fq, 
 #pragma unroll
         for (int i = 0; i < 8; ++i) e_acc[i] = (h == 0 ? 0.f : e_acc[i]) + __uint_as_float(ve[i]);
         if (h == C::kHalves - 1) {
-          const int t = (tc.q0 + row) * kPhases + tc.ph;
-          if (tc.q0 + row < p.Fq && t < p.T)
-            update_e_row(p.e + (static_cast<size_t>(tc.b) * p.T + t) * 8, e_acc, p.accumulate_e != 0);
+          int rb, rq;
+          wide_row_coord(tc, row, rb, rq);
+          const int t = rq * kPhases + tc.ph;
+          if (rb < p.B && rq < p.Fq && t < p.T)
+            update_e_row(p.e + (static_cast<size_t>(rb) * p.T + t) * 8, e_acc, p.accumulate_e != 0);
         }
       }
     }
@@ -317,6 +355,10 @@ wn_res_wide_kernel(const __grid_constant__ CUtensorMap tm_acts,    // {NC, Fq, 3
                    const __grid_constant__ CUtensorMap tm_ident,   // {64, 32} box {64,32}
                    const __grid_constant__ CUtensorMap tm_a0,      // first layer: {16, Fq, 32 B} box {64,128,1}
                    const __grid_constant__ CUtensorMap tm_wc,      // first layer: {16, rows} box {64,256}
+                   const __grid_constant__ CUtensorMap tm_acts4,   // pack4: 4-D views {NC or 16, Fq, 32, B} box {64,32,1,4}
+                   const __grid_constant__ CUtensorMap tm_x4,
+                   const __grid_constant__ CUtensorMap tm_xout4,
+                   const __grid_constant__ CUtensorMap tm_a04,
                    const WideParams p) {
   using C = WideCfg<NC>;
   extern __shared__ uint8_t smem_raw[];
@@ -331,8 +373,7 @@ wn_res_wide_kernel(const __grid_constant__ CUtensorMap tm_acts,    // {NC, Fq, 3
   float* s_bias = reinterpret_cast<float*>(smem + C::b_bias);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_per_utt = kPhases * ((p.Fq + kTileM - 1) / kTileM);
-  const int n_tiles = tiles_per_utt * p.B;
+  const int n_tiles = wide_tile_count(p);
   const int my_tiles = (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const int n_units = my_tiles * C::kHalves;    // unit n = (tile it = n / kHalves, output half o = n % kHalves)
 
@@ -360,7 +401,7 @@ wn_res_wide_kernel(const __grid_constant__ CUtensorMap tm_acts,    // {NC, Fq, 3
   auto tile_of = [&](int it) {
     int tile = blockIdx.x + it * gridDim.x;
     if (p.reverse) tile = n_tiles - 1 - tile;
-    return decode_tile(tile, tiles_per_utt);
+    return decode_tile(tile, p);
   };
 
   if (warp == 0) {
@@ -385,7 +426,8 @@ wn_res_wide_kernel(const __grid_constant__ CUtensorMap tm_acts,    // {NC, Fq, 3
         uint8_t* sb = sa + kStageABytes;
         if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&full[s], kStageBytes);
-          ptx::tma_load_3d(sa, &tm_acts, &full[s], kb * kBlockK, tc.q0, tc.b * kPhases + tc.ph);
+          if (tc.packed) ptx::tma_load_4d(sa, &tm_acts4, &full[s], kb * kBlockK, tc.q0, tc.ph, tc.b);
+          else ptx::tma_load_3d(sa, &tm_acts, &full[s], kb * kBlockK, tc.q0, tc.b * kPhases + tc.ph);
           ptx::tma_load_2d(sb, &tm_wres, &full[s], kb * kBlockK, p.wres_row0 + o * 256);
         }
         __syncwarp();
@@ -398,7 +440,8 @@ wn_res_wide_kernel(const __grid_constant__ CUtensorMap tm_acts,    // {NC, Fq, 3
         ptx::mbar_wait(&empty[s], ph ^ 1);
         if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&full[s], kStageBytes);
-          ptx::tma_load_3d(smem + s * kStageBytes, &tm_a0, &full[s], 0, tc.q0, tc.b * kPhases + tc.ph);
+          if (tc.packed) ptx::tma_load_4d(smem + s * kStageBytes, &tm_a04, &full[s], 0, tc.q0, tc.ph, tc.b);
+          else ptx::tma_load_3d(smem + s * kStageBytes, &tm_a0, &full[s], 0, tc.q0, tc.b * kPhases + tc.ph);
           ptx::tma_load_2d(smem + s * kStageBytes + kStageABytes, &tm_wc, &full[s], 0, p.wc_row0 + 3 * 2 * NC + o * 256);
         }
         __syncwarp();
@@ -410,7 +453,8 @@ wn_res_wide_kernel(const __grid_constant__ CUtensorMap tm_acts,    // {NC, Fq, 3
         ptx::mbar_wait(&empty[s], ph ^ 1);
         if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&full[s], kStageABytes);
-          ptx::tma_load_3d(smem + s * kStageBytes, &tm_x_in, &full[s], o * 256 + j * kBlockK, tc.q0, tc.b * kPhases + tc.ph);
+          if (tc.packed) ptx::tma_load_4d(smem + s * kStageBytes, &tm_x4, &full[s], o * 256 + j * kBlockK, tc.q0, tc.ph, tc.b);
+          else ptx::tma_load_3d(smem + s * kStageBytes, &tm_x_in, &full[s], o * 256 + j * kBlockK, tc.q0, tc.b * kPhases + tc.ph);
         }
         __syncwarp();
       }
@@ -486,7 +530,9 @@ wn_res_wide_kernel(const __grid_constant__ CUtensorMap tm_acts,    // {NC, Fq, 3
       const int r = n & 1;
       const int o = n % C::kHalves;
       const TileCoord tc = tile_of(n / C::kHalves);
-      const int t = (tc.q0 + row) * kPhases + tc.ph;
+      int rb, rq;
+      wide_row_coord(tc, row, rb, rq);
+      const int t = rq * kPhases + tc.ph;
       // bias of this output half (all epilogue threads; previous readers are past their last use after the bar below)
       if (n > 0) {
         if (warp == 2 && lane == 0) ptx::tma_store_wait_read();      // staging buffer free again
@@ -496,15 +542,17 @@ wn_res_wide_kernel(const __grid_constant__ CUtensorMap tm_acts,    // {NC, Fq, 3
       asm volatile("bar.sync 1, 256;" ::: "memory");
       ptx::mbar_wait(&d_full[r], (n >> 1) & 1);
       ptx::tc_fence_after_sync();
-      stage_residual(lane_base + r * 256, s_bias, stage_out, hh, row, t < p.T, p.fmt);
+      stage_residual(lane_base + r * 256, s_bias, stage_out, hh, row, rb < p.B && rq < p.Fq && t < p.T, p.fmt);
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(&drained[r]);
       ptx::fence_proxy_async_smem();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (warp == 2 && lane == 0) {
 #pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4)
-          ptx::tma_store_3d(&tm_x_out, stage_out + s4 * (kTileM * 128), o * 256 + s4 * kBlockK, tc.q0, tc.b * kPhases + tc.ph);
+        for (int s4 = 0; s4 < 4; ++s4) {
+          if (tc.packed) ptx::tma_store_4d(&tm_xout4, stage_out + s4 * (kTileM * 128), o * 256 + s4 * kBlockK, tc.q0, tc.ph, tc.b);
+          else ptx::tma_store_3d(&tm_x_out, stage_out + s4 * (kTileM * 128), o * 256 + s4 * kBlockK, tc.q0, tc.b * kPhases + tc.ph);
+        }
         ptx::tma_store_commit();
       }
     }
