@@ -66,6 +66,7 @@ struct wg_engine {
   int force_seg = 0;                  // WG_SEG env (tests/diagnostics): force the segment size (128 / 64 / 32) of the continuous pair kernel
   bool pair_cont = false;             // ... with the continuous-issue schedule (wg_layer_pair_cont_tc.cuh); WG_PAIR=1 selects the older pair kernel
   bool first_comp = false;            // continuous pair kernel: start conv composed into the first layer of each flow (WG_FIRST=0 disables)
+  bool trim_grid = true;              // smallest grid with the same number of tile rounds (WG_TRIM=0 disables)
   bool pdl = true;                    // continuous pair kernel: programmatic dependent launch between layer launches (WG_PDL=0 disables)
   bool pack4 = true;                  // continuous pair kernel: pack the ragged last frames of 4 utterances into shared tiles (WG_PACK4=0 disables)
   int g2_at_first = 7;                // g2_at of those first layers (8 k-blocks per chunk; WG_G2AT0 overrides)
@@ -387,6 +388,8 @@ int wg_create(const wg_config* cfg, wg_engine** out) {
   if (e->g2_at < 0 || e->g2_at >= kKB1) return fail(e, WG_ERR_INVALID_ARGUMENT, "WG_G2AT must be in [0, %d)", kKB1);
   const char* first_env = getenv("WG_FIRST");
   e->first_comp = (e->pair_cont || e->wide) && !(first_env && atoi(first_env) == 0);
+  const char* trim_env = getenv("WG_TRIM");
+  e->trim_grid = !(trim_env && atoi(trim_env) == 0);
   const char* pdl_env = getenv("WG_PDL");
   e->pdl = !(pdl_env && atoi(pdl_env) == 0);
   const char* pack_env = getenv("WG_PACK4");
@@ -983,7 +986,12 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
           n_tiles = n4;
         }
       }
-      dim3 grid(n_tiles < e->num_sms ? n_tiles : e->num_sms);
+      int n_ctas = n_tiles < e->num_sms ? n_tiles : e->num_sms;
+      if (e->trim_grid) {
+        const int rounds = (n_tiles + n_ctas - 1) / n_ctas;
+        n_ctas = (n_tiles + rounds - 1) / rounds;
+      }
+      dim3 grid(n_ctas);
       if (nc == 512) {
         wn_gate_wide_kernel<512><<<grid, kTcThreads, WideCfg<512>::a_total + 1024, st>>>(tm_x[*cur], *tm_cond, e->tm_w1, e->tm_v,
                                                                                       e->tm_w2b, tm_x[2], tm_a0[0], e->tm_wc256, tm_p4[*cur], tm_p4[2], tm_p4[3], tm_p4[4], wp);
@@ -1049,7 +1057,14 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
           }
         }
         const int n_ptiles = kPhases * best_pe;
-        const int n_pairs = n_ptiles < e->num_sms / 2 ? n_ptiles : e->num_sms / 2;
+        int n_pairs = n_ptiles < e->num_sms / 2 ? n_ptiles : e->num_sms / 2;
+        if (e->trim_grid) {
+          // the launch lasts ceil(tiles / pairs) rounds of tiles; the smallest grid with the same number of rounds leaves
+          // the other SMs idle instead of half-used, which the power-capped clock pays back (1728 pair-tiles: 72 pairs x 24
+          // instead of 74 pairs of which 48 do 23)
+          const int rounds = (n_ptiles + n_pairs - 1) / n_pairs;
+          n_pairs = (n_ptiles + rounds - 1) / rounds;
+        }
         lp.wse = static_cast<const uint16_t*>(e->d_w2) + (li * kW2Rows + 256) * 256;
         lp.first = e->first_comp && i == 0 && has_res;
         lp.wc_row0 = k * 7 * nc;
