@@ -66,7 +66,8 @@ struct wg_engine {
   int force_seg = 0;                  // WG_SEG env (tests/diagnostics): force the segment size (128 / 64 / 32) of the continuous pair kernel
   bool pair_cont = false;             // ... with the continuous-issue schedule (wg_layer_pair_cont_tc.cuh); WG_PAIR=1 selects the older pair kernel
   bool first_comp = false;            // continuous pair kernel: start conv composed into the first layer of each flow (WG_FIRST=0 disables)
-  bool trim_grid = true;              // smallest grid with the same number of tile rounds (WG_TRIM=0 disables)
+  bool trim_grid = false;             // WG_TRIM=1: smallest grid with the same number of tile rounds (measured 0.7 % SLOWER on
+                                      // config 2 than letting all 74 pairs run, profiles/r01/ab_trim_g2at_v12.txt: off by default)
   bool pdl = true;                    // continuous pair kernel: programmatic dependent launch between layer launches (WG_PDL=0 disables)
   bool pack4 = true;                  // continuous pair kernel: pack the ragged last frames of 4 utterances into shared tiles (WG_PACK4=0 disables)
   int g2_at_first = 7;                // g2_at of those first layers (8 k-blocks per chunk; WG_G2AT0 overrides)
@@ -389,7 +390,7 @@ int wg_create(const wg_config* cfg, wg_engine** out) {
   const char* first_env = getenv("WG_FIRST");
   e->first_comp = (e->pair_cont || e->wide) && !(first_env && atoi(first_env) == 0);
   const char* trim_env = getenv("WG_TRIM");
-  e->trim_grid = !(trim_env && atoi(trim_env) == 0);
+  e->trim_grid = trim_env && atoi(trim_env) != 0;
   const char* pdl_env = getenv("WG_PDL");
   e->pdl = !(pdl_env && atoi(pdl_env) == 0);
   const char* pack_env = getenv("WG_PACK4");
@@ -1059,9 +1060,9 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
         const int n_ptiles = kPhases * best_pe;
         int n_pairs = n_ptiles < e->num_sms / 2 ? n_ptiles : e->num_sms / 2;
         if (e->trim_grid) {
-          // the launch lasts ceil(tiles / pairs) rounds of tiles; the smallest grid with the same number of rounds leaves
-          // the other SMs idle instead of half-used, which the power-capped clock pays back (1728 pair-tiles: 72 pairs x 24
-          // instead of 74 pairs of which 48 do 23)
+          // experiment: the launch lasts ceil(tiles / pairs) rounds of tiles; the smallest grid with the same number of
+          // rounds leaves the other SMs idle instead of half-used (1728 pair-tiles: 72 pairs x 24 instead of 74 pairs of
+          // which 48 do 23).  The power-capped clock did not pay it back.
           const int rounds = (n_ptiles + n_pairs - 1) / n_pairs;
           n_pairs = (n_ptiles + rounds - 1) / rounds;
         }
