@@ -119,3 +119,23 @@ def test_synthetic_checkpoint_is_deterministic_and_non_degenerate():
   b = synthetic_state_dict(hp, 7)
   assert all(torch.equal(a[k], b[k]) for k in a)
   assert float(a["WN.0.end.weight"].abs().max()) > 0   # the reference zero-inits `end`: would hide the WN kernels
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+  """`bench.py --impl reference` (the one place besides tests / smoke that may execute oracle/) runs on the host cores and
+  prints ONE JSON line with the contract's keys; no GPU, no CUDA library involved."""
+  import json
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                     capture_output=True, text=True, timeout=900, cwd=root)
+  assert r.returncode == 0, r.stderr[-500:]
+  lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+  assert len(lines) == 1
+  d = json.loads(lines[0])
+  assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["higher_is_better"] is True and d["n_gpus"] == 1
+  assert d["value"] > 0 and d["steps"] == 1 and d["scaling"] == "weak" and d["vs_baseline"] is None
+  assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+  assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+  assert "workload" in d["config"] and "model" not in d["config"]
