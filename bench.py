@@ -307,9 +307,9 @@ def main():
                            "wn_layer_pair_cont_kernel" if args.channels == 256 else "wn_gate_wide_kernel + wn_res_wide_kernel"),
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel on this workload, averaged over the 8
-                # layers of a flow, from profiles/r01/ncu_full_layer_v9_first_and_generic_summary.csv (ncu --set full: generic
-                # layer 268 + 213 MB, first layer 34 + 189 MB); only valid for the default workload
-                "traffic": 449e6 if (args.batch == 16 and args.frames == 861 and args.precision == "fp16" and args.channels == 256) else None,
+                # layers of a flow, from profiles/r01/ncu_full_layer_v12_first_and_generic_summary.csv (ncu --set full: generic
+                # layer 271 + 214 MB, first layer 34 + 195 MB); only valid for the default workload
+                "traffic": 453e6 if (args.batch == 16 and args.frames == 861 and args.precision == "fp16" and args.channels == 256) else None,
                 "traffic_unit": "bytes per launch (ncu)",
                 "peak_source": peak_src, "launch_ms": per_launch_ms, "launches_per_step": layer_launches,
                 "algorithmic_flop_per_launch": per_launch_flops,
