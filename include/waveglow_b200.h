@@ -111,10 +111,12 @@ int wg_infer(wg_engine* e, const float* mel, int32_t batch, int32_t frames,
  *  z_out    [batch, n_group, T'] fp32 (reference layout, channel-major), T' = n_samples / n_group
  *  log_s_out   optional (may be NULL): n_flows device pointers, each [batch, n_half_k, T'] fp32
  *  log_s_sum   [n_flows] fp32 device: sum over all elements of log_s of flow k
- *  log_det_w   [n_flows] fp32 device: batch * T' * logdet(W_k)   (model.py:63) */
+ *  log_det_w   [n_flows] fp32 device: batch * T' * logdet(W_k)   (model.py:63)
+ *  z_sq_sum    optional (may be NULL): [1] fp32 device: sum over all elements of z^2 (train.py:41), reduced by the kernel
+ *              that writes z_out, so WaveGlowLoss needs no pass over z or log_s */
 int wg_forward(wg_engine* e, const float* mel, int32_t batch, int32_t frames,
                const float* audio_in, int32_t n_samples, float* z_out,
-               float* const* log_s_out, float* log_s_sum, float* log_det_w,
+               float* const* log_s_out, float* log_s_sum, float* log_det_w, float* z_sq_sum,
                void* workspace, size_t ws_bytes, void* stream);
 
 /* Number of kernel launches the last wg_infer / wg_forward call enqueued (for bench.py's gpu_launches). */

@@ -1,0 +1,135 @@
+"""GPU parity at the shapes BASELINE.json names (configs 2-5), through the C ABI.
+
+Two references per case:
+  * the CPU oracle computed live on the same seeded inputs (full tensor: max-abs and SNR gates of north_star);
+  * the decimated golden vectors tools/make_golden_large.py produced with the UNMODIFIED reference at that very shape (and
+    against which the oracle was asserted bit-identical there): every 61st sample + 1024-sample head and tail per utterance.
+Gates (BASELINE.json north_star / SURVEY.md §8d): tensor-core mode max-abs <= 2e-3 and SNR >= 40 dB; fp32 mode max-abs <= 1e-5;
+forward: the same on z and log_s, sums relative 1e-4 (fp16) / 1e-6 (fp32) to the scale of the summands.
+"""
+import pytest
+import torch
+
+from oracle import waveglow_oracle as O
+from tests.helpers import FP16_MAX_ABS, FP16_MIN_SNR_DB, FP32_MAX_ABS, load_golden, max_abs, snr_db, synthetic_weights
+from tests.test_gpu_parity import get_model, run
+from waveglow_b200.synthetic import synthetic_mel, synthetic_noise
+
+pytestmark = pytest.mark.gpu
+
+
+def check_decimated(g, out: torch.Tensor, tol: float, what: str):
+  """out [B, n] against the reference's decimated golden of the same case."""
+  stride, edge = int(g["stride"]), int(g["edge"])
+  parts = {"strided": out[:, ::stride], "head": out[:, :edge], "tail": out[:, -edge:]}
+  worst = 0.0
+  for key, got in parts.items():
+    ref = torch.from_numpy(g[key])
+    assert got.shape == ref.shape, (key, tuple(got.shape), tuple(ref.shape))
+    worst = max(worst, max_abs(ref, got))
+  ref_s = torch.from_numpy(g["strided"])
+  snr = snr_db(ref_s, parts["strided"])
+  print(f"{what} vs reference golden (decimated): max-abs {worst:.3e}  snr {snr:.1f} dB")
+  assert worst <= tol
+  return worst, snr
+
+
+@pytest.mark.parametrize("name,precision", [
+  ("large_infer_c256_b2_f861", "fp16"),       # configs[1]: utterances 0, 1 of the bench batch (same seeds as bench.py)
+  ("large_infer_c256_b2_f861", "fp32"),
+  ("large_infer_c256_b1_f5168", "fp16"),      # configs[3]: 60 s single utterance
+  ("large_infer_c512_b1_f140", "fp16"),       # configs[2] architecture, one whole tile + packed tail
+  ("large_infer_c512_b1_f140", "fp32"),
+  ("large_infer_c512_b2_f300", "fp16"),       # ... multi-tile
+])
+def test_infer_at_baseline_shapes_vs_oracle_and_reference_golden(name, precision):
+  g = load_golden(name)
+  nc, B, F = int(g["n_channels"]), int(g["batch"]), int(g["frames"])
+  hp, sd, w, dims = synthetic_weights(nc)
+  mel = synthetic_mel(B, F, int(g["mel_seed"]))
+  zs = synthetic_noise(hp, B, F * 32, int(g["noise_seed"]))
+  sigma = float(g["sigma"])
+  out = run(get_model(nc, precision), mel, zs, sigma)
+  assert out.shape == (B, F * 256) and torch.isfinite(out).all()
+  tol = FP32_MAX_ABS if precision == "fp32" else FP16_MAX_ABS
+  _, snr_g = check_decimated(g, out, tol, f"{precision} {name}")
+  with torch.no_grad():
+    ref = O.infer(w, dims, mel, sigma, zs)
+  # the live oracle reproduces the committed reference vectors exactly (same torch CPU ops on the same inputs)
+  stride = int(g["stride"])
+  assert max_abs(torch.from_numpy(g["strided"]), ref[:, ::stride]) <= 1e-6
+  err, snr = max_abs(ref, out), snr_db(ref, out)
+  print(f"{precision} {name} vs oracle (full): max-abs {err:.3e}  snr {snr:.1f} dB  (ref absmax {float(ref.abs().max()):.2f})")
+  assert err <= tol
+  if precision != "fp32":
+    assert snr >= FP16_MIN_SNR_DB and snr_g >= FP16_MIN_SNR_DB
+
+
+@pytest.mark.parametrize("nc,B,F", [(256, 16, 861), (512, 8, 861)])
+def test_full_batch_fp16_engine_vs_fp32_engine(nc, B, F):
+  """The whole headline batch (config 2: 16 x 861; config 3's architecture and length at 8 utterances per call): the
+  tensor-core engine against the fp32 engine mode on the same inputs.  The fp32 mode is itself oracle-checked at this
+  utterance length above, so this closes the gap between 'two utterances vs the oracle' and 'the batch the bench times'."""
+  hp, sd, w, dims = synthetic_weights(nc)
+  mel = synthetic_mel(B, F, 1002)
+  zs = synthetic_noise(hp, B, F * 32, 7)
+  a = run(get_model(nc, "fp16"), mel, zs, 0.666)
+  b = run(get_model(nc, "fp32"), mel, zs, 0.666)
+  err, snr = max_abs(b, a), snr_db(b, a)
+  per_utt = [(max_abs(b[i], a[i])) for i in range(B)]
+  print(f"fp16 vs fp32 engine, {nc} ch, B{B} x F{F}: max-abs {err:.3e}  snr {snr:.1f} dB  (worst utterance {max(per_utt):.3e}, best {min(per_utt):.3e})")
+  assert torch.isfinite(a).all() and err <= FP16_MAX_ABS and snr >= FP16_MIN_SNR_DB
+  if nc == 256:
+    # utterances 0 and 1 are the reference-golden case above
+    g = load_golden("large_infer_c256_b2_f861")
+    check_decimated(g, a[:2], FP16_MAX_ABS, "fp16 full batch, utterances 0-1")
+
+
+@pytest.mark.parametrize("precision", ["fp16", "fp32"])
+def test_forward_at_config5_shape_vs_oracle_and_reference_golden(precision):
+  """BASELINE configs[4]: forward (training direction) on 24 x 16000-sample segments, F = 63: two whole utterances per
+  tile / packed tails in the forward direction, T' = 2000 (not a multiple of 32)."""
+  from waveglow_b200.model import WaveGlowLoss
+  g = load_golden("large_forward_c256_b24_t16000")
+  B, T, F = int(g["batch"]), int(g["samples"]), int(g["frames"])
+  hp, sd, w, dims = synthetic_weights(256)
+  mel = synthetic_mel(B, F, int(g["mel_seed"]))
+  audio = torch.rand((B, T), generator=torch.Generator().manual_seed(int(g["audio_seed"]))) * 2 - 1
+  model = get_model(256, precision)
+  out = model((mel.cuda(), audio.cuda()))
+  torch.cuda.synchronize()
+  z, log_s_list, log_det_list = out
+  tol = FP32_MAX_ABS if precision == "fp32" else FP16_MAX_ABS
+  zc = z.cpu()
+  check_decimated(g, zc.reshape(B, -1), tol, f"forward {precision} z")
+  stride = int(g["stride"])
+  for k in (0, 11):
+    ref = torch.from_numpy(g[f"log_s{k}_strided"])
+    assert max_abs(ref, log_s_list[k].cpu().reshape(B, -1)[:, ::stride]) <= tol
+  with torch.no_grad():
+    z_ref, ls_ref, ld_ref = O.forward(w, dims, mel, audio)
+  ez, snr = max_abs(z_ref, zc), snr_db(z_ref, zc)
+  print(f"forward {precision} B{B} x {T}: z max-abs {ez:.3e}  snr {snr:.1f} dB (ref absmax {float(z_ref.abs().max()):.2f})")
+  assert ez <= tol and (precision == "fp32" or snr >= FP16_MIN_SNR_DB)
+  rel = 1e-6 if precision == "fp32" else 1e-4
+  stats = model.last_forward_stats
+  n = B * (T // 8)
+  for k in range(12):
+    assert max_abs(ls_ref[k], log_s_list[k].cpu()) <= tol
+    scale = float(g["log_s_abs_sum"][k])
+    assert abs(float(stats["log_s_sum"][k]) - float(g["log_s_sum"][k])) <= rel * scale + 1e-6, k
+    assert abs(float(log_det_list[k]) - float(g["log_det_w"][k])) <= 2e-6 * n + 1e-5 * abs(float(g["log_det_w"][k]))
+  # sum z^2 is reduced by the engine (the kernel that writes z): relative to the sum itself (all terms positive)
+  zsq, zsq_ref = float(stats["z_sq_sum"][0]), float(g["z_sq_sum"])
+  print(f"forward {precision}: fused sum z^2 {zsq:.4f} ref {zsq_ref:.4f}")
+  assert abs(zsq - zsq_ref) <= (1e-5 if precision == "fp32" else 1e-3) * zsq_ref
+  crit = WaveGlowLoss(1.0)
+  loss = float(crit(out))
+  assert crit.used_fused_stats            # no pass over z / log_s: the engine's reductions were consumed
+  loss_ref = float(g["loss"])
+  print(f"forward {precision}: fused loss {loss:.6f} ref {loss_ref:.6f}")
+  assert abs(loss - loss_ref) <= (1e-5 if precision == "fp32" else 5e-4) * max(1.0, abs(loss_ref))
+  # on foreign tensors (copies) the loss reduces with torch like the reference and agrees with the fused value
+  foreign = (z.clone(), [t.clone() for t in log_s_list], log_det_list)
+  loss2 = float(crit(foreign))
+  assert not crit.used_fused_stats and abs(loss2 - loss) <= 1e-5 * max(1.0, abs(loss))

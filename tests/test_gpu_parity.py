@@ -19,11 +19,9 @@ _MODELS = {}
 
 
 def get_model(n_channels: int, precision: str, style: str = "parametrized") -> WaveGlow:
-  """precision: "fp32", "fp16" (default tensor-core path: fused layer on CTA pairs, continuous-issue schedule),
-  "fp16-pair1" (WG_PAIR=1: the older CTA-pair schedule with the skip-end outputs on tcgen05), "fp16-single" (WG_PAIR=0: the
-  same fused layer on single CTAs) or "fp16-wide" (WG_WIDE=1: the two-kernel layer of 512-channel models, forced onto the
-  256-channel model so that it can be checked against the same references); "fp16-seg32" / "fp16-seg64" (WG_SEG) force
-  the segment size of the default kernel's tiles; "fp16-nopack" (WG_PACK4=0) switches the packed ragged tails off and
+  """precision: "fp32", "fp16" (the tensor-core path: fused layer on CTA pairs, continuous-issue schedule; 256 and 512
+  channels run the same templated kernel), or the fp16 engine with one of its switches set: "fp16-seg32" / "fp16-seg64"
+  (WG_SEG) force the segment size of the tiles; "fp16-nopack" (WG_PACK4=0) switches the packed ragged tails off and
   "fp16-nofirst" (WG_FIRST=0) the composition of the start conv into each flow's first layer."""
   import os
   key = (n_channels, precision, style)
@@ -32,23 +30,15 @@ def get_model(n_channels: int, precision: str, style: str = "parametrized") -> W
     m = WaveGlow(hp, precision="fp16" if precision.startswith("fp16") else precision).to("cuda:0")
     m.load_state_dict(sd)
     m = WaveGlow.remove_weightnorm(m).eval()
-    if precision in ("fp16-wide", "fp16-wide-nopack"):
-      os.environ["WG_WIDE"] = "1"
-    if precision == "fp16-single":
-      os.environ["WG_PAIR"] = "0"
-    if precision == "fp16-pair1":
-      os.environ["WG_PAIR"] = "1"
     if precision.startswith("fp16-seg"):
       os.environ["WG_SEG"] = precision[len("fp16-seg"):]
-    if precision in ("fp16-nopack", "fp16-wide-nopack"):
+    if precision == "fp16-nopack":
       os.environ["WG_PACK4"] = "0"
     if precision == "fp16-nofirst":
       os.environ["WG_FIRST"] = "0"
     try:
-      m.engine()          # the engine reads WG_WIDE / WG_PAIR when it is created
+      m.engine()          # the engine reads its switches when it is created
     finally:
-      os.environ.pop("WG_WIDE", None)
-      os.environ.pop("WG_PAIR", None)
       os.environ.pop("WG_SEG", None)
       os.environ.pop("WG_PACK4", None)
       os.environ.pop("WG_FIRST", None)
@@ -92,13 +82,13 @@ def test_tcgen05_cta_pair_gemm():
   assert err <= 2e-3
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16", "fp16-wide", "fp16-single", "fp16-pair1"])
-def test_stagewise_first_flow(precision):
+@pytest.mark.parametrize("precision,nc", [("fp32", 256), ("fp16", 256), ("fp16-nofirst", 256), ("fp16", 512), ("fp16-nofirst", 512)])
+def test_stagewise_first_flow(precision, nc):
   """cond (upsample+squeeze), start conv, then every WN layer of the first flow, then the coupling step."""
   op_dtype = torch.float32 if precision == "fp32" else torch.float16
   tol = 2e-5 if precision == "fp32" else 6e-3      # intermediates are O(1..10); fp16 has 2^-11 relative steps
-  hp, sd, w, dims = synthetic_weights(256)
-  model = get_model(256, precision)
+  hp, sd, w, dims = synthetic_weights(nc)
+  model = get_model(nc, precision)
   eng = model.engine()
   B, F = 2, 7            # T' = 224: one full and one ragged 128-tile, dilation 128 reaches across both
   T = F * 32
@@ -107,7 +97,7 @@ def test_stagewise_first_flow(precision):
   sigma = 0.8
   trace = []
   phase_cond = precision != "fp32"     # tensor-core mode composes the upsampler into the conditioning weights
-  first_composed = precision in ("fp16", "fp16-wide")  # ... and the default / wide kernels compose the start conv into each flow's first layer
+  first_composed = precision == "fp16"  # ... and the start conv into each flow's first layer
   with torch.no_grad():
     ref_audio = E.infer(w, dims, mel, sigma, zs, op_dtype, trace, phase_cond=phase_cond, first_composed=first_composed)
   k = dims.n_flows - 1
@@ -123,13 +113,13 @@ def test_stagewise_first_flow(precision):
     """engine x buffer -> time-major [B, T, 256] (tensor-core mode keeps it phase-major [B][32][T/32][256])"""
     raw = eng.debug_view(buf, B, F).float().cpu()
     if precision != "fp32":
-      return raw.view(B, 32, T // 32, 256).permute(0, 2, 1, 3).reshape(B, T, 256)
-    return raw.view(B, T, 256)
+      return raw.view(B, 32, T // 32, nc).permute(0, 2, 1, 3).reshape(B, T, nc)
+    return raw.view(B, T, nc)
 
   def check(name, got, ref, t=tol):
     err = float((got.double() - ref.double()).abs().max())
     scale = float(ref.abs().max())
-    print(f"[{precision}] {name}: max err {err:.3e} (ref absmax {scale:.3f})")
+    print(f"[{precision} {nc}] {name}: max err {err:.3e} (ref absmax {scale:.3f})")
     if not err <= t * max(1.0, scale):
       failures.append(f"{name}: {err:.3e}")
 
@@ -166,21 +156,6 @@ def test_stagewise_first_flow(precision):
     eng.debug_stop_after(-1, 0)
   out = run(model, mel, zs, sigma)
   check("final audio vs engine model", out, ref_audio, t=(2e-5 if precision == "fp32" else 2e-3))
-  if precision == "fp16-single":
-    same = run(get_model(256, "fp16-pair1"), mel, zs, sigma)
-    print(f"[fp16-single] vs CTA-pair kernel (WG_PAIR=1): max-abs {max_abs(same, out):.3e}")
-    assert torch.equal(same, out)      # same operands, same accumulation order: bit-identical
-  if precision == "fp16-pair1":
-    # the default kernel sums the 8 skip-end outputs with mma.sync instead of tcgen05 (another fp32 summation order)
-    same = run(get_model(256, "fp16"), mel, zs, sigma)
-    print(f"[fp16-pair1] vs continuous-issue pair kernel: max-abs {max_abs(same, out):.3e}")
-    assert max_abs(same, out) <= 1e-3
-  if precision == "fp16-wide":
-    # both tensor-core layer implementations use the same rounded operands but sum in a different order (fp32), and the
-    # fp16 re-rounding of x amplifies that: they agree to about the fp16 noise floor, each within the gate of the reference
-    same = run(get_model(256, "fp16"), mel, zs, sigma)
-    print(f"[fp16-wide] vs fused fp16 kernel: max-abs {max_abs(same, out):.3e}")
-    assert max_abs(same, out) <= 1e-3
   assert not failures, "; ".join(failures)
 
 
@@ -209,18 +184,16 @@ def test_fp16_tensor_core_mode_matches_reference_golden(name):
   assert err <= FP16_MAX_ABS and snr >= FP16_MIN_SNR_DB
 
 
-@pytest.mark.parametrize("name,nc,mode", [("infer_c512_b1_f10", 512, "fp16"), ("infer_c256_b1_f40", 256, "fp16-wide"),
-                                          ("infer_c256_b3_f7_ragged", 256, "fp16-wide"), ("infer_c256_b1_f40", 256, "fp16-single"),
-                                          ("infer_c256_b3_f7_ragged", 256, "fp16-single"), ("infer_c256_b2_f12", 256, "fp16-single")])
-def test_wide_tensor_core_path_matches_reference_golden(name, nc, mode):
-  """The two-kernel tensor-core layer (wg_layer_wide_tc.cuh): 512-channel model (BASELINE config 3 architecture) and,
-  forced with WG_WIDE=1, the 256-channel model."""
-  g = load_golden(name)
-  model = get_model(nc, mode, str(g["weight_style"]))
+@pytest.mark.parametrize("mode", ["fp16", "fp16-seg32", "fp16-nofirst"])
+def test_512_channel_tensor_core_path_matches_reference_golden(mode):
+  """The 512-channel instantiation of the fused layer kernel (BASELINE config 3 architecture): 4 accumulator chunks, two x'
+  halves, 128 KB of gated activations in shared memory."""
+  g = load_golden("infer_c512_b1_f10")
+  model = get_model(512, mode, str(g["weight_style"]))
   out = run(model, torch.from_numpy(g["mel"]), golden_noise(g), float(g["sigma"]))
   ref = torch.from_numpy(g["audio"])
   err, snr = max_abs(ref, out), snr_db(ref, out)
-  print(f"{mode} {name}: max-abs {err:.3e}  snr {snr:.1f} dB")
+  print(f"512 channels {mode}: max-abs {err:.3e}  snr {snr:.1f} dB")
   assert out.shape == ref.shape and err <= FP16_MAX_ABS and snr >= FP16_MIN_SNR_DB
 
 
@@ -263,23 +236,15 @@ def test_packed_ragged_tails_vs_oracle_and_unpacked(B, F):
   assert torch.equal(out[B - 1:B], alone)
 
 
-@pytest.mark.parametrize("nc,mode", [(256, "fp16-wide"), (512, "fp16")])
-def test_packed_ragged_tails_on_the_wide_kernels(nc, mode):
-  """The two-kernel wide layer with packed tails (4-D TMA loads and stores of acts / x): bit-identical to the same kernels
-  without the packing; the forced-wide 256-channel model is also checked against the oracle."""
-  hp, sd, w, dims = synthetic_weights(nc)
+def test_packed_ragged_tails_512_channels():
+  """Packed tails on the 512-channel instantiation: bit-identical to the same kernel without the packing."""
+  hp, sd, w, dims = synthetic_weights(512)
   B, F = 6, 140
   mel = synthetic_mel(B, F, 611)
   zs = synthetic_noise(hp, B, F * 32, 612)
-  out = run(get_model(nc, mode), mel, zs, 0.666)
+  out = run(get_model(512, "fp16"), mel, zs, 0.666)
   assert torch.isfinite(out).all()
-  assert torch.equal(out, run(get_model(nc, mode + "-nopack" if mode != "fp16" else "fp16-nopack"), mel, zs, 0.666))
-  if nc == 256:
-    with torch.no_grad():
-      ref = O.infer(w, dims, mel, 0.666, zs)
-    err, snr = max_abs(ref, out), snr_db(ref, out)
-    print(f"wide kernels, packed tails, B{B} F{F}: max-abs {err:.3e}  snr {snr:.1f} dB")
-    assert err <= FP16_MAX_ABS and snr >= FP16_MIN_SNR_DB
+  assert torch.equal(out, run(get_model(512, "fp16-nopack"), mel, zs, 0.666))
 
 
 def test_first_layer_composition_vs_explicit_start_conv():
@@ -436,28 +401,7 @@ def test_forward_then_infer_round_trip_on_gpu():
   assert err <= 4e-3
 
 
-def test_bf16_operand_option_runs_and_documents_why_fp16_is_default():
-  """WG_B200_OPERAND=bf16 selects bf16 operands on the same kernels: SNR is fine, the 2e-3 max-abs gate is not met
-  (DESIGN.md precision decision), which is why fp16 operands are the default."""
-  import os
-  hp, sd, w, dims = synthetic_weights(256)
-  g = load_golden("infer_c256_b1_f40")
-  m = WaveGlow(hp, precision="fp16").to("cuda:0")
-  m.load_state_dict(sd)
-  m = WaveGlow.remove_weightnorm(m).eval()
-  os.environ["WG_B200_OPERAND"] = "bf16"
-  try:
-    m.engine()
-  finally:
-    os.environ.pop("WG_B200_OPERAND", None)
-  out = run(m, torch.from_numpy(g["mel"]), golden_noise(g), float(g["sigma"]))
-  ref = torch.from_numpy(g["audio"])
-  err, snr = max_abs(ref, out), snr_db(ref, out)
-  print(f"bf16 operands infer_c256_b1_f40: max-abs {err:.3e}  snr {snr:.1f} dB")
-  assert snr >= FP16_MIN_SNR_DB and err > FP16_MAX_ABS
-
-
-def test_wide_512_properties():
+def test_512_channel_properties():
   """512-channel tensor-core path at a moderate size: finite, deterministic, no cross-utterance interaction, and
   infer(forward(audio)) == audio."""
   hp, sd, w, dims = synthetic_weights(512)
@@ -506,3 +450,47 @@ def test_errors_are_loud():
     model.infer_with_noise(mel, [torch.zeros(1, 4, 128).cuda()], 1.0)
   with pytest.raises(ValueError):
     model.infer_with_noise(torch.zeros(1, 3, 4).cuda(), [], 1.0)
+  # raw pointers cross the ABI: a noise tensor of the wrong channel count, length, batch or device must not reach the kernels
+  good = [torch.zeros(1, 4, 128), torch.zeros(1, 2, 128), torch.zeros(1, 2, 128)]
+  for i, bad in ((0, torch.zeros(1, 2, 128)), (1, torch.zeros(1, 2, 96)), (2, torch.zeros(2, 2, 128))):
+    zs = [z.cuda() for z in good]
+    zs[i] = bad.cuda()
+    with pytest.raises(WgError, match=f"noise tensor {i} has shape"):
+      model.infer_with_noise(mel, zs, 1.0)
+  with pytest.raises(WgError, match="is on cpu"):
+    model.infer_with_noise(mel, [good[0].cuda(), good[1], good[2].cuda()], 1.0)
+
+
+def test_reloaded_weights_invalidate_cuda_graphs_and_pack_cache(tmp_path):
+  """a captured CUDA graph bakes in the pointers of the packed weights, and the packed-weight cache identifies
+  the checkpoint FILE, not the live parameters.  After load_state_dict both must be dropped: the next call runs the NEW
+  weights (eagerly and through a fresh graph)."""
+  from waveglow_b200.checkpoint import CheckpointWaveglow
+  from waveglow_b200.synthesizer import Synthesizer
+  from waveglow_b200.synthetic import synthetic_state_dict
+  hp, sd, w, dims = synthetic_weights(256)
+  sd2 = synthetic_state_dict(hp, 4321)
+  mel = synthetic_mel(1, 24, 95)
+  zs = synthetic_noise(hp, 1, 24 * 32, 96)
+  cache = tmp_path / "ck.b200pack"
+  synth = Synthesizer(CheckpointWaveglow.from_state_dict(sd, hp, iteration=1), device=torch.device("cuda:0"), pack_cache=cache,
+                      pack_fingerprint=77)
+  model = synth.model
+  assert cache.is_file() and model.pack_cache is not None
+  model.use_cuda_graphs = True
+  old = run(model, mel, zs, 0.7)
+  assert torch.equal(old, run(model, mel, zs, 0.7))             # replayed
+  assert torch.equal(old, run(get_model(256, "fp16"), mel, zs, 0.7))
+  # new weights into the same module (keys of the folded layout: remove_weightnorm already ran)
+  fresh = WaveGlow(hp).to("cuda:0")
+  fresh.load_state_dict(sd2)
+  fresh = WaveGlow.remove_weightnorm(fresh).eval()
+  expect = run(fresh, mel, zs, 0.7)
+  model.load_state_dict(fresh.state_dict())
+  assert model.pack_cache is None                               # the cache describes the old checkpoint file
+  new = run(model, mel, zs, 0.7)                                # graph path: must re-capture against the re-packed weights
+  assert not torch.equal(new, old) and torch.equal(new, expect)
+  assert torch.equal(new, run(model, mel, zs, 0.7))
+  model.use_cuda_graphs = False
+  assert torch.equal(new, run(model, mel, zs, 0.7))
+  assert model.pack_cache_hit is False

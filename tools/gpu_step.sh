@@ -1,0 +1,31 @@
+#!/bin/bash
+# One GPU session on the B200 box: named steps, each under its own timeout, logs under gpurun_out/<tag>/.
+# usage: bash tools/gpu_step.sh <tag> <step> [<step> ...]       steps: see the case statement
+TAG=$1; shift
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+run() { name=$1; lim=$2; shift 2; echo "=== $name"; timeout $lim "$@" > $OUT/$name.log 2>&1; rc=$?; echo "exit $rc"; tail -n ${TAILN:-6} $OUT/$name.log | cut -c1-600; return $rc; }
+for step in "$@"; do
+  case $step in
+    quick256)  TAILN=15 run quick256 300 python -m pytest tests/test_gpu_parity.py -q -x -s -k "gemm or (stagewise and 256) or golden and not 512" ;;
+    quick512)  TAILN=30 run quick512 300 python -m pytest tests/test_gpu_parity.py -q -x -s -k "(stagewise and 512) or 512_channel" ;;
+    tests)     TAILN=8 run tests 1500 python -m pytest tests -q -m gpu -x --timeout 900 ;;
+    tests_all) TAILN=25 run tests_all 1500 python -m pytest tests -q -m gpu --timeout 900 ;;
+    shapes)    TAILN=30 run shapes 1200 python -m pytest tests/test_gpu_baseline_shapes.py -q -s --timeout 900 ;;
+    smoke)     TAILN=4 run smoke 300 python -c "import __graft_entry__ as g; g.smoke()" ;;
+    bench)     TAILN=1 run bench 600 python bench.py --steps 10 --warmup 3 ;;
+    bench_fast) TAILN=1 run bench_fast 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-parity ;;
+    bench512)  TAILN=1 run bench512 600 python bench.py --channels 512 --batch 32 --steps 5 --warmup 3 --no-cpu-baseline ;;
+    bench512_b8) TAILN=1 run bench512_b8 600 python bench.py --channels 512 --batch 8 --steps 5 --warmup 3 --no-cpu-baseline --no-parity ;;
+    ref)       TAILN=1 run ref 900 python bench.py --impl reference --steps 2 --warmup 1 ;;
+    configs)   TAILN=8 run configs 600 python tools/measure_configs.py ;;
+    timeline256) TAILN=40 run timeline256 300 python tools/timeline.py ;;
+    timeline512) TAILN=40 run timeline512 300 python tools/timeline.py --channels 512 --batch 8 ;;
+    layers)    TAILN=12 run layers 300 python tools/layer_times.py ;;
+    ncu_list)  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 260 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity > $OUT/ncu_launches.log 2>&1; echo "launch list exit $?" ;;
+    ncu_full)  timeout 900 ncu --set full --clock-control none --import-source on -k regex:wn_layer_pair -s 120 -c 3 -o $OUT/prof_layer -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity > $OUT/ncu_full.log 2>&1; echo "full set exit $?" ;;
+    ncu_list512) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 350 -c 130 --csv --log-file $OUT/launches512.csv python bench.py --channels 512 --batch 8 --steps 1 --warmup 3 --no-cpu-baseline --no-parity > $OUT/ncu_launches512.log 2>&1; echo "launch list 512 exit $?" ;;
+    ncu_full512) timeout 900 ncu --set full --clock-control none --import-source on -k regex:wn_layer_pair -s 120 -c 3 -o $OUT/prof_layer512 -f python bench.py --channels 512 --batch 8 --steps 1 --warmup 3 --no-cpu-baseline --no-parity > $OUT/ncu_full512.log 2>&1; echo "full set 512 exit $?" ;;
+    *) echo "unknown step $step" ;;
+  esac
+done

@@ -12,7 +12,8 @@ from waveglow_b200.synthetic import synthetic_mel, synthetic_noise, synthetic_st
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 F = int(sys.argv[2]) if len(sys.argv) > 2 else 861
-hp = HParams()
+NC = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+hp = HParams(n_channels=NC)
 dev = torch.device("cuda:0")
 model = WaveGlow(hp).to(dev)
 model.load_state_dict(synthetic_state_dict(hp, 1234))

@@ -1,10 +1,12 @@
 """Per-phase clock64 timeline of the fused WN layer kernel (diagnostics; run on the GPU box).
 
-  python tools/timeline.py [--batch 16] [--frames 861]
+  python tools/timeline.py [--batch 16] [--frames 861] [--channels 256|512] [--layer 3]
 
-Slots: 0 entry | 1 MMA thread ready | 2 first operands landed | 3 G1a issued | 4 G1b issued | 5 acc a done (epilogue sees it)
-| 6 gate a done | 7 acc b done | 8 gate b done | 9 MMA sees acts | 10 G2 issued | 11 D2 done | 12 x' staged | 13 x' stored | 14 exit | 15 first operands of tile 2 (continuous
-pair kernel only: there GEMM2 of tile 1 is issued inside tile 2's chunk a, so 9..12 lie after 15)
+Stamps are of the SECOND tile of every leader CTA (steady state).  Slots (wg_layer_pair_cont_tc.cuh): 0 kernel entry | 1 MMA warp
+ready | 2 first operands of tile 1 landed | 3 last GEMM1 chunk of tile 1 issued | 4 GEMM2 (tile 1) may start: every gate done |
+5 last GEMM2 half issued | 6 first accumulator chunk complete (gate warps see it) | 7 first gate done | 8 last chunk complete |
+9 last gate done | 10 first x' half complete | 11 last x' half drained and stored | 12 first operands of tile 2 landed |
+13 epilogue warps done | 14 exit.  GEMM2 of tile 1 is issued inside tile 2's first chunk, so 4, 5, 10, 11 lie after 12.
 """
 import argparse
 import os
@@ -17,16 +19,18 @@ from waveglow_b200.hparams import HParams  # noqa: E402
 from waveglow_b200.model import WaveGlow  # noqa: E402
 from waveglow_b200.synthetic import synthetic_mel, synthetic_noise, synthetic_state_dict  # noqa: E402
 
-NAMES = ["entry", "mma_ready", "first_full", "g1a_issued", "g1b_issued", "acc_a_done", "gate_a_done", "acc_b_done",
-         "gate_b_done", "mma_sees_acts", "g2_issued", "d2_done", "x_staged", "x_stored", "exit"]
+NAMES = ["entry", "mma_ready", "t1_first_full", "t1_g1_issued", "t1_all_gated", "t1_g2_issued", "t1_acc0_done", "t1_gate0_done",
+         "t1_accL_done", "t1_gateL_done", "t1_d2h0_done", "t1_drained", "t2_first_full", "epilogue_done", "exit"]
 
 
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--batch", type=int, default=16)
   ap.add_argument("--frames", type=int, default=861)
+  ap.add_argument("--channels", type=int, default=256)
+  ap.add_argument("--layer", type=int, default=3)
   a = ap.parse_args()
-  hp = HParams()
+  hp = HParams(n_channels=a.channels)
   dev = torch.device("cuda:0")
   model = WaveGlow(hp).to(dev)
   model.load_state_dict(synthetic_state_dict(hp, 1234))
@@ -39,33 +43,30 @@ def main():
   n_cta = 148
   buf = torch.zeros((n_cta, 16), dtype=torch.int64, device=dev)
   eng.debug_timeline(buf)
-  eng.debug_stop_after(hp.n_flows - 1, 3)       # stamps of the 4th layer launch (dilation 8) remain
+  eng.debug_stop_after(hp.n_flows - 1, a.layer)       # stamps of this layer launch of the first flow remain
   model.infer_with_noise(mel, zs, 0.666)
   torch.cuda.synchronize()
   eng.debug_timeline(None)
   eng.debug_stop_after(-1, 0)
   t = buf.cpu().double()
-  t = t[(t[:, 0] > 0) & (t[:, 5] > 0)]           # persistent kernel: one row per CTA; phase stamps are of its 2nd tile
-  n_tiles = a.batch * 32 * ((a.frames + 127) // 128)
-  print(f"rows with stamps: {t.size(0)}; tiles {n_tiles}; per-CTA tiles ~ {n_tiles / max(1, t.size(0)):.2f}")
+  t = t[(t[:, 0] > 0) & (t[:, 6] > 0)]           # persistent kernel: one row per leader CTA; phase stamps are of its 2nd tile
+  print(f"leader CTAs with a second tile: {t.size(0)}")
   rel = t[:, 1:15] - t[:, 0:1]
   med = rel.median(dim=0).values
-  print(f"CTAs {n_cta}; median cycles since kernel entry of each CTA:")
-  prev = 0.0
+  print("median cycles since kernel entry (in slot order; see the docstring for which lie in the next tile):")
   for i, name in enumerate(NAMES[1:]):
-    print(f"  {name:14s} {med[i]:10.0f}   (+{med[i] - prev:8.0f})")
-    prev = float(med[i])
+    print(f"  {i + 1:2d} {name:16s} {med[i]:10.0f}")
   dur = (t[:, 14] - t[:, 0])
   print(f"CTA lifetime cycles: median {dur.median():.0f}  p10 {dur.quantile(0.1):.0f}  p90 {dur.quantile(0.9):.0f}")
-  span = t[:, 11] - t[:, 2]
-  print(f"steady-state tile: first operands of G1a -> D2 done: median {span.median():.0f} cycles")
-  if (t[:, 15] > 0).any():
-    per = (t[:, 15] - t[:, 2])[t[:, 15] > 0]
-    print(f"tile period (first operands of tile 1 -> first operands of tile 2): median {per.median():.0f} cycles")
-  g1a = t[:, 5] - t[:, 2]
-  g1b = t[:, 7] - t[:, 5]
-  print(f"G1a (first operands -> acc a done): median {g1a.median():.0f} cycles = {g1a.median() / 68:.1f} per UTCHMMA (ideal 128)")
-  print(f"G1b (acc a done -> acc b done):     median {g1b.median():.0f} cycles = {g1b.median() / 68:.1f} per UTCHMMA")
+  n_mma1 = (5 + 3 * a.channels // 64) * 4 * (a.channels // 128) if a.layer > 0 else (5 * 4 + 3) * (a.channels // 128)
+  if (t[:, 12] > 0).any():
+    per = (t[:, 12] - t[:, 2])[t[:, 12] > 0]
+    print(f"tile period (first operands of tile 1 -> first operands of tile 2): median {per.median():.0f} cycles "
+          f"({n_mma1} GEMM1 MMAs of 128 cycles = {n_mma1 * 128})")
+  print(f"GEMM1 issue (t1 first operands -> last chunk issued): median {(t[:, 3] - t[:, 2]).median():.0f}")
+  print(f"first gate: {(t[:, 7] - t[:, 6]).median():.0f}   last gate: {(t[:, 9] - t[:, 8]).median():.0f}")
+  print(f"last gate done -> GEMM2 may start (MMA warp sees it): {(t[:, 4] - t[:, 9]).median():.0f}")
+  print(f"GEMM2 issue (all halves): {(t[:, 5] - t[:, 4]).median():.0f}   first x' half complete -> all drained: {(t[:, 11] - t[:, 10]).median():.0f}")
 
 
 if __name__ == "__main__":

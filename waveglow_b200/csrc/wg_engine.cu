@@ -15,10 +15,7 @@
 
 #include "../../include/waveglow_b200.h"
 #include "wg_kernels.cuh"
-#include "wg_layer_tc.cuh"
-#include "wg_layer_pair_tc.cuh"
 #include "wg_layer_pair_cont_tc.cuh"
-#include "wg_layer_wide_tc.cuh"
 
 namespace {
 
@@ -59,20 +56,17 @@ struct wg_engine {
   void* d_ident = nullptr;            // [64][64] 16-bit identity
   float* d_bias1 = nullptr;           // [flows*layers][512] packed order
   float* d_bias_res = nullptr;        // [flows*layers][256]
-  CUtensorMap tm_w1{}, tm_v{}, tm_w2a{}, tm_w2b{}, tm_ident{};
-  CUtensorMap tm_w1h{}, tm_vh{}, tm_w2h{}, tm_se8{}, tm_ident16{};   // half-height boxes for the CTA-pair kernel
-  bool pair = false;                  // fused layer on CTA pairs (cta_group::2); default for 256 channels, WG_PAIR=0 disables
-  int g2_at = 6;                      // see LayerTcParams::g2_at (WG_G2AT env overrides, diagnostics)
-  int force_seg = 0;                  // WG_SEG env (tests/diagnostics): force the segment size (128 / 64 / 32) of the continuous pair kernel
-  bool pair_cont = false;             // ... with the continuous-issue schedule (wg_layer_pair_cont_tc.cuh); WG_PAIR=1 selects the older pair kernel
-  bool first_comp = false;            // continuous pair kernel: start conv composed into the first layer of each flow (WG_FIRST=0 disables)
+  CUtensorMap tm_w1h{}, tm_vh{}, tm_w2h{}, tm_ident16{};   // 128-row boxes: each CTA of a pair stages half of every B operand
+  int g2_at[kMaxHalves] = {6, 6};     // see LayerTcParams::g2_at: generic layers (WG_G2AT / WG_G2AT1 env override, diagnostics)
+  int g2_at_first[kMaxHalves] = {7, 7};   // ... first layer of a flow with the start conv composed in (8 k-blocks per chunk; WG_G2AT0)
+  int force_seg = 0;                  // WG_SEG env (tests/diagnostics): force the segment size (128 / 64 / 32) of the tiles
+  bool first_comp = false;            // start conv composed into the first layer of each flow (WG_FIRST=0 disables)
   bool trim_grid = false;             // WG_TRIM=1: smallest grid with the same number of tile rounds (measured 0.7 % SLOWER on
                                       // config 2 than letting all 74 pairs run, profiles/r01/ab_trim_g2at_v12.txt: off by default)
-  bool pdl = true;                    // continuous pair kernel: programmatic dependent launch between layer launches (WG_PDL=0 disables)
-  bool pack4 = true;                  // continuous pair kernel: pack the ragged last frames of 4 utterances into shared tiles (WG_PACK4=0 disables)
-  int g2_at_first = 7;                // g2_at of those first layers (8 k-blocks per chunk; WG_G2AT0 overrides)
-  void* d_wc = nullptr;               // [flows][3 taps x 512 packed rows + 256 carry rows][16] 16-bit composed start weights
-  CUtensorMap tm_wc{}, tm_wc256{};    // 128-row boxes (CTA pairs stage half of B each) / 256-row boxes (wide kernels)
+  bool pdl = true;                    // programmatic dependent launch between layer launches (WG_PDL=0 disables)
+  bool pack4 = true;                  // pack the ragged last frames of 4 utterances into shared tiles (WG_PACK4=0 disables)
+  void* d_wc = nullptr;               // [flows][3 taps x 2 nc packed rows + nc carry rows][16] 16-bit composed start weights
+  CUtensorMap tm_wc{};                // 128-row boxes
   // fp32 path
   float* d_w1f = nullptr;             // [flows*layers][K1][2nc]
   float* d_bias1f = nullptr;          // [flows*layers][2nc]
@@ -84,12 +78,12 @@ struct wg_engine {
   int ev_flows = 0;                   // flows recorded by the last call
   bool profiling = true;              // record the per-flow events (switched off while a CUDA graph is being captured)
   long long* dbg_timeline = nullptr;  // device buffer for clock64 stamps of layer launches (tests/diagnostics)
-  bool wide = false;                  // two-kernel tensor-core layer (n_channels = 512; WG_WIDE=1 forces it for 256)
   int num_sms = 148;
   int dbg_flags = 0;                  // WG_DBG_FLAGS env (diagnostics; see LayerTcParams::dbg_flags)
   // device arrays that make up the packed weights, by tag: what wg_save_packed writes and wg_load_packed restores
   std::map<std::string, std::pair<void**, size_t>> sections;
-  int op_fmt = 0;                     // 0 = fp16 operands, 1 = bf16 (WG_B200_OPERAND=bf16; fails the max-abs gate, kept for study)
+  int op_fmt = 0;                     // 0 = fp16 operands.  (bf16 operands fail the 2e-3 max-abs gate: 5e-3..9e-3 by CPU emulation,
+                                      // tests/test_oracle.py, and on hardware in round 1, profiles/r01 -- the layer kernel is fp16 only)
 };
 
 namespace {
@@ -109,6 +103,31 @@ int fail(wg_engine* e, int code, const char* fmt, ...) {
     cudaError_t _st = (call);                                                                     \
     if (_st != cudaSuccess) return fail((e), WG_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_st)); \
   } while (0)
+
+// Makes `dev` the calling thread's current device for the scope of an ABI call and restores the previous one on every exit
+// path: a process that drives several GPUs (and torch, which shares the thread's current device) must not find its
+// device changed behind its back.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t status = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    status = cudaGetDevice(&prev);
+    if (status == cudaSuccess && prev != dev) {
+      status = cudaSetDevice(dev);
+      switched = status == cudaSuccess;
+    }
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+#define WG_DEVICE(e, dev)          \
+  DeviceGuard _dev_guard(dev);     \
+  WG_CUDA(e, _dev_guard.status)
 
 float h2f(uint16_t v, int fmt);
 
@@ -226,53 +245,36 @@ int finish_tensor_core_load(wg_engine* e) {
   for (int k = 0; k < NF; ++k) {
     dim3 grid(kUpKdim / 64, 2 * nc / 64, L * kUpPhases);
     const size_t v_off = static_cast<size_t>(k) * L * kUpPhases * 2 * nc * kUpKdim;
-    if (e->op_fmt == 1)
-      compose_cond_kernel<__nv_bfloat16><<<grid, 256>>>(e->flows[k].d_w_cond, e->d_up_w, static_cast<__nv_bfloat16*>(e->d_v) + v_off, nc);
-    else
-      compose_cond_kernel<__half><<<grid, 256>>>(e->flows[k].d_w_cond, e->d_up_w, static_cast<__half*>(e->d_v) + v_off, nc);
+    compose_cond_kernel<__half><<<grid, 256>>>(e->flows[k].d_w_cond, e->d_up_w, static_cast<__half*>(e->d_v) + v_off, nc);
   }
   WG_CUDA(e, cudaDeviceSynchronize());
-  const CUtensorMapDataType dt = e->op_fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const uint32_t boxh[2] = {64, 128};      // half of a 256-row B operand: the other CTA of the pair stages the other half
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(K1x), static_cast<uint64_t>(NF) * L * 2 * nc};
     const uint64_t str[1] = {static_cast<uint64_t>(K1x) * 2};
-    const uint32_t box[2] = {64, 256};
-    if ((rc = make_map(e, &e->tm_w1, e->d_w1, 2, dims, str, box, dt))) return rc;
-    const uint32_t boxh[2] = {64, 128};
     if ((rc = make_map(e, &e->tm_w1h, e->d_w1, 2, dims, str, boxh, dt))) return rc;
   }
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(kUpKdim), static_cast<uint64_t>(NF) * L * kUpPhases * 2 * nc};
     const uint64_t str[1] = {static_cast<uint64_t>(kUpKdim) * 2};
-    const uint32_t box[2] = {64, 256};
-    if ((rc = make_map(e, &e->tm_v, e->d_v, 2, dims, str, box, dt))) return rc;
-    const uint32_t boxh[2] = {64, 128};
     if ((rc = make_map(e, &e->tm_vh, e->d_v, 2, dims, str, boxh, dt))) return rc;
   }
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(nc), static_cast<uint64_t>(NF) * L * w2rows};
     const uint64_t str[1] = {static_cast<uint64_t>(nc) * 2};
-    const uint32_t boxa[2] = {64, 256}, boxb[2] = {64, 16};
-    if ((rc = make_map(e, &e->tm_w2a, e->d_w2, 2, dims, str, boxa, dt))) return rc;
-    if ((rc = make_map(e, &e->tm_w2b, e->d_w2, 2, dims, str, boxb, dt))) return rc;
-    const uint32_t boxh[2] = {64, 128}, box8[2] = {64, 8};
     if ((rc = make_map(e, &e->tm_w2h, e->d_w2, 2, dims, str, boxh, dt))) return rc;
-    if ((rc = make_map(e, &e->tm_se8, e->d_w2, 2, dims, str, box8, dt))) return rc;
   }
+  e->tm_wc = e->tm_w2h;      // placeholder (never dereferenced) when the first layers are not composed
   if (e->first_comp) {
     // 16 real columns; the 64-wide box reads the other 48 as zeros (out-of-bounds fill)
     const uint64_t dims[2] = {16, static_cast<uint64_t>(NF) * kWcRows};
     const uint64_t str[1] = {32};
-    const uint32_t boxh[2] = {64, 128};
     if ((rc = make_map(e, &e->tm_wc, e->d_wc, 2, dims, str, boxh, dt))) return rc;
-    const uint32_t box256[2] = {64, 256};
-    if ((rc = make_map(e, &e->tm_wc256, e->d_wc, 2, dims, str, box256, dt))) return rc;
   }
   {
     const uint64_t dims[2] = {64, static_cast<uint64_t>(kIdentN)};
     const uint64_t str[1] = {128};
-    const uint32_t box[2] = {64, static_cast<uint32_t>(kIdentN)};
-    if ((rc = make_map(e, &e->tm_ident, e->d_ident, 2, dims, str, box, dt))) return rc;
     const uint32_t box16[2] = {64, static_cast<uint32_t>(kIdentN / 2)};
     if ((rc = make_map(e, &e->tm_ident16, e->d_ident, 2, dims, str, box16, dt))) return rc;
   }
@@ -283,7 +285,6 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
   int Tpad;                        // x rows per utterance: T rounded up to a multiple of 32 (phase view of the TMA maps)
-  size_t acts;                     // wide tensor-core path only: gated activations [B][32][Fq][nc] 16-bit
   size_t state, sums;              // forward only: time-major state [B,T,8] fp32; double accumulators [n_flows]
   size_t a0;                       // start conv composed into the first layer: [B][32][Fq][16] 16-bit rows [a0 | 1]
   size_t cond, x0, x1, e, total;   // cond: fp32 mode = upsampled conditioning S [B,T,640]; fp16 mode = mel windows MW [B,Fq,320]
@@ -309,12 +310,10 @@ WsLayout ws_layout(const wg_engine* e, int B, int T) {
   off = align_up(off + nppos * e->cfg.n_channels * L.elt, 1024);
   L.e = off;
   off = align_up(off + npos * kGroup * sizeof(float), 1024);
-  L.acts = off;
-  if (e->wide) off = align_up(off + nppos * e->cfg.n_channels * L.elt, 1024);
   L.state = off;
   off = align_up(off + npos * kGroup * sizeof(float), 1024);
   L.sums = off;
-  off = align_up(off + static_cast<size_t>(e->cfg.n_flows) * sizeof(double), 1024);
+  off = align_up(off + static_cast<size_t>(e->cfg.n_flows + 1) * sizeof(double), 1024);      // + 1: sum z^2
   L.a0 = off;
   if (e->first_comp) off = align_up(off + nppos * 16 * L.elt, 1024);
   L.total = off;
@@ -322,6 +321,23 @@ WsLayout ws_layout(const wg_engine* e, int B, int T) {
 }
 
 int frames_to_T(int frames) { return frames * kUpStride / kGroup; }
+
+// The fused layer kernel is a template over everything that selects code (channel count, first layer of a flow, tile mode).
+using LayerKernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                             const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                             const CUtensorMap, const LayerTcParams);
+
+template <int NC>
+LayerKernel layer_kernel_nc(int first, int mode) {
+  static const LayerKernel table[2][3] = {
+      {wn_layer_pair_cont_kernel<NC, false, kTileBlocks>, wn_layer_pair_cont_kernel<NC, false, kTilePacked>,
+       wn_layer_pair_cont_kernel<NC, false, kTileSegments>},
+      {wn_layer_pair_cont_kernel<NC, true, kTileBlocks>, wn_layer_pair_cont_kernel<NC, true, kTilePacked>,
+       wn_layer_pair_cont_kernel<NC, true, kTileSegments>}};
+  return table[first][mode];
+}
+
+LayerKernel layer_kernel(int nc, int first, int mode) { return nc == 512 ? layer_kernel_nc<512>(first, mode) : layer_kernel_nc<256>(first, mode); }
 
 }  // namespace
 
@@ -360,6 +376,15 @@ int wg_create(const wg_config* cfg, wg_engine** out) {
     if (n_rem < 2) return fail(e, WG_ERR_INVALID_ARGUMENT, "early outputs exhaust the audio channels at flow %d", k);
     e->flowC.push_back(n_rem);
   }
+  {
+    // wg_infer takes one noise tensor per early output plus the initial one; NoiseParams (a kernel parameter) holds 8
+    int n_early = 0;
+    for (int k = 1; k < cfg->n_flows; ++k)
+      if (k % cfg->n_early_every == 0) n_early++;
+    if (1 + n_early > kMaxNoise)
+      return fail(e, WG_ERR_UNSUPPORTED, "n_flows=%d with n_early_every=%d needs %d noise tensors; the engine supports %d",
+                  cfg->n_flows, cfg->n_early_every, 1 + n_early, kMaxNoise);
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(e, WG_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
@@ -368,49 +393,59 @@ int wg_create(const wg_config* cfg, wg_engine** out) {
   WG_CUDA(e, cudaGetDeviceProperties(&prop, cfg->device));
   if (prop.major != 10)
     return fail(e, WG_ERR_UNSUPPORTED, "device %d is sm_%d%d; kernels are built for sm_100a only", cfg->device, prop.major, prop.minor);
-  WG_CUDA(e, cudaSetDevice(cfg->device));
+  WG_DEVICE(e, cfg->device);
   e->num_sms = prop.multiProcessorCount;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   WG_CUDA(e, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   if (!fn || qres != cudaDriverEntryPointSuccess) return fail(e, WG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   e->encode = reinterpret_cast<PFN_encodeTiled>(fn);
-  const char* fmt_env = getenv("WG_B200_OPERAND");
-  e->op_fmt = (fmt_env && strcmp(fmt_env, "bf16") == 0) ? 1 : 0;
-  const char* wide_env = getenv("WG_WIDE");
-  e->wide = cfg->precision == WG_PRECISION_FP16 && (cfg->n_channels == 512 || (wide_env && atoi(wide_env) != 0));
-  const char* pair_env = getenv("WG_PAIR");
-  // default for 256 channels: the fused layer on CTA pairs (bit-identical to the single-CTA kernel, ~3 % faster); WG_PAIR=0 disables
-  e->pair = cfg->precision == WG_PRECISION_FP16 && cfg->n_channels == 256 && !e->wide && !(pair_env && atoi(pair_env) == 0) &&
-            prop.multiProcessorCount >= 2;
-  e->pair_cont = e->pair && !(pair_env && atoi(pair_env) == 1);
+  const bool tc = cfg->precision == WG_PRECISION_FP16;
+  if (tc && prop.multiProcessorCount < 2) return fail(e, WG_ERR_UNSUPPORTED, "the fused layer kernel runs on CTA pairs: needs >= 2 SMs");
+  const int nc = cfg->n_channels;
+  const int n_kb = kMwKB + 3 * (nc / 64), n_kb_first = kMwKB + 3, n_halves = nc / 256;
+  // GEMM2 of tile i-1 is issued inside the first chunk of tile i.  256 channels: before k-block 6 (measured optimum, r01).
+  // 512 channels: half 0 once the last gate of the tile had time to finish (10 k-blocks = 5.1k cycles of MMA work), half 1
+  // after the drain of half 0 (14 more k-blocks = 7.2k cycles).
+  if (nc == 512) {
+    e->g2_at[0] = 10;
+    e->g2_at[1] = 24;
+  }
   const char* g2_env = getenv("WG_G2AT");
-  if (g2_env) e->g2_at = atoi(g2_env);
-  if (e->g2_at < 0 || e->g2_at >= kKB1) return fail(e, WG_ERR_INVALID_ARGUMENT, "WG_G2AT must be in [0, %d)", kKB1);
+  if (g2_env) e->g2_at[0] = atoi(g2_env);
+  const char* g21_env = getenv("WG_G2AT1");
+  if (g21_env) e->g2_at[1] = atoi(g21_env);
+  const char* g20_env = getenv("WG_G2AT0");
+  if (g20_env) e->g2_at_first[0] = e->g2_at_first[1] = atoi(g20_env);
+  if (n_halves == 1) {
+    e->g2_at[1] = e->g2_at[0];
+    e->g2_at_first[1] = e->g2_at_first[0];
+  }
+  for (int h = 0; h < kMaxHalves; ++h) {
+    if (e->g2_at[h] < 0 || e->g2_at[h] >= n_kb) return fail(e, WG_ERR_INVALID_ARGUMENT, "WG_G2AT / WG_G2AT1 must be in [0, %d)", n_kb);
+    if (e->g2_at_first[h] < 0 || e->g2_at_first[h] >= n_kb_first) return fail(e, WG_ERR_INVALID_ARGUMENT, "WG_G2AT0 must be in [0, %d)", n_kb_first);
+  }
+  if (e->g2_at[1] < e->g2_at[0]) return fail(e, WG_ERR_INVALID_ARGUMENT, "WG_G2AT1 must not be smaller than WG_G2AT");
   const char* first_env = getenv("WG_FIRST");
-  e->first_comp = (e->pair_cont || e->wide) && !(first_env && atoi(first_env) == 0);
+  // (with a single layer per flow that layer has no residual output and runs the generic form, which needs x)
+  e->first_comp = tc && cfg->n_layers >= 2 && !(first_env && atoi(first_env) == 0);
   const char* trim_env = getenv("WG_TRIM");
   e->trim_grid = trim_env && atoi(trim_env) != 0;
   const char* pdl_env = getenv("WG_PDL");
   e->pdl = !(pdl_env && atoi(pdl_env) == 0);
   const char* pack_env = getenv("WG_PACK4");
   e->pack4 = !(pack_env && atoi(pack_env) == 0);
-  const char* g20_env = getenv("WG_G2AT0");
-  if (g20_env) e->g2_at_first = atoi(g20_env);
-  if (e->g2_at_first < 0 || e->g2_at_first >= kMwKB + 3) return fail(e, WG_ERR_INVALID_ARGUMENT, "WG_G2AT0 must be in [0, %d)", kMwKB + 3);
   const char* seg_env = getenv("WG_SEG");
   e->force_seg = seg_env ? atoi(seg_env) : 0;
   if (e->force_seg != 0 && e->force_seg != 128 && e->force_seg != 64 && e->force_seg != 32)
     return fail(e, WG_ERR_INVALID_ARGUMENT, "WG_SEG must be 128, 64 or 32 (got %d)", e->force_seg);
-  WG_CUDA(e, cudaFuncSetAttribute(wn_layer_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem::total + 1024));
-  WG_CUDA(e, cudaFuncSetAttribute(wn_layer_pair_cont_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ContSmem::total + 1024));
   const char* dbg_env = getenv("WG_DBG_FLAGS");
   e->dbg_flags = dbg_env ? atoi(dbg_env) : 0;
-  WG_CUDA(e, cudaFuncSetAttribute(wn_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total + 1024));
-  WG_CUDA(e, cudaFuncSetAttribute(wn_gate_wide_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideCfg<256>::a_total + 1024));
-  WG_CUDA(e, cudaFuncSetAttribute(wn_gate_wide_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideCfg<512>::a_total + 1024));
-  WG_CUDA(e, cudaFuncSetAttribute(wn_res_wide_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideCfg<256>::b_total + 1024));
-  WG_CUDA(e, cudaFuncSetAttribute(wn_res_wide_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideCfg<512>::b_total + 1024));
+  for (int first = 0; first < 2; ++first)
+    for (int mode = 0; mode < 3; ++mode) {
+      WG_CUDA(e, cudaFuncSetAttribute(layer_kernel(256, first, mode), cudaFuncAttributeMaxDynamicSharedMemorySize, ContCfg<256>::launch_bytes));
+      WG_CUDA(e, cudaFuncSetAttribute(layer_kernel(512, first, mode), cudaFuncAttributeMaxDynamicSharedMemorySize, ContCfg<512>::launch_bytes));
+    }
   WG_CUDA(e, cudaFuncSetAttribute(debug_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 49152 + 1024 + 128));
   WG_CUDA(e, cudaFuncSetAttribute(wn_layer_fp32_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (kF32KC * kF32Pos + kF32KC * 512 + kF32Pos * 256) * 4));
@@ -447,7 +482,7 @@ void wg_destroy(wg_engine* e) {
 int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) {
   if (!e || !descs || n_descs <= 0) return WG_ERR_INVALID_ARGUMENT;
   if (!e->encode) return fail(e, WG_ERR_INVALID_ARGUMENT, "engine was not created successfully");
-  WG_CUDA(e, cudaSetDevice(e->cfg.device));
+  WG_DEVICE(e, e->cfg.device);
   const int nc = e->cfg.n_channels, L = e->cfg.n_layers, NF = e->cfg.n_flows;
   e->sections.clear();
   e->loaded = false;
@@ -718,7 +753,7 @@ int wg_debug_view(const wg_engine* e, const char* name, int32_t batch, int32_t f
 // ------------------------------------------------------------------------------------------ packed-weight cache
 namespace {
 
-constexpr uint32_t kPackVersion = 4;
+constexpr uint32_t kPackVersion = 5;
 
 struct PackHeader {
   char magic[8];             // "WGB200PK"
@@ -773,6 +808,37 @@ void** section_slot(wg_engine* e, const std::string& tag) {
   return nullptr;
 }
 
+// Size in bytes that section `tag` must have for this engine's configuration (0: unknown tag).  wg_load_packed checks every
+// section against it: the kernels index these arrays by the configuration alone, so a short section behind a valid header
+// would become an out-of-bounds device read.
+size_t expected_section_bytes(const wg_engine* e, const std::string& tag) {
+  const size_t nc = e->cfg.n_channels, L = e->cfg.n_layers, NF = e->cfg.n_flows;
+  const size_t K1 = 3 * nc + kCond;
+  if (tag == "up_w") return static_cast<size_t>(kUpPhases) * kUpKdim * kCond * 4;
+  if (tag == "up_b") return kMel * 4;
+  if (tag == "bias_res") return NF * L * nc * 4;
+  if (tag == "logdet") return NF * sizeof(double);
+  if (tag == "w1") return NF * L * 2 * nc * 3 * nc * 2;
+  if (tag == "w2") return NF * L * (nc + 16) * nc * 2;
+  if (tag == "ident") return static_cast<size_t>(kIdentN) * 64 * 2;
+  if (tag == "bias1") return NF * L * 2 * nc * 4;
+  if (tag == "wc") return NF * 7 * nc * 16 * 2;
+  if (tag == "w1f") return NF * L * K1 * 2 * nc * 4;
+  if (tag == "bias1f") return NF * L * 2 * nc * 4;
+  if (tag == "wresf") return NF * L * nc * nc * 4;
+  if (tag == "wsef") return NF * L * nc * kGroup * 4;
+  const size_t dot = tag.find('.');
+  if (dot != std::string::npos) {
+    const int k = atoi(tag.c_str() + dot + 1);
+    if (k < 0 || k >= static_cast<int>(e->flowC.size())) return 0;
+    const std::string base = tag.substr(0, dot);
+    if (base == "w_start") return nc * (e->flowC[k] / 2) * 4;
+    if (base == "b_start") return nc * 4;
+    if (base == "w_cond") return 2 * nc * L * kCond * 4;
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -780,7 +846,7 @@ extern "C" {
 int wg_save_packed(wg_engine* e, const char* path, uint64_t fingerprint) {
   if (!e || !path) return WG_ERR_INVALID_ARGUMENT;
   if (!e->loaded) return fail(e, WG_ERR_WEIGHTS, "wg_load_weights has not been called");
-  WG_CUDA(e, cudaSetDevice(e->cfg.device));
+  WG_DEVICE(e, e->cfg.device);
   const std::string tmp = std::string(path) + ".tmp";
   FILE* f = fopen(tmp.c_str(), "wb");
   if (!f) return fail(e, WG_ERR_INVALID_ARGUMENT, "cannot open '%s' for writing", tmp.c_str());
@@ -790,7 +856,7 @@ int wg_save_packed(wg_engine* e, const char* path, uint64_t fingerprint) {
   fill_cfg(e, h.cfg);
   h.op_fmt = e->op_fmt;
   h.first_comp = e->first_comp ? 1 : 0;
-  h.wide = e->wide ? 1 : 0;
+  h.wide = 0;
   h.n_flows = static_cast<int32_t>(e->flows.size());
   h.n_sections = static_cast<int32_t>(e->sections.size());
   h.fingerprint = fingerprint;
@@ -810,6 +876,12 @@ int wg_save_packed(wg_engine* e, const char* path, uint64_t fingerprint) {
     SectionHeader sh{};
     snprintf(sh.tag, sizeof(sh.tag), "%s", kv.first.c_str());
     sh.bytes = kv.second.second;
+    if (sh.bytes != expected_section_bytes(e, kv.first)) {      // the loader's size table has drifted from the packer
+      fclose(f);
+      remove(tmp.c_str());
+      return fail(e, WG_ERR_WEIGHTS, "section '%s' has %llu bytes, expected %zu", sh.tag, static_cast<unsigned long long>(sh.bytes),
+                  expected_section_bytes(e, kv.first));
+    }
     host.resize(sh.bytes);
     if (cudaMemcpy(host.data(), *kv.second.first, sh.bytes, cudaMemcpyDeviceToHost) != cudaSuccess) {
       fclose(f);
@@ -829,7 +901,7 @@ int wg_save_packed(wg_engine* e, const char* path, uint64_t fingerprint) {
 int wg_load_packed(wg_engine* e, const char* path, uint64_t fingerprint) {
   if (!e || !path) return WG_ERR_INVALID_ARGUMENT;
   if (!e->encode) return fail(e, WG_ERR_INVALID_ARGUMENT, "engine was not created successfully");
-  WG_CUDA(e, cudaSetDevice(e->cfg.device));
+  WG_DEVICE(e, e->cfg.device);
   FILE* f = fopen(path, "rb");
   if (!f) return fail(e, WG_ERR_WEIGHTS, "packed-weight cache '%s' not found", path);
   struct Closer {
@@ -842,7 +914,7 @@ int wg_load_packed(wg_engine* e, const char* path, uint64_t fingerprint) {
   if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "WGB200PK", 8) != 0 || h.version != kPackVersion)
     return fail(e, WG_ERR_WEIGHTS, "'%s' is not a packed-weight cache of this library version", path);
   if (memcmp(h.cfg, want, sizeof(want)) != 0 || h.op_fmt != e->op_fmt || h.first_comp != (e->first_comp ? 1 : 0) ||
-      h.wide != (e->wide ? 1 : 0) || h.n_flows != e->cfg.n_flows)
+      h.wide != 0 || h.n_flows != e->cfg.n_flows)
     return fail(e, WG_ERR_WEIGHTS, "'%s' was packed for another engine configuration", path);
   if (h.fingerprint != fingerprint) return fail(e, WG_ERR_WEIGHTS, "'%s' was packed from other weights (fingerprint mismatch)", path);
   e->loaded = false;
@@ -871,7 +943,9 @@ int wg_load_packed(wg_engine* e, const char* path, uint64_t fingerprint) {
     if (fread(&sh, sizeof(sh), 1, f) != 1) return fail(e, WG_ERR_WEIGHTS, "'%s' is truncated", path);
     sh.tag[sizeof(sh.tag) - 1] = 0;
     void** slot = section_slot(e, sh.tag);
-    if (!slot || sh.bytes == 0 || sh.bytes > (size_t(1) << 34)) return fail(e, WG_ERR_WEIGHTS, "'%s': bad section '%s'", path, sh.tag);
+    if (!slot || sh.bytes == 0 || sh.bytes != expected_section_bytes(e, sh.tag))
+      return fail(e, WG_ERR_WEIGHTS, "'%s': section '%s' has %llu bytes, this configuration needs %zu", path, sh.tag,
+                  static_cast<unsigned long long>(sh.bytes), expected_section_bytes(e, sh.tag));
     host.resize(sh.bytes);
     if (fread(host.data(), 1, sh.bytes, f) != sh.bytes) return fail(e, WG_ERR_WEIGHTS, "'%s' is truncated", path);
     if (*slot) cudaFree(*slot);
@@ -923,8 +997,6 @@ void flow_step_any(wg_engine* e, const FlowStepParams& fs_in, float* state, cons
   if (!e->first_comp) fs.a0_out = nullptr;
   if (e->cfg.precision == WG_PRECISION_FP32)
     launch_flow_step<float>(fs, state, ebuf, x, B, T, Tpad, st);
-  else if (e->op_fmt == 1)
-    launch_flow_step<__nv_bfloat16>(fs, state, ebuf, x, B, T, Tpad, st);
   else
     launch_flow_step<__half>(fs, state, ebuf, x, B, T, Tpad, st);
   e->launches++;
@@ -957,57 +1029,7 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
   for (int i = 0; i < NL; ++i) {
     const size_t li = static_cast<size_t>(k) * NL + i;
     const int has_res = i < NL - 1;
-    if (tc && e->wide) {
-      WideParams wp{};
-      wp.T = T;
-      wp.Fq = L.Tpad / kUpPhases;
-      wp.B = B;
-      wp.dilation = 1 << i;
-      wp.reverse = static_cast<int>(li & 1);
-      wp.w1_row0 = static_cast<int>(li * 2 * nc);
-      wp.v_row0 = static_cast<int>(li * kUpPhases * 2 * nc);
-      wp.wres_row0 = static_cast<int>(li * (nc + 16));
-      wp.se_row0 = wp.wres_row0 + nc;
-      wp.accumulate_e = i > 0;
-      wp.fmt = e->op_fmt;
-      wp.bias1 = e->d_bias1 + li * 2 * nc;
-      wp.bias_res = e->d_bias_res + li * nc;
-      wp.e = ebuf;
-      wp.first = e->first_comp && i == 0 && has_res;
-      wp.wc_row0 = k * 7 * nc;
-      int n_tiles = kPhases * ((wp.Fq + kTileM - 1) / kTileM) * B;
-      if (e->pack4) {
-        // packed ragged tails, as in the continuous pair kernel
-        const int n_full = wp.Fq / kTileM, rem = wp.Fq - n_full * kTileM, n_rem = (rem + 31) / 32;
-        const int n4 = kPhases * (B * n_full + ((B + 3) / 4) * n_rem);
-        if (rem > 0 && n4 < n_tiles) {
-          wp.pack4 = 1;
-          wp.n_full = n_full;
-          wp.n_rem = n_rem;
-          n_tiles = n4;
-        }
-      }
-      int n_ctas = n_tiles < e->num_sms ? n_tiles : e->num_sms;
-      if (e->trim_grid) {
-        const int rounds = (n_tiles + n_ctas - 1) / n_ctas;
-        n_ctas = (n_tiles + rounds - 1) / rounds;
-      }
-      dim3 grid(n_ctas);
-      if (nc == 512) {
-        wn_gate_wide_kernel<512><<<grid, kTcThreads, WideCfg<512>::a_total + 1024, st>>>(tm_x[*cur], *tm_cond, e->tm_w1, e->tm_v,
-                                                                                      e->tm_w2b, tm_x[2], tm_a0[0], e->tm_wc256, tm_p4[*cur], tm_p4[2], tm_p4[3], tm_p4[4], wp);
-        if (has_res)
-          wn_res_wide_kernel<512><<<grid, kTcThreads, WideCfg<512>::b_total + 1024, st>>>(tm_x[2], tm_x[*cur], tm_x[*cur ^ 1],
-                                                                                       e->tm_w2a, e->tm_ident, tm_a0[0], e->tm_wc256, tm_p4[4], tm_p4[*cur], tm_p4[*cur ^ 1], tm_p4[3], wp);
-      } else {
-        wn_gate_wide_kernel<256><<<grid, kTcThreads, WideCfg<256>::a_total + 1024, st>>>(tm_x[*cur], *tm_cond, e->tm_w1, e->tm_v,
-                                                                                      e->tm_w2b, tm_x[2], tm_a0[0], e->tm_wc256, tm_p4[*cur], tm_p4[2], tm_p4[3], tm_p4[4], wp);
-        if (has_res)
-          wn_res_wide_kernel<256><<<grid, kTcThreads, WideCfg<256>::b_total + 1024, st>>>(tm_x[2], tm_x[*cur], tm_x[*cur ^ 1],
-                                                                                       e->tm_w2a, e->tm_ident, tm_a0[0], e->tm_wc256, tm_p4[4], tm_p4[*cur], tm_p4[*cur ^ 1], tm_p4[3], wp);
-      }
-      e->launches += has_res ? 1 : 0;
-    } else if (tc) {
+    if (tc) {
       LayerTcParams lp{};
       lp.T = T;
       lp.Fq = L.Tpad / kUpPhases;
@@ -1016,109 +1038,75 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
       lp.reverse = static_cast<int>(li & 1);
       lp.w1_row0 = static_cast<int>(li * 2 * nc);
       lp.v_row0 = static_cast<int>(li * kUpPhases * 2 * nc);
-      lp.w2_row0 = static_cast<int>(li * kW2Rows);
+      lp.w2_row0 = static_cast<int>(li * (nc + 16));
+      lp.wc_row0 = k * 7 * nc;
       lp.has_res = has_res;
       lp.accumulate_e = i > 0;
-      lp.fmt = e->op_fmt;
       lp.bias1 = e->d_bias1 + li * 2 * nc;
       lp.bias_res = e->d_bias_res + li * nc;
+      lp.wse = static_cast<const uint16_t*>(e->d_w2) + (li * (nc + 16) + nc) * nc;
+      lp.x_out = xb[*cur ^ 1];
       lp.e = ebuf;
       lp.timeline = e->dbg_timeline;
       lp.dbg_flags = e->dbg_flags;
-      const int n_tiles = kPhases * ((lp.Fq + kTileM - 1) / kTileM) * B;
-      if (e->pair && e->pair_cont) {
-        // tiles are built from 128-, 64- or 32-frame segments (one TMA box each).  Smaller boxes cost tile time (measured on
-        // config 2: 4 x 32-row boxes per operand load = +5.4 % per tile, so 861 frames as 27 x 32 instead of 7 x 128 is a wash),
-        // so a smaller segment is taken only when it saves clearly more pair-tiles than that (two whole 63-frame training
-        // segments per tile: -50 %; 40-frame utterances as 2 x 32: -20 %)
-        static const double kBoxCost[3] = {1.0, 1.02, 1.06};
-        int best_pe = 0, best_idx = 0;
-        for (int idx = 0; idx < 3; ++idx) {
-          const int seg = kTileM >> idx;
-          const int n_entries = (B * ((lp.Fq + seg - 1) / seg) + (1 << idx) - 1) >> idx;
-          const int n_pe = (n_entries + 1) / 2;
-          if (e->force_seg ? seg == e->force_seg : (idx == 0 || n_pe * kBoxCost[idx] < best_pe * kBoxCost[best_idx])) {
-            best_pe = n_pe;
-            best_idx = idx;
-          }
+      lp.seg_rows = kTileM;
+      // Which rows share a tile.  Default: 128 consecutive frames of one utterance per tile (one TMA box per operand).  Tiles
+      // built from 64- or 32-frame SEGMENTS (one box each; a tile may span utterances) cost tile time (measured on config 2:
+      // 4 x 32-row boxes per operand load = +5.4 % per tile), so a smaller segment is taken only when it saves clearly more
+      // pair-tiles than that (two whole 63-frame training segments per tile: -50 %; 40-frame utterances as 2 x 32: -20 %).
+      static const double kBoxCost[3] = {1.0, 1.02, 1.06};
+      int best_pe = 0, best_idx = 0;
+      for (int idx = 0; idx < 3; ++idx) {
+        const int seg = kTileM >> idx;
+        const int n_entries = (B * ((lp.Fq + seg - 1) / seg) + (1 << idx) - 1) >> idx;
+        const int n_pe = (n_entries + 1) / 2;
+        if (e->force_seg ? seg == e->force_seg : (idx == 0 || n_pe * kBoxCost[idx] < best_pe * kBoxCost[best_idx])) {
+          best_pe = n_pe;
+          best_idx = idx;
         }
-        lp.seg_rows = kTileM >> best_idx;
-        // ragged tail: n_full whole 128-frame blocks per utterance, then the remaining frames of 4 consecutive utterances
-        // share tiles of 32 frames x 4 utterances (one 4-D TMA box per operand load, so no box cost)
-        if (e->pack4 && !e->force_seg) {
-          const int n_full = lp.Fq / kTileM, rem = lp.Fq - n_full * kTileM, n_rem = (rem + 31) / 32;
-          const int n_pe4 = (B * n_full + ((B + 3) / 4) * n_rem + 1) / 2;
-          if (rem > 0 && n_pe4 < best_pe * kBoxCost[best_idx]) {
-            lp.pack4 = 1;
-            lp.n_full = n_full;
-            lp.n_rem = n_rem;
-            lp.seg_rows = kTileM;
-            best_idx = 0;
-            best_pe = n_pe4;
-          }
-        }
-        const int n_ptiles = kPhases * best_pe;
-        int n_pairs = n_ptiles < e->num_sms / 2 ? n_ptiles : e->num_sms / 2;
-        if (e->trim_grid) {
-          // experiment: the launch lasts ceil(tiles / pairs) rounds of tiles; the smallest grid with the same number of
-          // rounds leaves the other SMs idle instead of half-used (1728 pair-tiles: 72 pairs x 24 instead of 74 pairs of
-          // which 48 do 23).  The power-capped clock did not pay it back.
-          const int rounds = (n_ptiles + n_pairs - 1) / n_pairs;
-          n_pairs = (n_ptiles + rounds - 1) / rounds;
-        }
-        lp.wse = static_cast<const uint16_t*>(e->d_w2) + (li * kW2Rows + 256) * 256;
-        lp.first = e->first_comp && i == 0 && has_res;
-        lp.wc_row0 = k * 7 * nc;
-        lp.g2_at = lp.first ? e->g2_at_first : e->g2_at;
-        lp.x_out = xb[*cur ^ 1];
-        const CUtensorMap* seg_maps = tm_x + (best_idx == 0 ? 0 : (best_idx == 1 ? 3 : 6));      // {x0, x1, .., mel windows}
-        const CUtensorMap& tm_mw_seg = best_idx == 0 ? *tm_cond : seg_maps[2];
-        {
-          // programmatic dependent launch: this grid's CTAs may start their prologue and conditioning K-blocks while the
-          // previous layer's last tiles drain (griddepcontrol.wait in the kernel guards every dependent access)
-          cudaLaunchConfig_t cfg{};
-          cfg.gridDim = dim3(2 * n_pairs);
-          cfg.blockDim = dim3(kContThreads);
-          cfg.dynamicSmemBytes = ContSmem::total + 1024;
-          cfg.stream = st;
-          cudaLaunchAttribute attr[1];
-          attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-          attr[0].val.programmaticStreamSerializationAllowed = 1;
-          cfg.attrs = attr;
-          cfg.numAttrs = e->pdl ? 1 : 0;
-          WG_CUDA(e, cudaLaunchKernelEx(&cfg, wn_layer_pair_cont_kernel, seg_maps[*cur], tm_mw_seg, e->tm_w1h, e->tm_vh, e->tm_w2h,
-                                        e->tm_ident16, tm_a0[best_idx], e->tm_wc, tm_p4[*cur], tm_p4[2], tm_p4[3], lp));
-        }
-        e->launches++;
-        if (has_res) *cur ^= 1;
-        if (e->dbg_flow == k && e->dbg_layer == i) {
-          *stopped = true;
-          return WG_OK;
-        }
-        continue;
       }
-      if (e->pair) {
-        // two whole utterances per tile when they are short (config 5's 63-frame training segments)
-        lp.seg_rows = (lp.Fq <= 64 && B >= 2) ? 64 : 128;
-        const int n_tile_entries = lp.seg_rows == 64 ? (B + 1) / 2 : ((lp.Fq + kTileM - 1) / kTileM) * B;
-        const int n_ptiles = kPhases * ((n_tile_entries + 1) / 2);
-        const int n_pairs = n_ptiles < e->num_sms / 2 ? n_ptiles : e->num_sms / 2;
-        {
-          wn_layer_pair_kernel<<<dim3(2 * n_pairs), kTcThreads, PairSmem::total + 1024, st>>>(
-              tm_x[*cur], tm_x[*cur ^ 1], *tm_cond, e->tm_w1h, e->tm_vh, e->tm_w2h, e->tm_se8, e->tm_ident16, tm_x[3 + *cur],
-              tm_x[3 + (*cur ^ 1)], tm_x[5], lp);
+      int mode = best_idx == 0 ? kTileBlocks : kTileSegments;
+      lp.seg_rows = kTileM >> best_idx;
+      // PACKED ragged tails: n_full whole 128-frame blocks per utterance, then the remaining frames of 4 consecutive
+      // utterances share tiles of 32 frames x 4 utterances (one 4-D TMA box per operand load, so no box cost)
+      if (e->pack4 && !e->force_seg) {
+        const int n_full = lp.Fq / kTileM, rem = lp.Fq - n_full * kTileM, n_rem = (rem + 31) / 32;
+        const int n_pe4 = (B * n_full + ((B + 3) / 4) * n_rem + 1) / 2;
+        if (rem > 0 && n_pe4 < best_pe * kBoxCost[best_idx]) {
+          mode = kTilePacked;
+          lp.n_full = n_full;
+          lp.n_rem = n_rem;
+          lp.seg_rows = kTileM;
+          best_idx = 0;
+          best_pe = n_pe4;
         }
-        e->launches++;
-        if (has_res) *cur ^= 1;
-        if (e->dbg_flow == k && e->dbg_layer == i) {
-          *stopped = true;
-          return WG_OK;
-        }
-        continue;
       }
-      dim3 grid(n_tiles < e->num_sms ? n_tiles : e->num_sms);
-      wn_layer_tc_kernel<<<grid, kTcThreads, TcSmem::total + 1024, st>>>(tm_x[*cur], tm_x[*cur ^ 1], *tm_cond, e->tm_w1, e->tm_v,
-                                                                        e->tm_w2a, e->tm_w2b, e->tm_ident, lp);
+      const int n_ptiles = kPhases * best_pe;
+      int n_pairs = n_ptiles < e->num_sms / 2 ? n_ptiles : e->num_sms / 2;
+      if (e->trim_grid) {
+        // experiment: the launch lasts ceil(tiles / pairs) rounds of tiles; the smallest grid with the same number of
+        // rounds leaves the other SMs idle instead of half-used.  The power-capped clock did not pay it back.
+        const int rounds = (n_ptiles + n_pairs - 1) / n_pairs;
+        n_pairs = (n_ptiles + rounds - 1) / rounds;
+      }
+      const int first = (e->first_comp && i == 0 && has_res) ? 1 : 0;
+      for (int h = 0; h < kMaxHalves; ++h) lp.g2_at[h] = first ? e->g2_at_first[h] : e->g2_at[h];
+      const CUtensorMap* seg_maps = tm_x + (best_idx == 0 ? 0 : (best_idx == 1 ? 3 : 6));      // {x0, x1, mel windows} per box height
+      const CUtensorMap& tm_mw_seg = best_idx == 0 ? *tm_cond : seg_maps[2];
+      // programmatic dependent launch: this grid's CTAs may start their prologue and conditioning K-blocks while the
+      // previous layer's last tiles drain (griddepcontrol.wait in the kernel guards every dependent access)
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(2 * n_pairs);
+      cfg.blockDim = dim3(kContThreads);
+      cfg.dynamicSmemBytes = nc == 512 ? ContCfg<512>::launch_bytes : ContCfg<256>::launch_bytes;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = e->pdl ? 1 : 0;
+      WG_CUDA(e, cudaLaunchKernelEx(&cfg, layer_kernel(nc, first, mode), seg_maps[*cur], tm_mw_seg, e->tm_w1h, e->tm_vh, e->tm_w2h,
+                                    e->tm_ident16, tm_a0[best_idx], e->tm_wc, tm_p4[*cur], tm_p4[2], tm_p4[3], lp));
     } else {
       LayerF32Params lp{};
       lp.T = T;
@@ -1159,10 +1147,7 @@ void launch_conditioning(wg_engine* e, const float* mel, int B, int frames, int 
     // tensor-core mode: the upsampler is composed into the conditioning weights; only the 4-frame mel windows are formed
     const size_t total = static_cast<size_t>(B) * Fq * kUpKdim;
     const unsigned g1 = static_cast<unsigned>((total + 255) / 256);
-    if (e->op_fmt == 1)
-      mel_window_kernel<__nv_bfloat16><<<g1, 256, 0, st>>>(mel, reinterpret_cast<__nv_bfloat16*>(ws + L.cond), B, frames, Fq);
-    else
-      mel_window_kernel<__half><<<g1, 256, 0, st>>>(mel, reinterpret_cast<__half*>(ws + L.cond), B, frames, Fq);
+    mel_window_kernel<__half><<<g1, 256, 0, st>>>(mel, reinterpret_cast<__half*>(ws + L.cond), B, frames, Fq);
   } else {
     // ConvTranspose1d + squeeze (model.py:225-232 / 186-193); keeps the first T group-steps (T = 32 F for infer)
     dim3 grid(kUpPhases, B * ((Fq + kUpFrames - 1) / kUpFrames));
@@ -1174,10 +1159,10 @@ void launch_conditioning(wg_engine* e, const float* mel, int B, int frames, int 
 
 int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CUtensorMap* tm_x, CUtensorMap* tm_cond,
                   CUtensorMap* tm_a0, CUtensorMap* tm_p4) {
-  // tm_x[0], tm_x[1]: residual stream ping-pong; tm_x[2]: gated activations of the wide path (same geometry);
+  // tm_x[0], tm_x[1]: residual stream ping-pong, 128-row boxes; tm_x[2]: unused;
   // tm_x[3], tm_x[4]: the ping-pong buffers again with 64-row boxes, tm_x[5]: mel windows with 64-row boxes;
-  // tm_x[6], tm_x[7], tm_x[8]: the same three with 32-row boxes (segment tiles of the CTA-pair kernels)
-  const CUtensorMapDataType dt = e->op_fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  // tm_x[6], tm_x[7], tm_x[8]: the same three with 32-row boxes (segment tiles)
+  const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const int nc = e->cfg.n_channels;
   int rc;
   const int Fq = L.Tpad / kUpPhases;
@@ -1188,7 +1173,7 @@ int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CU
     const uint32_t box[3] = {64, static_cast<uint32_t>(kTileM), 1};
     if ((rc = make_map(e, &tm_x[0], ws + L.x0, 3, dims, str, box, dt))) return rc;
     if ((rc = make_map(e, &tm_x[1], ws + L.x1, 3, dims, str, box, dt))) return rc;
-    if (e->wide && (rc = make_map(e, &tm_x[2], ws + L.acts, 3, dims, str, box, dt))) return rc;
+    tm_x[2] = tm_x[0];
     const uint32_t box64[3] = {64, 64, 1}, box32[3] = {64, 32, 1};
     if ((rc = make_map(e, &tm_x[3], ws + L.x0, 3, dims, str, box64, dt))) return rc;
     if ((rc = make_map(e, &tm_x[4], ws + L.x1, 3, dims, str, box64, dt))) return rc;
@@ -1204,9 +1189,9 @@ int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CU
     if ((rc = make_map(e, &tm_x[5], ws + L.cond, 3, dims, str, box64, dt))) return rc;
     if ((rc = make_map(e, &tm_x[8], ws + L.cond, 3, dims, str, box32, dt))) return rc;
   }
-  if (e->pair_cont || e->wide) {
-    // packed ragged tails (LayerTcParams::pack4): 32 frames x 4 consecutive utterances per box.  tm_p4[0], [1]: x ping-pong
-    // as {nc, Fq, 32 phases, B}; [2]: mel windows; [3]: [a0 | 1] rows; [4]: gated activations of the wide path
+  {
+    // packed ragged tails: 32 frames x 4 consecutive utterances per box.  tm_p4[0], [1]: x ping-pong as {nc, Fq, 32 phases, B};
+    // [2]: mel windows; [3]: [a0 | 1] rows
     const uint64_t dims[4] = {static_cast<uint64_t>(nc), static_cast<uint64_t>(Fq), kUpPhases, static_cast<uint64_t>(B)};
     const uint64_t str[3] = {static_cast<uint64_t>(nc) * 2, static_cast<uint64_t>(nc) * 2 * Fq, static_cast<uint64_t>(nc) * 2 * Fq * kUpPhases};
     const uint32_t box[4] = {64, 32, 1, 4};
@@ -1216,15 +1201,15 @@ int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CU
     const uint64_t mstr[2] = {static_cast<uint64_t>(kUpKdim) * 2, static_cast<uint64_t>(kUpKdim) * 2 * Fq};
     const uint32_t mbox[3] = {64, 32, 4};
     if ((rc = make_map(e, &tm_p4[2], ws + L.cond, 3, mdims, mstr, mbox, dt))) return rc;
-    tm_p4[3] = tm_p4[2];
+    tm_p4[3] = tm_p4[2];      // placeholders (never dereferenced) without the first-layer composition
     tm_p4[4] = tm_p4[0];
-    if (e->wide && (rc = make_map(e, &tm_p4[4], ws + L.acts, 4, dims, str, box, dt))) return rc;
     if (e->first_comp) {
       const uint64_t adims[4] = {16, static_cast<uint64_t>(Fq), kUpPhases, static_cast<uint64_t>(B)};
       const uint64_t astr[3] = {32, static_cast<uint64_t>(32) * Fq, static_cast<uint64_t>(32) * Fq * kUpPhases};
       if ((rc = make_map(e, &tm_p4[3], ws + L.a0, 4, adims, astr, box, dt))) return rc;
     }
   }
+  for (int idx = 0; idx < 3; ++idx) tm_a0[idx] = tm_x[0];      // placeholders without the first-layer composition
   if (e->first_comp) {
     // [a0 | 1] rows of the composed first layer, phase-major like x; 16 real channels, the 64-wide boxes zero-fill the rest
     const uint64_t dims[3] = {16, static_cast<uint64_t>(Fq), static_cast<uint64_t>(B) * kUpPhases};
@@ -1250,13 +1235,13 @@ int wg_infer(wg_engine* e, const float* mel, int32_t batch, int32_t frames, cons
   int n_early = 0;
   for (int k = 1; k < NF; ++k)
     if (k % e->cfg.n_early_every == 0) n_early++;
-  if (n_z != 1 + n_early) return fail(e, WG_ERR_INVALID_ARGUMENT, "expected %d noise tensors, got %d", 1 + n_early, n_z);
+  if (n_z != 1 + n_early || n_z > kMaxNoise) return fail(e, WG_ERR_INVALID_ARGUMENT, "expected %d noise tensors, got %d", 1 + n_early, n_z);
   const int B = batch, T = frames_to_T(frames);
   const WsLayout L = ws_layout(e, B, T);
   if (ws_bytes < L.total) return fail(e, WG_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, L.total);
   if (reinterpret_cast<uintptr_t>(workspace) % 1024) return fail(e, WG_ERR_WORKSPACE, "workspace must be 1024-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  WG_CUDA(e, cudaSetDevice(e->cfg.device));
+  WG_DEVICE(e, e->cfg.device);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   const size_t npos = static_cast<size_t>(B) * T;
   const bool tc = e->cfg.precision == WG_PRECISION_FP16;
@@ -1364,8 +1349,8 @@ int wg_profile_layers(wg_engine* e, float* total_ms, int32_t* n_launches) {
 }
 
 int wg_forward(wg_engine* e, const float* mel, int32_t batch, int32_t frames, const float* audio_in, int32_t n_samples,
-               float* z_out, float* const* log_s_out, float* log_s_sum, float* log_det_w, void* workspace, size_t ws_bytes,
-               void* stream) {
+               float* z_out, float* const* log_s_out, float* log_s_sum, float* log_det_w, float* z_sq_sum, void* workspace,
+               size_t ws_bytes, void* stream) {
   if (!e) return WG_ERR_INVALID_ARGUMENT;
   if (!e->loaded) return fail(e, WG_ERR_WEIGHTS, "wg_load_weights has not been called");
   if (!mel || !audio_in || !z_out || !log_s_sum || !log_det_w || !workspace || batch <= 0 || frames <= 0 || n_samples <= 0)
@@ -1379,7 +1364,7 @@ int wg_forward(wg_engine* e, const float* mel, int32_t batch, int32_t frames, co
   if (ws_bytes < L.total) return fail(e, WG_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, L.total);
   if (reinterpret_cast<uintptr_t>(workspace) % 1024) return fail(e, WG_ERR_WORKSPACE, "workspace must be 1024-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  WG_CUDA(e, cudaSetDevice(e->cfg.device));
+  WG_DEVICE(e, e->cfg.device);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   const size_t npos = static_cast<size_t>(B) * T;
   const bool tc = e->cfg.precision == WG_PRECISION_FP16;
@@ -1389,7 +1374,7 @@ int wg_forward(wg_engine* e, const float* mel, int32_t batch, int32_t frames, co
   float* state = reinterpret_cast<float*>(ws + L.state);
   double* sums = reinterpret_cast<double*>(ws + L.sums);
   WG_CUDA(e, cudaMemcpyAsync(state, audio_in, npos * kGroup * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  WG_CUDA(e, cudaMemsetAsync(sums, 0, NF * sizeof(double), st));
+  WG_CUDA(e, cudaMemsetAsync(sums, 0, (NF + 1) * sizeof(double), st));
   launch_conditioning(e, mel, B, frames, T, ws, L, st);
   CUtensorMap tm_x[9], tm_cond, tm_a0[3], tm_p4[5];
   if (tc) {
@@ -1429,8 +1414,8 @@ int wg_forward(wg_engine* e, const float* mel, int32_t batch, int32_t frames, co
     int rc = run_wn_layers(e, k, B, T, ws, L, tm_x, &tm_cond, tm_a0, tm_p4, &cur, st, &stopped);
     if (rc) return rc;
   }
-  state_to_channel_major_kernel<<<static_cast<unsigned>((npos + 255) / 256), 256, 0, st>>>(state, z_out, B, T);
-  finalize_forward_stats_kernel<<<1, 64, 0, st>>>(sums, e->d_logdet, log_s_sum, log_det_w, NF, static_cast<double>(B) * T);
+  state_to_channel_major_kernel<<<static_cast<unsigned>((npos + 255) / 256), 256, 0, st>>>(state, z_out, z_sq_sum ? sums + NF : nullptr, B, T);
+  finalize_forward_stats_kernel<<<1, 96, 0, st>>>(sums, e->d_logdet, log_s_sum, log_det_w, z_sq_sum, NF, static_cast<double>(B) * T);
   e->launches += 2;
   WG_CUDA(e, cudaGetLastError());
   return WG_OK;
@@ -1442,6 +1427,7 @@ int wg_debug_gemm(wg_engine* e, const void* A, const void* Bm, float* D, int32_t
                   void* stream) {
   if (!e || !e->encode) return WG_ERR_INVALID_ARGUMENT;
   if (M % 128 || N % 256 || K % 64) return fail(e, WG_ERR_INVALID_ARGUMENT, "debug gemm needs M%%128==0, N%%256==0, K%%64==0");
+  WG_DEVICE(e, e->cfg.device);
   const CUtensorMapDataType dt = fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUtensorMap ta, tb;
   int rc;
@@ -1468,6 +1454,7 @@ int wg_debug_gemm2(wg_engine* e, const void* A, const void* Bm, float* D, int32_
                    void* stream) {
   if (!e || !e->encode) return WG_ERR_INVALID_ARGUMENT;
   if (M % 256 || N % 256 || K % 64) return fail(e, WG_ERR_INVALID_ARGUMENT, "debug gemm2 needs M%%256==0, N%%256==0, K%%64==0");
+  WG_DEVICE(e, e->cfg.device);
   const CUtensorMapDataType dt = fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUtensorMap ta, tb;
   int rc;

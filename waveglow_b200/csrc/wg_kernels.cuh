@@ -29,10 +29,11 @@ template <> __device__ __forceinline__ float to_float<__half>(__half v) { return
 template <> __device__ __forceinline__ float to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
 // ------------------------------------------------------------------------------------------ noise
+constexpr int kMaxNoise = 8;     // noise tensors per call: the initial one plus one per early output (wg_create rejects more)
 struct NoiseParams {
-  const float* z[8];   // z[i]: [B, ch[i], T]
-  int ch[8];
-  int slot0[8];        // first state slot of z[i]
+  const float* z[kMaxNoise];   // z[i]: [B, ch[i], T]
+  int ch[kMaxNoise];
+  int slot0[kMaxNoise];        // first state slot of z[i]
   int n;
 };
 
@@ -371,26 +372,41 @@ flow_step_kernel(FlowStepParams p, float* __restrict__ state, const float* __res
   }
 }
 
-// z_out[b, c, t] = state[b, t, c]  (forward returns the reference's channel-major layout, model.py:220-221)
-__global__ void state_to_channel_major_kernel(const float* __restrict__ state, float* __restrict__ z, int B, int T) {
+// z_out[b, c, t] = state[b, t, c]  (forward returns the reference's channel-major layout, model.py:220-221), and the
+// first reduction of WaveGlowLoss, sum z^2 (train.py:41), on the way: per-thread fp32 sum of 8 squares, warp shuffle,
+// one double atomic per warp into *z_sq (may be null).
+__global__ void state_to_channel_major_kernel(const float* __restrict__ state, float* __restrict__ z, double* __restrict__ z_sq,
+                                              int B, int T) {
   const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (idx >= static_cast<size_t>(B) * T) return;
-  const int b = static_cast<int>(idx / T), t = static_cast<int>(idx % T);
-  const float4* sp = reinterpret_cast<const float4*>(state + idx * kGroup);
-  const float4 s0 = sp[0], s1 = sp[1];
-  const float row[kGroup] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  float sq = 0.f;
+  if (idx < static_cast<size_t>(B) * T) {
+    const int b = static_cast<int>(idx / T), t = static_cast<int>(idx % T);
+    const float4* sp = reinterpret_cast<const float4*>(state + idx * kGroup);
+    const float4 s0 = sp[0], s1 = sp[1];
+    const float row[kGroup] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
-  for (int c = 0; c < kGroup; ++c) z[(static_cast<size_t>(b) * kGroup + c) * T + t] = row[c];
+    for (int c = 0; c < kGroup; ++c) {
+      z[(static_cast<size_t>(b) * kGroup + c) * T + t] = row[c];
+      sq = fmaf(row[c], row[c], sq);
+    }
+  }
+  if (z_sq) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((threadIdx.x & 31) == 0 && sq != 0.f) atomicAdd(z_sq, static_cast<double>(sq));
+  }
 }
 
-// out_sum[k] = (float) acc[k];  out_det[k] = logdet[k] * B * T   (model.py:63)
+// out_sum[k] = (float) acc[k];  out_det[k] = logdet[k] * B * T   (model.py:63);  out_zsq[0] = (float) acc[n]
 __global__ void finalize_forward_stats_kernel(const double* __restrict__ acc, const double* __restrict__ logdet,
-                                              float* __restrict__ out_sum, float* __restrict__ out_det, int n, double bt) {
+                                              float* __restrict__ out_sum, float* __restrict__ out_det, float* __restrict__ out_zsq,
+                                              int n, double bt) {
   const int k = threadIdx.x;
   if (k < n) {
     out_sum[k] = static_cast<float>(acc[k]);
     out_det[k] = static_cast<float>(logdet[k] * bt);
   }
+  if (k == n && out_zsq) out_zsq[0] = static_cast<float>(acc[n]);
 }
 
 // ------------------------------------------------------------------------------------------ fp32 layer

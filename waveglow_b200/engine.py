@@ -60,7 +60,7 @@ def load_library() -> ctypes.CDLL:
   lib.wg_workspace_bytes.restype = ctypes.c_size_t
   lib.wg_infer.argtypes = [vp, vp, i32, i32, ctypes.POINTER(vp), i32, f32, vp, vp, ctypes.c_size_t, vp]
   lib.wg_infer.restype = ctypes.c_int
-  lib.wg_forward.argtypes = [vp, vp, i32, i32, vp, i32, vp, ctypes.POINTER(vp), vp, vp, vp, ctypes.c_size_t, vp]
+  lib.wg_forward.argtypes = [vp, vp, i32, i32, vp, i32, vp, ctypes.POINTER(vp), vp, vp, vp, vp, ctypes.c_size_t, vp]
   lib.wg_forward.restype = ctypes.c_int
   lib.wg_last_launch_count.argtypes = [vp]
   lib.wg_save_packed.argtypes = [vp, ctypes.c_char_p, ctypes.c_uint64]
@@ -115,6 +115,35 @@ class Engine:
       self.close()
       raise WgError(f"wg_create failed ({rc}): {msg}")
     self._ws: Optional[torch.Tensor] = None
+    self._graphs = {}
+    self._expected_z = self._noise_channels(hparams)
+    self._flow_halves = self._half_channels(hparams)
+
+  @staticmethod
+  def _noise_channels(hparams) -> List[int]:
+    """Channel counts of the noise tensors `wg_infer` consumes, in the reference's draw order (model.py:239-243, 266-270)."""
+    n_rem = hparams.n_group
+    n_early = 0
+    for k in range(hparams.n_flows):
+      if k % hparams.n_early_every == 0 and k > 0:
+        n_rem -= hparams.n_early_size
+        n_early += 1
+    return [n_rem] + [hparams.n_early_size] * n_early
+
+  @staticmethod
+  def _half_channels(hparams) -> List[int]:
+    """n_half of every flow k (model.py:160-175): the channel count of its log_s."""
+    n_rem = hparams.n_group
+    out = []
+    for k in range(hparams.n_flows):
+      if k % hparams.n_early_every == 0 and k > 0:
+        n_rem -= hparams.n_early_size
+      out.append(n_rem // 2)
+    return out
+
+  def _drop_graphs(self) -> None:
+    """Captured CUDA graphs bake in the pointers of the packed weights and their tensor maps: re-packing frees both."""
+    self._graphs = {}
 
   def _err(self) -> str:
     if not self._h:
@@ -149,6 +178,7 @@ class Engine:
       for j in range(t.dim()):
         descs[i].shape[j] = t.size(j)
     torch.cuda.synchronize(self.device)
+    self._drop_graphs()
     self._check(self.lib.wg_load_weights(self._h, descs, len(folded)), "wg_load_weights")
 
   def save_packed(self, path, fingerprint: int) -> None:
@@ -159,6 +189,7 @@ class Engine:
   def load_packed(self, path, fingerprint: int) -> bool:
     """Restore packed weights written by `save_packed`.  False (with the reason in `last_cache_miss`) if the file is missing,
     stale, or was packed for another configuration -- the caller then packs from the state_dict as usual."""
+    self._drop_graphs()
     rc = self.lib.wg_load_packed(self._h, os.fsencode(str(path)), ctypes.c_uint64(fingerprint & (2 ** 64 - 1)))
     if rc == 0:
       return True
@@ -184,7 +215,19 @@ class Engine:
       raise WgError(f"mel is on {mel.device}, engine on {self.device}")
     mel = mel.to(torch.float32).contiguous()
     B, _, F = mel.shape
+    # wg_infer takes raw pointers: a wrong channel count, length, batch or device would be an out-of-bounds device read
+    n_groups = F * 256 // self.n_group
+    if len(zs) != len(self._expected_z):
+      raise WgError(f"expected {len(self._expected_z)} noise tensors, got {len(zs)}")
+    for i, (z, ch) in enumerate(zip(zs, self._expected_z)):
+      if tuple(z.shape) != (B, ch, n_groups):
+        raise WgError(f"noise tensor {i} has shape {tuple(z.shape)}, expected {(B, ch, n_groups)} for a [{B}, *, {F}] mel")
+      if z.device != self.device:
+        raise WgError(f"noise tensor {i} is on {z.device}, engine on {self.device}")
     zs = [z.to(torch.float32).contiguous() for z in zs]
+    if out is not None and (tuple(out.shape) != (B, F * 256) or out.dtype != torch.float32 or out.device != self.device
+                            or not out.is_contiguous()):
+      raise WgError(f"out must be a contiguous fp32 [{B}, {F * 256}] tensor on {self.device}")
     audio = out if out is not None else torch.empty((B, F * 256), dtype=torch.float32, device=self.device)
     ws = self.workspace(B, F)
     zp = (ctypes.c_void_p * len(zs))(*[z.data_ptr() for z in zs])
@@ -196,36 +239,37 @@ class Engine:
 
   def forward(self, mel: torch.Tensor, audio: torch.Tensor, flow_halves: Sequence[int], want_log_s: bool = True):
     """Training-direction flow.  mel [B,80,F], audio [B, n_samples] fp32 cuda.
-    Returns (z [B,8,T'], [log_s_k [B,h_k,T']] or None, log_s_sum [n_flows], log_det_w [n_flows])."""
+    Returns (z [B,8,T'], [log_s_k [B,h_k,T']] or None, log_s_sum [n_flows], log_det_w [n_flows], z_sq_sum [1])."""
     if mel.device != self.device or audio.device != self.device:
       raise WgError(f"inputs must be on {self.device}")
     mel = mel.to(torch.float32).contiguous()
     audio = audio.to(torch.float32).contiguous()
     B, _, F = mel.shape
     n_samples = audio.shape[1]
-    if audio.shape[0] != B or n_samples % self.n_group:
+    if audio.dim() != 2 or audio.shape[0] != B or n_samples % self.n_group:
       raise WgError("audio must be [B, n_samples] with n_samples a multiple of n_group")
+    if len(flow_halves) != len(self._flow_halves) or list(flow_halves) != self._flow_halves:
+      raise WgError(f"flow_halves must be {self._flow_halves}")
     T = n_samples // self.n_group
     n_flows = len(flow_halves)
     z = torch.empty((B, self.n_group, T), dtype=torch.float32, device=self.device)
     log_s = [torch.empty((B, h, T), dtype=torch.float32, device=self.device) for h in flow_halves] if want_log_s else None
     sums = torch.empty((n_flows,), dtype=torch.float32, device=self.device)
     dets = torch.empty((n_flows,), dtype=torch.float32, device=self.device)
+    zsq = torch.empty((1,), dtype=torch.float32, device=self.device)
     ws = self.workspace(B, F)
     lsp = (ctypes.c_void_p * n_flows)(*[t.data_ptr() for t in log_s]) if want_log_s else None
     stream = torch.cuda.current_stream(self.device).cuda_stream
     rc = self.lib.wg_forward(self._h, mel.data_ptr(), B, F, audio.data_ptr(), n_samples, z.data_ptr(), lsp, sums.data_ptr(),
-                             dets.data_ptr(), self._aligned_ptr(ws), ws.numel() - 1024, stream)
+                             dets.data_ptr(), zsq.data_ptr(), self._aligned_ptr(ws), ws.numel() - 1024, stream)
     self._check(rc, "wg_forward")
-    return z, log_s, sums, dets
+    return z, log_s, sums, dets, zsq
 
   def infer_graphed(self, mel: torch.Tensor, zs: Sequence[torch.Tensor], sigma: float) -> torch.Tensor:
     """Same result as `infer`, replayed from a CUDA graph (one graph per (batch, frames, sigma)): the ~110 kernel launches of
     a call collapse into one graph launch, which matters when a single short utterance is launch-bound (config 1)."""
     B, _, F = mel.shape
     key = (B, F, float(sigma))
-    if not hasattr(self, "_graphs"):
-      self._graphs = {}
     ent = self._graphs.get(key)
     if ent is None:
       s_mel = torch.empty((B, mel.shape[1], F), dtype=torch.float32, device=self.device)

@@ -92,6 +92,8 @@ class WaveGlow(torch.nn.Module):
     self._precision = precision
     self._engine: Optional[_engine.Engine] = None
     self._packed = False
+    self.pack_cache = None         # (path, fingerprint), set by Synthesizer(pack_cache=...) right after it built the model
+    self.pack_cache_hit = False
     # opt-in: replay each (batch, frames, sigma) shape from a CUDA graph (latency of short single utterances)
     self.use_cuda_graphs = False
 
@@ -111,12 +113,15 @@ class WaveGlow(torch.nn.Module):
 
   def invalidate_packed_weights(self) -> None:
     """Call after changing parameters in place; the reference has the same staleness for its cached
-    `W_inverse` (model.py:49-58).  load_state_dict / remove_weightnorm / .to() call it for you."""
+    `W_inverse` (model.py:49-58).  load_state_dict / remove_weightnorm / .to() call it for you.
+    A packed-weight cache (`pack_cache`) identifies the CHECKPOINT FILE the model was built from, not the live
+    parameters, so it is only good for the first pack after construction: it is dropped here."""
     self._packed = False
+    self.pack_cache = None
 
   def load_state_dict(self, *args, **kwargs):
     res = super().load_state_dict(*args, **kwargs)
-    self._packed = False
+    self.invalidate_packed_weights()
     return res
 
   def _apply(self, fn, *args, **kwargs):
@@ -150,7 +155,7 @@ class WaveGlow(torch.nn.Module):
       self._engine = _engine.Engine(self.hparams, prec, device)
       self._packed = False
     if not self._packed:
-      cache = getattr(self, "pack_cache", None)          # (path, fingerprint) set by Synthesizer(pack_cache=...)
+      cache = self.pack_cache
       if cache is not None and os.path.isfile(cache[0]) and self._engine.load_packed(cache[0], cache[1]):
         self.pack_cache_hit = True
       else:
@@ -204,8 +209,10 @@ class WaveGlow(torch.nn.Module):
     eng = self.engine()
     halves = [c // 2 for c in flow_channels(self.hparams)]
     with torch.no_grad():
-      z, log_s_list, sums, dets = eng.forward(spect, audio, halves, want_log_s=True)
-    self.last_forward_stats = {"log_s_sum": sums, "log_det_w": dets}
+      z, log_s_list, sums, dets, zsq = eng.forward(spect, audio, halves, want_log_s=True)
+    self.last_forward_stats = ForwardStats(z, log_s_list, sums, dets, zsq)
+    # the fused reductions travel WITH the output tuple, so WaveGlowLoss can tell an engine output from foreign tensors
+    z._wg_forward_stats = self.last_forward_stats
     return z, log_s_list, [dets[k] for k in range(self.n_flows)]
 
   @staticmethod
@@ -221,22 +228,52 @@ class WaveGlow(torch.nn.Module):
     return model
 
 
+class ForwardStats(dict):
+  """Reductions the engine fuses into `wg_forward`: `log_s_sum[k]` = sum of flow k's log_s (reduced in
+  double by the coupling kernel), `log_det_w[k]` = B * T' * log|det W_k|, `z_sq_sum` = sum z^2 (reduced by the kernel that
+  writes z).  Remembers which tensors they describe so a loss computed on other tensors does not pick them up."""
+
+  def __init__(self, z, log_s_list, log_s_sum, log_det_w, z_sq_sum):
+    super().__init__(log_s_sum=log_s_sum, log_det_w=log_det_w, z_sq_sum=z_sq_sum)
+    self._z = z
+    self._log_s = list(log_s_list) if log_s_list is not None else None
+
+  def describes(self, z, log_s_list) -> bool:
+    if z is not self._z or z._version != 0:
+      return False
+    if self._log_s is None or len(log_s_list) != len(self._log_s):
+      return False
+    return all(a is b and a._version == 0 for a, b in zip(log_s_list, self._log_s))
+
+
 class WaveGlowLoss(torch.nn.Module):
-  """Mirror of train.py:26-45: (sum z^2 / (2 sigma^2) - sum log_s - sum log_det_W) / (B * 8 * T')."""
+  """Mirror of train.py:26-45: (sum z^2 / (2 sigma^2) - sum log_s - sum log_det_W) / (B * 8 * T').
+
+  Called on the output of `WaveGlow.forward` of this package it consumes the reductions the engine already made inside
+  `wg_forward` (no pass over z or the log_s tensors: three tiny ops on [n_flows] vectors); called on any other tensors
+  (or on engine outputs that were modified in place since) it reduces them with torch exactly like the reference."""
 
   def __init__(self, sigma: float = 1.0):
     super().__init__()
     self.sigma = sigma
+    self.used_fused_stats = False
 
   def forward(self, model_output):
     z, log_s_list, log_det_W_list = model_output
+    stats = getattr(z, "_wg_forward_stats", None)
+    n = z.size(0) * z.size(1) * z.size(2)
+    if isinstance(stats, ForwardStats) and stats.describes(z, log_s_list) and len(log_det_W_list) == stats["log_det_w"].numel():
+      self.used_fused_stats = True
+      loss = stats["z_sq_sum"][0] / (2 * self.sigma * self.sigma) - stats["log_s_sum"].sum() - stats["log_det_w"].sum()
+      return loss / n
+    self.used_fused_stats = False
     log_s_total = 0
     log_det_W_total = 0
     for i, log_s in enumerate(log_s_list):
       log_s_total = log_s_total + torch.sum(log_s)
       log_det_W_total = log_det_W_total + log_det_W_list[i]
     loss = torch.sum(z * z) / (2 * self.sigma * self.sigma) - log_s_total - log_det_W_total
-    return loss / (z.size(0) * z.size(1) * z.size(2))
+    return loss / n
 
 
 def load_model(hparams: HParams, state_dict: Optional[dict], device: torch.device, precision: str = "fp16") -> WaveGlow:

@@ -5,8 +5,13 @@ independent engines: rank r synthesises utterances [r*B/N, (r+1)*B/N).  Nothing 
 collective is the final gather of the fp32 audio (north_star: "NCCL is used only for the final gather").
 Noise is drawn for the GLOBAL batch with one seed and sliced per rank, so the audio does not depend on N.
 Works with any torch.distributed backend (nccl on the GPU box, gloo in the CPU tests).
+
+The gather is kept OFF the critical path: `AudioGather.start()` issues the all-gather asynchronously (on NCCL's own
+stream; the compute stream is not made to wait), the next batch's kernels run while the audio of the previous batch crosses
+NVLink, and `wait()` joins it when the audio is needed.  Even shards land in their final place: the output of
+`all_gather_into_tensor` IS the concatenated batch, no copy follows (round 1 paid a `torch.cat` of the whole batch per step).
 """
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -27,20 +32,49 @@ def shard_inputs(mel: torch.Tensor, zs: Sequence[torch.Tensor], rank: int, world
   return mel[lo:hi], [z[lo:hi] for z in zs]
 
 
+class AudioGather:
+  """One in-flight gather of the per-rank audio [B_r, T] into the full [global_batch, T] batch on every rank."""
+
+  def __init__(self, local_audio: torch.Tensor, global_batch: int, group=None):
+    self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+    self.global_batch = global_batch
+    self._local = local_audio          # kept alive until wait(): the collective reads it from another stream
+    self._work = None
+    self._out: Optional[torch.Tensor] = None
+    self._result: Optional[torch.Tensor] = None
+    if self.world == 1:
+      self._result = local_audio
+      return
+    rank = dist.get_rank(group)
+    self._sizes = [shard_range(global_batch, r, self.world) for r in range(self.world)]
+    lo, hi = self._sizes[rank]
+    if local_audio.size(0) != hi - lo:
+      raise ValueError(f"rank {rank} holds {local_audio.size(0)} utterances, its shard of {global_batch} is {hi - lo}")
+    max_n = max(h - l for l, h in self._sizes)
+    self._even = all(h - l == max_n for l, h in self._sizes)
+    T = local_audio.size(1)
+    send = local_audio.contiguous()
+    if send.size(0) < max_n:           # uneven shards: pad to the largest one (all_gather needs equal sizes)
+      send = torch.cat([send, send.new_zeros(max_n - send.size(0), T)], 0)
+    self._send = send
+    self._out = local_audio.new_empty((self.world * max_n, T))
+    self._max_n = max_n
+    self._work = dist.all_gather_into_tensor(self._out, send, group=group, async_op=True)
+
+  def wait(self) -> torch.Tensor:
+    """The full batch (on every rank).  Makes the current stream wait for the collective."""
+    if self._result is not None:
+      return self._result
+    self._work.wait()
+    if self._even:
+      self._result = self._out          # already [global_batch, T] in rank order: no copy
+    else:
+      parts: List[torch.Tensor] = [self._out[r * self._max_n: r * self._max_n + (hi - lo)] for r, (lo, hi) in enumerate(self._sizes)]
+      self._result = torch.cat(parts, 0)
+    self._local = self._send = None
+    return self._result
+
+
 def gather_audio(local_audio: torch.Tensor, global_batch: int, group=None) -> torch.Tensor:
-  """All ranks receive the full [global_batch, T] audio.  Handles uneven shards by padding to the largest shard."""
-  world = dist.get_world_size(group) if dist.is_initialized() else 1
-  if world == 1:
-    return local_audio
-  rank = dist.get_rank(group)
-  sizes = [shard_range(global_batch, r, world) for r in range(world)]
-  max_n = max(hi - lo for lo, hi in sizes)
-  T = local_audio.size(1)
-  padded = local_audio
-  if local_audio.size(0) < max_n:
-    padded = torch.cat([local_audio, local_audio.new_zeros(max_n - local_audio.size(0), T)], 0)
-  out = local_audio.new_empty((world * max_n, T))
-  dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
-  parts: List[torch.Tensor] = [out[r * max_n: r * max_n + (hi - lo)] for r, (lo, hi) in enumerate(sizes)]
-  assert parts[rank].size(0) == local_audio.size(0)
-  return torch.cat(parts, 0)
+  """All ranks receive the full [global_batch, T] audio (blocking form of AudioGather)."""
+  return AudioGather(local_audio, global_batch, group).wait()
