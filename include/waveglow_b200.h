@@ -136,9 +136,11 @@ int wg_set_profiling(wg_engine* e, int32_t enabled);
 int wg_debug_gemm(wg_engine* e, const void* a, const void* b, float* d, int32_t m, int32_t n, int32_t k,
                   int32_t fmt, void* stream);
 
-/* Same through tcgen05.mma.cta_group::2 on CTA pairs (M % 256 == 0): validates the 2-CTA mechanisms in isolation. */
+/* Same through tcgen05.mma.cta_group::2 on CTA pairs (M % 256 == 0): validates the 2-CTA mechanisms in isolation.
+ * ks = K elements per operand stage: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B) -- the two
+ * operand-ring formats of the layer kernel. */
 int wg_debug_gemm2(wg_engine* e, const void* a, const void* b, float* d, int32_t m, int32_t n, int32_t k,
-                   int32_t fmt, void* stream);
+                   int32_t fmt, int32_t ks, void* stream);
 
 /* Diagnostics: when set (device pointer to [n_ctas][16] int64), every fused layer launch writes clock64
  * stamps of its pipeline phases per CTA (slot meaning: tools/timeline.py).  NULL disables (default). */

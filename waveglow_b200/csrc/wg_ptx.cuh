@@ -176,6 +176,18 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// Same for a 64-byte-swizzled tile: rows of 64 bytes (32 x 16-bit), 8-row groups 512 bytes apart (TMA box {32, rows} with
+// CU_TENSOR_MAP_SWIZZLE_64B into 512B-aligned smem); layout type 4 = SWIZZLE_64B.
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
+
 // Instruction descriptor, kind::f16: D fp32, A/B 16-bit float (fmt 0 = fp16, 1 = bf16), both K-major.
 //   bits [4,6) D format (1 = f32)  [7,10) A fmt  [10,13) B fmt  bit 15/16 A/B major (0 = K)
 //   bits [17,23) N >> 3            [24,29) M >> 4

@@ -74,7 +74,7 @@ def load_library() -> ctypes.CDLL:
   lib.wg_debug_view.restype = ctypes.c_int
   lib.wg_debug_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
   lib.wg_debug_gemm.restype = ctypes.c_int
-  lib.wg_debug_gemm2.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
+  lib.wg_debug_gemm2.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
   lib.wg_debug_gemm2.restype = ctypes.c_int
   lib.wg_set_profiling.argtypes = [vp, i32]
   lib.wg_set_profiling.restype = ctypes.c_int
@@ -330,15 +330,16 @@ class Engine:
       return raw.view(torch.float32)
     return raw.view(torch.float16)
 
-  def debug_gemm2(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """D = A @ B^T through the cta_group::2 (CTA pair) diagnostic kernel."""
+  def debug_gemm2(self, a: torch.Tensor, b: torch.Tensor, ks: int = 64) -> torch.Tensor:
+    """D = A @ B^T through the cta_group::2 (CTA pair) diagnostic kernel; ks = K elements per operand stage (64: SWIZZLE_128B,
+    32: SWIZZLE_64B)."""
     assert a.dtype == b.dtype and a.dtype in (torch.float16, torch.bfloat16)
     a = a.contiguous()
     b = b.contiguous()
     d = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=self.device)
     stream = torch.cuda.current_stream(self.device).cuda_stream
     self._check(self.lib.wg_debug_gemm2(self._h, a.data_ptr(), b.data_ptr(), d.data_ptr(), a.shape[0], b.shape[0], a.shape[1],
-                                        0 if a.dtype == torch.float16 else 1, stream), "wg_debug_gemm2")
+                                        0 if a.dtype == torch.float16 else 1, ks, stream), "wg_debug_gemm2")
     return d
 
   def debug_gemm(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
