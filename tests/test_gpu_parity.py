@@ -22,8 +22,7 @@ def get_model(n_channels: int, precision: str, style: str = "parametrized") -> W
   """precision: "fp32", "fp16" (the tensor-core path: fused layer on CTA pairs, continuous-issue schedule; 256 and 512
   channels run the same templated kernel), or the fp16 engine with one of its switches set: "fp16-seg32" / "fp16-seg64"
   (WG_SEG) force the segment size of the tiles; "fp16-nopack" (WG_PACK4=0) switches the packed ragged tails off and
-  "fp16-nofirst" (WG_FIRST=0) the composition of the start conv into each flow's first layer; "fp16-ks32" / "fp16-ks64" (WG_KS)
-  select the width of the operand-ring stages (32 channels: SWIZZLE_64B, twice as many stages)."""
+  "fp16-nofirst" (WG_FIRST=0) the composition of the start conv into each flow's first layer."""
   import os
   key = (n_channels, precision, style)
   if key not in _MODELS:
@@ -37,15 +36,12 @@ def get_model(n_channels: int, precision: str, style: str = "parametrized") -> W
       os.environ["WG_PACK4"] = "0"
     if precision == "fp16-nofirst":
       os.environ["WG_FIRST"] = "0"
-    if precision.startswith("fp16-ks"):
-      os.environ["WG_KS"] = precision[len("fp16-ks"):]
     try:
       m.engine()          # the engine reads its switches when it is created
     finally:
       os.environ.pop("WG_SEG", None)
       os.environ.pop("WG_PACK4", None)
       os.environ.pop("WG_FIRST", None)
-      os.environ.pop("WG_KS", None)
     _MODELS[key] = m
   return _MODELS[key]
 
@@ -87,8 +83,7 @@ def test_tcgen05_cta_pair_gemm():
     assert err <= 2e-3
 
 
-@pytest.mark.parametrize("precision,nc", [("fp32", 256), ("fp16-ks64", 256), ("fp16-ks32", 256), ("fp16-nofirst", 256), ("fp16-ks64", 512),
-                                          ("fp16-ks32", 512), ("fp16-nofirst", 512)])
+@pytest.mark.parametrize("precision,nc", [("fp32", 256), ("fp16", 256), ("fp16-nofirst", 256), ("fp16", 512), ("fp16-nofirst", 512)])
 def test_stagewise_first_flow(precision, nc):
   """cond (upsample+squeeze), start conv, then every WN layer of the first flow, then the coupling step."""
   op_dtype = torch.float32 if precision == "fp32" else torch.float16
@@ -103,7 +98,7 @@ def test_stagewise_first_flow(precision, nc):
   sigma = 0.8
   trace = []
   phase_cond = precision != "fp32"     # tensor-core mode composes the upsampler into the conditioning weights
-  first_composed = precision in ("fp16", "fp16-ks64", "fp16-ks32")  # ... and the start conv into each flow's first layer
+  first_composed = precision == "fp16"  # ... and the start conv into each flow's first layer
   with torch.no_grad():
     ref_audio = E.infer(w, dims, mel, sigma, zs, op_dtype, trace, phase_cond=phase_cond, first_composed=first_composed)
   k = dims.n_flows - 1
@@ -201,19 +196,6 @@ def test_512_channel_tensor_core_path_matches_reference_golden(mode):
   err, snr = max_abs(ref, out), snr_db(ref, out)
   print(f"512 channels {mode}: max-abs {err:.3e}  snr {snr:.1f} dB")
   assert out.shape == ref.shape and err <= FP16_MAX_ABS and snr >= FP16_MIN_SNR_DB
-
-
-@pytest.mark.parametrize("nc,B,F", [(256, 6, 140), (512, 3, 150), (256, 9, 40)])
-def test_ring_stage_width_does_not_change_the_result(nc, B, F):
-  """Operand-ring stages of 32 channels (SWIZZLE_64B, WG_KS=32) and of 64 channels (SWIZZLE_128B, WG_KS=64) issue the same
-  K = 16 MMA steps in the same order: the audio must be bit-identical (whole blocks, packed tails, first and last layers)."""
-  hp, sd, w, dims = synthetic_weights(nc)
-  mel = synthetic_mel(B, F, 700 + F)
-  zs = synthetic_noise(hp, B, F * 32, 701 + F)
-  a = run(get_model(nc, "fp16-ks64"), mel, zs, 0.666)
-  b = run(get_model(nc, "fp16-ks32"), mel, zs, 0.666)
-  assert torch.isfinite(a).all() and torch.equal(a, b)
-  assert torch.equal(a, run(get_model(nc, "fp16"), mel, zs, 0.666))      # whichever of the two is the default
 
 
 @pytest.mark.parametrize("mode", ["fp16-seg32", "fp16-seg64"])

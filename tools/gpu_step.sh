@@ -13,9 +13,6 @@ for step in "$@"; do
     tests_all) TAILN=25 run tests_all 1500 python -m pytest tests -q -m gpu --timeout 900 ;;
     shapes)    TAILN=30 run shapes 1200 python -m pytest tests/test_gpu_baseline_shapes.py -q -s --timeout 900 ;;
     smoke)     TAILN=4 run smoke 300 python -c "import __graft_entry__ as g; g.smoke()" ;;
-    ks)        TAILN=30 run ks 300 python -m pytest tests/test_gpu_parity.py -q -x -s -k "pair_gemm or ring_stage or (stagewise and ks32)" ;;
-    ab_ks)     for v in 64 32 64 32; do echo "WG_KS=$v"; WG_KS=$v python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | python tools/bench_brief.py; done | tee $OUT/ab_ks256.txt
-               for v in 64 32 64 32; do echo "WG_KS=$v"; WG_KS=$v python bench.py --channels 512 --batch 8 --steps 5 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | python tools/bench_brief.py; done | tee $OUT/ab_ks512.txt ;;
     bench)     TAILN=1 run bench 600 python bench.py --steps 10 --warmup 3 ;;
     bench_fast) TAILN=1 run bench_fast 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-parity ;;
     bench512)  TAILN=1 run bench512 600 python bench.py --channels 512 --batch 32 --steps 5 --warmup 3 --no-cpu-baseline ;;

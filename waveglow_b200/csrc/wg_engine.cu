@@ -59,7 +59,7 @@ struct wg_engine {
   CUtensorMap tm_w1h{}, tm_vh{}, tm_w2h{}, tm_ident16{};   // 128-row boxes: each CTA of a pair stages half of every B operand
   int g2_at[kMaxHalves] = {6, 6};     // see LayerTcParams::g2_at: generic layers (WG_G2AT / WG_G2AT1 env override, diagnostics)
   int g2_at_first[kMaxHalves] = {7, 7};   // ... first layer of a flow with the start conv composed in (8 k-blocks per chunk; WG_G2AT0)
-  int ks = 64;                        // channels per operand-ring stage of the layer kernel: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B); WG_KS env
+  const int ks = 64;                  // channels per operand-ring stage of the layer kernel (ContCfg<NC, KS>; see layer_kernel())
   int force_seg = 0;                  // WG_SEG env (tests/diagnostics): force the segment size (128 / 64 / 32) of the tiles
   bool first_comp = false;            // start conv composed into the first layer of each flow (WG_FIRST=0 disables)
   bool trim_grid = false;             // WG_TRIM=1: smallest grid with the same number of tile rounds (measured 0.7 % SLOWER on
@@ -343,14 +343,17 @@ LayerKernel layer_kernel_nk(int first, int mode) {
   return table[first][mode];
 }
 
+// Only 64-channel ring stages are instantiated for production: 32-channel stages (SWIZZLE_64B, twice as many stages in the
+// same bytes) pass the same parity tests but were measured 33 % (256 channels) / 24 % (512 channels) slower,
+// profiles/r02/ab_ring_stage_width.txt.  To repeat the A/B, add the <NC, 32> rows here and read WG_KS in wg_create.
 LayerKernel layer_kernel(int nc, int ks, int first, int mode) {
-  if (nc == 512) return ks == 32 ? layer_kernel_nk<512, 32>(first, mode) : layer_kernel_nk<512, 64>(first, mode);
-  return ks == 32 ? layer_kernel_nk<256, 32>(first, mode) : layer_kernel_nk<256, 64>(first, mode);
+  (void)ks;
+  return nc == 512 ? layer_kernel_nk<512, 64>(first, mode) : layer_kernel_nk<256, 64>(first, mode);
 }
 
 int layer_launch_bytes(int nc, int ks) {
-  if (nc == 512) return ks == 32 ? ContCfg<512, 32>::launch_bytes : ContCfg<512, 64>::launch_bytes;
-  return ks == 32 ? ContCfg<256, 32>::launch_bytes : ContCfg<256, 64>::launch_bytes;
+  (void)ks;
+  return nc == 512 ? ContCfg<512, 64>::launch_bytes : ContCfg<256, 64>::launch_bytes;
 }
 
 }  // namespace
@@ -417,9 +420,6 @@ int wg_create(const wg_config* cfg, wg_engine** out) {
   const bool tc = cfg->precision == WG_PRECISION_FP16;
   if (tc && prop.multiProcessorCount < 2) return fail(e, WG_ERR_UNSUPPORTED, "the fused layer kernel runs on CTA pairs: needs >= 2 SMs");
   const int nc = cfg->n_channels;
-  const char* ks_env = getenv("WG_KS");
-  if (ks_env) e->ks = atoi(ks_env);
-  if (e->ks != 64 && e->ks != 32) return fail(e, WG_ERR_INVALID_ARGUMENT, "WG_KS must be 64 or 32 (got %d)", e->ks);
   const int ks = e->ks;
   const int n_kb = (kMwK + 3 * nc) / ks, n_kb_first = kMwK / ks + 3, n_halves = nc / 256;
   // GEMM2 of tile i-1 is issued inside the first chunk of tile i, before ring stage g2_at[h] of it.  256 channels: after 384
