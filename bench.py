@@ -407,14 +407,13 @@ def main():
   # tensor FLOPs the layer kernels actually issue per group-step, averaged over the 8 layers of a flow:
   # GEMM1 K = 3 nc + 320 (upsampler composed into the conditioning), K = 320 + 3 x 16 in a flow's first layer (start conv
   # composed in); GEMM2 N = nc residual + identity carry (one K = 16 step in the first layer, none in the last);
-  # skip->end fold (8 outputs on mma.sync in the 256-channel kernel, 16 tcgen05 columns in the wide path)
+  # skip->end fold (8 outputs per group-step on warp-level mma.sync)
   nc = args.channels
-  se = 2 * nc * (8 if nc == 256 else 16)
+  se = 2 * nc * 8
   g1_full, g1_first = 2 * (3 * nc + 320) * 2 * nc, 2 * (320 + 3 * 16) * 2 * nc
   g2_mid, g2_first = 2 * nc * nc + 2 * nc * 32, 2 * nc * nc + 2 * 16 * nc
   exec_per_step_layer = ((g1_first + g2_first + se) + 6 * (g1_full + g2_mid + se) + (g1_full + se)) / 8
-  kernel = ("wn_layer_fp32_kernel" if args.precision == "fp32" else
-            "wn_layer_pair_cont_kernel" if args.channels == 256 else "wn_gate_wide_kernel + wn_res_wide_kernel")
+  kernel = "wn_layer_fp32_kernel" if args.precision == "fp32" else f"wn_layer_pair_cont_kernel<{args.channels}, 64, first, mode>"
   # ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over a flow's launches: taken from the committed
   # capture of this workload (profiles/traffic.json names the .csv it came from), null when this workload was not captured
   traffic, traffic_src = None, None

@@ -119,6 +119,16 @@ int wg_forward(wg_engine* e, const float* mel, int32_t batch, int32_t frames,
                float* const* log_s_out, float* log_s_sum, float* log_det_w, float* z_sq_sum,
                void* workspace, size_t ws_bytes, void* stream);
 
+/* Replaces: the per-call arithmetic of Denoiser.forward between its two STFTs (denoiser.py:51-57 with stft.py:155-165:
+ * magnitude, atan2 phase, bias subtraction, clamp, cos / sin recombination) by the equivalent in-place real scaling
+ *   X <- X * max(|X| - strength * bias[f], 0) / |X|       (0 where |X| == 0, like the reference)
+ *  spec     interleaved (re, im) fp32, device: element (b, f, t) at complex index b*stride_b + f*stride_f + t*stride_t
+ *           (strides in complex elements: the [B, n_freq, n_frames] view torch.stft returns is not contiguous)
+ *  bias     [n_freq] fp32, device: the model's bias magnitude spectrum (denoiser.py:47-49)
+ * Stateless (no engine handle): `device` is the CUDA ordinal the pointers live on; stream-ordered on `stream`. */
+int wg_denoise_spectrum(float* spec, const float* bias, float strength, int32_t batch, int32_t n_freq, int32_t n_frames,
+                        int64_t stride_b, int64_t stride_f, int64_t stride_t, int32_t device, void* stream);
+
 /* Number of kernel launches the last wg_infer / wg_forward call enqueued (for bench.py's gpu_launches). */
 int wg_last_launch_count(const wg_engine* e);
 

@@ -181,3 +181,41 @@ def test_packed_weight_cache_round_trip(tmp_path):
   cache.write_bytes(data[: len(data) // 2])
   f, _ = build(precision="fp32", pack_cache=cache, pack_fingerprint=124)
   assert f.model.pack_cache_hit is False and cache.stat().st_size == len(data)
+
+
+def test_fused_denoiser_kernel_matches_reference_golden():
+  """Denoiser on cuda:0 = cuFFT STFT -> wg_denoise_spectrum (one in-place kernel: X * max(|X| - s b, 0) / |X|) -> cuFFT inverse,
+  against the outputs of the reference's own conv-basis STFT / Denoiser classes (denoiser.py:51-57, stft.py:135-198) for three
+  strengths incl. one that clamps most bins to zero; gate 1e-5.  Also the raw kernel against the torch
+  formula on a non-contiguous spectrum view."""
+  from tests.helpers import load_golden
+  from waveglow_b200.denoiser import Denoiser
+  from waveglow_b200.engine import denoise_spectrum_
+  from waveglow_b200.hparams import HParams
+  g = load_golden("denoiser_b2_n6144")
+  dev = torch.device("cuda:0")
+
+  class FakeWaveglow:
+    upsample = torch.nn.ConvTranspose1d(1, 1, 4).to(dev)
+
+    def infer(self, mel, sigma=1.0):
+      assert tuple(mel.shape) == (1, 80, 88) and sigma == 0.0 and mel.is_cuda
+      return torch.from_numpy(g["bias_audio"]).to(dev)
+
+  den = Denoiser(FakeWaveglow(), HParams(), mode="zeros", device=dev)
+  audio = torch.from_numpy(g["audio"]).to(dev)
+  for i, s in enumerate(g["strengths"]):
+    out = den(audio, strength=float(s))
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(g[f"denoised_{i}"])
+    err = float((out.cpu() - ref).abs().max())
+    print(f"fused denoiser, strength {float(s):g}: max-abs {err:.3e}")
+    assert out.is_cuda and out.shape == ref.shape and err <= 1e-5
+  gen = torch.Generator().manual_seed(3)
+  spec = torch.complex(torch.randn((3, 40, 513), generator=gen), torch.randn((3, 40, 513), generator=gen)).to(dev).transpose(1, 2)
+  spec[0, 5, 7] = 0                                          # |X| == 0 stays 0 (atan2(0, 0) = 0 in the reference)
+  bias = torch.rand(513, generator=gen).to(dev)
+  mag = spec.abs()
+  expect = spec * torch.where(mag > 0, torch.clamp(mag - bias[None, :, None] * 0.7, min=0) / mag.clamp_min(1e-30), torch.zeros_like(mag))
+  got = denoise_spectrum_(spec.clone(memory_format=torch.preserve_format), bias, 0.7)
+  assert not got.is_contiguous() and float((got - expect).abs().max()) <= 1e-6 and complex(got[0, 5, 7]) == 0

@@ -8,7 +8,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from waveglow_b200.hparams import HParams
-from waveglow_b200.sharding import gather_audio, shard_inputs, shard_range
+from waveglow_b200.sharding import AudioGather, gather_audio, shard_inputs, shard_range
 from waveglow_b200.synthetic import synthetic_mel, synthetic_noise
 
 
@@ -32,6 +32,21 @@ def _worker(rank, world, port, global_batch, frames, out_dir):
     full = gather_audio(local, global_batch)
     expect = _fake_infer(mel, zs, 0.666)
     ok = torch.equal(full, expect)
+    # the asynchronous form bench.py uses: the gather of step i is joined after step i + 1 was computed
+    pending, results = None, []
+    for step in range(3):
+      out = _fake_infer(m, z, 0.5 + step)
+      if pending is not None:
+        results.append(pending.wait())
+      pending = AudioGather(out, global_batch)
+    results.append(pending.wait())
+    for step, got in enumerate(results):
+      ok = ok and torch.equal(got, _fake_infer(mel, zs, 0.5 + step))
+    try:
+      AudioGather(local[:0], global_batch)          # a shard of the wrong size is refused, not silently gathered
+      ok = False
+    except ValueError:
+      pass
     torch.save({"ok": ok, "n_local": local.size(0)}, os.path.join(out_dir, f"r{rank}.pt"))
   finally:
     dist.destroy_process_group()

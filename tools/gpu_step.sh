@@ -13,11 +13,14 @@ for step in "$@"; do
     tests_all) TAILN=25 run tests_all 1500 python -m pytest tests -q -m gpu --timeout 900 ;;
     shapes)    TAILN=30 run shapes 1200 python -m pytest tests/test_gpu_baseline_shapes.py -q -s --timeout 900 ;;
     smoke)     TAILN=4 run smoke 300 python -c "import __graft_entry__ as g; g.smoke()" ;;
+    flags)     for f in 0 1 4 8 16 128 29 0; do echo "WG_DBG_FLAGS=$f (256 ch, B16 x 861)"; WG_DBG_FLAGS=$f python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | python tools/bench_brief.py; done | tee $OUT/flags256.txt
+               for f in 0 1 4 8 16 29 0; do echo "WG_DBG_FLAGS=$f (512 ch, B8 x 861)"; WG_DBG_FLAGS=$f python bench.py --channels 512 --batch 8 --steps 4 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | python tools/bench_brief.py; done | tee $OUT/flags512.txt ;;
     bench)     TAILN=1 run bench 600 python bench.py --steps 10 --warmup 3 ;;
     bench_fast) TAILN=1 run bench_fast 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-parity ;;
     bench512)  TAILN=1 run bench512 600 python bench.py --channels 512 --batch 32 --steps 5 --warmup 3 --no-cpu-baseline ;;
     bench512_b8) TAILN=1 run bench512_b8 600 python bench.py --channels 512 --batch 8 --steps 5 --warmup 3 --no-cpu-baseline --no-parity ;;
     ref)       TAILN=1 run ref 900 python bench.py --impl reference --steps 2 --warmup 1 ;;
+    callers)   TAILN=12 run callers 900 python tools/profile_callers.py ;;
     configs)   TAILN=8 run configs 600 python tools/measure_configs.py ;;
     timeline256) TAILN=40 run timeline256 300 python tools/timeline.py ;;
     timeline512) TAILN=40 run timeline512 300 python tools/timeline.py --channels 512 --batch 8 ;;

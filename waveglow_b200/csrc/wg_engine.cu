@@ -1441,6 +1441,21 @@ int wg_forward(wg_engine* e, const float* mel, int32_t batch, int32_t frames, co
   return WG_OK;
 }
 
+// Denoiser core: in-place X <- X * max(|X| - strength * bias[f], 0) / |X| on an interleaved complex fp32
+// spectrum [batch, n_freq, n_frames] addressed by element strides; stateless (no engine), stream-ordered.
+int wg_denoise_spectrum(float* spec, const float* bias, float strength, int32_t batch, int32_t n_freq, int32_t n_frames,
+                        int64_t stride_b, int64_t stride_f, int64_t stride_t, int32_t device, void* stream) {
+  if (!spec || !bias || batch <= 0 || n_freq <= 0 || n_frames <= 0 || stride_f <= 0 || stride_t <= 0 || stride_b < 0)
+    return WG_ERR_INVALID_ARGUMENT;
+  DeviceGuard guard(device);
+  if (guard.status != cudaSuccess) return WG_ERR_CUDA;
+  const long long total = static_cast<long long>(batch) * n_freq * n_frames;
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  denoise_spectrum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<float2*>(spec), bias, strength, n_freq,
+                                                                               n_frames, stride_b, stride_f, stride_t, total);
+  return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
+}
+
 // Diagnostic: D[M x N] fp32 = A[M x K] . B[N x K]^T with 16-bit device operands (fmt 0 fp16 / 1 bf16).
 // M % 128 == 0, N % 256 == 0, K % 64 == 0.  Exercises TMA(SW128) -> tcgen05.mma -> tcgen05.ld in isolation.
 int wg_debug_gemm(wg_engine* e, const void* A, const void* Bm, float* D, int32_t M, int32_t N, int32_t K, int32_t fmt,

@@ -409,6 +409,37 @@ __global__ void finalize_forward_stats_kernel(const double* __restrict__ acc, co
   if (k == n && out_zsq) out_zsq[0] = static_cast<float>(acc[n]);
 }
 
+// ------------------------------------------------------------------------------------------ denoiser
+// The reference Denoiser (denoiser.py:51-57, stft.py:155-165) turns the STFT X into magnitude and phase (sqrt, atan2),
+// subtracts the bias magnitude, clamps at 0 and rebuilds the spectrum with cos / sin of the phase:
+//     X' = max(|X| - strength * bias[f], 0) * (cos(atan2(im, re)) + i sin(atan2(im, re)))  ==  X * max(|X| - strength * bias[f], 0) / |X|
+// i.e. a real scaling of X: one pass over the spectrum, no transcendentals, in place.  |X| == 0 gives 0 like the reference
+// (atan2(0, 0) = 0, clamp(-strength * bias, 0) = 0).  `spec` is interleaved (re, im) fp32 addressed by element strides (in
+// complex elements) so that the non-contiguous [B, n_freq, n_frames] view torch.stft returns needs no copy.
+__global__ void denoise_spectrum_kernel(float2* __restrict__ spec, const float* __restrict__ bias, float strength, int n_freq,
+                                        int n_frames, long long stride_b, long long stride_f, long long stride_t, long long total) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  // the fastest index follows the smaller stride, so consecutive threads touch consecutive memory in either layout
+  int f, t;
+  long long b;
+  if (stride_f <= stride_t) {
+    f = static_cast<int>(idx % n_freq);
+    t = static_cast<int>((idx / n_freq) % n_frames);
+    b = idx / (static_cast<long long>(n_freq) * n_frames);
+  } else {
+    t = static_cast<int>(idx % n_frames);
+    f = static_cast<int>((idx / n_frames) % n_freq);
+    b = idx / (static_cast<long long>(n_freq) * n_frames);
+  }
+  float2* p = spec + b * stride_b + f * stride_f + t * stride_t;
+  const float2 x = *p;
+  const float mag = sqrtf(x.x * x.x + x.y * x.y);                 // stft.py:155
+  const float den = fmaxf(mag - __ldg(bias + f) * strength, 0.f);  // denoiser.py:55-56
+  const float scale = mag > 0.f ? den / mag : 0.f;
+  *p = make_float2(x.x * scale, x.y * scale);
+}
+
 // ------------------------------------------------------------------------------------------ fp32 layer
 // One WN layer in fp32 on CUDA cores.  Block = 256 threads, tile = 32 group-steps of one utterance.
 //   W1  [K1 = 3 NC + 640][2 NC]  (k-major rows, natural channel order: tanh half | sigmoid half)

@@ -41,11 +41,13 @@ class STFT(torch.nn.Module):
     spec = self._complex(input_data)
     return spec.abs(), torch.atan2(spec.imag, spec.real)        # stft.py:155-159
 
-  def inverse(self, magnitude: torch.Tensor, phase: torch.Tensor) -> torch.Tensor:
-    spec = torch.complex(magnitude * torch.cos(phase), magnitude * torch.sin(phase))   # stft.py:164-165
+  def inverse_complex(self, spec: torch.Tensor) -> torch.Tensor:
     out = torch.istft(spec, n_fft=self.filter_length, hop_length=self.hop_length, win_length=self.win_length,
                       window=self.window, center=True, normalized=False, onesided=True)
     return out.unsqueeze(1)                                      # the reference returns [B, 1, n]
+
+  def inverse(self, magnitude: torch.Tensor, phase: torch.Tensor) -> torch.Tensor:
+    return self.inverse_complex(torch.complex(magnitude * torch.cos(phase), magnitude * torch.sin(phase)))   # stft.py:164-165
 
   def forward(self, input_data: torch.Tensor) -> torch.Tensor:
     return self.inverse(*self.transform(input_data))
@@ -72,10 +74,15 @@ class Denoiser(torch.nn.Module):
     self.register_buffer("bias_spec", bias_spec[:, :, 0][:, :, None])
 
   def forward(self, audio: torch.Tensor, strength: float) -> torch.Tensor:
+    """denoiser.py:51-57.  The reference rebuilds the spectrum from clamp(|X| - strength * bias, 0) and the phase of X with
+    atan2 / cos / sin; that is the real scaling X * max(|X| - strength * bias, 0) / |X|, done here in place by ONE kernel
+    (`wg_denoise_spectrum`) between the two cuFFT transforms: no magnitude / phase / cos / sin tensors, no transcendentals."""
     audio = audio.to(self.device)
     spec = self.stft._complex(audio)
+    if spec.is_cuda:
+      from .engine import denoise_spectrum_
+      return self.stft.inverse_complex(denoise_spectrum_(spec, self.bias_spec.reshape(-1), strength))
+    # host tensors (the CPU tests that pin this arithmetic to the reference's golden vectors): the same scaling with torch ops
     mag = spec.abs()
-    # clamp(|X| - strength * bias, 0) with the phase of X  ==  X * max(0, 1 - strength * bias / |X|)
-    denoised = torch.clamp(mag - self.bias_spec * strength, min=0.0)
-    phase = torch.atan2(spec.imag, spec.real)
-    return self.stft.inverse(denoised, phase)
+    scale = torch.where(mag > 0, torch.clamp(mag - self.bias_spec * strength, min=0.0) / mag.clamp_min(1e-30), torch.zeros_like(mag))
+    return self.stft.inverse_complex(spec * scale)

@@ -19,7 +19,7 @@ PRECISION_FP16 = 1
 EXPORTED_SYMBOLS = [
   "wg_create", "wg_load_weights", "wg_save_packed", "wg_load_packed", "wg_workspace_bytes", "wg_infer", "wg_forward", "wg_last_launch_count",
   "wg_debug_stop_after", "wg_debug_view", "wg_debug_gemm", "wg_debug_gemm2", "wg_debug_timeline", "wg_set_profiling", "wg_profile_layers", "wg_last_error", "wg_version",
-  "wg_destroy",
+  "wg_destroy", "wg_denoise_spectrum",
 ]
 
 
@@ -88,8 +88,31 @@ def load_library() -> ctypes.CDLL:
   lib.wg_version.restype = ctypes.c_char_p
   lib.wg_destroy.argtypes = [vp]
   lib.wg_destroy.restype = None
+  lib.wg_denoise_spectrum.argtypes = [vp, vp, f32, i32, i32, i32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, i32, vp]
+  lib.wg_denoise_spectrum.restype = ctypes.c_int
   _lib = lib
   return lib
+
+
+def denoise_spectrum_(spec: torch.Tensor, bias: torch.Tensor, strength: float) -> torch.Tensor:
+  """In place: spec[b, f, t] *= max(|spec| - strength * bias[f], 0) / |spec| (0 where |spec| == 0) -- the arithmetic of the
+  reference's Denoiser.forward between its two STFTs (denoiser.py:51-57) as ONE kernel.  spec: complex64 [B, n_freq, n_frames]
+  on a CUDA device, any strides (the view torch.stft returns is used as it is); bias: fp32 [n_freq] on the same device."""
+  if spec.dtype != torch.complex64 or spec.dim() != 3 or not spec.is_cuda:
+    raise WgError("denoise_spectrum_ needs a complex64 [B, n_freq, n_frames] tensor on a CUDA device (no CPU fallback)")
+  bias = bias.reshape(-1)
+  if bias.dtype != torch.float32 or bias.device != spec.device or bias.numel() != spec.size(1) or not bias.is_contiguous():
+    raise WgError(f"bias must be a contiguous fp32 [{spec.size(1)}] tensor on {spec.device}")
+  sb, sf, st = spec.stride()
+  if sf <= 0 or st <= 0 or sb < 0:
+    raise WgError("spec must have positive frequency / frame strides")
+  lib = load_library()
+  stream = torch.cuda.current_stream(spec.device).cuda_stream
+  rc = lib.wg_denoise_spectrum(spec.data_ptr(), bias.data_ptr(), float(strength), spec.size(0), spec.size(1), spec.size(2),
+                               sb, sf, st, spec.device.index, stream)
+  if rc != 0:
+    raise WgError(f"wg_denoise_spectrum failed ({rc})")
+  return spec
 
 
 class Engine:

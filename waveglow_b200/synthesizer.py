@@ -97,8 +97,13 @@ class Synthesizer():
         audio_denoised = self.denoiser(audio, strength=denoiser_strength)
         self._sync()
         denoising_duration = time.perf_counter() - start_denoising
-    audio_np: np.ndarray = audio.squeeze().cpu().numpy()
-    audio_denoised_np: np.ndarray = audio_denoised.squeeze().cpu().numpy()
+    # ONE device -> host copy for both wavs (the reference does two, synthesizer.py:69-70)
+    if audio_denoised is audio:
+      audio_np: np.ndarray = audio.squeeze().cpu().numpy()
+      audio_denoised_np: np.ndarray = audio_np
+    else:
+      both = torch.stack([audio.squeeze(), audio_denoised.squeeze()]).cpu().numpy()
+      audio_np, audio_denoised_np = both[0], both[1]
     was_overamplified = False
     if is_overamp(audio_np):
       was_overamplified = True
