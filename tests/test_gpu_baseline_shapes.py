@@ -34,15 +34,27 @@ def check_decimated(g, out: torch.Tensor, tol: float, what: str):
   return worst, snr
 
 
-@pytest.mark.parametrize("name,precision", [
-  ("large_infer_c256_b2_f861", "fp16"),       # configs[1]: utterances 0, 1 of the bench batch (same seeds as bench.py)
-  ("large_infer_c256_b2_f861", "fp32"),
-  ("large_infer_c256_b1_f5168", "fp16"),      # configs[3]: 60 s single utterance
-  ("large_infer_c512_b1_f140", "fp16"),       # configs[2] architecture, one whole tile + packed tail
-  ("large_infer_c512_b1_f140", "fp32"),
-  ("large_infer_c512_b2_f300", "fp16"),       # ... multi-tile
+_ORACLE = {}
+
+
+def live_oracle(name, w, dims, mel, sigma, zs):
+  """The CPU oracle at this shape, computed once per case (both precisions compare with it)."""
+  if name not in _ORACLE:
+    with torch.no_grad():
+      _ORACLE[name] = O.infer(w, dims, mel, sigma, zs)
+  return _ORACLE[name]
+
+
+@pytest.mark.parametrize("name,precision,live", [
+  ("large_infer_c256_b2_f861", "fp16", True),        # configs[1]: two utterances at the headline length
+  ("large_infer_c256_b2_f861", "fp32", True),
+  ("large_infer_c256_b1_f5168", "fp16", False),      # configs[3]: 60 s single utterance (the oracle needs minutes and ~10 GB here:
+  ("large_infer_c256_b1_f5168", "fp32", False),      #   the committed vectors of the unmodified reference are the check)
+  ("large_infer_c512_b1_f140", "fp16", False),       # configs[2] architecture, one whole tile + packed tail
+  ("large_infer_c512_b1_f140", "fp32", False),
+  ("large_infer_c512_b2_f300", "fp16", True),        # ... multi-tile
 ])
-def test_infer_at_baseline_shapes_vs_oracle_and_reference_golden(name, precision):
+def test_infer_at_baseline_shapes_vs_oracle_and_reference_golden(name, precision, live):
   g = load_golden(name)
   nc, B, F = int(g["n_channels"]), int(g["batch"]), int(g["frames"])
   hp, sd, w, dims = synthetic_weights(nc)
@@ -53,17 +65,18 @@ def test_infer_at_baseline_shapes_vs_oracle_and_reference_golden(name, precision
   assert out.shape == (B, F * 256) and torch.isfinite(out).all()
   tol = FP32_MAX_ABS if precision == "fp32" else FP16_MAX_ABS
   _, snr_g = check_decimated(g, out, tol, f"{precision} {name}")
-  with torch.no_grad():
-    ref = O.infer(w, dims, mel, sigma, zs)
-  # the live oracle reproduces the committed reference vectors exactly (same torch CPU ops on the same inputs)
+  assert precision == "fp32" or snr_g >= FP16_MIN_SNR_DB
+  if not live:
+    return
+  ref = live_oracle(name, w, dims, mel, sigma, zs)
+  # the live oracle reproduces the committed reference vectors (same torch CPU ops on the same inputs) to fp32
+  # summation-order noise: the GPU box's host CPU blocks the convolutions differently from the build container's
   stride = int(g["stride"])
-  # (to fp32 summation-order noise: the GPU box's host CPU blocks the convolutions differently from the build container's)
   assert max_abs(torch.from_numpy(g["strided"]), ref[:, ::stride]) <= 1e-5
   err, snr = max_abs(ref, out), snr_db(ref, out)
   print(f"{precision} {name} vs oracle (full): max-abs {err:.3e}  snr {snr:.1f} dB  (ref absmax {float(ref.abs().max()):.2f})")
   assert err <= tol
-  if precision != "fp32":
-    assert snr >= FP16_MIN_SNR_DB and snr_g >= FP16_MIN_SNR_DB
+  assert precision == "fp32" or snr >= FP16_MIN_SNR_DB
 
 
 @pytest.mark.parametrize("nc,B,F", [(256, 16, 861), (512, 8, 861)])
@@ -80,10 +93,6 @@ def test_full_batch_fp16_engine_vs_fp32_engine(nc, B, F):
   per_utt = [(max_abs(b[i], a[i])) for i in range(B)]
   print(f"fp16 vs fp32 engine, {nc} ch, B{B} x F{F}: max-abs {err:.3e}  snr {snr:.1f} dB  (worst utterance {max(per_utt):.3e}, best {min(per_utt):.3e})")
   assert torch.isfinite(a).all() and err <= FP16_MAX_ABS and snr >= FP16_MIN_SNR_DB
-  if nc == 256:
-    # utterances 0 and 1 are the reference-golden case above
-    g = load_golden("large_infer_c256_b2_f861")
-    check_decimated(g, a[:2], FP16_MAX_ABS, "fp16 full batch, utterances 0-1")
 
 
 @pytest.mark.parametrize("precision", ["fp16", "fp32"])

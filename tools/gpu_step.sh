@@ -9,9 +9,9 @@ for step in "$@"; do
   case $step in
     quick256)  TAILN=15 run quick256 300 python -m pytest tests/test_gpu_parity.py -q -x -s -k "gemm or (stagewise and 256) or golden and not 512" ;;
     quick512)  TAILN=30 run quick512 300 python -m pytest tests/test_gpu_parity.py -q -x -s -k "(stagewise and 512) or 512_channel" ;;
-    tests)     TAILN=8 run tests 1500 python -m pytest tests -q -m gpu -x --timeout 900 ;;
-    tests_all) TAILN=25 run tests_all 1500 python -m pytest tests -q -m gpu --timeout 900 ;;
-    shapes)    TAILN=30 run shapes 1200 python -m pytest tests/test_gpu_baseline_shapes.py -q -s --timeout 900 ;;
+    tests)     TAILN=8 run tests 1500 python -m pytest tests -q -m gpu -x --timeout 600 --durations=12 ;;
+    tests_all) TAILN=25 run tests_all 1500 python -m pytest tests -q -m gpu --timeout 600 --durations=12 ;;
+    shapes)    TAILN=30 run shapes 1200 python -m pytest tests/test_gpu_baseline_shapes.py -q -s --timeout 600 --durations=12 ;;
     smoke)     TAILN=4 run smoke 300 python -c "import __graft_entry__ as g; g.smoke()" ;;
     flags)     for f in 0 1 4 8 16 128 29 0; do echo "WG_DBG_FLAGS=$f (256 ch, B16 x 861)"; WG_DBG_FLAGS=$f python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | python tools/bench_brief.py; done | tee $OUT/flags256.txt
                for f in 0 1 4 8 16 29 0; do echo "WG_DBG_FLAGS=$f (512 ch, B8 x 861)"; WG_DBG_FLAGS=$f python bench.py --channels 512 --batch 8 --steps 4 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | python tools/bench_brief.py; done | tee $OUT/flags512.txt ;;

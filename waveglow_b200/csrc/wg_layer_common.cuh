@@ -65,9 +65,17 @@ __device__ __forceinline__ void stamp(const LayerTcParams& p, int slot) {
   if (p.timeline) p.timeline[(static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 16 + slot] = clock64();
 }
 
+// tanh(a) * sigmoid(b) (model.py:13-20) from TWO exponentials and ONE reciprocal:
+//     tanh(a) = (u - 1) / (u + 1), u = e^(2a);  sigmoid(b) = 1 / (1 + v), v = e^(-b)   =>   (u - 1) / ((u + 1) (1 + v))
+// 3 MUFU operations (ex2.approx, ex2.approx, rcp.approx: relative error ~2^-22 each) per activation.  Round 1 used
+// tanh.approx.f32 twice (2 MUFU, relative error 2^-11 -- the size of the fp16 rounding of the result itself, and not
+// unbiased: at BASELINE shapes it put the 512-channel model at 2.09e-3 max-abs against the 2e-3 gate and a 2e-3 relative bias
+// on sum(log_s) of the forward direction, profiles/r02/gpu_tests_run4.txt).  |a| is clamped at 15 (tanh(15) = 1 - 2e-13: exact
+// in fp32) so that u stays finite; b needs no clamp: v = inf gives rcp(inf) = 0, v = 0 gives sigmoid = 1.
 __device__ __forceinline__ float gate_one(float a, float b) {
-  // tanh(a) * sigmoid(b), sigmoid(b) = 0.5 + 0.5 tanh(b/2)   (model.py:13-20)
-  return ptx::tanh_approx(a) * fmaf(0.5f, ptx::tanh_approx(0.5f * b), 0.5f);
+  const float u = ptx::ex2_approx(fminf(fmaxf(a, -15.f), 15.f) * 2.8853900817779268f);      // e^(2a) = 2^(2a log2 e)
+  const float v = ptx::ex2_approx(b * -1.4426950408889634f);                                // e^(-b)
+  return (u - 1.f) * ptx::rcp_approx(fmaf(u, v, u) + v + 1.f);                              // (u + 1)(1 + v) = uv + u + v + 1
 }
 
 // Gate of one 256-column accumulator chunk ([tanh 128 | sigmoid 128], model.py:13-20) for SIXTEEN epilogue warps: column
