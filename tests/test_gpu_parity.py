@@ -22,7 +22,8 @@ def get_model(n_channels: int, precision: str, style: str = "parametrized") -> W
   """precision: "fp32", "fp16" (the tensor-core path: fused layer on CTA pairs, continuous-issue schedule; 256 and 512
   channels run the same templated kernel), or the fp16 engine with one of its switches set: "fp16-seg32" / "fp16-seg64"
   (WG_SEG) force the segment size of the tiles; "fp16-nopack" (WG_PACK4=0) switches the packed ragged tails off and
-  "fp16-nofirst" (WG_FIRST=0) the composition of the start conv into each flow's first layer."""
+  "fp16-nofirst" (WG_FIRST=0) the composition of the start conv into each flow's first layer, "fp16-nochain" (WG_CHAIN=0) the
+  chaining of a flow's generic layers into one launch with tile-level dependencies (one launch per layer instead)."""
   import os
   key = (n_channels, precision, style)
   if key not in _MODELS:
@@ -36,12 +37,15 @@ def get_model(n_channels: int, precision: str, style: str = "parametrized") -> W
       os.environ["WG_PACK4"] = "0"
     if precision == "fp16-nofirst":
       os.environ["WG_FIRST"] = "0"
+    if precision == "fp16-nochain":
+      os.environ["WG_CHAIN"] = "0"
     try:
       m.engine()          # the engine reads its switches when it is created
     finally:
       os.environ.pop("WG_SEG", None)
       os.environ.pop("WG_PACK4", None)
       os.environ.pop("WG_FIRST", None)
+      os.environ.pop("WG_CHAIN", None)
     _MODELS[key] = m
   return _MODELS[key]
 
@@ -148,8 +152,7 @@ def test_stagewise_first_flow(precision, nc):
       lt = flow_tr["layers"][i]
       check(f"e after layer {i}", eng.debug_view("e", B, F).view(B, T, 8).cpu()[..., : 2 * pf.h], lt["e"])
       if i < dims.n_layers - 1:
-        buf = "x1" if (i + 1) % 2 == 1 else "x0"
-        check(f"x after layer {i}", x_view(buf), lt["x"])
+        check(f"x after layer {i}", x_view(f"x{i + 1}"), lt["x"])      # the buffer layer i + 1 reads
     eng.debug_stop_after(k, dims.n_layers)
     state = run(model, mel, zs, sigma).view(B, T, 8)
     check("state after first flow", state, flow_tr["state"], t=tol)
@@ -196,6 +199,24 @@ def test_512_channel_tensor_core_path_matches_reference_golden(mode):
   err, snr = max_abs(ref, out), snr_db(ref, out)
   print(f"512 channels {mode}: max-abs {err:.3e}  snr {snr:.1f} dB")
   assert out.shape == ref.shape and err <= FP16_MAX_ABS and snr >= FP16_MIN_SNR_DB
+
+
+@pytest.mark.parametrize("nc,B,F", [(256, 1, 200), (256, 6, 140), (256, 3, 861), (256, 9, 40), (256, 1, 5), (512, 1, 200), (512, 5, 300)])
+def test_chained_layers_equal_one_launch_per_layer(nc, B, F):
+  """The generic layers of a flow run as ONE launch whose tiles wait only for the tiles of the previous layer that produced
+  their tap windows (completion counters in global memory, polled by the TMA warp).  Per tile the arithmetic is the one of
+  the per-layer launches (WG_CHAIN=0), so the audio must be BIT-IDENTICAL: any dependency missed (a tile reading x or e rows
+  before they were written) shows up here.  Shapes: config 1 (one short utterance: 64 pair-tiles on 74 CTA pairs, consecutive
+  items of a pair depend on each other), packed tails with missing utterances, the headline length, no whole block at all, a
+  single 5-frame tile, and 512 channels (two x' halves).  Run three times: the schedule is timing dependent."""
+  hp, sd, w, dims = synthetic_weights(nc)
+  mel = synthetic_mel(B, F, 800 + F)
+  zs = synthetic_noise(hp, B, F * 32, 801 + F)
+  ref = run(get_model(nc, "fp16-nochain"), mel, zs, 0.666)
+  assert torch.isfinite(ref).all()
+  for rep in range(3):
+    out = run(get_model(nc, "fp16"), mel, zs, 0.666)
+    assert torch.equal(out, ref), f"repetition {rep}: max-abs {max_abs(ref, out):.3e}"
 
 
 @pytest.mark.parametrize("mode", ["fp16-seg32", "fp16-seg64"])

@@ -65,6 +65,7 @@ struct wg_engine {
   bool trim_grid = false;             // WG_TRIM=1: smallest grid with the same number of tile rounds (measured 0.7 % SLOWER on
                                       // config 2 than letting all 74 pairs run, profiles/r01/ab_trim_g2at_v12.txt: off by default)
   bool pdl = true;                    // programmatic dependent launch between layer launches (WG_PDL=0 disables)
+  bool chain = true;                  // the generic layers of a flow in ONE launch with tile-level dependencies (WG_CHAIN=0: one launch per layer)
   bool pack4 = true;                  // pack the ragged last frames of 4 utterances into shared tiles (WG_PACK4=0 disables)
   void* d_wc = nullptr;               // [flows][3 taps x 2 nc packed rows + nc carry rows][16] 16-bit composed start weights
   CUtensorMap tm_wc{};                // 128-row boxes
@@ -292,7 +293,11 @@ struct WsLayout {
   int Tpad;                        // x rows per utterance: T rounded up to a multiple of 32 (phase view of the TMA maps)
   size_t state, sums;              // forward only: time-major state [B,T,8] fp32; double accumulators [n_flows]
   size_t a0;                       // start conv composed into the first layer: [B][32][Fq][16] 16-bit rows [a0 | 1]
-  size_t cond, x0, x1, e, total;   // cond: fp32 mode = upsampled conditioning S [B,T,640]; fp16 mode = mel windows MW [B,Fq,320]
+  size_t cond, e, total;           // cond: fp32 mode = upsampled conditioning S [B,T,640]; fp16 mode = mel windows MW [B,Fq,320]
+  size_t x[16];                    // residual stream buffers.  Tensor-core mode: one per layer (layer i reads x[i], writes x[i + 1]:
+  int n_x;                         // chained launches have no write-after-read hazards); fp32 mode: 2, ping-pong
+  size_t flags, flags_bytes;       // tensor-core mode: completion counters of chained launches [n_flows][n_layers][pair-tiles] uint32
+  int ptiles_cap;                  // pair-tiles the flags of one layer are sized for
   size_t cond_bytes;
   size_t elt;   // operand element size
 };
@@ -309,10 +314,17 @@ WsLayout ws_layout(const wg_engine* e, int B, int T) {
                      ? npos * kCond * L.elt
                      : static_cast<size_t>(B) * ((T + kUpPhases - 1) / kUpPhases) * kUpKdim * L.elt;
   off = align_up(off + L.cond_bytes, 1024);
-  L.x0 = off;
-  off = align_up(off + nppos * e->cfg.n_channels * L.elt, 1024);
-  L.x1 = off;
-  off = align_up(off + nppos * e->cfg.n_channels * L.elt, 1024);
+  L.n_x = e->cfg.precision == WG_PRECISION_FP16 ? e->cfg.n_layers : 2;
+  for (int i = 0; i < L.n_x; ++i) {
+    L.x[i] = off;
+    off = align_up(off + nppos * e->cfg.n_channels * L.elt, 1024);
+  }
+  // most pair-tiles any tile mode can make of this shape: 32-frame segments
+  L.ptiles_cap = kUpPhases * ((B * ((L.Tpad / kUpPhases + 31) / 32) + 1) / 2 + 1);
+  L.flags = off;
+  L.flags_bytes = e->cfg.precision == WG_PRECISION_FP16
+                      ? static_cast<size_t>(e->cfg.n_flows) * e->cfg.n_layers * L.ptiles_cap * sizeof(uint32_t) : 0;
+  off = align_up(off + L.flags_bytes, 1024);
   L.e = off;
   off = align_up(off + npos * kGroup * sizeof(float), 1024);
   L.state = off;
@@ -329,9 +341,9 @@ int frames_to_T(int frames) { return frames * kUpStride / kGroup; }
 
 // The fused layer kernel is a template over everything that selects code (channel count, ring stage width, first layer of a
 // flow, tile mode).
-using LayerKernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+using LayerKernel = void (*)(const XMaps, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                              const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
-                             const CUtensorMap, const LayerTcParams);
+                             const LayerTcParams);
 
 template <int NC, int KS>
 LayerKernel layer_kernel_nk(int first, int mode) {
@@ -453,6 +465,8 @@ int wg_create(const wg_config* cfg, wg_engine** out) {
   e->trim_grid = trim_env && atoi(trim_env) != 0;
   const char* pdl_env = getenv("WG_PDL");
   e->pdl = !(pdl_env && atoi(pdl_env) == 0);
+  const char* chain_env = getenv("WG_CHAIN");
+  e->chain = !(chain_env && atoi(chain_env) == 0);
   const char* pack_env = getenv("WG_PACK4");
   e->pack4 = !(pack_env && atoi(pack_env) == 0);
   const char* seg_env = getenv("WG_SEG");
@@ -749,11 +763,11 @@ int wg_debug_view(const wg_engine* e, const char* name, int32_t batch, int32_t f
   if (!strcmp(name, "cond")) {
     *ptr = base + L.cond;
     *bytes = L.cond_bytes;
-  } else if (!strcmp(name, "x0")) {
-    *ptr = base + L.x0;
-    *bytes = static_cast<size_t>(batch) * L.Tpad * e->cfg.n_channels * L.elt;
-  } else if (!strcmp(name, "x1")) {
-    *ptr = base + L.x1;
+  } else if (name[0] == 'x' && name[1] >= '0' && name[1] <= '9') {
+    // "x<i>": the residual stream that layer i READS (layer i - 1 wrote it).  fp32 mode ping-pongs two buffers.
+    const int i = atoi(name + 1);
+    if (i < 0 || i >= e->cfg.n_layers) return WG_ERR_INVALID_ARGUMENT;
+    *ptr = base + L.x[i % L.n_x];
     *bytes = static_cast<size_t>(batch) * L.Tpad * e->cfg.n_channels * L.elt;
   } else if (!strcmp(name, "a0") && e->first_comp) {
     *ptr = base + L.a0;
@@ -1021,14 +1035,21 @@ void flow_step_any(wg_engine* e, const FlowStepParams& fs_in, float* state, cons
   e->launches++;
 }
 
-// Runs the WN layers of flow k.  x buffers alternate; returns the index of the buffer holding the
-// current residual stream through *cur.  Returns 1 if the debug stop triggered.
-int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout& L, const CUtensorMap* tm_x,
-                  const CUtensorMap* tm_cond, const CUtensorMap* tm_a0, const CUtensorMap* tm_p4, int* cur, cudaStream_t st,
+// Tensor maps over the caller's workspace for one call (tensor-core mode), per box height idx (0: 128 rows, 1: 64, 2: 32):
+// x3[idx][i] = x buffer i as {nc, Fq, 32 B}; mw[idx] = mel windows; a0[idx] = [a0 | 1] rows; and the 4-D views of the packed
+// ragged tails (32 frames x 4 utterances per box): x4[i], mw4, a04.
+struct ActMaps {
+  CUtensorMap x3[3][16], mw[3], a0[3];
+  CUtensorMap x4[16], mw4, a04;
+};
+
+// Runs the WN layers of flow k.  Tensor-core mode: layer i reads x buffer i and writes x buffer i + 1 (the flow step has written
+// buffer 0, or the [a0 | 1] rows when the start conv is composed into the first layer); fp32 mode: two buffers alternate and *cur
+// is the one holding the current residual stream.  *stopped is set if the debug stop triggered.
+int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout& L, const ActMaps* am, int* cur, cudaStream_t st,
                   bool* stopped) {
   const int nc = e->cfg.n_channels, NL = e->cfg.n_layers;
   const bool tc = e->cfg.precision == WG_PRECISION_FP16;
-  void* xb[2] = {ws + L.x0, ws + L.x1};
   float* ebuf = reinterpret_cast<float*>(ws + L.e);
   *stopped = false;
   if (e->ev.size() < static_cast<size_t>(2 * e->cfg.n_flows)) {
@@ -1045,75 +1066,102 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
       e->ev_flows++;
     }
   } record_end{e, st};
-  for (int i = 0; i < NL; ++i) {
-    const size_t li = static_cast<size_t>(k) * NL + i;
-    const int has_res = i < NL - 1;
-    if (tc) {
+  const int stop_layer = e->dbg_flow == k ? e->dbg_layer : NL;      // debug: the last layer to run (>= NL: all)
+
+  if (tc) {
+    const int Fq = L.Tpad / kUpPhases;
+    // Which rows share a tile (the same for every layer of the flow).  Default: 128 consecutive frames of one utterance per tile
+    // (one TMA box per operand).  Tiles built from 64- or 32-frame SEGMENTS (one box each; a tile may span utterances) cost tile
+    // time (measured on config 2: 4 x 32-row boxes per operand load = +5.4 % per tile), so a smaller segment is taken only when
+    // it saves clearly more pair-tiles than that (two whole 63-frame training segments per tile: -50 %).
+    static const double kBoxCost[3] = {1.0, 1.02, 1.06};
+    int best_pe = 0, best_idx = 0;
+    for (int idx = 0; idx < 3; ++idx) {
+      const int seg = kTileM >> idx;
+      const int n_entries = (B * ((Fq + seg - 1) / seg) + (1 << idx) - 1) >> idx;
+      const int n_pe = (n_entries + 1) / 2;
+      if (e->force_seg ? seg == e->force_seg : (idx == 0 || n_pe * kBoxCost[idx] < best_pe * kBoxCost[best_idx])) {
+        best_pe = n_pe;
+        best_idx = idx;
+      }
+    }
+    int mode = best_idx == 0 ? kTileBlocks : kTileSegments;
+    int n_full = 0, n_rem = 0;
+    // PACKED ragged tails: n_full whole 128-frame blocks per utterance, then the remaining frames of 4 consecutive
+    // utterances share tiles of 32 frames x 4 utterances (one 4-D TMA box per operand load, so no box cost)
+    if (e->pack4 && !e->force_seg) {
+      const int nf = Fq / kTileM, rem = Fq - nf * kTileM, nr = (rem + 31) / 32;
+      const int n_pe4 = (B * nf + ((B + 3) / 4) * nr + 1) / 2;
+      if (rem > 0 && n_pe4 < best_pe * kBoxCost[best_idx]) {
+        mode = kTilePacked;
+        n_full = nf;
+        n_rem = nr;
+        best_idx = 0;
+        best_pe = n_pe4;
+      }
+    }
+    const int n_ptiles = kPhases * best_pe;
+    if (n_ptiles > L.ptiles_cap) return fail(e, WG_ERR_WORKSPACE, "internal: %d pair-tiles exceed the flag capacity %d", n_ptiles, L.ptiles_cap);
+    int n_pairs = n_ptiles < e->num_sms / 2 ? n_ptiles : e->num_sms / 2;
+    if (e->trim_grid) {
+      // experiment: the smallest grid with the same number of tile rounds.  The power-capped clock did not pay it back.
+      const int rounds = (n_ptiles + n_pairs - 1) / n_pairs;
+      n_pairs = (n_ptiles + rounds - 1) / rounds;
+    }
+    auto desc = [&](int i) {
+      const size_t li = static_cast<size_t>(k) * NL + i;
+      LayerDesc d{};
+      d.dilation = 1 << i;
+      d.w1_row0 = static_cast<int>(li * 2 * nc);
+      d.v_row0 = static_cast<int>(li * kUpPhases * 2 * nc);
+      d.w2_row0 = static_cast<int>(li * (nc + 16));
+      d.has_res = i < NL - 1;
+      d.accumulate_e = i > 0;
+      d.bias1 = e->d_bias1 + li * 2 * nc;
+      d.bias_res = e->d_bias_res + li * nc;
+      d.wse = static_cast<const uint16_t*>(e->d_w2) + (li * (nc + 16) + nc) * nc;
+      d.x_out = ws + L.x[(i + 1) % L.n_x];
+      return d;
+    };
+    // one launch of layers [i0, i1)
+    auto launch = [&](int i0, int i1, bool first) -> int {
       LayerTcParams lp{};
       lp.T = T;
-      lp.Fq = L.Tpad / kUpPhases;
+      lp.Fq = Fq;
       lp.B = B;
-      lp.dilation = 1 << i;
-      lp.reverse = static_cast<int>(li & 1);
-      lp.w1_row0 = static_cast<int>(li * 2 * nc);
-      lp.v_row0 = static_cast<int>(li * kUpPhases * 2 * nc);
-      lp.w2_row0 = static_cast<int>(li * (nc + 16));
+      lp.seg_rows = kTileM >> best_idx;
+      lp.n_full = n_full;
+      lp.n_rem = n_rem;
       lp.wc_row0 = k * 7 * nc;
-      lp.has_res = has_res;
-      lp.accumulate_e = i > 0;
-      lp.bias1 = e->d_bias1 + li * 2 * nc;
-      lp.bias_res = e->d_bias_res + li * nc;
-      lp.wse = static_cast<const uint16_t*>(e->d_w2) + (li * (nc + 16) + nc) * nc;
-      lp.x_out = xb[*cur ^ 1];
       lp.e = ebuf;
       lp.timeline = e->dbg_timeline;
       lp.dbg_flags = e->dbg_flags;
-      lp.seg_rows = kTileM;
-      // Which rows share a tile.  Default: 128 consecutive frames of one utterance per tile (one TMA box per operand).  Tiles
-      // built from 64- or 32-frame SEGMENTS (one box each; a tile may span utterances) cost tile time (measured on config 2:
-      // 4 x 32-row boxes per operand load = +5.4 % per tile), so a smaller segment is taken only when it saves clearly more
-      // pair-tiles than that (two whole 63-frame training segments per tile: -50 %; 40-frame utterances as 2 x 32: -20 %).
-      static const double kBoxCost[3] = {1.0, 1.02, 1.06};
-      int best_pe = 0, best_idx = 0;
-      for (int idx = 0; idx < 3; ++idx) {
-        const int seg = kTileM >> idx;
-        const int n_entries = (B * ((lp.Fq + seg - 1) / seg) + (1 << idx) - 1) >> idx;
-        const int n_pe = (n_entries + 1) / 2;
-        if (e->force_seg ? seg == e->force_seg : (idx == 0 || n_pe * kBoxCost[idx] < best_pe * kBoxCost[best_idx])) {
-          best_pe = n_pe;
-          best_idx = idx;
-        }
+      lp.n_layers = i1 - i0;
+      // single-layer launches alternate the direction of the tile walk: the tail of the previous layer's x' is still in L2
+      lp.reverse = lp.n_layers == 1 ? static_cast<int>((static_cast<size_t>(k) * NL + i0) & 1) : 0;
+      lp.flags = reinterpret_cast<uint32_t*>(ws + L.flags) + static_cast<size_t>(k) * NL * L.ptiles_cap + static_cast<size_t>(i0) * n_ptiles;
+      XMaps xm{};
+      for (int j = 0; j < lp.n_layers; ++j) {
+        lp.ly[j] = desc(i0 + j);
+        lp.ly[j].x_in = j;
+        xm.m3[j] = am->x3[best_idx][i0 + j];
+        xm.m4[j] = am->x4[i0 + j];
       }
-      int mode = best_idx == 0 ? kTileBlocks : kTileSegments;
-      lp.seg_rows = kTileM >> best_idx;
-      // PACKED ragged tails: n_full whole 128-frame blocks per utterance, then the remaining frames of 4 consecutive
-      // utterances share tiles of 32 frames x 4 utterances (one 4-D TMA box per operand load, so no box cost)
-      if (e->pack4 && !e->force_seg) {
-        const int n_full = lp.Fq / kTileM, rem = lp.Fq - n_full * kTileM, n_rem = (rem + 31) / 32;
-        const int n_pe4 = (B * n_full + ((B + 3) / 4) * n_rem + 1) / 2;
-        if (rem > 0 && n_pe4 < best_pe * kBoxCost[best_idx]) {
-          mode = kTilePacked;
-          lp.n_full = n_full;
-          lp.n_rem = n_rem;
-          lp.seg_rows = kTileM;
-          best_idx = 0;
-          best_pe = n_pe4;
-        }
+      for (int j = lp.n_layers; j < kMaxLayersPerLaunch; ++j) {      // unused slots: valid maps, never dereferenced
+        xm.m3[j] = xm.m3[0];
+        xm.m4[j] = xm.m4[0];
       }
-      const int n_ptiles = kPhases * best_pe;
-      int n_pairs = n_ptiles < e->num_sms / 2 ? n_ptiles : e->num_sms / 2;
-      if (e->trim_grid) {
-        // experiment: the launch lasts ceil(tiles / pairs) rounds of tiles; the smallest grid with the same number of
-        // rounds leaves the other SMs idle instead of half-used.  The power-capped clock did not pay it back.
-        const int rounds = (n_ptiles + n_pairs - 1) / n_pairs;
-        n_pairs = (n_ptiles + rounds - 1) / rounds;
-      }
-      const int first = (e->first_comp && i == 0 && has_res) ? 1 : 0;
       for (int h = 0; h < kMaxHalves; ++h) lp.g2_at[h] = first ? e->g2_at_first[h] : e->g2_at[h];
-      const CUtensorMap* seg_maps = tm_x + (best_idx == 0 ? 0 : (best_idx == 1 ? 3 : 6));      // {x0, x1, mel windows} per box height
-      const CUtensorMap& tm_mw_seg = best_idx == 0 ? *tm_cond : seg_maps[2];
+      if (lp.n_layers > 1 && n_ptiles < 160) {
+        // chained launch on a small shape: consecutive work items of a CTA pair can depend on each other (item w and item
+        // w + pairs are the same rows one or two layers apart), so GEMM2 of the previous item must be loaded BEFORE the TMA warp
+        // polls the flags of the next item's tap windows (at the first stage after the mel-window stages)
+        const int mw_stages = kMwK / e->ks;
+        for (int h = 0; h < kMaxHalves; ++h)
+          if (lp.g2_at[h] > mw_stages) lp.g2_at[h] = mw_stages;
+      }
       // programmatic dependent launch: this grid's CTAs may start their prologue and conditioning K-blocks while the
-      // previous layer's last tiles drain (griddepcontrol.wait in the kernel guards every dependent access)
+      // previous launch's last tiles drain (griddepcontrol.wait in the kernel guards every dependent access)
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(2 * n_pairs);
       cfg.blockDim = dim3(kContThreads);
@@ -1124,9 +1172,36 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
       attr[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr;
       cfg.numAttrs = e->pdl ? 1 : 0;
-      WG_CUDA(e, cudaLaunchKernelEx(&cfg, layer_kernel(nc, e->ks, first, mode), seg_maps[*cur], tm_mw_seg, e->tm_w1h, e->tm_vh, e->tm_w2h,
-                                    e->tm_ident16, tm_a0[best_idx], e->tm_wc, tm_p4[*cur], tm_p4[2], tm_p4[3], lp));
-    } else {
+      WG_CUDA(e, cudaLaunchKernelEx(&cfg, layer_kernel(nc, e->ks, first ? 1 : 0, mode), xm, am->mw[best_idx], e->tm_w1h, e->tm_vh,
+                                    e->tm_w2h, e->tm_ident16, am->a0[best_idx], e->tm_wc, am->mw4, am->a04, lp));
+      e->launches++;
+      return WG_OK;
+    };
+    const int last = stop_layer < NL - 1 ? stop_layer : NL - 1;      // last layer to run
+    int rc;
+    int i = 0;
+    if (last < 0) return WG_OK;
+    if (e->first_comp) {
+      if ((rc = launch(0, 1, true))) return rc;
+      i = 1;
+    }
+    // the generic layers: chained in one launch when the tile mode has tile-level dependencies (blocks / packed) and the
+    // dilations keep a tap window within two entries; else one launch per layer
+    const bool chain = e->chain && mode != kTileSegments && NL <= kMaxLayersPerLaunch;
+    while (i <= last) {
+      const int i1 = chain ? last + 1 : i + 1;
+      if ((rc = launch(i, i1, false))) return rc;
+      i = i1;
+    }
+    if (stop_layer < NL) *stopped = true;
+    return WG_OK;
+  }
+
+  void* xb[2] = {ws + L.x[0], ws + L.x[1]};
+  for (int i = 0; i < NL; ++i) {
+    const size_t li = static_cast<size_t>(k) * NL + i;
+    const int has_res = i < NL - 1;
+    {
       LayerF32Params lp{};
       lp.T = T;
       lp.Tpad = L.Tpad;
@@ -1176,68 +1251,52 @@ void launch_conditioning(wg_engine* e, const float* mel, int B, int frames, int 
   e->launches++;
 }
 
-int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, CUtensorMap* tm_x, CUtensorMap* tm_cond,
-                  CUtensorMap* tm_a0, CUtensorMap* tm_p4) {
-  // tm_x[0], tm_x[1]: residual stream ping-pong, 128-row boxes; tm_x[2]: unused;
-  // tm_x[3], tm_x[4]: the ping-pong buffers again with 64-row boxes, tm_x[5]: mel windows with 64-row boxes;
-  // tm_x[6], tm_x[7], tm_x[8]: the same three with 32-row boxes (segment tiles)
+int make_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, ActMaps* am) {
   const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const int nc = e->cfg.n_channels;
   const uint32_t ks = static_cast<uint32_t>(e->ks);
   int rc;
   const int Fq = L.Tpad / kUpPhases;
+  const uint32_t rows[3] = {static_cast<uint32_t>(kTileM), 64, 32};
+  const uint32_t box4[4] = {ks, 32, 1, 4};
   {
     // phase-major residual stream x[B][phase][frame][nc]: group-step t = 32 * frame + phase; frames outside [0, Fq) read as zero
     const uint64_t dims[3] = {static_cast<uint64_t>(nc), static_cast<uint64_t>(Fq), static_cast<uint64_t>(B) * kUpPhases};
     const uint64_t str[2] = {static_cast<uint64_t>(nc) * 2, static_cast<uint64_t>(nc) * 2 * Fq};
-    const uint32_t box[3] = {ks, static_cast<uint32_t>(kTileM), 1};
-    if ((rc = make_map(e, &tm_x[0], ws + L.x0, 3, dims, str, box, dt))) return rc;
-    if ((rc = make_map(e, &tm_x[1], ws + L.x1, 3, dims, str, box, dt))) return rc;
-    tm_x[2] = tm_x[0];
-    const uint32_t box64[3] = {ks, 64, 1}, box32[3] = {ks, 32, 1};
-    if ((rc = make_map(e, &tm_x[3], ws + L.x0, 3, dims, str, box64, dt))) return rc;
-    if ((rc = make_map(e, &tm_x[4], ws + L.x1, 3, dims, str, box64, dt))) return rc;
-    if ((rc = make_map(e, &tm_x[6], ws + L.x0, 3, dims, str, box32, dt))) return rc;
-    if ((rc = make_map(e, &tm_x[7], ws + L.x1, 3, dims, str, box32, dt))) return rc;
+    const uint64_t dims4[4] = {static_cast<uint64_t>(nc), static_cast<uint64_t>(Fq), kUpPhases, static_cast<uint64_t>(B)};
+    const uint64_t str4[3] = {static_cast<uint64_t>(nc) * 2, static_cast<uint64_t>(nc) * 2 * Fq, static_cast<uint64_t>(nc) * 2 * Fq * kUpPhases};
+    for (int i = 0; i < L.n_x; ++i) {
+      for (int idx = 0; idx < 3; ++idx) {
+        const uint32_t box[3] = {ks, rows[idx], 1};
+        if ((rc = make_map(e, &am->x3[idx][i], ws + L.x[i], 3, dims, str, box, dt))) return rc;
+      }
+      if ((rc = make_map(e, &am->x4[i], ws + L.x[i], 4, dims4, str4, box4, dt))) return rc;
+    }
   }
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(kUpKdim), static_cast<uint64_t>(Fq), static_cast<uint64_t>(B)};
     const uint64_t str[2] = {static_cast<uint64_t>(kUpKdim) * 2, static_cast<uint64_t>(kUpKdim) * 2 * Fq};
-    const uint32_t box[3] = {ks, static_cast<uint32_t>(kTileM), 1};
-    if ((rc = make_map(e, tm_cond, ws + L.cond, 3, dims, str, box, dt))) return rc;
-    const uint32_t box64[3] = {ks, 64, 1}, box32[3] = {ks, 32, 1};
-    if ((rc = make_map(e, &tm_x[5], ws + L.cond, 3, dims, str, box64, dt))) return rc;
-    if ((rc = make_map(e, &tm_x[8], ws + L.cond, 3, dims, str, box32, dt))) return rc;
-  }
-  {
-    // packed ragged tails: 32 frames x 4 consecutive utterances per box.  tm_p4[0], [1]: x ping-pong as {nc, Fq, 32 phases, B};
-    // [2]: mel windows; [3]: [a0 | 1] rows
-    const uint64_t dims[4] = {static_cast<uint64_t>(nc), static_cast<uint64_t>(Fq), kUpPhases, static_cast<uint64_t>(B)};
-    const uint64_t str[3] = {static_cast<uint64_t>(nc) * 2, static_cast<uint64_t>(nc) * 2 * Fq, static_cast<uint64_t>(nc) * 2 * Fq * kUpPhases};
-    const uint32_t box[4] = {ks, 32, 1, 4};
-    if ((rc = make_map(e, &tm_p4[0], ws + L.x0, 4, dims, str, box, dt))) return rc;
-    if ((rc = make_map(e, &tm_p4[1], ws + L.x1, 4, dims, str, box, dt))) return rc;
-    const uint64_t mdims[3] = {static_cast<uint64_t>(kUpKdim), static_cast<uint64_t>(Fq), static_cast<uint64_t>(B)};
-    const uint64_t mstr[2] = {static_cast<uint64_t>(kUpKdim) * 2, static_cast<uint64_t>(kUpKdim) * 2 * Fq};
-    const uint32_t mbox[3] = {ks, 32, 4};
-    if ((rc = make_map(e, &tm_p4[2], ws + L.cond, 3, mdims, mstr, mbox, dt))) return rc;
-    tm_p4[3] = tm_p4[2];      // placeholders (never dereferenced) without the first-layer composition
-    tm_p4[4] = tm_p4[0];
-    if (e->first_comp) {
-      const uint64_t adims[4] = {16, static_cast<uint64_t>(Fq), kUpPhases, static_cast<uint64_t>(B)};
-      const uint64_t astr[3] = {32, static_cast<uint64_t>(32) * Fq, static_cast<uint64_t>(32) * Fq * kUpPhases};
-      if ((rc = make_map(e, &tm_p4[3], ws + L.a0, 4, adims, astr, box, dt))) return rc;
+    for (int idx = 0; idx < 3; ++idx) {
+      const uint32_t box[3] = {ks, rows[idx], 1};
+      if ((rc = make_map(e, &am->mw[idx], ws + L.cond, 3, dims, str, box, dt))) return rc;
     }
+    const uint32_t mbox[3] = {ks, 32, 4};
+    if ((rc = make_map(e, &am->mw4, ws + L.cond, 3, dims, str, mbox, dt))) return rc;
   }
-  for (int idx = 0; idx < 3; ++idx) tm_a0[idx] = tm_x[0];      // placeholders without the first-layer composition
+  // without the first-layer composition these are placeholders (valid maps, never dereferenced)
+  for (int idx = 0; idx < 3; ++idx) am->a0[idx] = am->x3[idx][0];
+  am->a04 = am->x4[0];
   if (e->first_comp) {
-    // [a0 | 1] rows of the composed first layer, phase-major like x; 16 real channels, the 64-wide boxes zero-fill the rest
+    // [a0 | 1] rows of the composed first layer, phase-major like x; 16 real channels, the boxes zero-fill the rest
     const uint64_t dims[3] = {16, static_cast<uint64_t>(Fq), static_cast<uint64_t>(B) * kUpPhases};
     const uint64_t str[2] = {32, static_cast<uint64_t>(32) * Fq};
     for (int idx = 0; idx < 3; ++idx) {
-      const uint32_t box[3] = {ks, static_cast<uint32_t>(kTileM >> idx), 1};
-      if ((rc = make_map(e, &tm_a0[idx], ws + L.a0, 3, dims, str, box, dt))) return rc;
+      const uint32_t box[3] = {ks, rows[idx], 1};
+      if ((rc = make_map(e, &am->a0[idx], ws + L.a0, 3, dims, str, box, dt))) return rc;
     }
+    const uint64_t adims[4] = {16, static_cast<uint64_t>(Fq), kUpPhases, static_cast<uint64_t>(B)};
+    const uint64_t astr[3] = {32, static_cast<uint64_t>(32) * Fq, static_cast<uint64_t>(32) * Fq * kUpPhases};
+    if ((rc = make_map(e, &am->a04, ws + L.a0, 4, adims, astr, box4, dt))) return rc;
   }
   return WG_OK;
 }
@@ -1288,15 +1347,16 @@ int wg_infer(wg_engine* e, const float* mel, int32_t batch, int32_t frames, cons
   }
   // 2. conditioning operand (mel windows in tensor-core mode, upsampled + squeezed mel in fp32 mode)
   launch_conditioning(e, mel, B, frames, T, ws, L, st);
-  CUtensorMap tm_x[9], tm_cond, tm_a0[3], tm_p4[5];
+  ActMaps am;
   if (tc) {
-    int rc = make_act_maps(e, ws, L, B, T, tm_x, &tm_cond, tm_a0, tm_p4);
+    int rc = make_act_maps(e, ws, L, B, T, &am);
     if (rc) return rc;
+    WG_CUDA(e, cudaMemsetAsync(ws + L.flags, 0, L.flags_bytes, st));      // completion counters of the chained layer launches
   }
   float* ebuf = reinterpret_cast<float*>(ws + L.e);
-  int cur = 0;
+  int cur = 0;      // fp32 mode: which of the two x buffers holds the residual stream; tensor-core mode: always 0 (layer 0 reads x[0])
   auto flow_step = [&](const FlowStepParams& fs, void* xdst) { flow_step_any(e, fs, audio, ebuf, xdst, B, T, L.Tpad, st); };
-  void* xb[2] = {ws + L.x0, ws + L.x1};
+  void* xb[2] = {ws + L.x[0], ws + L.x[1]};
   // 3. start conv of the first (last-indexed) flow
   {
     FlowStepParams fs{};
@@ -1313,7 +1373,7 @@ int wg_infer(wg_engine* e, const float* mel, int32_t batch, int32_t frames, cons
   }
   bool stopped = (e->dbg_flow == NF - 1 && e->dbg_layer == -1);
   for (int k = NF - 1; k >= 0 && !stopped; --k) {
-    int rc = run_wn_layers(e, k, B, T, ws, L, tm_x, &tm_cond, tm_a0, tm_p4, &cur, st, &stopped);
+    int rc = run_wn_layers(e, k, B, T, ws, L, &am, &cur, st, &stopped);
     if (rc) return rc;
     if (stopped) break;
     FlowStepParams fs{};
@@ -1396,13 +1456,14 @@ int wg_forward(wg_engine* e, const float* mel, int32_t batch, int32_t frames, co
   WG_CUDA(e, cudaMemcpyAsync(state, audio_in, npos * kGroup * sizeof(float), cudaMemcpyDeviceToDevice, st));
   WG_CUDA(e, cudaMemsetAsync(sums, 0, (NF + 1) * sizeof(double), st));
   launch_conditioning(e, mel, B, frames, T, ws, L, st);
-  CUtensorMap tm_x[9], tm_cond, tm_a0[3], tm_p4[5];
+  ActMaps am;
   if (tc) {
-    int rc = make_act_maps(e, ws, L, B, T, tm_x, &tm_cond, tm_a0, tm_p4);
+    int rc = make_act_maps(e, ws, L, B, T, &am);
     if (rc) return rc;
+    WG_CUDA(e, cudaMemsetAsync(ws + L.flags, 0, L.flags_bytes, st));
   }
   float* ebuf = reinterpret_cast<float*>(ws + L.e);
-  void* xb[2] = {ws + L.x0, ws + L.x1};
+  void* xb[2] = {ws + L.x[0], ws + L.x[1]};
   int cur = 0;
   // flows run k = 0 .. NF-1; early outputs (model.py:201-203) simply stop being "live": the state keeps them in place
   for (int k = 0; k <= NF; ++k) {
@@ -1431,7 +1492,7 @@ int wg_forward(wg_engine* e, const float* mel, int32_t batch, int32_t frames, co
     flow_step_any(e, fs, state, ebuf, xb[cur], B, T, L.Tpad, st);
     if (k == NF) break;
     bool stopped = false;
-    int rc = run_wn_layers(e, k, B, T, ws, L, tm_x, &tm_cond, tm_a0, tm_p4, &cur, st, &stopped);
+    int rc = run_wn_layers(e, k, B, T, ws, L, &am, &cur, st, &stopped);
     if (rc) return rc;
   }
   state_to_channel_major_kernel<<<static_cast<unsigned>((npos + 255) / 256), 256, 0, st>>>(state, z_out, z_sq_sum ? sums + NF : nullptr, B, T);

@@ -33,32 +33,51 @@ constexpr int kPhases = 32;      // group-steps per mel frame (256 / n_group)
 constexpr int kIdentN = 32;      // identity block width of the residual carry
 constexpr int kMaxHalves = 2;    // GEMM2 output halves of 256 columns (NC = 512)
 
-// Parameters of ONE layer launch of the fused kernel.  What selects code (channel count, first layer of a flow, tile mode) is
-// a template parameter of the kernel; what is here is data.
-struct LayerTcParams {
-  int T;              // valid group-steps per utterance
-  int Fq;             // mel frame slots per utterance = ceil(T / 32); the x buffers have 32 * Fq rows per utterance
-  int B;              // utterances
+constexpr int kMaxLayersPerLaunch = 8;   // layers one launch of the fused kernel may chain (dilations up to 128)
+constexpr uint32_t kTileDoneCount = 40;  // arrivals that complete a pair-tile's flag: (16 drain warps + 4 skip-end warps) x 2 CTAs
+
+// What differs between the layers a launch chains.
+struct LayerDesc {
   int dilation;
-  int seg_rows;       // tile mode "segments": frames per segment (64 or 32; 128 / seg_rows segments per tile, a tile may span utterances)
-  int reverse;        // walk the tiles backwards (alternate per layer: the tail of the previous layer's x' is still in L2)
   int w1_row0;        // first packed-W1x row of this (flow, layer)
   int v_row0;         // first packed-V row of this (flow, layer): + phase * 2 NC
   int w2_row0;        // first packed-W2 row of this (flow, layer): NC residual rows, then 16 skip-end rows
-  int wc_row0;        // first layer of a flow: first row of its composed start weights (3 taps x 2 NC packed rows, then NC carry rows)
-  int has_res;        // 0 for the last layer (no residual output, model.py:107-110)
+  int has_res;        // 0 for the last layer of a flow (no residual output, model.py:107-110)
   int accumulate_e;   // 0 for the first layer (e' = ...), 1 afterwards (e' = e + ...)
-  int g2_at[kMaxHalves];  // GEMM2 half h of tile i-1 is issued before this k-block of chunk 0 of tile i
-  int n_full, n_rem;  // tile mode "packed tails": n_full whole 128-frame blocks per utterance, then n_rem tiles of 32 frames x 4
-                      // consecutive utterances per group of 4 (one 4-D TMA box per operand)
+  int x_in;           // which of the launch's x tensor maps (XMaps) this layer reads
+  int pad_;
   const float* bias1;     // [2 NC] packed order, b_in + b_cond (+ W_cond . b_up)
   const float* bias_res;  // [NC]
   const void* wse;        // this layer's skip-end weights, 16-bit [8][NC] (rows NC.. of its packed W2)
   void* x_out;            // the residual stream it writes (phase-major [B][32][Fq][NC], 16-bit), plain stores
+};
+
+// Parameters of one launch of the fused kernel: n_layers consecutive layers of one flow.  What selects code (channel count,
+// first layer of a flow, tile mode) is a template parameter of the kernel; what is here is data.
+struct LayerTcParams {
+  int T;              // valid group-steps per utterance
+  int Fq;             // mel frame slots per utterance = ceil(T / 32); the x buffers have 32 * Fq rows per utterance
+  int B;              // utterances
+  int seg_rows;       // tile mode "segments": frames per segment (64 or 32; 128 / seg_rows segments per tile, a tile may span utterances)
+  int reverse;        // single-layer launches: walk the tiles backwards (alternate per layer: the tail of the previous layer's x' is still in L2)
+  int n_full, n_rem;  // tile mode "packed tails": n_full whole 128-frame blocks per utterance, then n_rem tiles of 32 frames x 4
+                      // consecutive utterances per group of 4 (one 4-D TMA box per operand)
+  int wc_row0;        // first layer of a flow: first row of its composed start weights (3 taps x 2 NC packed rows, then NC carry rows)
+  int g2_at[kMaxHalves];  // GEMM2 half h of tile i-1 is issued before this ring stage of chunk 0 of tile i
+  int n_layers;       // layers chained by this launch (1 .. kMaxLayersPerLaunch)
+  LayerDesc ly[kMaxLayersPerLaunch];
   float* e;               // [B, T, 8] fp32
+  uint32_t* flags;        // n_layers > 1: [n_layers][pair-tiles] completion counters, zero at launch (see kTileDoneCount)
   int dbg_flags;          // diagnostics only (results invalid): 1 skip all operand loads, 4 skip the gate math, 8 skip the x' stores,
                           // 16 skip the skip-end GEMM, 64 stamp the start of every tile, 128 no identity carry
   long long* timeline;    // optional [n_ctas][16] clock64 stamps (diagnostics; nullptr in production)
+};
+
+// The residual-stream tensor maps of a launch: m3[i] = x buffer i as {NC, Fq, 32 B} (box {KS, rows, 1}), m4[i] = the same
+// buffer as {NC, Fq, 32, B} (box {KS, 32, 1, 4}, packed tails).  LayerDesc::x_in indexes them.
+struct XMaps {
+  CUtensorMap m3[kMaxLayersPerLaunch];
+  CUtensorMap m4[kMaxLayersPerLaunch];
 };
 
 __device__ __forceinline__ void stamp(const LayerTcParams& p, int slot) {

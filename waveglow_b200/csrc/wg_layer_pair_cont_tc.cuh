@@ -36,6 +36,17 @@
 //          2..17: gates and x' drains -- thread = (TMEM lane, column quarter); x' goes to global memory straight from registers
 //                 with 32-byte stores (no staging tile, no TMA store to wait for);
 //          18..21: skip-end GEMM, 32 rows per warp.
+//   layers A launch may CHAIN up to 8 consecutive generic layers of a flow (LayerTcParams::n_layers): the work list is
+//          (layer, pair-tile) in layer-major order, dealt round-robin to the CTA pairs, so a pair starts tiles of layer l + 1 as
+//          soon as it runs out of tiles of layer l -- no grid-wide barrier, no idle tail per layer.  A tile of layer l + 1 needs
+//          only the tiles of layer l that produced its three tap windows (<= 2 entries per tap and utterance): every pair-tile
+//          has a completion counter in global memory (raised by its 2 x 20 epilogue warps after their x' / e stores), and the TMA
+//          warp polls the counters of exactly those tiles, one candidate per lane, before the first tap load of a tile.  Every
+//          layer of a launch writes its own x buffer (no write-after-read hazards), and tiles are walked forward (a tile's
+//          producers finished a whole layer ago).  All dependencies point to earlier work items and every CTA pair takes its
+//          items in order, so the schedule cannot deadlock as long as the grid is co-resident (<= 1 CTA per SM, by construction)
+//          and GEMM2 of a pair's previous item is loaded BEFORE the poll (g2_at <= the mel-window stages when consecutive
+//          items of a pair can depend on each other; the host checks).
 //   sync   full[s] lives in the leader CTA and is completed by the TMA bytes of both CTAs; empty[s], acc_full[c], d2_full[h]
 //          exist in both CTAs and are signalled by the leader's MULTICAST tcgen05.commit; acts_ready[c], res_drained[h] live in
 //          the leader and receive one remote arrive per gate warp of both CTAs; acts_local[c], e_done are per CTA.
@@ -69,22 +80,19 @@ struct ContCfg {
   static constexpr int kStageA = kTileM * KS * 2;    // own 128 rows of an A operand block
   static constexpr int kStageB = 128 * KS * 2;       // own half (128 rows) of a 256-row B operand block
   static constexpr int kStageBytes = kStageA + kStageB;
-  // 512 channels: the gated activations of a tile are 128 KB, which leaves 96 KB for the operand ring and nothing else: biases
-  // and skip-end weight fragments are then read from global memory through L1, and the dynamic shared memory is taken
-  // without alignment slack (its base is 1024-byte aligned when the kernel has no static shared memory; checked at run time)
+  // 512 channels: the gated activations of a tile are 128 KB, which leaves 96 KB for the operand ring and nothing else; the
+  // dynamic shared memory is then taken without alignment slack (its base is 1024-byte aligned when the kernel has no static
+  // shared memory; checked at run time).  Biases and skip-end weight fragments are read from global memory through L1 (they
+  // change with the layer inside a launch).
   static constexpr int kRingBytes = NC == 256 ? 131072 : 98304;
   static constexpr int kStages = kRingBytes / kStageBytes;
   static_assert(kStages <= 8, "barrier arrays hold 8 stages");
-  static constexpr bool kSmemConst = NC == 256;
   static constexpr int kActsBytes = kTileM * NC * 2;
   static constexpr int acts = kRingBytes;
   static constexpr int ident = acts + kActsBytes;
-  static constexpr int bias1 = ident + kPairIdentBytes;
-  static constexpr int bias_res = bias1 + (kSmemConst ? 2 * NC * 4 : 0);
-  static constexpr int wse = bias_res + (kSmemConst ? NC * 4 : 0);      // skip-end weights as mma.sync B fragments [NC / 8 registers][32 lanes]
-  static constexpr int bars = wse + (kSmemConst ? (NC / 8) * 32 * 4 : 0);
+  static constexpr int bars = ident + kPairIdentBytes;
   static constexpr int total = bars + 320;
-  static constexpr int kAlignSlack = kSmemConst ? 1024 : 0;
+  static constexpr int kAlignSlack = NC == 256 ? 1024 : 0;
   static constexpr int launch_bytes = total + kAlignSlack;
   static_assert(launch_bytes <= 232448, "shared memory budget exceeded");
 };
@@ -97,7 +105,8 @@ __device__ __forceinline__ uint64_t ring_desc(uint32_t smem_addr) {
 
 template <int NC, int KS, bool kFirst, int kMode>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kContThreads, 1)
-wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC, Fq, 32 B} box {KS, rows, 1}; rows = 128 (seg_rows in segment mode)
+wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x buffers: m3 {NC, Fq, 32 B} box {KS, rows, 1} (rows = 128; seg_rows in
+                                                                          // segment mode), m4 {NC, Fq, 32, B} box {KS, 32, 1, 4} (packed tails)
                           const __grid_constant__ CUtensorMap tm_mw,      // {320, Fq, B} box {KS, rows, 1}
                           const __grid_constant__ CUtensorMap tm_w1h,     // {3 NC, rows} box {KS,128}
                           const __grid_constant__ CUtensorMap tm_vh,      // {320, rows} box {KS,128}
@@ -105,7 +114,6 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
                           const __grid_constant__ CUtensorMap tm_ident16, // {64, 32} box {64,16} (SWIZZLE_128B whatever KS is)
                           const __grid_constant__ CUtensorMap tm_a0,      // first layer: {16, Fq, 32 B} box {KS, rows, 1}
                           const __grid_constant__ CUtensorMap tm_wc,      // first layer: {16, rows} box {KS,128}
-                          const __grid_constant__ CUtensorMap tm_x4,      // packed tails: x_in as {NC, Fq, 32, B} box {KS, 32, 1, 4}
                           const __grid_constant__ CUtensorMap tm_mw4,     // packed tails: {320, Fq, B} box {KS, 32, 4}
                           const __grid_constant__ CUtensorMap tm_a04,     // packed tails, first layer: {16, Fq, 32, B} box {KS, 32, 1, 4}
                           const LayerTcParams p) {
@@ -130,9 +138,6 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
   uint64_t* ident_full = bars + 32;               // [1] leader
   uint64_t* e_done = bars + 33;                   // [1] per CTA, 4 arrivals: the skip-end GEMM has read the acts slabs (-> gate warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 34);
-  float* s_bias1 = reinterpret_cast<float*>(smem + C::bias1);
-  float* s_bias_res = reinterpret_cast<float*>(smem + C::bias_res);
-  uint32_t* s_wse = reinterpret_cast<uint32_t*>(smem + C::wse);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = blockIdx.x & 1;     // == %cluster_ctarank for cluster dims (2,1,1)
@@ -150,18 +155,31 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
                         : kMode == kTilePacked ? n_class1 + ((p.B + 3) >> 2) * p.n_rem : (total_segs + n_sub - 1) / n_sub;
   const int n_pe = (n_entries + 1) / 2;
   const int n_ptiles = n_pe * kPhases;
-  const int my_tiles = (n_ptiles - pair + n_pairs - 1) / n_pairs;
+  // work items: (layer of this launch, pair-tile), layer-major, dealt round-robin to the CTA pairs
+  const int n_items = p.n_layers * n_ptiles;
+  const int my_tiles = (n_items - pair + n_pairs - 1) / n_pairs;
 
   struct Coord {
-    int ph, en;      // phase; entry
+    int ph, en, l, pt;      // phase; entry; layer (index into p.ly); pair-tile
   };
   auto tile_of = [&](int it) {
-    int pt = pair + it * n_pairs;
-    if (p.reverse) pt = n_ptiles - 1 - pt;
+    const int w = pair + it * n_pairs;
     Coord c;
-    c.ph = pt % kPhases;
-    c.en = 2 * (pt / kPhases) + static_cast<int>(rank);
+    c.l = w / n_ptiles;
+    c.pt = w - c.l * n_ptiles;
+    if (p.reverse) c.pt = n_ptiles - 1 - c.pt;      // single-layer launches only
+    c.ph = c.pt % kPhases;
+    c.en = 2 * (c.pt / kPhases) + static_cast<int>(rank);
     return c;
+  };
+  // (utterance, frame) -> entry that holds it (blocks and packed modes)
+  auto entry_of = [&](int b, int q) {
+    if constexpr (kMode == kTilePacked) {
+      const int qt = q - p.n_full * kTileM;
+      return qt < 0 ? b * p.n_full + (q >> 7) : n_class1 + (b >> 2) * p.n_rem + (qt >> 5);
+    } else {
+      return b * nqb + (q >> 7);
+    }
   };
   // where the rows of an entry come from.  blocks: 128 frames from (b[0], q[0]); packed: the same, or (packed) 32 frames from q[0]
   // of utterances b[0] .. b[0] + 3 (row = 32 * utterance + frame); segments: n_sub segments of seg_rows frames from (b[i], q[i])
@@ -212,19 +230,6 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
   };
 
   if (threadIdx.x == 0 && rank == 0) stamp(p, 0);
-  if constexpr (C::kSmemConst) {
-    for (int i = threadIdx.x; i < 2 * NC; i += kContThreads) s_bias1[i] = p.bias1[i];
-    for (int i = threadIdx.x; i < NC; i += kContThreads) s_bias_res[i] = p.has_res ? p.bias_res[i] : 0.f;
-    if (warp == 2) {
-      // skip-end weights Wse [8 x NC] (16-bit, K-major) as mma.sync B fragments: K-step i covers channels 16 i .. 16 i + 15;
-      // lane (n = lane / 4, kq = lane % 4) holds {k = 2 kq, 2 kq + 1} (fragment 2 i) and {k + 8, k + 9} (fragment 2 i + 1) of column n
-      const uint32_t* w32 = reinterpret_cast<const uint32_t*>(p.wse) + (lane >> 2) * (NC / 2) + (lane & 3);
-      for (int i = 0; i < NC / 16; ++i) {
-        s_wse[(2 * i) * 32 + lane] = __ldg(w32 + i * 8);
-        s_wse[(2 * i + 1) * 32 + lane] = __ldg(w32 + i * 8 + 4);
-      }
-    }
-  }
   if (threadIdx.x == 0) {
     for (int i = 0; i < ST; ++i) {
       ptx::mbar_init(&full[i], 1);
@@ -264,11 +269,11 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
   if (warp == 0) {
     // =============================== TMA producer (both CTAs) ===============================
     if (ptx::elect_one()) {
-      ptx::prefetch_tmap(&tm_x_in);
+      ptx::prefetch_tmap(&xm.m3[0]);
       ptx::prefetch_tmap(&tm_mw);
       ptx::prefetch_tmap(&tm_w1h);
       ptx::prefetch_tmap(&tm_vh);
-      if (!kFirst && p.has_res) {
+      if (!kFirst) {
         // launch-constant operand (own half): identity rows of the residual carry
         if (rank == 0) ptx::mbar_arrive_expect_tx(ident_full, 2 * kPairIdentBytes);
         ptx::tma_load_2d_pair(smem + C::ident, &tm_ident16, ptx::map_to_cta(ident_full, 0), 0, static_cast<int>(rank) * (kIdentN / 2));
@@ -332,10 +337,34 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
         ptx::tma_load_3d_pair(sa, &tm_mw, lb, kb * KS, tr.q[0], tr.b[0]);
       }
     };
+    // Tile-level dependencies inside a chained launch: before the first tap load of a tile of layer l > 0, wait until the tiles
+    // of layer l - 1 that wrote its three tap windows (and, through the centre tap, its own rows of e) have completed.  One
+    // candidate per lane: (tap, utterance of a packed tile, first / last row of the window); a window of <= 128 frames touches
+    // at most two entries (|frame shift| <= 4).
+    auto wait_deps = [&](const Coord& tc) {
+      const LayerDesc& L = p.ly[tc.l];
+      const int tap = lane >> 3, u = (lane >> 1) & 3, last = lane & 1;
+      bool need = tap < 3 && (tr.packed || u == 0);
+      int pt_dep = 0;
+      if (need) {
+        const int pp = tc.ph + (tap - 1) * L.dilation;
+        const int dq = pp >> 5;
+        const int b = tr.b[0] + (tr.packed ? u : 0);
+        int qa = tr.q[0] + dq, qb = qa + (tr.packed ? 31 : kTileM - 1);
+        need = b < p.B && qb >= 0 && qa < p.Fq;
+        qa = qa < 0 ? 0 : qa;
+        qb = qb >= p.Fq ? p.Fq - 1 : qb;
+        pt_dep = (entry_of(b < p.B ? b : 0, last ? qb : qa) >> 1) * kPhases + (pp - (dq << 5));
+      }
+      if (need) ptx::wait_flag_at_least(p.flags + static_cast<size_t>(tc.l - 1) * n_ptiles + pt_dep, kTileDoneCount);
+      __syncwarp();
+      ptx::fence_proxy_async_global();      // the generic-proxy stores just acquired -> this warp's TMA (async proxy) loads
+    };
     // GEMM2 half h of a tile: per stage j, W_res rows of that half (own 128), K block j + (j < 256 / KS) the x(t) channel block
     // 256 h / KS + j for the identity carry; first layer: W_res only, then one stage with [a0 | 1](t) and the carry weights
     // [W_start | b_start]
     auto load_gemm2 = [&](const Coord& tc, int h) {
+      const LayerDesc& L = p.ly[tc.l];
       tr = rows_of(tc.en);
       for (int j = 0; j < CB; ++j) {
         next_stage();
@@ -343,8 +372,8 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
         if (ptx::elect_one()) {
           const uint32_t lb = arm(with_x ? 2 * kStageBytes : 2 * kStageB);
           if (!skip_loads) {
-            ptx::tma_load_2d_pair(sb, &tm_w2h, lb, j * KS, p.w2_row0 + h * 256 + static_cast<int>(rank) * 128);
-            if (with_x) load_rows(&tm_x_in, &tm_x4, lb, h * 256 + j * KS, 0, tc.ph);
+            ptx::tma_load_2d_pair(sb, &tm_w2h, lb, j * KS, L.w2_row0 + h * 256 + static_cast<int>(rank) * 128);
+            if (with_x) load_rows(&xm.m3[L.x_in], &xm.m4[L.x_in], lb, h * 256 + j * KS, 0, tc.ph);
           }
         }
         __syncwarp();
@@ -363,22 +392,28 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
     };
     for (int it = 0; it < my_tiles; ++it) {
       const Coord tc = tile_of(it);
+      const LayerDesc& L = p.ly[tc.l];
+      const Coord prev = tile_of(it > 0 ? it - 1 : 0);
+      const bool prev_res = it > 0 && p.ly[prev.l].has_res;
       tr = rows_of(tc.en);
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
 #pragma unroll 1
         for (int kb = 0; kb < n_kb; ++kb) {
-          if (c == 0 && it > 0 && p.has_res) {
+          if (c == 0 && prev_res) {
 #pragma unroll
             for (int h = 0; h < NH; ++h)
               if (kb == p.g2_at[h]) {
-                load_gemm2(tile_of(it - 1), h);
+                load_gemm2(prev, h);
                 tr = rows_of(tc.en);
               }
           }
-          if (kb == MWKB && !dep_ok) {
-            ptx::griddep_wait();
-            dep_ok = true;
+          if (kb == MWKB) {
+            if (!dep_ok) {
+              ptx::griddep_wait();
+              dep_ok = true;
+            }
+            if (c == 0 && tc.l > 0) wait_deps(tc);
           }
           next_stage();
           if (ptx::elect_one()) {
@@ -386,7 +421,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
             if (!skip_loads) {
               if (kb < MWKB) {
                 load_mw(lb, kb);
-                ptx::tma_load_2d_pair(sb, &tm_vh, lb, kb * KS, p.v_row0 + tc.ph * (2 * NC) + c * 256 + static_cast<int>(rank) * 128);
+                ptx::tma_load_2d_pair(sb, &tm_vh, lb, kb * KS, L.v_row0 + tc.ph * (2 * NC) + c * 256 + static_cast<int>(rank) * 128);
               } else if constexpr (kFirst) {
                 const int tap = kb - MWKB;         // 0..2: a0 at t-1, t, t+1 (dilation 1)
                 const int pp = tc.ph + tap - 1;
@@ -395,10 +430,10 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
                 ptx::tma_load_2d_pair(sb, &tm_wc, lb, 0, p.wc_row0 + tap * (2 * NC) + c * 256 + static_cast<int>(rank) * 128);
               } else {
                 const int j = kb - MWKB;           // tap (j / CB) in {t-d, t, t+d}, channel block (j % CB)
-                const int pp = tc.ph + (j / CB - 1) * p.dilation;
+                const int pp = tc.ph + (j / CB - 1) * L.dilation;
                 const int dq = pp >> 5;            // floor division by 32
-                load_rows(&tm_x_in, &tm_x4, lb, (j % CB) * KS, dq, pp - (dq << 5));
-                ptx::tma_load_2d_pair(sb, &tm_w1h, lb, j * KS, p.w1_row0 + c * 256 + static_cast<int>(rank) * 128);
+                load_rows(&xm.m3[L.x_in], &xm.m4[L.x_in], lb, (j % CB) * KS, dq, pp - (dq << 5));
+                ptx::tma_load_2d_pair(sb, &tm_w1h, lb, j * KS, L.w1_row0 + c * 256 + static_cast<int>(rank) * 128);
               }
             }
           }
@@ -406,7 +441,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
         }
       }
     }
-    if (my_tiles > 0 && p.has_res) {
+    if (my_tiles > 0 && p.ly[tile_of(my_tiles - 1).l].has_res) {
       if (!dep_ok) ptx::griddep_wait();
       for (int h = 0; h < NH; ++h) load_gemm2(tile_of(my_tiles - 1), h);
     }
@@ -426,15 +461,16 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
       // tile (acts complete; the last gate also read region Q); half h > 0 needs the drain of half h - 1.
       auto gemm2 = [&](int j, int h) {
         const uint32_t pj = j & 1;
+        const bool has_res = p.ly[tile_of(j).l].has_res != 0;
         if (h == 0) {
 #pragma unroll
           for (int c = 0; c < NCH; ++c) ptx::mbar_wait(&acts_ready[c], pj);
-        } else if (p.has_res) {
+        } else if (has_res) {
           ptx::mbar_wait(&res_drained[h - 1], pj);
         }
         ptx::tc_fence_after_sync();
         if (j == 1 && h == 0 && lane == 0) stamp(p, 4);
-        if (!p.has_res) return;
+        if (!has_res) return;
         if (!kFirst && !ident_seen) {
           ptx::mbar_wait(ident_full, 0);
           ident_seen = true;
@@ -499,7 +535,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
             if (c == 0) {
               ptx::mbar_wait(&acts_ready[NCH - 2], par ^ 1);
               ptx::tc_fence_after_sync();
-            } else if (p.has_res) {
+            } else if (p.ly[tile_of(it - 1).l].has_res) {
               ptx::mbar_wait(&res_drained[NH - 1], par ^ 1);
               ptx::tc_fence_after_sync();
             }
@@ -558,13 +594,14 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint8_t* acts = smem + C::acts;
-    const float* bias1 = C::kSmemConst ? s_bias1 : p.bias1;
-    const float* bias_res = C::kSmemConst ? s_bias_res : p.bias_res;
     ptx::griddep_wait();      // these warps write x' over the previous grid's input
 
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t par = it & 1;
       const Coord tc = tile_of(it);
+      const LayerDesc& L = p.ly[tc.l];
+      const float* bias1 = L.bias1;
+      const float* bias_res = L.bias_res;
       const bool tl = (it == 1) && threadIdx.x == 64 && rank == 0;
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
@@ -574,7 +611,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
         if (tl && c == 0) stamp(p, 6);
         if (tl && c == NCH - 1) stamp(p, 8);
         if (c == 0 && it > 0) ptx::mbar_wait(e_done, par ^ 1);      // ... and so has the skip-end GEMM
-        if (!(p.dbg_flags & 4)) gate_chunk_quarter<!C::kSmemConst>(lane_base + (c & 1) * 256, acts, c, cq, row, bias1 + c * 256);
+        if (!(p.dbg_flags & 4)) gate_chunk_quarter<true>(lane_base + (c & 1) * 256, acts, c, cq, row, bias1 + c * 256);
         ptx::tc_fence_before_sync();
         ptx::fence_proxy_async_smem();
         __syncwarp();
@@ -586,14 +623,14 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
         if (tl && c == NCH - 1) stamp(p, 9);
       }
 
-      if (p.has_res) {
+      if (L.has_res) {
         // ---- x' (16-bit): per half, 64 columns of region Q -> + bias -> this row of the phase-major x buffer, 32-byte stores from registers
         const Rows tr = rows_of(tc.en);
         int row_b, row_q;
         row_coord(tr, row, row_b, row_q);
         const bool in_buf = row_b < p.B && row_q < p.Fq;                      // the row exists in the x buffer
         const bool live = in_buf && row_q * kPhases + tc.ph < p.T;           // ... and is a real group-step (else: exact zeros)
-        uint8_t* dst = static_cast<uint8_t*>(p.x_out) + ((static_cast<size_t>(row_b) * kPhases + tc.ph) * p.Fq + row_q) * (NC * 2) + cq * 128;
+        uint8_t* dst = static_cast<uint8_t*>(L.x_out) + ((static_cast<size_t>(row_b) * kPhases + tc.ph) * p.Fq + row_q) * (NC * 2) + cq * 128;
 #pragma unroll 1
         for (int h = 0; h < NH; ++h) {
           ptx::mbar_wait(&d2_full[h], par);
@@ -609,8 +646,8 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
             const float4* bp = reinterpret_cast<const float4*>(bias_res + h * 256 + cq * 64 + g2 * 32);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 b4 = C::kSmemConst ? bp[i] : __ldg(bp + i);
-              const float4 c4 = C::kSmemConst ? bp[4 + i] : __ldg(bp + 4 + i);
+              const float4 b4 = __ldg(bp + i);
+              const float4 c4 = __ldg(bp + 4 + i);
               pk[g2 * 16 + 2 * i] = live ? ptx::pack_half2(__uint_as_float(v0[4 * i]) + b4.x, __uint_as_float(v0[4 * i + 1]) + b4.y) : 0u;
               pk[g2 * 16 + 2 * i + 1] = live ? ptx::pack_half2(__uint_as_float(v0[4 * i + 2]) + b4.z, __uint_as_float(v0[4 * i + 3]) + b4.w) : 0u;
               pk[g2 * 16 + 8 + 2 * i] = live ? ptx::pack_half2(__uint_as_float(v1[4 * i]) + c4.x, __uint_as_float(v1[4 * i + 1]) + c4.y) : 0u;
@@ -628,6 +665,16 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
           }
           if (tl && h == NH - 1) stamp(p, 11);
         }
+        if (tc.l + 1 < p.n_layers) {
+          // chained launch: this warp's share of the tile's x' is stored -- count it on the tile's flag (release at gpu scope
+          // after the warp's stores; the consumers are TMA loads in other CTAs, hence the proxy fence)
+          ptx::fence_proxy_async_global();
+          __syncwarp();
+          if (lane == 0) {
+            __threadfence();
+            ptx::red_release_gpu_add(p.flags + static_cast<size_t>(tc.l) * n_ptiles + tc.pt, 1u);
+          }
+        }
       }
     }
     if (threadIdx.x == 64 && rank == 0) stamp(p, 13);
@@ -642,11 +689,14 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
     const int lm_row = 32 * q + (lane & 7) + ((lane >> 3) & 1) * 8;      // + 16 for the second 16-row block (same swizzle phase)
     const uint32_t lm_base = acts_u32 + lm_row * 128;
     const int lm_sw = lm_row & 7, lm_hi = lane >> 4;
-    const uint32_t* g_wse = reinterpret_cast<const uint32_t*>(p.wse) + (lane >> 2) * (NC / 2) + (lane & 3);
     ptx::griddep_wait();      // e is read-modify-written across the layers of a flow
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t par = it & 1;
       const Coord tc = tile_of(it);
+      const LayerDesc& L = p.ly[tc.l];
+      // skip-end weights Wse [8 x NC] (16-bit, K-major) as mma.sync B fragments: K-step i covers channels 16 i .. 16 i + 15; lane
+      // (n = lane / 4, kq = lane % 4) holds {k = 2 kq, 2 kq + 1} (fragment 2 i) and {k + 8, k + 9} (fragment 2 i + 1) of column n
+      const uint32_t* g_wse = reinterpret_cast<const uint32_t*>(L.wse) + (lane >> 2) * (NC / 2) + (lane & 3);
       float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
       // the slabs of chunk c (channels 128 c .. 128 c + 127) are there a whole GEMM chunk before those of chunk c + 1: only the
       // last chunk's share of the work is left for the time after the last gate, when these mma.sync compete with the x' drain
@@ -657,8 +707,8 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const int ks = s * 4 + kk;
-          const uint32_t b0 = C::kSmemConst ? s_wse[(2 * ks) * 32 + lane] : __ldg(g_wse + ks * 8);
-          const uint32_t b1 = C::kSmemConst ? s_wse[(2 * ks + 1) * 32 + lane] : __ldg(g_wse + ks * 8 + 4);
+          const uint32_t b0 = __ldg(g_wse + ks * 8);
+          const uint32_t b1 = __ldg(g_wse + ks * 8 + 4);
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt) {
             uint32_t a[4];
@@ -669,26 +719,35 @@ wn_layer_pair_cont_kernel(const __grid_constant__ CUtensorMap tm_x_in,    // {NC
       }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(e_done);
-      if (p.dbg_flags & 16) continue;
-      const Rows tr = rows_of(tc.en);
+      if (!(p.dbg_flags & 16)) {
+        const Rows tr = rows_of(tc.en);
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
+        for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
-        for (int hr = 0; hr < 2; ++hr) {
-          const int r = 32 * q + 16 * mt + (lane >> 2) + 8 * hr;
-          int r_b, r_q;
-          row_coord(tr, r, r_b, r_q);
-          const int t = r_q * kPhases + tc.ph;
-          if (r_b < p.B && r_q < p.Fq && t < p.T) {
-            float2* ep = reinterpret_cast<float2*>(p.e + (static_cast<size_t>(r_b) * p.T + t) * 8 + 2 * (lane & 3));
-            float2 v = make_float2(acc[mt][2 * hr], acc[mt][2 * hr + 1]);
-            if (p.accumulate_e) {
-              const float2 o = *ep;
-              v.x += o.x;
-              v.y += o.y;
+          for (int hr = 0; hr < 2; ++hr) {
+            const int r = 32 * q + 16 * mt + (lane >> 2) + 8 * hr;
+            int r_b, r_q;
+            row_coord(tr, r, r_b, r_q);
+            const int t = r_q * kPhases + tc.ph;
+            if (r_b < p.B && r_q < p.Fq && t < p.T) {
+              float2* ep = reinterpret_cast<float2*>(p.e + (static_cast<size_t>(r_b) * p.T + t) * 8 + 2 * (lane & 3));
+              float2 v = make_float2(acc[mt][2 * hr], acc[mt][2 * hr + 1]);
+              if (L.accumulate_e) {
+                const float2 o = __ldcg(ep);      // written by another SM one layer ago (chained launch): not through this SM's L1
+                v.x += o.x;
+                v.y += o.y;
+              }
+              *ep = v;
             }
-            *ep = v;
           }
+        }
+      }
+      if (tc.l + 1 < p.n_layers) {
+        // chained launch: this warp's share of the tile's e rows is stored (the next layer read-modify-writes them)
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence();
+          ptx::red_release_gpu_add(p.flags + static_cast<size_t>(tc.l) * n_ptiles + tc.pt, 1u);
         }
       }
     }

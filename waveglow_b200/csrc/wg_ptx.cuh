@@ -77,6 +77,33 @@ __device__ __forceinline__ void tc_fence_after_sync() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
+// generic-proxy global writes / reads <-> async-proxy (TMA) reads of global memory
+__device__ __forceinline__ void fence_proxy_async_global() {
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+// inter-CTA completion flags in global memory (tile-level dependencies between the layers of one launch)
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Fail-fast spin on a flag another CTA raises (same watchdog as mbar_wait)
+__device__ __forceinline__ void wait_flag_at_least(const uint32_t* p, uint32_t target) {
+  if (ld_acquire_gpu(p) >= target) return;
+  const long long t0 = clock64();
+  while (ld_acquire_gpu(p) < target) {
+    __nanosleep(64);
+    if (clock64() - t0 > 8000000000LL) {
+      printf("waveglow_b200: tile flag wait timed out (block %d thread %d flag %p value %u target %u)\n", blockIdx.x, threadIdx.x,
+             static_cast<const void*>(p), ld_acquire_gpu(p), target);
+      __trap();
+    }
+  }
+}
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
