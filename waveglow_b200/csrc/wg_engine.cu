@@ -1108,6 +1108,33 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
       const int rounds = (n_ptiles + n_pairs - 1) / n_pairs;
       n_pairs = (n_ptiles + rounds - 1) / rounds;
     }
+    // Smallest distance, in work items of a chained launch, between a tile of layer l + 1 and a tile of layer l it depends on
+    // (its tap windows: frames shifted by up to +-4, phases by up to 31).  Blocks: the neighbouring 128-frame block is the
+    // neighbouring entry.  Packed tails: the tail entries of an utterance sit behind ALL whole blocks in the entry order.
+    int min_dep_distance = n_ptiles;
+    {
+      auto pe_of = [&](int b, int q) {
+        const int nqb = (Fq + kTileM - 1) / kTileM;
+        int en;
+        if (mode == kTilePacked) {
+          const int qt = q - n_full * kTileM;
+          en = qt < 0 ? b * n_full + q / kTileM : B * n_full + (b / 4) * n_rem + qt / 32;
+        } else {
+          en = b * nqb + q / kTileM;
+        }
+        return en / 2;
+      };
+      int min_dpe = 0;      // most negative (consumer pair-entry) - (producer pair-entry)
+      if (mode != kTileSegments)
+        for (int b = 0; b < B; ++b)
+          for (int q0 = 0; q0 < Fq; q0 += 32)                       // every 32-frame piece of every utterance, as consumer rows
+            for (int dq = -4; dq <= 4; dq += 8) {
+              const int q = q0 + dq < 0 ? 0 : (q0 + dq + 31 >= Fq ? Fq - 1 : q0 + dq + (dq > 0 ? 31 : 0));
+              const int dpe = pe_of(b, q0) - pe_of(b, q);
+              if (dpe < min_dpe) min_dpe = dpe;
+            }
+      min_dep_distance = n_ptiles + kPhases * min_dpe - (kPhases - 1);
+    }
     auto desc = [&](int i) {
       const size_t li = static_cast<size_t>(k) * NL + i;
       LayerDesc d{};
@@ -1152,10 +1179,11 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
         xm.m4[j] = xm.m4[0];
       }
       for (int h = 0; h < kMaxHalves; ++h) lp.g2_at[h] = first ? e->g2_at_first[h] : e->g2_at[h];
-      if (lp.n_layers > 1 && n_ptiles < 160) {
-        // chained launch on a small shape: consecutive work items of a CTA pair can depend on each other (item w and item
-        // w + pairs are the same rows one or two layers apart), so GEMM2 of the previous item must be loaded BEFORE the TMA warp
-        // polls the flags of the next item's tap windows (at the first stage after the mel-window stages)
+      if (lp.n_layers > 1 && min_dep_distance <= n_pairs) {
+        // Chained launch where a work item can depend on an item fewer than `pairs` positions before it: GEMM2 of a pair's
+        // previous item is issued inside the next item's first chunk, so that item completes only once the next one is past
+        // its flag poll (at the first stage after the mel-window stages) -- which may itself wait for an item in the same
+        // state: a cycle.  Loading GEMM2 BEFORE the poll makes every item complete independently of its successor.
         const int mw_stages = kMwK / e->ks;
         for (int h = 0; h < kMaxHalves; ++h)
           if (lp.g2_at[h] > mw_stages) lp.g2_at[h] = mw_stages;
