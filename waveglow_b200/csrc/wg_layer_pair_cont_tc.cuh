@@ -82,15 +82,21 @@ struct ContCfg {
   static constexpr int kStageBytes = kStageA + kStageB;
   // 512 channels: the gated activations of a tile are 128 KB, which leaves 96 KB for the operand ring and nothing else; the
   // dynamic shared memory is then taken without alignment slack (its base is 1024-byte aligned when the kernel has no static
-  // shared memory; checked at run time).  Biases and skip-end weight fragments are read from global memory through L1 (they
-  // change with the layer inside a launch).
+  // shared memory; checked at run time), and biases / skip-end weight fragments are read from global memory through L1.
+  // 256 channels: they live in shared memory, one copy per LAYER PARITY (a chained launch changes layer while the other
+  // warps of the CTA may still be one item behind); measured on one box: 4 % of the step (profiles/r02/ab_const_smem.txt).
   static constexpr int kRingBytes = NC == 256 ? 131072 : 98304;
   static constexpr int kStages = kRingBytes / kStageBytes;
   static_assert(kStages <= 8, "barrier arrays hold 8 stages");
+  static constexpr bool kConstSmem = NC == 256;
+  static constexpr int kBiasFloats = 3 * NC;                 // [2 NC] packed GEMM1 bias, then [NC] residual bias
+  static constexpr int kWseWords = (NC / 8) * 32;            // skip-end weights as mma.sync B fragments [NC / 8 registers][32 lanes]
   static constexpr int kActsBytes = kTileM * NC * 2;
   static constexpr int acts = kRingBytes;
   static constexpr int ident = acts + kActsBytes;
-  static constexpr int bars = ident + kPairIdentBytes;
+  static constexpr int cbias = ident + kPairIdentBytes;      // [2][kBiasFloats] fp32
+  static constexpr int cwse = cbias + (kConstSmem ? 2 * kBiasFloats * 4 : 0);      // [2][kWseWords]
+  static constexpr int bars = cwse + (kConstSmem ? 2 * kWseWords * 4 : 0);
   static constexpr int total = bars + 320;
   static constexpr int kAlignSlack = NC == 256 ? 1024 : 0;
   static constexpr int launch_bytes = total + kAlignSlack;
@@ -594,6 +600,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint8_t* acts = smem + C::acts;
+    int cur_layer = -1;
     ptx::griddep_wait();      // these warps write x' over the previous grid's input
 
     for (int it = 0; it < my_tiles; ++it) {
@@ -602,6 +609,20 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
       const LayerDesc& L = p.ly[tc.l];
       const float* bias1 = L.bias1;
       const float* bias_res = L.bias_res;
+      if constexpr (C::kConstSmem) {
+        // biases of this item's layer in shared memory, one copy per layer parity: the 16 gate warps walk the same item
+        // sequence, so the copy of layer l - 2 is dead when the first of them reaches layer l
+        float* cb = reinterpret_cast<float*>(smem + C::cbias) + (tc.l & 1) * C::kBiasFloats;
+        if (tc.l != cur_layer) {
+          cur_layer = tc.l;
+          const int tid = threadIdx.x - 64;      // 0 .. 511
+          for (int i = tid; i < 2 * NC; i += 512) cb[i] = __ldg(L.bias1 + i);
+          for (int i = tid; i < NC; i += 512) cb[2 * NC + i] = L.has_res ? __ldg(L.bias_res + i) : 0.f;
+          asm volatile("bar.sync 1, 512;" ::: "memory");
+        }
+        bias1 = cb;
+        bias_res = cb + 2 * NC;
+      }
       const bool tl = (it == 1) && threadIdx.x == 64 && rank == 0;
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
@@ -611,7 +632,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
         if (tl && c == 0) stamp(p, 6);
         if (tl && c == NCH - 1) stamp(p, 8);
         if (c == 0 && it > 0) ptx::mbar_wait(e_done, par ^ 1);      // ... and so has the skip-end GEMM
-        if (!(p.dbg_flags & 4)) gate_chunk_quarter<true>(lane_base + (c & 1) * 256, acts, c, cq, row, bias1 + c * 256);
+        if (!(p.dbg_flags & 4)) gate_chunk_quarter<!C::kConstSmem>(lane_base + (c & 1) * 256, acts, c, cq, row, bias1 + c * 256);
         ptx::tc_fence_before_sync();
         ptx::fence_proxy_async_smem();
         __syncwarp();
@@ -646,8 +667,8 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
             const float4* bp = reinterpret_cast<const float4*>(bias_res + h * 256 + cq * 64 + g2 * 32);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 b4 = __ldg(bp + i);
-              const float4 c4 = __ldg(bp + 4 + i);
+              const float4 b4 = C::kConstSmem ? bp[i] : __ldg(bp + i);
+              const float4 c4 = C::kConstSmem ? bp[4 + i] : __ldg(bp + 4 + i);
               pk[g2 * 16 + 2 * i] = live ? ptx::pack_half2(__uint_as_float(v0[4 * i]) + b4.x, __uint_as_float(v0[4 * i + 1]) + b4.y) : 0u;
               pk[g2 * 16 + 2 * i + 1] = live ? ptx::pack_half2(__uint_as_float(v0[4 * i + 2]) + b4.z, __uint_as_float(v0[4 * i + 3]) + b4.w) : 0u;
               pk[g2 * 16 + 8 + 2 * i] = live ? ptx::pack_half2(__uint_as_float(v1[4 * i]) + c4.x, __uint_as_float(v1[4 * i + 1]) + c4.y) : 0u;
@@ -689,6 +710,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
     const int lm_row = 32 * q + (lane & 7) + ((lane >> 3) & 1) * 8;      // + 16 for the second 16-row block (same swizzle phase)
     const uint32_t lm_base = acts_u32 + lm_row * 128;
     const int lm_sw = lm_row & 7, lm_hi = lane >> 4;
+    int cur_layer = -1;
     ptx::griddep_wait();      // e is read-modify-written across the layers of a flow
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t par = it & 1;
@@ -697,6 +719,18 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
       // skip-end weights Wse [8 x NC] (16-bit, K-major) as mma.sync B fragments: K-step i covers channels 16 i .. 16 i + 15; lane
       // (n = lane / 4, kq = lane % 4) holds {k = 2 kq, 2 kq + 1} (fragment 2 i) and {k + 8, k + 9} (fragment 2 i + 1) of column n
       const uint32_t* g_wse = reinterpret_cast<const uint32_t*>(L.wse) + (lane >> 2) * (NC / 2) + (lane & 3);
+      const uint32_t* s_wse = reinterpret_cast<const uint32_t*>(smem + C::cwse) + (tc.l & 1) * C::kWseWords;
+      if constexpr (C::kConstSmem) {
+        if (tc.l != cur_layer) {      // fragments of this item's layer, one copy per layer parity (the 4 skip-end warps move together)
+          cur_layer = tc.l;
+          uint32_t* dst = reinterpret_cast<uint32_t*>(smem + C::cwse) + (tc.l & 1) * C::kWseWords;
+          for (int i = q; i < NC / 16; i += 4) {
+            dst[(2 * i) * 32 + lane] = __ldg(g_wse + i * 8);
+            dst[(2 * i + 1) * 32 + lane] = __ldg(g_wse + i * 8 + 4);
+          }
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+        }
+      }
       float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
       // the slabs of chunk c (channels 128 c .. 128 c + 127) are there a whole GEMM chunk before those of chunk c + 1: only the
       // last chunk's share of the work is left for the time after the last gate, when these mma.sync compete with the x' drain
@@ -707,8 +741,8 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const int ks = s * 4 + kk;
-          const uint32_t b0 = __ldg(g_wse + ks * 8);
-          const uint32_t b1 = __ldg(g_wse + ks * 8 + 4);
+          const uint32_t b0 = C::kConstSmem ? s_wse[(2 * ks) * 32 + lane] : __ldg(g_wse + ks * 8);
+          const uint32_t b1 = C::kConstSmem ? s_wse[(2 * ks + 1) * 32 + lane] : __ldg(g_wse + ks * 8 + 4);
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt) {
             uint32_t a[4];

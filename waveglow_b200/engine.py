@@ -39,7 +39,8 @@ class _WeightDesc(ctypes.Structure):
 
 
 def lib_path() -> str:
-  return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+  # WG_B200_LIB: developer switch for A/B runs of two builds of the library on one box (tools/gpu_step.sh ab_lib)
+  return os.environ.get("WG_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 
 def load_library() -> ctypes.CDLL:
