@@ -19,8 +19,8 @@ for step in "$@"; do
     ab_chain)  for v in 0 1 0 1; do echo "WG_CHAIN=$v (256 ch, B16 x 861)"; WG_CHAIN=$v python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | python tools/bench_brief.py; done | tee $OUT/ab_chain256.txt
                for v in 0 1 0 1; do echo "WG_CHAIN=$v (512 ch, B8 x 861)"; WG_CHAIN=$v python bench.py --channels 512 --batch 8 --steps 5 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | python tools/bench_brief.py; done | tee $OUT/ab_chain512.txt
                for v in 0 1; do echo "WG_CHAIN=$v"; WG_CHAIN=$v python tools/measure_configs.py 2>/dev/null; done | tee $OUT/ab_chain_configs.txt ;;
-    fwd)       for env in "WG_CHAIN=1" "WG_CHAIN=0" "WG_CHAIN=1 WG_PDL=0" "WG_CHAIN=1 WG_PACK4=0"; do env $env python tools/forward_times.py 2>&1 | tail -2; done | tee $OUT/forward_times.txt ;;
-    ab_lib)    for rep in 1 2; do for v in "WG_B200_LIB=$PWD/waveglow_b200/libwaveglow_b200_prev.so" "WG_CHAIN=0" "WG_CHAIN=1"; do echo "$v"; env $v python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | python tools/bench_brief.py; done; done | tee $OUT/ab_lib.txt ;;
+    fwd)       for env in "WG_CHAIN=1" "WG_CHAIN=0"; do env $env python tools/forward_times.py 2>&1 | tail -3; env $env python tools/forward_times.py --after-big 2>&1 | tail -3; done | tee $OUT/forward_times.txt ;;
+    ab_lib)    for rep in 1 2 3; do for v in "WG_B200_LIB=$PWD/waveglow_b200/libwaveglow_b200_prev.so" "WG_CHAIN=1"; do echo "$v"; env $v python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | python tools/bench_brief.py; done; done | tee $OUT/ab_lib.txt ;;
     bench)     TAILN=1 run bench 600 python bench.py --steps 10 --warmup 3 ;;
     bench_fast) TAILN=1 run bench_fast 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-parity ;;
     bench512)  TAILN=1 run bench512 600 python bench.py --channels 512 --batch 32 --steps 5 --warmup 3 --no-cpu-baseline ;;

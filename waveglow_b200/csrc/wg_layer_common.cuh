@@ -84,17 +84,26 @@ __device__ __forceinline__ void stamp(const LayerTcParams& p, int slot) {
   if (p.timeline) p.timeline[(static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 16 + slot] = clock64();
 }
 
-// tanh(a) * sigmoid(b) (model.py:13-20) from TWO exponentials and ONE reciprocal:
-//     tanh(a) = (u - 1) / (u + 1), u = e^(2a);  sigmoid(b) = 1 / (1 + v), v = e^(-b)   =>   (u - 1) / ((u + 1) (1 + v))
-// 3 MUFU operations (ex2.approx, ex2.approx, rcp.approx: relative error ~2^-22 each) per activation.  Round 1 used
-// tanh.approx.f32 twice (2 MUFU, relative error 2^-11 -- the size of the fp16 rounding of the result itself, and not
-// unbiased: at BASELINE shapes it put the 512-channel model at 2.09e-3 max-abs against the 2e-3 gate and a 2e-3 relative bias
-// on sum(log_s) of the forward direction, profiles/r02/gpu_tests_run4.txt).  |a| is clamped at 15 (tanh(15) = 1 - 2e-13: exact
-// in fp32) so that u stays finite; b needs no clamp: v = inf gives rcp(inf) = 0, v = 0 gives sigmoid = 1.
+// tanh(a) * sigmoid(b) (model.py:13-20), two forms:
+//   kAccurate = false: tanh.approx.f32 twice (sigmoid(b) = 0.5 + 0.5 tanh(b / 2)): 2 MUFU operations, relative error 2^-11 -- the
+//     size of the fp16 rounding of the result itself.  256-channel models: 1.2e-3 max-abs against the 2e-3 gate at the
+//     headline shape; the accurate form changes that by < 10 % (the fp16 residual stream is 58 % of the error budget, the
+//     rounded weights 26 %) and was measured 2.5 % SLOWER per step on one box (profiles/r02/ab_gate_math.txt).
+//   kAccurate = true: two exponentials and one reciprocal,
+//       tanh(a) = (u - 1) / (u + 1), u = e^(2a);  sigmoid(b) = 1 / (1 + v), v = e^(-b)   =>   (u - 1) / ((u + 1) (1 + v))
+//     3 MUFU operations (ex2.approx, ex2.approx, rcp.approx: relative error ~2^-22 each).  512-channel models, which sit AT the
+//     gate (8 x 861 frames against the fp32 engine: 2.09e-3 with the approximate form, <= 2e-3 with this one) and whose
+//     epilogue has slack.  |a| is clamped at 15 (tanh(15) = 1 - 2e-13: exact in fp32) so that u stays finite; b needs no clamp:
+//     v = inf gives rcp(inf) = 0, v = 0 gives sigmoid = 1.
+template <bool kAccurate>
 __device__ __forceinline__ float gate_one(float a, float b) {
-  const float u = ptx::ex2_approx(fminf(fmaxf(a, -15.f), 15.f) * 2.8853900817779268f);      // e^(2a) = 2^(2a log2 e)
-  const float v = ptx::ex2_approx(b * -1.4426950408889634f);                                // e^(-b)
-  return (u - 1.f) * ptx::rcp_approx(fmaf(u, v, u) + v + 1.f);                              // (u + 1)(1 + v) = uv + u + v + 1
+  if constexpr (!kAccurate) {
+    return ptx::tanh_approx(a) * fmaf(0.5f, ptx::tanh_approx(0.5f * b), 0.5f);
+  } else {
+    const float u = ptx::ex2_approx(fminf(fmaxf(a, -15.f), 15.f) * 2.8853900817779268f);      // e^(2a) = 2^(2a log2 e)
+    const float v = ptx::ex2_approx(b * -1.4426950408889634f);                                // e^(-b)
+    return (u - 1.f) * ptx::rcp_approx(fmaf(u, v, u) + v + 1.f);                              // (u + 1)(1 + v) = uv + u + v + 1
+  }
 }
 
 // Gate of one 256-column accumulator chunk ([tanh 128 | sigmoid 128], model.py:13-20) for SIXTEEN epilogue warps: column
@@ -102,7 +111,7 @@ __device__ __forceinline__ float gate_one(float a, float b) {
 // TMEM latency.  The activations go, as fp16, to the 128-byte-swizzled K-major acts slab (2 * chunk + cq / 2) that GEMM2 and
 // the skip-end GEMM read as their A operand.  `bias` points at the chunk's packed bias (tanh half at [0,128), sigmoid half at
 // [128,256)): shared memory, or (kGlobalBias) global memory read through L1 -- every lane reads the same 16 bytes.
-template <bool kGlobalBias>
+template <bool kGlobalBias, bool kAccurate>
 __device__ __forceinline__ void gate_chunk_quarter(uint32_t rc, uint8_t* acts, int chunk, int cq, int row, const float* bias) {
   uint8_t* slab_row = acts + (2 * chunk + (cq >> 1)) * (kTileM * 128) + row * 128;
   const float* bt = bias + cq * 32;
@@ -125,8 +134,8 @@ __device__ __forceinline__ void gate_chunk_quarter(uint32_t rc, uint8_t* acts, i
     uint32_t pk[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      pk[i] = ptx::pack_half2(gate_one(__uint_as_float(vt[2 * i]) + bt_[2 * i], __uint_as_float(vs[2 * i]) + bs_[2 * i]),
-                              gate_one(__uint_as_float(vt[2 * i + 1]) + bt_[2 * i + 1], __uint_as_float(vs[2 * i + 1]) + bs_[2 * i + 1]));
+      pk[i] = ptx::pack_half2(gate_one<kAccurate>(__uint_as_float(vt[2 * i]) + bt_[2 * i], __uint_as_float(vs[2 * i]) + bs_[2 * i]),
+                              gate_one<kAccurate>(__uint_as_float(vt[2 * i + 1]) + bt_[2 * i + 1], __uint_as_float(vs[2 * i + 1]) + bs_[2 * i + 1]));
     }
     // 16-byte chunk index inside the 128-byte slab row, XOR-swizzled by (row mod 8)
     const int c0 = ((cq & 1) * 4 + 2 * g) ^ (row & 7);

@@ -632,7 +632,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
         if (tl && c == 0) stamp(p, 6);
         if (tl && c == NCH - 1) stamp(p, 8);
         if (c == 0 && it > 0) ptx::mbar_wait(e_done, par ^ 1);      // ... and so has the skip-end GEMM
-        if (!(p.dbg_flags & 4)) gate_chunk_quarter<!C::kConstSmem>(lane_base + (c & 1) * 256, acts, c, cq, row, bias1 + c * 256);
+        if (!(p.dbg_flags & 4)) gate_chunk_quarter<!C::kConstSmem, NC == 512>(lane_base + (c & 1) * 256, acts, c, cq, row, bias1 + c * 256);
         ptx::tc_fence_before_sync();
         ptx::fence_proxy_async_smem();
         __syncwarp();
