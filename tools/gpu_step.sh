@@ -21,6 +21,10 @@ for step in "$@"; do
                for v in 0 1; do echo "WG_CHAIN=$v"; WG_CHAIN=$v python tools/measure_configs.py 2>/dev/null; done | tee $OUT/ab_chain_configs.txt ;;
     fwd)       for env in "WG_CHAIN=1" "WG_CHAIN=0"; do env $env python tools/forward_times.py 2>&1 | tail -3; env $env python tools/forward_times.py --after-big 2>&1 | tail -3; done | tee $OUT/forward_times.txt ;;
     ab_lib)    for rep in 1 2 3; do for v in "WG_B200_LIB=$PWD/waveglow_b200/libwaveglow_b200_prev.so" "WG_CHAIN=1"; do echo "$v"; env $v python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | python tools/bench_brief.py; done; done | tee $OUT/ab_lib.txt ;;
+    scale*)    N=${step#scale}
+               TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
+               TAILN=1 run weak_n$N 900 $TR bench.py --gpus $N --steps 10 --warmup 3 --no-parity
+               TAILN=1 run strong512_n$N 900 $TR bench.py --gpus $N --steps 5 --warmup 3 --scaling strong --channels 512 --global-batch 32 --no-parity ;;
     bench)     TAILN=1 run bench 600 python bench.py --steps 10 --warmup 3 ;;
     bench_fast) TAILN=1 run bench_fast 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-parity ;;
     bench512)  TAILN=1 run bench512 600 python bench.py --channels 512 --batch 32 --steps 5 --warmup 3 --no-cpu-baseline ;;

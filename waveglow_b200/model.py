@@ -9,6 +9,7 @@ of `infer` (model.py:223-274) is done by hand-written sm_100a kernels behind the
 without the built library raises.
 """
 import os
+import weakref
 from logging import getLogger
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -235,15 +236,18 @@ class ForwardStats(dict):
 
   def __init__(self, z, log_s_list, log_s_sum, log_det_w, z_sq_sum):
     super().__init__(log_s_sum=log_s_sum, log_det_w=log_det_w, z_sq_sum=z_sq_sum)
-    self._z = z
-    self._log_s = list(log_s_list) if log_s_list is not None else None
+    # WEAK references: z carries this object as an attribute, so a strong reference back would be a cycle that keeps every
+    # forward output alive until Python's cyclic collector runs (measured: 10-120 ms stalls per call from the CUDA caching
+    # allocator growing and trimming, profiles/r02/forward_times_cycle.txt)
+    self._z = weakref.ref(z)
+    self._log_s = [weakref.ref(t) for t in log_s_list] if log_s_list is not None else None
 
   def describes(self, z, log_s_list) -> bool:
-    if z is not self._z or z._version != 0:
+    if z is not self._z() or z._version != 0:
       return False
     if self._log_s is None or len(log_s_list) != len(self._log_s):
       return False
-    return all(a is b and a._version == 0 for a, b in zip(log_s_list, self._log_s))
+    return all(a is b() and a._version == 0 for a, b in zip(log_s_list, self._log_s))
 
 
 class WaveGlowLoss(torch.nn.Module):
