@@ -25,6 +25,8 @@ for step in "$@"; do
                TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
                TAILN=1 run weak_n$N 900 $TR bench.py --gpus $N --steps 10 --warmup 3 --no-parity
                TAILN=1 run strong512_n$N 900 $TR bench.py --gpus $N --steps 5 --warmup 3 --scaling strong --channels 512 --global-batch 32 --no-parity ;;
+    sweep_g2)  for v in 7 5 3 2 1 7; do echo "WG_G2AT0=$v (256 ch, B16 x 861)"; WG_G2AT0=$v python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | python tools/bench_brief.py; done | tee $OUT/sweep_g2at0_256.txt
+               for v in "10 24" "6 20" "4 14" "8 18" "12 26" "10 24"; do set -- $v; echo "WG_G2AT=$1 WG_G2AT1=$2 (512 ch, B8 x 861)"; WG_G2AT=$1 WG_G2AT1=$2 python bench.py --channels 512 --batch 8 --steps 5 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | python tools/bench_brief.py; done | tee $OUT/sweep_g2at_512.txt ;;
     bench)     TAILN=1 run bench 600 python bench.py --steps 10 --warmup 3 ;;
     bench_fast) TAILN=1 run bench_fast 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-parity ;;
     bench512)  TAILN=1 run bench512 600 python bench.py --channels 512 --batch 32 --steps 5 --warmup 3 --no-cpu-baseline ;;
@@ -32,8 +34,9 @@ for step in "$@"; do
     ref)       TAILN=1 run ref 900 python bench.py --impl reference --steps 2 --warmup 1 ;;
     callers)   TAILN=12 run callers 900 python tools/profile_callers.py ;;
     configs)   TAILN=8 run configs 600 python tools/measure_configs.py ;;
-    timeline256) TAILN=40 run timeline256 300 python tools/timeline.py ;;
-    timeline512) TAILN=40 run timeline512 300 python tools/timeline.py --channels 512 --batch 8 ;;
+    timeline256) TAILN=40 run timeline256 300 env WG_CHAIN=0 python tools/timeline.py ;;
+    timeline_first) TAILN=40 run timeline_first 300 env WG_CHAIN=0 python tools/timeline.py --layer 0 ;;
+    timeline512) TAILN=40 run timeline512 300 env WG_CHAIN=0 python tools/timeline.py --channels 512 --batch 8 ;;
     layers)    TAILN=12 run layers 300 python tools/layer_times.py ;;
     ncu_list)  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 260 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity > $OUT/ncu_launches.log 2>&1; echo "launch list exit $?" ;;
     ncu_full)  timeout 900 ncu --set full --clock-control none --import-source on -k regex:wn_layer_pair -s 120 -c 3 -o $OUT/prof_layer -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity > $OUT/ncu_full.log 2>&1; echo "full set exit $?" ;;

@@ -66,7 +66,7 @@ struct wg_engine {
   float* d_bias_res = nullptr;        // [flows*layers][256]
   CUtensorMap tm_w1h{}, tm_vh{}, tm_w2h{}, tm_ident16{};   // 128-row boxes: each CTA of a pair stages half of every B operand
   int g2_at[kMaxHalves] = {6, 6};     // see LayerTcParams::g2_at: generic layers (WG_G2AT / WG_G2AT1 env override, diagnostics)
-  int g2_at_first[kMaxHalves] = {7, 7};   // ... first layer of a flow with the start conv composed in (8 k-blocks per chunk; WG_G2AT0)
+  int g2_at_first[kMaxHalves] = {3, 3};   // ... first layer of a flow with the start conv composed in (8 stages per chunk; WG_G2AT0)
   const int ks = 64;                  // channels per operand-ring stage of the layer kernel (ContCfg<NC, KS>; see layer_kernel())
   int force_seg = 0;                  // WG_SEG env (tests/diagnostics): force the segment size (128 / 64 / 32) of the tiles
   bool first_comp = false;            // start conv composed into the first layer of each flow (WG_FIRST=0 disables)
@@ -455,7 +455,9 @@ int wg_create(const wg_config* cfg, wg_engine** out) {
     e->g2_at[0] = 640 / ks;
     e->g2_at[1] = 1536 / ks;
   }
-  e->g2_at_first[0] = e->g2_at_first[1] = n_kb_first - 1;
+  // first layer of a flow (8 stages per chunk, epilogue-bound): early, so that the MMA warp is already waiting at the hook when
+  // the tile's last gate finishes (profiles/r02/timeline_first_layer_v14.txt: at the last stage it arrived 2.6k cycles late)
+  e->g2_at_first[0] = e->g2_at_first[1] = 192 / ks;
   const char* g2_env = getenv("WG_G2AT");
   if (g2_env) e->g2_at[0] = atoi(g2_env);
   const char* g21_env = getenv("WG_G2AT1");
