@@ -152,6 +152,10 @@ int wg_debug_gemm(wg_engine* e, const void* a, const void* b, float* d, int32_t 
 int wg_debug_gemm2(wg_engine* e, const void* a, const void* b, float* d, int32_t m, int32_t n, int32_t k,
                    int32_t fmt, int32_t ks, void* stream);
 
+/* Test helper: n_ctas CTAs that each hold one SM (200 KB of shared memory, 64 threads) for `cycles` clock ticks on `stream`.
+ * tests/ use it to take SMs away from a chained layer launch: claimed work items must still complete (no co-residency assumption). */
+int wg_debug_occupy(wg_engine* e, int32_t n_ctas, int64_t cycles, void* stream);
+
 /* Diagnostics: when set (device pointer to [n_ctas][16] int64), every fused layer launch writes clock64
  * stamps of its pipeline phases per CTA (slot meaning: tools/timeline.py).  NULL disables (default). */
 int wg_debug_timeline(wg_engine* e, long long* device_buffer);

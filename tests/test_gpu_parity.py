@@ -219,6 +219,28 @@ def test_chained_layers_equal_one_launch_per_layer(nc, B, F):
     assert torch.equal(out, ref), f"repetition {rep}: max-abs {max_abs(ref, out):.3e}"
 
 
+@pytest.mark.parametrize("n_held", [1, 60, 131])
+def test_chained_launch_completes_when_part_of_the_gpu_is_taken(n_held):
+  """The chained launch spins on flags raised by other CTAs of the same grid.  It must not assume that the whole grid is
+  resident: here another stream holds `n_held` SMs (a CTA with 200 KB of shared memory each) for ~60 ms while `infer` runs, so
+  only some CTA pairs can be scheduled -- with 131 held at most 8 pairs, and with 1 held a pair is split.  Work items are
+  claimed in order by whichever pairs run, so the call completes (late) with bit-identical audio.  A static assignment of
+  items to pairs would wait forever for tiles owned by pairs that cannot start (the watchdog would trap after seconds)."""
+  hp, sd, w, dims = synthetic_weights(256)
+  model = get_model(256, "fp16")
+  eng = model.engine()
+  mel = synthetic_mel(2, 300, 901)
+  zs = synthetic_noise(hp, 2, 300 * 32, 902)
+  ref = run(model, mel, zs, 0.666)
+  side = torch.cuda.Stream()
+  mel_d, zs_d = mel.cuda(), [z.cuda() for z in zs]
+  torch.cuda.synchronize()
+  eng.debug_occupy(n_held, 120_000_000, side)        # ~60 ms at 2 GHz
+  out = model.infer_with_noise(mel_d, zs_d, 0.666)   # enqueued while the other stream holds its SMs
+  torch.cuda.synchronize()
+  assert torch.equal(out.cpu(), ref)
+
+
 @pytest.mark.parametrize("mode", ["fp16-seg32", "fp16-seg64"])
 @pytest.mark.parametrize("name", ["infer_c256_b2_f12", "infer_c256_b1_f40", "infer_c256_b3_f7_ragged"])
 def test_segment_tiles_match_reference_golden(name, mode):

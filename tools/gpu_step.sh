@@ -16,6 +16,7 @@ for step in "$@"; do
     flags)     for f in 0 1 4 8 16 128 29 0; do echo "WG_DBG_FLAGS=$f (256 ch, B16 x 861)"; WG_DBG_FLAGS=$f python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | python tools/bench_brief.py; done | tee $OUT/flags256.txt
                for f in 0 1 4 8 16 29 0; do echo "WG_DBG_FLAGS=$f (512 ch, B8 x 861)"; WG_DBG_FLAGS=$f python bench.py --channels 512 --batch 8 --steps 4 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | python tools/bench_brief.py; done | tee $OUT/flags512.txt ;;
     chain)     TAILN=30 run chain 600 python -m pytest tests/test_gpu_parity.py -q -x -s --timeout 300 -k "chained or (stagewise and fp16) or golden" ;;
+    chain2)    TAILN=30 run chain2 600 python -m pytest tests/test_gpu_parity.py -q -x -s --timeout 300 -k "chained" ;;
     ab_chain)  for v in 0 1 0 1; do echo "WG_CHAIN=$v (256 ch, B16 x 861)"; WG_CHAIN=$v python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | python tools/bench_brief.py; done | tee $OUT/ab_chain256.txt
                for v in 0 1 0 1; do echo "WG_CHAIN=$v (512 ch, B8 x 861)"; WG_CHAIN=$v python bench.py --channels 512 --batch 8 --steps 5 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | python tools/bench_brief.py; done | tee $OUT/ab_chain512.txt
                for v in 0 1; do echo "WG_CHAIN=$v"; WG_CHAIN=$v python tools/measure_configs.py 2>/dev/null; done | tee $OUT/ab_chain_configs.txt ;;

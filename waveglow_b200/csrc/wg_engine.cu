@@ -309,7 +309,8 @@ struct WsLayout {
   size_t cond, e, total;           // cond: fp32 mode = upsampled conditioning S [B,T,640]; fp16 mode = mel windows MW [B,Fq,320]
   size_t x[16];                    // residual stream buffers.  Tensor-core mode: one per layer (layer i reads x[i], writes x[i + 1]:
   int n_x;                         // chained launches have no write-after-read hazards); fp32 mode: 2, ping-pong
-  size_t flags, flags_bytes;       // tensor-core mode: completion counters of chained launches [n_flows][n_layers][pair-tiles] uint32
+  size_t flags, flags_bytes;       // tensor-core mode: completion counters of chained launches [n_flows][n_layers][pair-tiles] uint32,
+                                   // then the work-item counters [n_flows]; zeroed at the start of every call
   int ptiles_cap;                  // pair-tiles the flags of one layer are sized for
   size_t cond_bytes;
   size_t elt;   // operand element size
@@ -335,8 +336,9 @@ WsLayout ws_layout(const wg_engine* e, int B, int T) {
   // most pair-tiles any tile mode can make of this shape: 32-frame segments
   L.ptiles_cap = kUpPhases * ((B * ((L.Tpad / kUpPhases + 31) / 32) + 1) / 2 + 1);
   L.flags = off;
+  // ... followed by one work-item counter per flow
   L.flags_bytes = e->cfg.precision == WG_PRECISION_FP16
-                      ? static_cast<size_t>(e->cfg.n_flows) * e->cfg.n_layers * L.ptiles_cap * sizeof(uint32_t) : 0;
+                      ? (static_cast<size_t>(e->cfg.n_flows) * e->cfg.n_layers * L.ptiles_cap + e->cfg.n_flows) * sizeof(uint32_t) : 0;
   off = align_up(off + L.flags_bytes, 1024);
   L.e = off;
   off = align_up(off + npos * kGroup * sizeof(float), 1024);
@@ -1116,33 +1118,6 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
       const int rounds = (n_ptiles + n_pairs - 1) / n_pairs;
       n_pairs = (n_ptiles + rounds - 1) / rounds;
     }
-    // Smallest distance, in work items of a chained launch, between a tile of layer l + 1 and a tile of layer l it depends on
-    // (its tap windows: frames shifted by up to +-4, phases by up to 31).  Blocks: the neighbouring 128-frame block is the
-    // neighbouring entry.  Packed tails: the tail entries of an utterance sit behind ALL whole blocks in the entry order.
-    int min_dep_distance = n_ptiles;
-    {
-      auto pe_of = [&](int b, int q) {
-        const int nqb = (Fq + kTileM - 1) / kTileM;
-        int en;
-        if (mode == kTilePacked) {
-          const int qt = q - n_full * kTileM;
-          en = qt < 0 ? b * n_full + q / kTileM : B * n_full + (b / 4) * n_rem + qt / 32;
-        } else {
-          en = b * nqb + q / kTileM;
-        }
-        return en / 2;
-      };
-      int min_dpe = 0;      // most negative (consumer pair-entry) - (producer pair-entry)
-      if (mode != kTileSegments)
-        for (int b = 0; b < B; ++b)
-          for (int q0 = 0; q0 < Fq; q0 += 32)                       // every 32-frame piece of every utterance, as consumer rows
-            for (int dq = -4; dq <= 4; dq += 8) {
-              const int q = q0 + dq < 0 ? 0 : (q0 + dq + 31 >= Fq ? Fq - 1 : q0 + dq + (dq > 0 ? 31 : 0));
-              const int dpe = pe_of(b, q0) - pe_of(b, q);
-              if (dpe < min_dpe) min_dpe = dpe;
-            }
-      min_dep_distance = n_ptiles + kPhases * min_dpe - (kPhases - 1);
-    }
     auto desc = [&](int i) {
       const size_t li = static_cast<size_t>(k) * NL + i;
       LayerDesc d{};
@@ -1187,14 +1162,15 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
         xm.m4[j] = xm.m4[0];
       }
       for (int h = 0; h < kMaxHalves; ++h) lp.g2_at[h] = first ? e->g2_at_first[h] : e->g2_at[h];
-      if (lp.n_layers > 1 && min_dep_distance <= n_pairs) {
-        // Chained launch where a work item can depend on an item fewer than `pairs` positions before it: GEMM2 of a pair's
-        // previous item is issued inside the next item's first chunk, so that item completes only once the next one is past
-        // its flag poll (at the first stage after the mel-window stages) -- which may itself wait for an item in the same
-        // state: a cycle.  Loading GEMM2 BEFORE the poll makes every item complete independently of its successor.
+      if (lp.n_layers > 1) {
+        // Chained launch: GEMM2 of a pair's previous item is issued inside the next item's first chunk, so it must be LOADED before
+        // the TMA warp polls the flags of that next item's tap windows (first stage after the mel-window stages): every claimed
+        // item then completes without waiting for a later one, whatever the pair's next item depends on.  (Measured: the hook
+        // position is within run-to-run noise on both channel counts, profiles/r02/sweep_g2_hooks.txt.)
         const int mw_stages = kMwK / e->ks;
         for (int h = 0; h < kMaxHalves; ++h)
           if (lp.g2_at[h] > mw_stages) lp.g2_at[h] = mw_stages;
+        lp.counter = reinterpret_cast<uint32_t*>(ws + L.flags + L.flags_bytes - sizeof(uint32_t) * e->cfg.n_flows) + k;
       }
       // programmatic dependent launch: this grid's CTAs may start their prologue and conditioning K-blocks while the
       // previous launch's last tiles drain (griddepcontrol.wait in the kernel guards every dependent access)
@@ -1569,6 +1545,17 @@ int wg_denoise_spectrum(float* spec, const float* bias, float strength, int32_t 
   denoise_spectrum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<float2*>(spec), bias, strength, n_freq,
                                                                                n_frames, stride_b, stride_f, stride_t, total);
   return cudaGetLastError() == cudaSuccess ? WG_OK : WG_ERR_CUDA;
+}
+
+// Test helper: n_ctas CTAs that each hold one SM (200 KB of shared memory) for `cycles` clock ticks on `stream`.
+int wg_debug_occupy(wg_engine* e, int32_t n_ctas, int64_t cycles, void* stream) {
+  if (!e || n_ctas <= 0 || cycles <= 0) return WG_ERR_INVALID_ARGUMENT;
+  WG_DEVICE(e, e->cfg.device);
+  const int smem = 200 * 1024;
+  WG_CUDA(e, cudaFuncSetAttribute(occupy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  occupy_kernel<<<n_ctas, 64, smem, static_cast<cudaStream_t>(stream)>>>(cycles, nullptr);
+  WG_CUDA(e, cudaGetLastError());
+  return WG_OK;
 }
 
 // Diagnostic: D[M x N] fp32 = A[M x K] . B[N x K]^T with 16-bit device operands (fmt 0 fp16 / 1 bf16).

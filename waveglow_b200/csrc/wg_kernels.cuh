@@ -440,6 +440,17 @@ __global__ void denoise_spectrum_kernel(float2* __restrict__ spec, const float* 
   *p = make_float2(x.x * scale, x.y * scale);
 }
 
+// ------------------------------------------------------------------------------------------ test helper
+// Occupies an SM per CTA (the launch asks for most of its shared memory) for `cycles` clock ticks: tests use it to take SMs away
+// from a chained layer launch and check that claimed work items still complete (wg_debug_occupy).
+__global__ void occupy_kernel(long long cycles, int* sink) {
+  extern __shared__ uint8_t occupy_smem[];
+  const long long t0 = clock64();
+  int acc = 0;
+  while (clock64() - t0 < cycles) acc += occupy_smem[(threadIdx.x * 64 + (acc & 63)) & 1023];
+  if (acc == 0x7fffffff) *sink = acc;
+}
+
 // ------------------------------------------------------------------------------------------ fp32 layer
 // One WN layer in fp32 on CUDA cores.  Block = 256 threads, tile = 32 group-steps of one utterance.
 //   W1  [K1 = 3 NC + 640][2 NC]  (k-major rows, natural channel order: tanh half | sigmoid half)

@@ -68,6 +68,7 @@ struct LayerTcParams {
   LayerDesc ly[kMaxLayersPerLaunch];
   float* e;               // [B, T, 8] fp32
   uint32_t* flags;        // n_layers > 1: [n_layers][pair-tiles] completion counters, zero at launch (see kTileDoneCount)
+  uint32_t* counter;      // n_layers > 1: the next unclaimed work item of this launch, zero at launch
   int dbg_flags;          // diagnostics only (results invalid): 1 skip all operand loads, 4 skip the gate math, 8 skip the x' stores,
                           // 16 skip the skip-end GEMM, 64 stamp the start of every tile, 128 no identity carry
   long long* timeline;    // optional [n_ctas][16] clock64 stamps (diagnostics; nullptr in production)

@@ -37,16 +37,16 @@
 //                 with 32-byte stores (no staging tile, no TMA store to wait for);
 //          18..21: skip-end GEMM, 32 rows per warp.
 //   layers A launch may CHAIN up to 8 consecutive generic layers of a flow (LayerTcParams::n_layers): the work list is
-//          (layer, pair-tile) in layer-major order, dealt round-robin to the CTA pairs, so a pair starts tiles of layer l + 1 as
-//          soon as it runs out of tiles of layer l -- no grid-wide barrier, no idle tail per layer.  A tile of layer l + 1 needs
-//          only the tiles of layer l that produced its three tap windows (<= 2 entries per tap and utterance): every pair-tile
-//          has a completion counter in global memory (raised by its 2 x 20 epilogue warps after their x' / e stores), and the TMA
-//          warp polls the counters of exactly those tiles, one candidate per lane, before the first tap load of a tile.  Every
-//          layer of a launch writes its own x buffer (no write-after-read hazards), and tiles are walked forward (a tile's
-//          producers finished a whole layer ago).  All dependencies point to earlier work items and every CTA pair takes its
-//          items in order, so the schedule cannot deadlock as long as the grid is co-resident (<= 1 CTA per SM, by construction)
-//          and GEMM2 of a pair's previous item is loaded BEFORE the poll (g2_at <= the mel-window stages when consecutive
-//          items of a pair can depend on each other; the host checks).
+//          (layer, pair-tile) in layer-major order, and the CTA pairs CLAIM items from a global counter, so a pair starts tiles of
+//          layer l + 1 as soon as there are no tiles of layer l left -- no grid-wide barrier, no idle tail per layer.  A tile of
+//          layer l + 1 needs only the tiles of layer l that produced its three tap windows (<= 2 entries per tap and utterance):
+//          every pair-tile has a completion counter in global memory (raised by its 2 x 20 epilogue warps after their x' / e
+//          stores), and the TMA warp polls the counters of exactly those tiles, one candidate per lane, before the first tap
+//          load of a tile.  Every layer of a launch writes its own x buffer (no write-after-read hazards), and tiles are walked
+//          forward (a tile's producers finished a whole layer ago).  Deadlock freedom does not depend on the whole grid being
+//          resident: items are started in increasing order by whichever pairs run, every dependency is an earlier item, and a
+//          started item completes without waiting for anything later (the host places GEMM2 of a pair's previous item BEFORE
+//          the next item's flag poll in the operand ring).
 //   sync   full[s] lives in the leader CTA and is completed by the TMA bytes of both CTAs; empty[s], acc_full[c], d2_full[h]
 //          exist in both CTAs and are signalled by the leader's MULTICAST tcgen05.commit; acts_ready[c], res_drained[h] live in
 //          the leader and receive one remote arrive per gate warp of both CTAs; acts_local[c], e_done are per CTA.
@@ -97,7 +97,7 @@ struct ContCfg {
   static constexpr int cbias = ident + kPairIdentBytes;      // [2][kBiasFloats] fp32
   static constexpr int cwse = cbias + (kConstSmem ? 2 * kBiasFloats * 4 : 0);      // [2][kWseWords]
   static constexpr int bars = cwse + (kConstSmem ? 2 * kWseWords * 4 : 0);
-  static constexpr int total = bars + 320;
+  static constexpr int total = bars + 384;
   static constexpr int kAlignSlack = NC == 256 ? 1024 : 0;
   static constexpr int launch_bytes = total + kAlignSlack;
   static_assert(launch_bytes <= 232448, "shared memory budget exceeded");
@@ -144,6 +144,8 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
   uint64_t* ident_full = bars + 32;               // [1] leader
   uint64_t* e_done = bars + 33;                   // [1] per CTA, 4 arrivals: the skip-end GEMM has read the acts slabs (-> gate warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 34);
+  uint64_t* item_bar = bars + 35;                 // [8] per CTA, 1 arrival: slot s of the claimed-item ring is filled (chained launches)
+  volatile uint32_t* s_items = reinterpret_cast<volatile uint32_t*>(bars + 43);      // [8] work items claimed by the leader's TMA warp
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = blockIdx.x & 1;     // == %cluster_ctarank for cluster dims (2,1,1)
@@ -161,15 +163,21 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
                         : kMode == kTilePacked ? n_class1 + ((p.B + 3) >> 2) * p.n_rem : (total_segs + n_sub - 1) / n_sub;
   const int n_pe = (n_entries + 1) / 2;
   const int n_ptiles = n_pe * kPhases;
-  // work items: (layer of this launch, pair-tile), layer-major, dealt round-robin to the CTA pairs
+  // Work items: (layer of this launch, pair-tile), layer-major.  Single-layer launches deal them round-robin to the CTA pairs.
+  // CHAINED launches (n_layers > 1) CLAIM them: the TMA warp of a pair's leader CTA takes the next item from a global counter
+  // when the pair is ready to load it and publishes it to every warp of both CTAs through an 8-slot ring in shared memory
+  // (slot it % 8, one mbarrier per slot).  Items are thereby started in increasing order by whichever pairs are resident, and
+  // every dependency of an item is an earlier item -- claimed, hence held by a resident pair that completes it without waiting
+  // for anything later (GEMM2 of an item is loaded before the pair's next item polls its flags): the schedule cannot deadlock
+  // even if part of the grid is not resident (another kernel holding SMs), and a pair that starts late just claims later items.
+  // The roles of a CTA are at most 3 items apart (operand ring, TMEM regions, e_done), so 8 slots are never overrun.
   const int n_items = p.n_layers * n_ptiles;
-  const int my_tiles = (n_items - pair + n_pairs - 1) / n_pairs;
+  const bool claimed = p.n_layers > 1;
 
   struct Coord {
     int ph, en, l, pt;      // phase; entry; layer (index into p.ly); pair-tile
   };
-  auto tile_of = [&](int it) {
-    const int w = pair + it * n_pairs;
+  auto decode = [&](int w) {
     Coord c;
     c.l = w / n_ptiles;
     c.pt = w - c.l * n_ptiles;
@@ -177,6 +185,12 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
     c.ph = c.pt % kPhases;
     c.en = 2 * (c.pt / kPhases) + static_cast<int>(rank);
     return c;
+  };
+  // the it-th work item of this CTA pair (>= n_items: no more work); every role of both CTAs calls this once per iteration
+  auto item_of = [&](int it) -> int {
+    if (!claimed) return pair + it * n_pairs;
+    ptx::mbar_wait_cluster(&item_bar[it & 7], (it >> 3) & 1);
+    return static_cast<int>(s_items[it & 7]);
   };
   // (utterance, frame) -> entry that holds it (blocks and packed modes)
   auto entry_of = [&](int b, int q) {
@@ -253,6 +267,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
     }
     ptx::mbar_init(ident_full, 1);
     ptx::mbar_init(e_done, 4);
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(&item_bar[i], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -396,10 +411,24 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
         __syncwarp();
       }
     };
-    for (int it = 0; it < my_tiles; ++it) {
-      const Coord tc = tile_of(it);
+    Coord prev{};
+    int it = 0;
+    for (;; ++it) {
+      if (claimed && rank == 0) {
+        // claim the next work item for this pair and publish it to both CTAs
+        if (ptx::elect_one()) {
+          const uint32_t w_new = atomicAdd(p.counter, 1u);
+          s_items[it & 7] = w_new;
+          ptx::st_shared_cluster_u32(ptx::map_to_cta(const_cast<uint32_t*>(&s_items[it & 7]), 1), w_new);
+          ptx::mbar_arrive(&item_bar[it & 7]);
+          ptx::mbar_arrive_release_cluster(ptx::map_to_cta(&item_bar[it & 7], 1));
+        }
+        __syncwarp();
+      }
+      const int w = item_of(it);
+      if (w >= n_items) break;
+      const Coord tc = decode(w);
       const LayerDesc& L = p.ly[tc.l];
-      const Coord prev = tile_of(it > 0 ? it - 1 : 0);
       const bool prev_res = it > 0 && p.ly[prev.l].has_res;
       tr = rows_of(tc.en);
 #pragma unroll 1
@@ -446,10 +475,11 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
           __syncwarp();
         }
       }
+      prev = tc;
     }
-    if (my_tiles > 0 && p.ly[tile_of(my_tiles - 1).l].has_res) {
+    if (it > 0 && p.ly[prev.l].has_res) {
       if (!dep_ok) ptx::griddep_wait();
-      for (int h = 0; h < NH; ++h) load_gemm2(tile_of(my_tiles - 1), h);
+      for (int h = 0; h < NH; ++h) load_gemm2(prev, h);
     }
   } else if (warp == 1) {
     // =============================== MMA issuer (leader CTA only) ===============================
@@ -465,9 +495,8 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
       if (lane == 0) stamp(p, 1);
       // x' half h of tile j = acts(j) . W_res[half h]^T + x(j)[half h] . [I32 | 0] into region Q.  Half 0 needs every gate of the
       // tile (acts complete; the last gate also read region Q); half h > 0 needs the drain of half h - 1.
-      auto gemm2 = [&](int j, int h) {
+      auto gemm2 = [&](int j, int h, bool has_res) {      // j: iteration index of the tile, has_res: of its layer
         const uint32_t pj = j & 1;
-        const bool has_res = p.ly[tile_of(j).l].has_res != 0;
         if (h == 0) {
 #pragma unroll
           for (int c = 0; c < NCH; ++c) ptx::mbar_wait(&acts_ready[c], pj);
@@ -526,7 +555,12 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
         }
         if (j == 1 && h == NH - 1 && lane == 0) stamp(p, 5);
       };
-      for (int it = 0; it < my_tiles; ++it) {
+      bool prev_res = false;
+      int it = 0;
+      for (;; ++it) {
+        const int w = item_of(it);
+        if (w >= n_items) break;
+        const bool cur_res = p.ly[w / n_ptiles].has_res != 0;
         const uint32_t par = it & 1;
         const bool tl = (it == 1) && lane == 0;
 #pragma unroll 1
@@ -541,7 +575,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
             if (c == 0) {
               ptx::mbar_wait(&acts_ready[NCH - 2], par ^ 1);
               ptx::tc_fence_after_sync();
-            } else if (p.ly[tile_of(it - 1).l].has_res) {
+            } else if (prev_res) {
               ptx::mbar_wait(&res_drained[NH - 1], par ^ 1);
               ptx::tc_fence_after_sync();
             }
@@ -552,7 +586,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
             if (c == 0 && it > 0) {
 #pragma unroll
               for (int h = 0; h < NH; ++h)
-                if (kb == p.g2_at[h]) gemm2(it - 1, h);
+                if (kb == p.g2_at[h]) gemm2(it - 1, h, prev_res);
             }
             const int s = use % ST;
             const uint32_t ph = (use / ST) & 1;
@@ -585,10 +619,11 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
           }
           if (tl && c == NCH - 1) stamp(p, 3);
         }
+        prev_res = cur_res;
       }
-      if (my_tiles > 0) {
+      if (it > 0) {
 #pragma unroll
-        for (int h = 0; h < NH; ++h) gemm2(my_tiles - 1, h);
+        for (int h = 0; h < NH; ++h) gemm2(it - 1, h, prev_res);
       }
     }
   } else if (warp < 18) {
@@ -603,9 +638,11 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
     int cur_layer = -1;
     ptx::griddep_wait();      // these warps write x' over the previous grid's input
 
-    for (int it = 0; it < my_tiles; ++it) {
+    for (int it = 0;; ++it) {
+      const int w = item_of(it);
+      if (w >= n_items) break;
       const uint32_t par = it & 1;
-      const Coord tc = tile_of(it);
+      const Coord tc = decode(w);
       const LayerDesc& L = p.ly[tc.l];
       const float* bias1 = L.bias1;
       const float* bias_res = L.bias_res;
@@ -712,9 +749,11 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
     const int lm_sw = lm_row & 7, lm_hi = lane >> 4;
     int cur_layer = -1;
     ptx::griddep_wait();      // e is read-modify-written across the layers of a flow
-    for (int it = 0; it < my_tiles; ++it) {
+    for (int it = 0;; ++it) {
+      const int w = item_of(it);
+      if (w >= n_items) break;
       const uint32_t par = it & 1;
-      const Coord tc = tile_of(it);
+      const Coord tc = decode(w);
       const LayerDesc& L = p.ly[tc.l];
       // skip-end weights Wse [8 x NC] (16-bit, K-major) as mma.sync B fragments: K-step i covers channels 16 i .. 16 i + 15; lane
       // (n = lane / 4, kq = lane % 4) holds {k = 2 kq, 2 kq + 1} (fragment 2 i) and {k + 8, k + 9} (fragment 2 i + 1) of column n

@@ -19,7 +19,7 @@ PRECISION_FP16 = 1
 EXPORTED_SYMBOLS = [
   "wg_create", "wg_load_weights", "wg_save_packed", "wg_load_packed", "wg_workspace_bytes", "wg_infer", "wg_forward", "wg_last_launch_count",
   "wg_debug_stop_after", "wg_debug_view", "wg_debug_gemm", "wg_debug_gemm2", "wg_debug_timeline", "wg_set_profiling", "wg_profile_layers", "wg_last_error", "wg_version",
-  "wg_destroy", "wg_denoise_spectrum",
+  "wg_destroy", "wg_denoise_spectrum", "wg_debug_occupy",
 ]
 
 
@@ -89,6 +89,8 @@ def load_library() -> ctypes.CDLL:
   lib.wg_version.restype = ctypes.c_char_p
   lib.wg_destroy.argtypes = [vp]
   lib.wg_destroy.restype = None
+  lib.wg_debug_occupy.argtypes = [vp, i32, ctypes.c_int64, vp]
+  lib.wg_debug_occupy.restype = ctypes.c_int
   lib.wg_denoise_spectrum.argtypes = [vp, vp, f32, i32, i32, i32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, i32, vp]
   lib.wg_denoise_spectrum.restype = ctypes.c_int
   _lib = lib
@@ -353,6 +355,11 @@ class Engine:
     if name == "e" or self.precision == PRECISION_FP32:
       return raw.view(torch.float32)
     return raw.view(torch.float16)
+
+  def debug_occupy(self, n_ctas: int, cycles: int, stream: Optional[torch.cuda.Stream] = None) -> None:
+    """Test helper: n_ctas CTAs that each hold a whole SM for `cycles` clock ticks on `stream` (default: the current one)."""
+    st = (stream if stream is not None else torch.cuda.current_stream(self.device)).cuda_stream
+    self._check(self.lib.wg_debug_occupy(self._h, n_ctas, cycles, st), "wg_debug_occupy")
 
   def debug_gemm2(self, a: torch.Tensor, b: torch.Tensor, ks: int = 64) -> torch.Tensor:
     """D = A @ B^T through the cta_group::2 (CTA pair) diagnostic kernel; ks = K elements per operand stage (64: SWIZZLE_128B,
