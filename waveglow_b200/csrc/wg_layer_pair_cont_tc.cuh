@@ -411,20 +411,21 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
         __syncwarp();
       }
     };
+    // leader CTA, chained launch: claim the next work item for this pair and publish it to both CTAs (slot = iteration % 8)
+    auto claim = [&](int slot_it) {
+      if (ptx::elect_one()) {
+        const uint32_t w_new = atomicAdd(p.counter, 1u);
+        s_items[slot_it & 7] = w_new;
+        ptx::st_shared_cluster_u32(ptx::map_to_cta(const_cast<uint32_t*>(&s_items[slot_it & 7]), 1), w_new);
+        ptx::mbar_arrive(&item_bar[slot_it & 7]);
+        ptx::mbar_arrive_release_cluster(ptx::map_to_cta(&item_bar[slot_it & 7], 1));
+      }
+      __syncwarp();
+    };
     Coord prev{};
     int it = 0;
+    if (claimed && rank == 0) claim(0);
     for (;; ++it) {
-      if (claimed && rank == 0) {
-        // claim the next work item for this pair and publish it to both CTAs
-        if (ptx::elect_one()) {
-          const uint32_t w_new = atomicAdd(p.counter, 1u);
-          s_items[it & 7] = w_new;
-          ptx::st_shared_cluster_u32(ptx::map_to_cta(const_cast<uint32_t*>(&s_items[it & 7]), 1), w_new);
-          ptx::mbar_arrive(&item_bar[it & 7]);
-          ptx::mbar_arrive_release_cluster(ptx::map_to_cta(&item_bar[it & 7], 1));
-        }
-        __syncwarp();
-      }
       const int w = item_of(it);
       if (w >= n_items) break;
       const Coord tc = decode(w);
@@ -474,6 +475,9 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
           }
           __syncwarp();
         }
+        // The next item is claimed one ahead, here, after chunk 0's loads: the cluster-scope release of the publication is a
+        // heavy fence, and at this point the ring is full and this warp has slack (at the top of an item it cost ~1 % of the step)
+        if (c == 0 && claimed && rank == 0) claim(it + 1);
       }
       prev = tc;
     }
