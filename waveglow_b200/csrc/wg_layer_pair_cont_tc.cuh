@@ -362,10 +362,14 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
     // of layer l - 1 that wrote its three tap windows (and, through the centre tap, its own rows of e) have completed.  One
     // candidate per lane: (tap, utterance of a packed tile, first / last row of the window); a window of <= 128 frames touches
     // at most two entries (|frame shift| <= 4).
-    auto wait_deps = [&](const Coord& tc) {
+    const uint32_t* dep_flag = nullptr;      // this lane's candidate of the current tile (nullptr: none)
+    uint32_t dep_seen = 0;
+    // ... in two steps: the flag is READ at the top of the tile (the load's ~1 us of latency hides under the mel-window stages),
+    // and only a lane whose producer was not finished yet spins, right before the first tap load
+    auto deps_begin = [&](const Coord& tc) {
       const LayerDesc& L = p.ly[tc.l];
       const int tap = lane >> 3, u = (lane >> 1) & 3, last = lane & 1;
-      bool need = tap < 3 && (tr.packed || u == 0);
+      bool need = tc.l > 0 && tap < 3 && (tr.packed || u == 0);
       int pt_dep = 0;
       if (need) {
         const int pp = tc.ph + (tap - 1) * L.dilation;
@@ -377,7 +381,11 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
         qb = qb >= p.Fq ? p.Fq - 1 : qb;
         pt_dep = (entry_of(b < p.B ? b : 0, last ? qb : qa) >> 1) * kPhases + (pp - (dq << 5));
       }
-      if (need) ptx::wait_flag_at_least(p.flags + static_cast<size_t>(tc.l - 1) * n_ptiles + pt_dep, kTileDoneCount);
+      dep_flag = need ? p.flags + static_cast<size_t>(tc.l - 1) * n_ptiles + pt_dep : nullptr;
+      dep_seen = need ? ptx::ld_acquire_gpu(dep_flag) : kTileDoneCount;
+    };
+    auto deps_finish = [&]() {
+      if (dep_seen < kTileDoneCount) ptx::wait_flag_at_least(dep_flag, kTileDoneCount);
       __syncwarp();
       ptx::fence_proxy_async_global();      // the generic-proxy stores just acquired -> this warp's TMA (async proxy) loads
     };
@@ -432,6 +440,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
       const LayerDesc& L = p.ly[tc.l];
       const bool prev_res = it > 0 && p.ly[prev.l].has_res;
       tr = rows_of(tc.en);
+      if (claimed) deps_begin(tc);
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
 #pragma unroll 1
@@ -449,7 +458,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
               ptx::griddep_wait();
               dep_ok = true;
             }
-            if (c == 0 && tc.l > 0) wait_deps(tc);
+            if (c == 0 && tc.l > 0) deps_finish();
           }
           next_stage();
           if (ptx::elect_one()) {
