@@ -433,6 +433,9 @@ def main():
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read + write)", "traffic_source": traffic_src,
                 "peak_source": peak_src, "launch_ms": per_launch_ms, "launches_per_step": layer_launches,
+                "launch_unit": "one WN layer (the unit of launch_ms / launches_per_step / algorithmic_flop_per_launch); the generic "
+                               "layers of a flow run as one chained launch of this kernel, so a step has fewer launches than layers "
+                               "(gpu_launches counts real launches)",
                 "algorithmic_flop_per_launch": per_launch_flops,
                 "executed_tensor_tflops": exec_per_step_layer * (B * T / 8) / (per_launch_ms * 1e-3) / 1e12,
                 "executed_over_algorithmic": exec_per_step_layer * (B * T / 8) / per_launch_flops,

@@ -31,7 +31,7 @@ for step in "$@"; do
     ab_chain256) for v in 0 1 0 1 0 1; do echo "WG_CHAIN=$v (256 ch, B16 x 861)"; WG_CHAIN=$v python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | python tools/bench_brief.py; done | tee $OUT/ab_chain256.txt ;;
     bench)     TAILN=1 run bench 600 python bench.py --steps 10 --warmup 3 ;;
     bench_fast) TAILN=1 run bench_fast 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-parity ;;
-    bench512)  TAILN=1 run bench512 600 python bench.py --channels 512 --batch 32 --steps 5 --warmup 3 --no-cpu-baseline ;;
+    bench512)  TAILN=1 run bench512 600 python bench.py --channels 512 --scaling strong --global-batch 32 --steps 5 --warmup 3 --no-cpu-baseline ;;
     bench512_b8) TAILN=1 run bench512_b8 600 python bench.py --channels 512 --batch 8 --steps 5 --warmup 3 --no-cpu-baseline --no-parity ;;
     ref)       TAILN=1 run ref 900 python bench.py --impl reference --steps 2 --warmup 1 ;;
     callers)   TAILN=12 run callers 900 python tools/profile_callers.py ;;
