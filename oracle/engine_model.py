@@ -134,11 +134,15 @@ def shift_time(x: Tensor, s: int) -> Tensor:
 
 
 def wn_layers(pf: PackedFlow, dims: O.ModelDims, x: Tensor, S: Tensor, op_dtype: torch.dtype,
-              trace: Optional[list] = None, mw: Optional[Tensor] = None, a0: Optional[Tensor] = None) -> Tensor:
+              trace: Optional[list] = None, mw: Optional[Tensor] = None, a0: Optional[Tensor] = None,
+              exact_carry: bool = False) -> Tensor:
   """x: [B,T',nc] (already in op_dtype precision), S: [B,T',640] (or None with mw = mel windows [B,F',320]).
   a0 [B,T',h] (with mw): the first layer takes the live half of the audio state itself (start conv composed in).
+  exact_carry (the engine's 512-channel kernel): the residual stream is carried as a two-term split hi + lo in the operand
+  dtype, i.e. exactly to ~2^-22; only the dilated-conv taps see its rounded value.
   Returns e [B,T',2h] fp32 (without e_bias)."""
   nc = dims.n_channels
+  store = (lambda v: v) if exact_carry else (lambda v: rnd(v, op_dtype))
   e = torch.zeros(x.size(0), x.size(1), 2 * pf.h, dtype=torch.float32)
   for i in range(dims.n_layers):
     d = 2 ** i
@@ -166,15 +170,16 @@ def wn_layers(pf: PackedFlow, dims: O.ModelDims, x: Tensor, S: Tensor, op_dtype:
       pre = pre + cond.reshape(B, -1, 2 * nc)[:, :T]
       acts = rnd(torch.tanh(pre[..., :nc]) * torch.sigmoid(pre[..., nc:]), op_dtype)
       e = e + acts @ rnd(pf.w_se[0], op_dtype).t()
-      x = rnd(a01 @ split_cols(ws1).t() + acts @ rnd(pf.w_res[0], op_dtype).t() + pf.b_res[0], op_dtype)
+      x = store(a01 @ split_cols(ws1).t() + acts @ rnd(pf.w_res[0], op_dtype).t() + pf.b_res[0])
       if trace is not None:
         trace.append({"layer": 0, "acts": acts.clone(), "x": x.clone(), "e": e.clone()})
       continue
+    xt = rnd(x, op_dtype)                                                        # what the taps read (== x without exact_carry)
     if mw is None:
-      a = torch.cat([shift_time(x, -d), x, shift_time(x, d), S], dim=2)          # [B,T',3nc+640]
+      a = torch.cat([shift_time(xt, -d), xt, shift_time(xt, d), S], dim=2)       # [B,T',3nc+640]
       pre = a @ rnd(pf.w1[i], op_dtype).t() + pf.b1[i]                           # fp32 accumulate
     else:
-      a = torch.cat([shift_time(x, -d), x, shift_time(x, d)], dim=2)
+      a = torch.cat([shift_time(xt, -d), xt, shift_time(xt, d)], dim=2)
       pre = a @ rnd(pf.w1[i][:, : 3 * nc], op_dtype).t() + pf.b1p[i]
       B, T, P = x.size(0), x.size(1), 256 // dims.n_group
       cond = torch.einsum("bqk,pok->bqpo", mw, rnd(pf.v[i], op_dtype))           # [B,F',32,2nc]
@@ -182,7 +187,7 @@ def wn_layers(pf: PackedFlow, dims: O.ModelDims, x: Tensor, S: Tensor, op_dtype:
     acts = rnd(torch.tanh(pre[..., :nc]) * torch.sigmoid(pre[..., nc:]), op_dtype)
     e = e + acts @ rnd(pf.w_se[i], op_dtype).t()
     if pf.w_res[i] is not None:
-      x = rnd(x + acts @ rnd(pf.w_res[i], op_dtype).t() + pf.b_res[i], op_dtype)
+      x = store(x + acts @ rnd(pf.w_res[i], op_dtype).t() + pf.b_res[i])
     if trace is not None:
       trace.append({"layer": i, "acts": acts.clone(), "x": x.clone(), "e": e.clone()})
   return e
@@ -201,7 +206,7 @@ def pack_noise(dims: O.ModelDims, zs: Sequence[Tensor], sigma: float) -> Tensor:
 
 def infer(w: Dict[str, Tensor], dims: O.ModelDims, mel: Tensor, sigma: float, zs: Sequence[Tensor],
           op_dtype: torch.dtype = torch.float16, trace: Optional[list] = None, phase_cond: bool = False,
-          first_composed: bool = False) -> Tensor:
+          first_composed: bool = False, exact_carry: bool = False) -> Tensor:
   state = pack_noise(dims, zs, sigma)                   # [B,T',8] fp32
   G = dims.n_group
   if phase_cond:
@@ -216,9 +221,11 @@ def infer(w: Dict[str, Tensor], dims: O.ModelDims, mel: Tensor, sigma: float, zs
     c, h = pf.c, pf.h
     a0 = state[..., G - c: G - c + h]
     a1 = state[..., G - c + h:]
-    x = rnd(a0 @ pf.w_start.t() + pf.b_start, op_dtype)
+    x = a0 @ pf.w_start.t() + pf.b_start
+    if not exact_carry:
+      x = rnd(x, op_dtype)
     tr = [] if trace is not None else None
-    e = wn_layers(pf, dims, x, S, op_dtype, tr, mw, a0 if first_composed else None) + pf.e_bias
+    e = wn_layers(pf, dims, x, S, op_dtype, tr, mw, a0 if first_composed else None, exact_carry) + pf.e_bias
     b, s = e[..., :h], e[..., h:]
     a1 = (a1 - b) * torch.exp(-s)
     live = torch.cat([a0, a1], dim=2) @ pf.w_inv.t()

@@ -103,20 +103,27 @@ def test_stagewise_first_flow(precision, nc):
   trace = []
   phase_cond = precision != "fp32"     # tensor-core mode composes the upsampler into the conditioning weights
   first_composed = precision == "fp16"  # ... and the start conv into each flow's first layer
+  exact_carry = phase_cond and nc == 512      # the 512-channel kernel carries the residual stream as fp16 hi + fp16 lo
   with torch.no_grad():
-    ref_audio = E.infer(w, dims, mel, sigma, zs, op_dtype, trace, phase_cond=phase_cond, first_composed=first_composed)
+    ref_audio = E.infer(w, dims, mel, sigma, zs, op_dtype, trace, phase_cond=phase_cond, first_composed=first_composed,
+                        exact_carry=exact_carry)
   k = dims.n_flows - 1
   flow_tr = trace[0]
   assert flow_tr["flow"] == k
   S_ref = E.rnd(E.upsample_squeeze_tm(w, dims, mel), op_dtype)
   pf = E.PackedFlow(w, dims, k)
   state0 = E.pack_noise(dims, zs, sigma)
-  x0_ref = E.rnd(state0[..., 4:6] @ pf.w_start.t() + pf.b_start, op_dtype)
+  x0_ref = state0[..., 4:6] @ pf.w_start.t() + pf.b_start
+  if not exact_carry:
+    x0_ref = E.rnd(x0_ref, op_dtype)
   failures = []
 
   def x_view(buf):
-    """engine x buffer -> time-major [B, T, 256] (tensor-core mode keeps it phase-major [B][32][T/32][256])"""
+    """engine x buffer -> time-major [B, T, nc] (tensor-core mode keeps it phase-major [B][32][T/32][nc]; with the exact carry
+    the stream is the sum of the hi buffer and its rounding-residual buffer)"""
     raw = eng.debug_view(buf, B, F).float().cpu()
+    if exact_carry:
+      raw = raw + eng.debug_view(buf.replace("x", "xlo"), B, F).float().cpu()
     if precision != "fp32":
       return raw.view(B, 32, T // 32, nc).permute(0, 2, 1, 3).reshape(B, T, nc)
     return raw.view(B, T, nc)

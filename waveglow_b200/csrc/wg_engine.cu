@@ -42,6 +42,7 @@ struct FlowPack {
 struct ActMaps {
   CUtensorMap x3[3][16], mw[3], a0[3];
   CUtensorMap x4[16], mw4, a04;
+  CUtensorMap xl3[3][16], xl4[16];      // 512 channels: the rounding-residual buffers of the residual stream (exact carry)
 };
 
 }  // namespace
@@ -73,6 +74,7 @@ struct wg_engine {
   bool trim_grid = false;             // WG_TRIM=1: smallest grid with the same number of tile rounds (measured 0.7 % SLOWER on
                                       // config 2 than letting all 74 pairs run, profiles/r01/ab_trim_g2at_v12.txt: off by default)
   bool pdl = true;                    // programmatic dependent launch between layer launches (WG_PDL=0 disables)
+  bool carry_lo = false;              // 512-channel tensor-core mode: residual stream carried exactly as fp16 hi + fp16 lo (ContCfg::kCarryLo)
   bool chain = true;                  // the generic layers of a flow in ONE launch with tile-level dependencies (WG_CHAIN=0: one launch per layer)
   bool pack4 = true;                  // pack the ragged last frames of 4 utterances into shared tiles (WG_PACK4=0 disables)
   void* d_wc = nullptr;               // [flows][3 taps x 2 nc packed rows + nc carry rows][16] 16-bit composed start weights
@@ -307,6 +309,7 @@ struct WsLayout {
   size_t state, sums;              // forward only: time-major state [B,T,8] fp32; double accumulators [n_flows]
   size_t a0;                       // start conv composed into the first layer: [B][32][Fq][16] 16-bit rows [a0 | 1]
   size_t cond, e, total;           // cond: fp32 mode = upsampled conditioning S [B,T,640]; fp16 mode = mel windows MW [B,Fq,320]
+  size_t xlo[16];                  // 512-channel tensor-core mode: rounding residuals of x[i] (the stream is carried as hi + lo), else unused
   size_t x[16];                    // residual stream buffers.  Tensor-core mode: one per layer (layer i reads x[i], writes x[i + 1]:
   int n_x;                         // chained launches have no write-after-read hazards); fp32 mode: 2, ping-pong
   size_t flags, flags_bytes;       // tensor-core mode: completion counters of chained launches [n_flows][n_layers][pair-tiles] uint32,
@@ -333,6 +336,12 @@ WsLayout ws_layout(const wg_engine* e, int B, int T) {
     L.x[i] = off;
     off = align_up(off + nppos * e->cfg.n_channels * L.elt, 1024);
   }
+  for (int i = 0; i < 16; ++i) L.xlo[i] = L.x[0];
+  if (e->carry_lo)
+    for (int i = 0; i < L.n_x; ++i) {
+      L.xlo[i] = off;
+      off = align_up(off + nppos * e->cfg.n_channels * L.elt, 1024);
+    }
   // most pair-tiles any tile mode can make of this shape: 32-frame segments
   L.ptiles_cap = kUpPhases * ((B * ((L.Tpad / kUpPhases + 31) / 32) + 1) / 2 + 1);
   L.flags = off;
@@ -356,7 +365,7 @@ int frames_to_T(int frames) { return frames * kUpStride / kGroup; }
 
 // The fused layer kernel is a template over everything that selects code (channel count, ring stage width, first layer of a
 // flow, tile mode).
-using LayerKernel = void (*)(const XMaps, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+using LayerKernel = void (*)(const XMaps, const XLoMaps, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                              const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                              const LayerTcParams);
 
@@ -482,6 +491,7 @@ int wg_create(const wg_config* cfg, wg_engine** out) {
   e->trim_grid = trim_env && atoi(trim_env) != 0;
   const char* pdl_env = getenv("WG_PDL");
   e->pdl = !(pdl_env && atoi(pdl_env) == 0);
+  e->carry_lo = tc && nc == 512;
   const char* chain_env = getenv("WG_CHAIN");
   e->chain = !(chain_env && atoi(chain_env) == 0);
   const char* pack_env = getenv("WG_PACK4");
@@ -781,6 +791,11 @@ int wg_debug_view(const wg_engine* e, const char* name, int32_t batch, int32_t f
   if (!strcmp(name, "cond")) {
     *ptr = base + L.cond;
     *bytes = L.cond_bytes;
+  } else if (!strncmp(name, "xlo", 3) && e->carry_lo) {
+    const int i = atoi(name + 3);
+    if (i < 0 || i >= e->cfg.n_layers) return WG_ERR_INVALID_ARGUMENT;
+    *ptr = base + L.xlo[i % L.n_x];
+    *bytes = static_cast<size_t>(batch) * L.Tpad * e->cfg.n_channels * L.elt;
   } else if (name[0] == 'x' && name[1] >= '0' && name[1] <= '9') {
     // "x<i>": the residual stream that layer i READS (layer i - 1 wrote it).  fp32 mode ping-pongs two buffers.
     const int i = atoi(name + 1);
@@ -1046,6 +1061,7 @@ void flow_step_any(wg_engine* e, const FlowStepParams& fs_in, float* state, cons
   FlowStepParams fs = fs_in;
   fs.x_phase_major = e->cfg.precision == WG_PRECISION_FP16 ? 1 : 0;
   if (!e->first_comp) fs.a0_out = nullptr;
+  if (!e->carry_lo) fs.xlo_out = nullptr;
   if (e->cfg.precision == WG_PRECISION_FP32)
     launch_flow_step<float>(fs, state, ebuf, x, B, T, Tpad, st);
   else
@@ -1131,6 +1147,7 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
       d.bias_res = e->d_bias_res + li * nc;
       d.wse = static_cast<const uint16_t*>(e->d_w2) + (li * (nc + 16) + nc) * nc;
       d.x_out = ws + L.x[(i + 1) % L.n_x];
+      d.xlo_out = e->carry_lo ? ws + L.xlo[(i + 1) % L.n_x] : nullptr;
       return d;
     };
     // one launch of layers [i0, i1)
@@ -1151,15 +1168,20 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
       lp.reverse = lp.n_layers == 1 ? static_cast<int>((static_cast<size_t>(k) * NL + i0) & 1) : 0;
       lp.flags = reinterpret_cast<uint32_t*>(ws + L.flags) + static_cast<size_t>(k) * NL * L.ptiles_cap + static_cast<size_t>(i0) * n_ptiles;
       XMaps xm{};
+      XLoMaps xl{};
       for (int j = 0; j < lp.n_layers; ++j) {
         lp.ly[j] = desc(i0 + j);
         lp.ly[j].x_in = j;
         xm.m3[j] = am->x3[best_idx][i0 + j];
         xm.m4[j] = am->x4[i0 + j];
+        xl.m3[j] = am->xl3[best_idx][i0 + j];
+        xl.m4[j] = am->xl4[i0 + j];
       }
       for (int j = lp.n_layers; j < kMaxLayersPerLaunch; ++j) {      // unused slots: valid maps, never dereferenced
         xm.m3[j] = xm.m3[0];
         xm.m4[j] = xm.m4[0];
+        xl.m3[j] = xl.m3[0];
+        xl.m4[j] = xl.m4[0];
       }
       for (int h = 0; h < kMaxHalves; ++h) lp.g2_at[h] = first ? e->g2_at_first[h] : e->g2_at[h];
       if (lp.n_layers > 1) {
@@ -1184,7 +1206,7 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
       attr[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr;
       cfg.numAttrs = e->pdl ? 1 : 0;
-      WG_CUDA(e, cudaLaunchKernelEx(&cfg, layer_kernel(nc, e->ks, first ? 1 : 0, mode), xm, am->mw[best_idx], e->tm_w1h, e->tm_vh,
+      WG_CUDA(e, cudaLaunchKernelEx(&cfg, layer_kernel(nc, e->ks, first ? 1 : 0, mode), xm, xl, am->mw[best_idx], e->tm_w1h, e->tm_vh,
                                     e->tm_w2h, e->tm_ident16, am->a0[best_idx], e->tm_wc, am->mw4, am->a04, lp));
       e->launches++;
       return WG_OK;
@@ -1301,6 +1323,11 @@ int encode_act_maps(wg_engine* e, uint8_t* ws, const WsLayout& L, int B, int T, 
         if ((rc = make_map(e, &am->x3[idx][i], ws + L.x[i], 3, dims, str, box, dt))) return rc;
       }
       if ((rc = make_map(e, &am->x4[i], ws + L.x[i], 4, dims4, str4, box4, dt))) return rc;
+      for (int idx = 0; idx < 3; ++idx) {
+        const uint32_t box[3] = {ks, rows[idx], 1};
+        if ((rc = make_map(e, &am->xl3[idx][i], ws + L.xlo[i], 3, dims, str, box, dt))) return rc;
+      }
+      if ((rc = make_map(e, &am->xl4[i], ws + L.xlo[i], 4, dims4, str4, box4, dt))) return rc;
     }
   }
   {
@@ -1399,6 +1426,7 @@ int wg_infer(wg_engine* e, const float* mel, int32_t batch, int32_t frames, cons
     fs.w_start = f.d_w_start;
     fs.b_start = f.d_b_start;
     fs.a0_out = ws + L.a0;
+    fs.xlo_out = ws + L.xlo[0];
     flow_step(fs, xb[cur]);
   }
   bool stopped = (e->dbg_flow == NF - 1 && e->dbg_layer == -1);
@@ -1422,6 +1450,7 @@ int wg_infer(wg_engine* e, const float* mel, int32_t batch, int32_t frames, cons
       fs.w_start = g.d_w_start;
       fs.b_start = g.d_b_start;
       fs.a0_out = ws + L.a0;
+      fs.xlo_out = ws + L.xlo[0];
     }
     flow_step(fs, xb[cur]);
     if (e->dbg_flow == k && e->dbg_layer >= e->cfg.n_layers) stopped = true;
@@ -1518,6 +1547,7 @@ int wg_forward(wg_engine* e, const float* mel, int32_t batch, int32_t frames, co
       fs.w_start = g.d_w_start;
       fs.b_start = g.d_b_start;
       fs.a0_out = ws + L.a0;
+      fs.xlo_out = ws + L.xlo[0];
     }
     flow_step_any(e, fs, state, ebuf, xb[cur], B, T, L.Tpad, st);
     if (k == NF) break;

@@ -195,6 +195,8 @@ struct FlowStepParams {
   const float* w_start;       // [nc, h2]
   const float* b_start;       // [nc]
   int x_phase_major;          // 1: x is [B][phase 32][frame][nc] (tensor-core mode), 0: time-major [B][Tpad][nc]
+  void* xlo_out;              // 512-channel tensor-core mode: the rounding residual x - fp16(x) of the start conv's output, same layout as
+                              // x (the layer kernel carries the residual stream exactly as hi + lo); nullptr otherwise
   void* a0_out;               // tensor-core mode with the start conv composed into the first WN layer: instead of x, write the
                               // 16-bit rows [a_hi (4) | a_lo (4) | a_hi (4) | 1 | 1 | 0 | 0], phase-major [B][32][Fq][16], where
                               // a_hi + a_lo is the two-term 16-bit split of the live first-half channels a0 (h2 <= 4 of them)
@@ -365,6 +367,12 @@ flow_step_kernel(FlowStepParams p, float* __restrict__ state, const float* __res
 #pragma unroll
       for (int u = 0; u < 8; ++u) h[u] = from_float<XT>(v[u]);
       *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+      if (p.xlo_out) {
+        XT l[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) l[u] = from_float<XT>(v[u] - to_float<XT>(h[u]));
+        *reinterpret_cast<uint4*>(static_cast<XT*>(p.xlo_out) + row * p.nc + gidx * 8) = *reinterpret_cast<const uint4*>(l);
+      }
     } else {
       reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
       reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);

@@ -50,6 +50,8 @@ struct LayerDesc {
   const float* bias_res;  // [NC]
   const void* wse;        // this layer's skip-end weights, 16-bit [8][NC] (rows NC.. of its packed W2)
   void* x_out;            // the residual stream it writes (phase-major [B][32][Fq][NC], 16-bit), plain stores
+  void* xlo_out;          // 512 channels: the rounding residual of x_out, x' - fp16(x') (same layout): with it the stream is carried
+                          // exactly from layer to layer (the taps still see fp16(x)); nullptr for 256 channels
 };
 
 // Parameters of one launch of the fused kernel: n_layers consecutive layers of one flow.  What selects code (channel count,
@@ -80,6 +82,8 @@ struct XMaps {
   CUtensorMap m3[kMaxLayersPerLaunch];
   CUtensorMap m4[kMaxLayersPerLaunch];
 };
+// 512 channels: the same views of the rounding-residual buffers (LayerDesc::xlo_out of the previous layer); placeholders for 256
+typedef XMaps XLoMaps;
 
 __device__ __forceinline__ void stamp(const LayerTcParams& p, int slot) {
   if (p.timeline) p.timeline[(static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 16 + slot] = clock64();

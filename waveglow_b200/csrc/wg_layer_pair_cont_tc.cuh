@@ -89,6 +89,11 @@ struct ContCfg {
   static constexpr int kStages = kRingBytes / kStageBytes;
   static_assert(kStages <= 8, "barrier arrays hold 8 stages");
   static constexpr bool kConstSmem = NC == 256;
+  // 512 channels: EXACT residual carry.  x' is stored as fp16 hi + fp16 lo (two buffers); GEMM2 adds x_hi . I and x_lo . I, the
+  // dilated-conv taps read x_hi only.  Without it the rounding of x' accumulates over the layers of a flow (58 % of the error
+  // variance, tools/error_budget.py) and the 512-channel model misses north_star's 2e-3 max-abs at 10 s utterances (2.16e-3);
+  // the x_lo blocks ride in the A slots of GEMM2 stages 4..7, which carry only W_res for 512 channels: no extra stages.
+  static constexpr bool kCarryLo = NC == 512;
   static constexpr int kBiasFloats = 3 * NC;                 // [2 NC] packed GEMM1 bias, then [NC] residual bias
   static constexpr int kWseWords = (NC / 8) * 32;            // skip-end weights as mma.sync B fragments [NC / 8 registers][32 lanes]
   static constexpr int kActsBytes = kTileM * NC * 2;
@@ -113,6 +118,7 @@ template <int NC, int KS, bool kFirst, int kMode>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kContThreads, 1)
 wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x buffers: m3 {NC, Fq, 32 B} box {KS, rows, 1} (rows = 128; seg_rows in
                                                                           // segment mode), m4 {NC, Fq, 32, B} box {KS, 32, 1, 4} (packed tails)
+                          const __grid_constant__ XLoMaps xl,             // 512 channels: the rounding-residual buffers, same views
                           const __grid_constant__ CUtensorMap tm_mw,      // {320, Fq, B} box {KS, rows, 1}
                           const __grid_constant__ CUtensorMap tm_w1h,     // {3 NC, rows} box {KS,128}
                           const __grid_constant__ CUtensorMap tm_vh,      // {320, rows} box {KS,128}
@@ -398,11 +404,13 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
       for (int j = 0; j < CB; ++j) {
         next_stage();
         const bool with_x = !kFirst && j < 256 / KS;
+        const bool with_lo = C::kCarryLo && !kFirst && j >= 256 / KS;      // 512 channels: stages 4..7 carry the x_lo blocks 0..3
         if (ptx::elect_one()) {
-          const uint32_t lb = arm(with_x ? 2 * kStageBytes : 2 * kStageB);
+          const uint32_t lb = arm(with_x || with_lo ? 2 * kStageBytes : 2 * kStageB);
           if (!skip_loads) {
             ptx::tma_load_2d_pair(sb, &tm_w2h, lb, j * KS, L.w2_row0 + h * 256 + static_cast<int>(rank) * 128);
             if (with_x) load_rows(&xm.m3[L.x_in], &xm.m4[L.x_in], lb, h * 256 + j * KS, 0, tc.ph);
+            if (with_lo) load_rows(&xl.m3[L.x_in], &xl.m4[L.x_in], lb, h * 256 + (j - 256 / KS) * KS, 0, tc.ph);
           }
         }
         __syncwarp();
@@ -540,10 +548,12 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
               ptx::mma_f16_ss_pair(rQ, ptx::make_desc_sw128(a_addr + k * 32), ring_desc<KS>(b_addr + k * 32), idesc256, (jj | k) != 0);
             // K-step k of this stage's x block covers channels jj KS + 16 k .. +15 of this half; [I32 | 0] maps them onto the 32
             // output columns that contain them
-            if (!kFirst && jj < 256 / KS && !(p.dbg_flags & 128)) {
+            // (512 channels: stages 4..7 carry the x_lo blocks of channels (jj - 4) KS .. of this half, added the same way)
+            const int xb = jj < 256 / KS ? jj : jj - 256 / KS;
+            if (!kFirst && (jj < 256 / KS || C::kCarryLo) && !(p.dbg_flags & 128)) {
 #pragma unroll
               for (int k = 0; k < NS; ++k)
-                ptx::mma_f16_ss_pair(rQ + ((jj * KS + 16 * k) >> 5) * 32, ring_desc<KS>(x_addr + k * 32),
+                ptx::mma_f16_ss_pair(rQ + ((xb * KS + 16 * k) >> 5) * 32, ring_desc<KS>(x_addr + k * 32),
                                      ptx::make_desc_sw128(ident_addr + (k & 1) * 32), idesc32, 1);
             }
             ptx::mma_commit_pair(&empty[s], 3);
@@ -707,32 +717,72 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
           ptx::mbar_wait(&d2_full[h], par);
           ptx::tc_fence_after_sync();
           if (tl && h == 0) stamp(p, 10);
-          uint32_t pk[32];      // this thread's 64 channels, packed
+          if constexpr (!C::kCarryLo) {
+            uint32_t pk[32];      // this thread's 64 channels, packed
 #pragma unroll
-          for (int g2 = 0; g2 < 2; ++g2) {
-            uint32_t v0[16], v1[16];
-            ptx::tmem_ld16(lane_base + 256 + cq * 64 + g2 * 32, v0);
-            ptx::tmem_ld16(lane_base + 256 + cq * 64 + g2 * 32 + 16, v1);
-            ptx::tmem_ld_wait();
-            const float4* bp = reinterpret_cast<const float4*>(bias_res + h * 256 + cq * 64 + g2 * 32);
+            for (int g2 = 0; g2 < 2; ++g2) {
+              uint32_t v0[16], v1[16];
+              ptx::tmem_ld16(lane_base + 256 + cq * 64 + g2 * 32, v0);
+              ptx::tmem_ld16(lane_base + 256 + cq * 64 + g2 * 32 + 16, v1);
+              ptx::tmem_ld_wait();
+              const float4* bp = reinterpret_cast<const float4*>(bias_res + h * 256 + cq * 64 + g2 * 32);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 b4 = C::kConstSmem ? bp[i] : __ldg(bp + i);
-              const float4 c4 = C::kConstSmem ? bp[4 + i] : __ldg(bp + 4 + i);
-              pk[g2 * 16 + 2 * i] = live ? ptx::pack_half2(__uint_as_float(v0[4 * i]) + b4.x, __uint_as_float(v0[4 * i + 1]) + b4.y) : 0u;
-              pk[g2 * 16 + 2 * i + 1] = live ? ptx::pack_half2(__uint_as_float(v0[4 * i + 2]) + b4.z, __uint_as_float(v0[4 * i + 3]) + b4.w) : 0u;
-              pk[g2 * 16 + 8 + 2 * i] = live ? ptx::pack_half2(__uint_as_float(v1[4 * i]) + c4.x, __uint_as_float(v1[4 * i + 1]) + c4.y) : 0u;
-              pk[g2 * 16 + 8 + 2 * i + 1] = live ? ptx::pack_half2(__uint_as_float(v1[4 * i + 2]) + c4.z, __uint_as_float(v1[4 * i + 3]) + c4.w) : 0u;
+              for (int i = 0; i < 4; ++i) {
+                const float4 b4 = C::kConstSmem ? bp[i] : __ldg(bp + i);
+                const float4 c4 = C::kConstSmem ? bp[4 + i] : __ldg(bp + 4 + i);
+                pk[g2 * 16 + 2 * i] = live ? ptx::pack_half2(__uint_as_float(v0[4 * i]) + b4.x, __uint_as_float(v0[4 * i + 1]) + b4.y) : 0u;
+                pk[g2 * 16 + 2 * i + 1] = live ? ptx::pack_half2(__uint_as_float(v0[4 * i + 2]) + b4.z, __uint_as_float(v0[4 * i + 3]) + b4.w) : 0u;
+                pk[g2 * 16 + 8 + 2 * i] = live ? ptx::pack_half2(__uint_as_float(v1[4 * i]) + c4.x, __uint_as_float(v1[4 * i + 1]) + c4.y) : 0u;
+                pk[g2 * 16 + 8 + 2 * i + 1] = live ? ptx::pack_half2(__uint_as_float(v1[4 * i + 2]) + c4.z, __uint_as_float(v1[4 * i + 3]) + c4.w) : 0u;
+              }
             }
-          }
-          // region Q is read: the next x' half / the next tile's first odd chunk may overwrite it.  Signalled BEFORE the global
-          // stores: nothing in memory has to become visible to the other CTA.
-          ptx::tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive_cluster(ptx::map_to_cta(&res_drained[h], 0));
-          if (in_buf && !(p.dbg_flags & 8)) {
+            // region Q is read: the next x' half / the next tile's first odd chunk may overwrite it.  Signalled BEFORE the global
+            // stores: nothing in memory has to become visible to the other CTA.
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(ptx::map_to_cta(&res_drained[h], 0));
+            if (in_buf && !(p.dbg_flags & 8)) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) ptx::st_global_v8(dst + h * 512 + k * 32, *reinterpret_cast<uint32_t(*)[8]>(&pk[8 * k]));
+              for (int k = 0; k < 4; ++k) ptx::st_global_v8(dst + h * 512 + k * 32, *reinterpret_cast<uint32_t(*)[8]>(&pk[8 * k]));
+            }
+          } else {
+            // exact carry: x' = hi + lo, hi = fp16(x'), lo = fp16(x' - hi), to two buffers of the same layout.  32 columns at a time
+            // (16 + 16 packed registers); region Q is released after the second read, before that half's stores
+            uint8_t* dst_lo = static_cast<uint8_t*>(L.xlo_out) + (dst - static_cast<uint8_t*>(L.x_out));
+#pragma unroll
+            for (int g2 = 0; g2 < 2; ++g2) {
+              uint32_t v0[16], v1[16];
+              ptx::tmem_ld16(lane_base + 256 + cq * 64 + g2 * 32, v0);
+              ptx::tmem_ld16(lane_base + 256 + cq * 64 + g2 * 32 + 16, v1);
+              ptx::tmem_ld_wait();
+              if (g2 == 1) {
+                ptx::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_cluster(ptx::map_to_cta(&res_drained[h], 0));
+              }
+              const float4* bp = reinterpret_cast<const float4*>(bias_res + h * 256 + cq * 64 + g2 * 32);
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 b4 = __ldg(bp + i);
+                const uint32_t* v = i < 4 ? &v0[4 * i] : &v1[4 * (i - 4)];
+                const float f0 = __uint_as_float(v[0]) + b4.x, f1 = __uint_as_float(v[1]) + b4.y;
+                const float f2 = __uint_as_float(v[2]) + b4.z, f3 = __uint_as_float(v[3]) + b4.w;
+                const __half2 h01 = __floats2half2_rn(f0, f1), h23 = __floats2half2_rn(f2, f3);
+                const float2 r01 = __half22float2(h01), r23 = __half22float2(h23);
+                hi[2 * i] = live ? *reinterpret_cast<const uint32_t*>(&h01) : 0u;
+                hi[2 * i + 1] = live ? *reinterpret_cast<const uint32_t*>(&h23) : 0u;
+                lo[2 * i] = live ? ptx::pack_half2(f0 - r01.x, f1 - r01.y) : 0u;
+                lo[2 * i + 1] = live ? ptx::pack_half2(f2 - r23.x, f3 - r23.y) : 0u;
+              }
+              if (in_buf && !(p.dbg_flags & 8)) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                  ptx::st_global_v8(dst + h * 512 + g2 * 64 + k * 32, *reinterpret_cast<uint32_t(*)[8]>(&hi[8 * k]));
+                  ptx::st_global_v8(dst_lo + h * 512 + g2 * 64 + k * 32, *reinterpret_cast<uint32_t(*)[8]>(&lo[8 * k]));
+                }
+              }
+            }
           }
           if (tl && h == NH - 1) stamp(p, 11);
         }
