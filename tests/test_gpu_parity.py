@@ -23,7 +23,8 @@ def get_model(n_channels: int, precision: str, style: str = "parametrized") -> W
   channels run the same templated kernel), or the fp16 engine with one of its switches set: "fp16-seg32" / "fp16-seg64"
   (WG_SEG) force the segment size of the tiles; "fp16-nopack" (WG_PACK4=0) switches the packed ragged tails off and
   "fp16-nofirst" (WG_FIRST=0) the composition of the start conv into each flow's first layer, "fp16-nochain" (WG_CHAIN=0) the
-  chaining of a flow's generic layers into one launch with tile-level dependencies (one launch per layer instead)."""
+  chaining of a flow's generic layers into one launch with tile-level dependencies (one launch per layer instead),
+  "fp16-nocarry" (WG_EXACT_CARRY=0, 512 channels) the exact fp16 hi + lo residual carry (x' rounded to fp16 per layer)."""
   import os
   key = (n_channels, precision, style)
   if key not in _MODELS:
@@ -39,6 +40,8 @@ def get_model(n_channels: int, precision: str, style: str = "parametrized") -> W
       os.environ["WG_FIRST"] = "0"
     if precision == "fp16-nochain":
       os.environ["WG_CHAIN"] = "0"
+    if precision == "fp16-nocarry":
+      os.environ["WG_EXACT_CARRY"] = "0"
     try:
       m.engine()          # the engine reads its switches when it is created
     finally:
@@ -46,6 +49,7 @@ def get_model(n_channels: int, precision: str, style: str = "parametrized") -> W
       os.environ.pop("WG_PACK4", None)
       os.environ.pop("WG_FIRST", None)
       os.environ.pop("WG_CHAIN", None)
+      os.environ.pop("WG_EXACT_CARRY", None)
     _MODELS[key] = m
   return _MODELS[key]
 
@@ -87,7 +91,8 @@ def test_tcgen05_cta_pair_gemm():
     assert err <= 2e-3
 
 
-@pytest.mark.parametrize("precision,nc", [("fp32", 256), ("fp16", 256), ("fp16-nofirst", 256), ("fp16", 512), ("fp16-nofirst", 512)])
+@pytest.mark.parametrize("precision,nc", [("fp32", 256), ("fp16", 256), ("fp16-nofirst", 256), ("fp16", 512), ("fp16-nofirst", 512),
+                                          ("fp16-nocarry", 512)])
 def test_stagewise_first_flow(precision, nc):
   """cond (upsample+squeeze), start conv, then every WN layer of the first flow, then the coupling step."""
   op_dtype = torch.float32 if precision == "fp32" else torch.float16
@@ -102,8 +107,9 @@ def test_stagewise_first_flow(precision, nc):
   sigma = 0.8
   trace = []
   phase_cond = precision != "fp32"     # tensor-core mode composes the upsampler into the conditioning weights
-  first_composed = precision == "fp16"  # ... and the start conv into each flow's first layer
-  exact_carry = phase_cond and nc == 512      # the 512-channel kernel carries the residual stream as fp16 hi + fp16 lo
+  first_composed = precision in ("fp16", "fp16-nocarry")  # ... and the start conv into each flow's first layer
+  # the 512-channel kernel carries the residual stream as fp16 hi + fp16 lo (unless switched off)
+  exact_carry = phase_cond and nc == 512 and precision != "fp16-nocarry"
   with torch.no_grad():
     ref_audio = E.infer(w, dims, mel, sigma, zs, op_dtype, trace, phase_cond=phase_cond, first_composed=first_composed,
                         exact_carry=exact_carry)
@@ -118,11 +124,12 @@ def test_stagewise_first_flow(precision, nc):
     x0_ref = E.rnd(x0_ref, op_dtype)
   failures = []
 
-  def x_view(buf):
+  def x_view(buf, with_lo=True):
     """engine x buffer -> time-major [B, T, nc] (tensor-core mode keeps it phase-major [B][32][T/32][nc]; with the exact carry
-    the stream is the sum of the hi buffer and its rounding-residual buffer)"""
+    the stream is the sum of the hi buffer and its rounding-residual buffer, except for the input of the last layer, which has
+    no residual output: nothing would read its lo part, so it is not written)"""
     raw = eng.debug_view(buf, B, F).float().cpu()
-    if exact_carry:
+    if exact_carry and with_lo:
       raw = raw + eng.debug_view(buf.replace("x", "xlo"), B, F).float().cpu()
     if precision != "fp32":
       return raw.view(B, 32, T // 32, nc).permute(0, 2, 1, 3).reshape(B, T, nc)
@@ -159,7 +166,7 @@ def test_stagewise_first_flow(precision, nc):
       lt = flow_tr["layers"][i]
       check(f"e after layer {i}", eng.debug_view("e", B, F).view(B, T, 8).cpu()[..., : 2 * pf.h], lt["e"])
       if i < dims.n_layers - 1:
-        check(f"x after layer {i}", x_view(f"x{i + 1}"), lt["x"])      # the buffer layer i + 1 reads
+        check(f"x after layer {i}", x_view(f"x{i + 1}", with_lo=i + 1 < dims.n_layers - 1), lt["x"])      # the buffer layer i + 1 reads
     eng.debug_stop_after(k, dims.n_layers)
     state = run(model, mel, zs, sigma).view(B, T, 8)
     check("state after first flow", state, flow_tr["state"], t=tol)

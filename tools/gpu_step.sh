@@ -29,6 +29,7 @@ for step in "$@"; do
     sweep_g2)  for v in 7 5 3 2 1 7; do echo "WG_G2AT0=$v (256 ch, B16 x 861)"; WG_G2AT0=$v python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | python tools/bench_brief.py; done | tee $OUT/sweep_g2at0_256.txt
                for v in "10 24" "6 20" "4 14" "8 18" "12 26" "10 24"; do set -- $v; echo "WG_G2AT=$1 WG_G2AT1=$2 (512 ch, B8 x 861)"; WG_G2AT=$1 WG_G2AT1=$2 python bench.py --channels 512 --batch 8 --steps 5 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | python tools/bench_brief.py; done | tee $OUT/sweep_g2at_512.txt ;;
     ab_chain256) for v in 0 1 0 1 0 1; do echo "WG_CHAIN=$v (256 ch, B16 x 861)"; WG_CHAIN=$v python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | python tools/bench_brief.py; done | tee $OUT/ab_chain256.txt ;;
+    ab_carry)  for rep in 1 2 3; do for v in "WG_EXACT_CARRY=0" "WG_EXACT_CARRY=1"; do echo "$v (512 ch, B8 x 861)"; env $v python bench.py --channels 512 --batch 8 --steps 5 --warmup 3 --no-cpu-baseline --no-parity 2>/dev/null | python tools/bench_brief.py; done; done | tee $OUT/ab_carry.txt ;;
     bench)     TAILN=1 run bench 600 python bench.py --steps 10 --warmup 3 ;;
     bench_fast) TAILN=1 run bench_fast 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-parity ;;
     bench512)  TAILN=1 run bench512 600 python bench.py --channels 512 --scaling strong --global-batch 32 --steps 5 --warmup 3 --no-cpu-baseline ;;

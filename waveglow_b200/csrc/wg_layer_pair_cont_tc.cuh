@@ -89,11 +89,6 @@ struct ContCfg {
   static constexpr int kStages = kRingBytes / kStageBytes;
   static_assert(kStages <= 8, "barrier arrays hold 8 stages");
   static constexpr bool kConstSmem = NC == 256;
-  // 512 channels: EXACT residual carry.  x' is stored as fp16 hi + fp16 lo (two buffers); GEMM2 adds x_hi . I and x_lo . I, the
-  // dilated-conv taps read x_hi only.  Without it the rounding of x' accumulates over the layers of a flow (58 % of the error
-  // variance, tools/error_budget.py) and the 512-channel model misses north_star's 2e-3 max-abs at 10 s utterances (2.16e-3);
-  // the x_lo blocks ride in the A slots of GEMM2 stages 4..7, which carry only W_res for 512 channels: no extra stages.
-  static constexpr bool kCarryLo = NC == 512;
   static constexpr int kBiasFloats = 3 * NC;                 // [2 NC] packed GEMM1 bias, then [NC] residual bias
   static constexpr int kWseWords = (NC / 8) * 32;            // skip-end weights as mma.sync B fragments [NC / 8 registers][32 lanes]
   static constexpr int kActsBytes = kTileM * NC * 2;
@@ -114,7 +109,12 @@ __device__ __forceinline__ uint64_t ring_desc(uint32_t smem_addr) {
   return KS == 64 ? ptx::make_desc_sw128(smem_addr) : ptx::make_desc_sw64(smem_addr);
 }
 
-template <int NC, int KS, bool kFirst, int kMode>
+// kLo (512 channels): EXACT residual carry.  x' is stored as fp16 hi + fp16 lo (two buffers); GEMM2 adds x_hi . I and x_lo . I,
+// the dilated-conv taps read x_hi only.  Without it the rounding of x' accumulates over the layers of a flow (58 % of the error
+// variance, tools/error_budget.py) and the 512-channel model misses north_star's 2e-3 max-abs at 10 s utterances (2.16e-3; with
+// it 1.39e-3).  The x_lo blocks ride in the A slots of GEMM2 stages 4..7, which carry only W_res for 512 channels: no extra
+// stages; measured cost 7.7 % of the step (twice the x traffic to HBM, a longer drain), profiles/r02/ab_exact_carry_512.txt.
+template <int NC, int KS, bool kFirst, int kMode, bool kLo>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kContThreads, 1)
 wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x buffers: m3 {NC, Fq, 32 B} box {KS, rows, 1} (rows = 128; seg_rows in
                                                                           // segment mode), m4 {NC, Fq, 32, B} box {KS, 32, 1, 4} (packed tails)
@@ -130,6 +130,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
                           const __grid_constant__ CUtensorMap tm_a04,     // packed tails, first layer: {16, Fq, 32, B} box {KS, 32, 1, 4}
                           const LayerTcParams p) {
   using C = ContCfg<NC, KS>;
+  static_assert(!kLo || NC == 512, "the exact carry uses the free A slots of the 512-channel GEMM2 stages");
   constexpr int NCH = C::kChunks, NH = C::kHalves, CB = C::kCB, ST = C::kStages, NS = C::kSteps, MWKB = C::kMwKB;
   constexpr int kStageA = C::kStageA, kStageB = C::kStageB, kStageBytes = C::kStageBytes;
   constexpr int n_kb = kFirst ? MWKB + 3 : C::kKB;
@@ -404,7 +405,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
       for (int j = 0; j < CB; ++j) {
         next_stage();
         const bool with_x = !kFirst && j < 256 / KS;
-        const bool with_lo = C::kCarryLo && !kFirst && j >= 256 / KS;      // 512 channels: stages 4..7 carry the x_lo blocks 0..3
+        const bool with_lo = kLo && !kFirst && j >= 256 / KS;      // 512 channels: stages 4..7 carry the x_lo blocks 0..3
         if (ptx::elect_one()) {
           const uint32_t lb = arm(with_x || with_lo ? 2 * kStageBytes : 2 * kStageB);
           if (!skip_loads) {
@@ -550,7 +551,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
             // output columns that contain them
             // (512 channels: stages 4..7 carry the x_lo blocks of channels (jj - 4) KS .. of this half, added the same way)
             const int xb = jj < 256 / KS ? jj : jj - 256 / KS;
-            if (!kFirst && (jj < 256 / KS || C::kCarryLo) && !(p.dbg_flags & 128)) {
+            if (!kFirst && (jj < 256 / KS || kLo) && !(p.dbg_flags & 128)) {
 #pragma unroll
               for (int k = 0; k < NS; ++k)
                 ptx::mma_f16_ss_pair(rQ + ((xb * KS + 16 * k) >> 5) * 32, ring_desc<KS>(x_addr + k * 32),
@@ -717,7 +718,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
           ptx::mbar_wait(&d2_full[h], par);
           ptx::tc_fence_after_sync();
           if (tl && h == 0) stamp(p, 10);
-          if constexpr (!C::kCarryLo) {
+          if constexpr (!kLo) {
             uint32_t pk[32];      // this thread's 64 channels, packed
 #pragma unroll
             for (int g2 = 0; g2 < 2; ++g2) {
@@ -748,7 +749,9 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
           } else {
             // exact carry: x' = hi + lo, hi = fp16(x'), lo = fp16(x' - hi), to two buffers of the same layout.  32 columns at a time
             // (16 + 16 packed registers); region Q is released after the second read, before that half's stores
+            // (xlo_out is null when the next layer has no residual output: nothing would read the lo part)
             uint8_t* dst_lo = static_cast<uint8_t*>(L.xlo_out) + (dst - static_cast<uint8_t*>(L.x_out));
+            const bool write_lo = L.xlo_out != nullptr;
 #pragma unroll
             for (int g2 = 0; g2 < 2; ++g2) {
               uint32_t v0[16], v1[16];
@@ -779,7 +782,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                   ptx::st_global_v8(dst + h * 512 + g2 * 64 + k * 32, *reinterpret_cast<uint32_t(*)[8]>(&hi[8 * k]));
-                  ptx::st_global_v8(dst_lo + h * 512 + g2 * 64 + k * 32, *reinterpret_cast<uint32_t(*)[8]>(&lo[8 * k]));
+                  if (write_lo) ptx::st_global_v8(dst_lo + h * 512 + g2 * 64 + k * 32, *reinterpret_cast<uint32_t(*)[8]>(&lo[8 * k]));
                 }
               }
             }
