@@ -40,9 +40,10 @@ def full(rep):
 
 
 def launch_list(path, what):
+  """Aggregates per kernel name: all captured launches, and the LAST `infer` call of the run (from its pack_noise_kernel launch
+  to the end of the capture: the timed / end-to-end step of the profiled bench command)."""
   lines = [l for l in open(path) if not l.startswith("==")]
-  agg = collections.OrderedDict()
-  n, total = 0, 0.0
+  launches = []
   for row in csv.DictReader(lines):
     try:
       v = float(row["Metric Value"].replace(",", ""))
@@ -52,14 +53,23 @@ def launch_list(path, what):
       v /= 1e3
     elif row.get("Metric Unit", "") in ("ms", "msecond"):
       v *= 1e3
-    name = row["Kernel Name"].split("(")[0][:70]
-    agg.setdefault(name, []).append(v)
-    n += 1
-    total += v
+    launches.append((row["Kernel Name"].split("(")[0][:70], v))
+
+  def table(rows, title):
+    agg = collections.OrderedDict()
+    for name, v in rows:
+      agg.setdefault(name, []).append(v)
+    total = sum(v for _, v in rows)
+    print(f"{title}: {len(rows)} launches, total {total / 1e3:.2f} ms")
+    for name, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+      print(f"{name:72s} launches {len(v):4d}  total {sum(v) / 1e3:9.3f} ms  share {100 * sum(v) / total:5.1f}%  avg {sum(v) / len(v):8.1f} us")
+
   print(f"ncu launch list (gpu__time_duration.sum, cold-cache, serialised) of: {what}")
-  print(f"{n} launches captured, total {total / 1e3:.2f} ms")
-  for name, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
-    print(f"{name:72s} launches {len(v):4d}  total {sum(v) / 1e3:9.3f} ms  share {100 * sum(v) / total:5.1f}%  avg {sum(v) / len(v):8.1f} us")
+  starts = [i for i, (name, _) in enumerate(launches) if "pack_noise_kernel" in name]
+  if starts:
+    table(launches[starts[-1]:], "last infer call of the run (one step)")
+    print()
+  table(launches, "whole capture")
 
 
 if __name__ == "__main__":
