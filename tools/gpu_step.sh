@@ -41,7 +41,6 @@ for step in "$@"; do
     timeline_first) TAILN=40 run timeline_first 300 env WG_CHAIN=0 python tools/timeline.py --layer 0 ;;
     timeline512) TAILN=40 run timeline512 300 env WG_CHAIN=0 python tools/timeline.py --channels 512 --batch 8 ;;
     layers)    TAILN=12 run layers 300 python tools/layer_times.py ;;
-    sanitize)  TAILN=12 run sanitize 600 compute-sanitizer --tool memcheck --error-exitcode 3 python tools/sanitize_case.py ;;
     ncu_list)  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity > $OUT/ncu_launches.log 2>&1; echo "launch list exit $?" ;;
     ncu_full)  timeout 900 ncu --set full --clock-control none --import-source on -k regex:wn_layer_pair -s 48 -c 3 -o $OUT/prof_layer -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity > $OUT/ncu_full.log 2>&1; echo "full set exit $?" ;;
     ncu_list512) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches512.csv python bench.py --channels 512 --batch 8 --steps 1 --warmup 3 --no-cpu-baseline --no-parity > $OUT/ncu_launches512.log 2>&1; echo "launch list 512 exit $?" ;;
