@@ -356,6 +356,47 @@ def test_edge_shapes_vs_oracle(B, F, precision):
   assert err <= (FP32_MAX_ABS if precision == "fp32" else FP16_MAX_ABS)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("nc,n_flows,n_early_every,n_early_size,n_layers,B,F", [
+  (256, 6, 2, 2, 4, 2, 45),      # early outputs at k = 2, 4; 4 layers per WN (chained launch of 3)
+  (256, 4, 4, 2, 10, 1, 70),     # no early output at all (8 channels drawn at once); 10 layers: dilation 512, one launch per layer
+  (512, 3, 2, 4, 3, 2, 33),      # one early output of 4 channels: flows run on 8, 8, 4 channels
+  (256, 2, 4, 2, 1, 3, 20),      # a single layer per WN: no residual output anywhere, explicit start conv
+  (256, 5, 1, 0, 2, 2, 50),      # n_early_size 0: the "early output" every flow is empty
+])
+def test_non_default_hparams_vs_oracle(nc, n_flows, n_early_every, n_early_size, n_layers, B, F, precision):
+  """Architectures other than the published one (the reference builds them from the same nine hparams, model.py:142-176): the
+  engine derives its launch plan from the configuration, nothing is specialised to 12 flows x 8 layers."""
+  from waveglow_b200.hparams import HParams
+  from waveglow_b200.synthetic import synthetic_state_dict
+  fields = dict(n_channels=nc, n_flows=n_flows, n_early_every=n_early_every, n_early_size=n_early_size, n_layers=n_layers)
+  hp = HParams(**fields)
+  sd = synthetic_state_dict(hp, 77)
+  w, dims = O.fold_weight_norm(sd), O.ModelDims(**fields)
+  model = WaveGlow(hp, precision=precision).to("cuda:0")
+  model.load_state_dict(sd)
+  model = WaveGlow.remove_weightnorm(model).eval()
+  mel = synthetic_mel(B, F, 41)
+  zs = synthetic_noise(hp, B, F * 32, 42)
+  assert [z.shape[1] for z in zs] == [dims.n_remaining_channels] + [n_early_size] * (len(zs) - 1)
+  with torch.no_grad():
+    ref = O.infer(w, dims, mel, 0.7, zs)
+  out = run(model, mel, zs, 0.7)
+  err = max_abs(ref, out)
+  print(f"hparams {fields} {precision}: max-abs {err:.3e} (ref absmax {float(ref.abs().max()):.2f})")
+  assert out.shape == ref.shape == (B, F * 256) and torch.isfinite(out).all()
+  assert err <= (FP32_MAX_ABS if precision == "fp32" else FP16_MAX_ABS)
+  # and the training direction of the same architecture
+  audio = torch.rand((B, F * 256), generator=torch.Generator().manual_seed(43)) * 2 - 1
+  with torch.no_grad():
+    z_ref, ls_ref, ld_ref = O.forward(w, dims, mel, audio)
+  z, log_s_list, log_det_list = model((mel.cuda(), audio.cuda()))
+  torch.cuda.synchronize()
+  tol = FP32_MAX_ABS if precision == "fp32" else FP16_MAX_ABS
+  assert z.shape == z_ref.shape and max_abs(z_ref, z.cpu()) <= tol * max(1.0, float(z_ref.abs().max()))
+  assert len(log_s_list) == n_flows and all(max_abs(a, b.cpu()) <= tol for a, b in zip(ls_ref, log_s_list))
+
+
 def test_fp16_vs_oracle_medium_size():
   """B=4 x 2.3 s: against the oracle itself (CPU, a few seconds)."""
   hp, sd, w, dims = synthetic_weights(256)

@@ -1399,7 +1399,7 @@ int wg_infer(wg_engine* e, const float* mel, int32_t batch, int32_t frames, cons
     for (int i = 0; i < n_z; ++i) {
       const int ch = (i == 0) ? e->flowC[NF - 1] : e->cfg.n_early_size;
       slot -= ch;
-      if (!z[i]) return fail(e, WG_ERR_INVALID_ARGUMENT, "z[%d] is null", i);
+      if (!z[i] && ch > 0) return fail(e, WG_ERR_INVALID_ARGUMENT, "z[%d] is null", i);      // n_early_size 0: empty tensors have no storage
       np.z[i] = z[i];
       np.ch[i] = ch;
       np.slot0[i] = slot;
