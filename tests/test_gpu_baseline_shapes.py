@@ -146,3 +146,41 @@ def test_forward_at_config5_shape_vs_oracle_and_reference_golden(precision):
   foreign = (z.clone(), [t.clone() for t in log_s_list], log_det_list)
   loss2 = float(crit(foreign))
   assert not crit.used_fused_stats and abs(loss2 - loss) <= 1e-5 * max(1.0, abs(loss))
+
+
+@pytest.mark.parametrize("nc,B,need_gb", [(256, 306, 60), (512, 154, 110)])
+def test_buffers_beyond_4_gib_keep_utterances_independent(nc, B, need_gb):
+  """Maximum sizes: 306 x 861 frames at 256 channels (154 x 861 at 512) makes every x buffer 4.3 GB (2.16e9 fp16 elements: past
+  2^31 elements and 2^32 bytes), the workspace 35 GB (512 channels with the hi + lo residual buffers: 70 GB).  `infer` has no cross-utterance interaction, so the first and the LAST utterance of the batch
+  (lowest and highest addresses) must be BIT-identical to the same utterances synthesised alone; a 32-bit index anywhere on the
+  path would break the high one."""
+  from waveglow_b200.hparams import HParams
+  from waveglow_b200.model import WaveGlow
+  from waveglow_b200.synthetic import synthetic_state_dict
+  F = 861
+  torch.cuda.empty_cache()
+  free, _ = torch.cuda.mem_get_info()
+  if free < need_gb * 1e9:
+    pytest.skip(f"needs {need_gb} GB of free device memory, {free / 1e9:.0f} GB available")
+  hp = HParams(n_channels=nc)
+  model = WaveGlow(hp, precision="fp16").to("cuda:0")        # its own engine: the 35 GB workspace is released with it
+  model.load_state_dict(synthetic_state_dict(hp, 1234))
+  model = WaveGlow.remove_weightnorm(model).eval()
+  try:
+    base_mel = synthetic_mel(6, F, 2001)
+    base_zs = synthetic_noise(hp, 6, F * 32, 2002)
+    idx = torch.arange(B) % 6                                 # six distinct utterances, tiled over the batch
+    mel = base_mel[idx].cuda()
+    zs = [z[idx].cuda() for z in base_zs]
+    assert mel.size(0) * F * 32 * nc > 2 ** 31
+    out = model.infer_with_noise(mel, zs, 0.666)
+    torch.cuda.synchronize()
+    assert out.shape == (B, F * 256) and bool(torch.isfinite(out).all())
+    for b in (0, B - 1, B - 2):
+      alone = model.infer_with_noise(mel[b:b + 1].clone(), [z[b:b + 1].clone() for z in zs], 0.666)
+      assert torch.equal(out[b:b + 1], alone), b
+    # the same utterance at different batch positions (different tiles, different addresses): identical audio
+    assert torch.equal(out[0], out[6 * 20]) and torch.equal(out[B - 1 - 6], out[B - 1])
+  finally:
+    del model
+    torch.cuda.empty_cache()
