@@ -558,6 +558,12 @@ def test_errors_are_loud():
       model.infer_with_noise(mel, zs, 1.0)
   with pytest.raises(WgError, match="is on cpu"):
     model.infer_with_noise(mel, [good[0].cuda(), good[1], good[2].cuda()], 1.0)
+  # empty inputs: the reference raises as well (reshape of 0 elements / zero-length ConvTranspose1d input, model.py:225-232)
+  for shape in ((0, 80, 4), (1, 80, 0)):
+    with pytest.raises((WgError, ValueError, RuntimeError)):
+      model.infer(torch.zeros(shape).cuda(), sigma=0.5)
+  # ... and the engine still works afterwards
+  assert torch.isfinite(model.infer(mel, sigma=0.5)).all()
 
 
 def test_reloaded_weights_invalidate_cuda_graphs_and_pack_cache(tmp_path):
