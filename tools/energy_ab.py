@@ -27,12 +27,16 @@ VARIANTS_256 = [
   ("no packed ragged tails (WG_PACK4=0)", {"WG_PACK4": "0"}),
   ("explicit start conv (WG_FIRST=0)", {"WG_FIRST": "0"}),
   ("smallest grid with the same tile rounds (WG_TRIM=1)", {"WG_TRIM": "1"}),
-  ("[invalid] operand loads off (flags 1)", {"WG_DBG_FLAGS": "1"}),
+  ("[invalid] operand loads off (flags 1, per-layer launches)", {"WG_DBG_FLAGS": "1", "WG_CHAIN": "0"}),
   ("[invalid] gate math off (flags 4)", {"WG_DBG_FLAGS": "4"}),
   ("[invalid] x' stores off (flags 8)", {"WG_DBG_FLAGS": "8"}),
   ("[invalid] skip-end GEMM off (flags 16)", {"WG_DBG_FLAGS": "16"}),
   ("[invalid] identity carry off (flags 128)", {"WG_DBG_FLAGS": "128"}),
-  ("[invalid] all of the above off (flags 157)", {"WG_DBG_FLAGS": "157"}),
+  ("[invalid] all of the above off (flags 157, per-layer launches)", {"WG_DBG_FLAGS": "157", "WG_CHAIN": "0"}),
+  ("[diagnostic] chained, no dependency polls (flags 256)", {"WG_DBG_FLAGS": "256"}),
+  ("[diagnostic] chained, no polls, no completion counts (flags 768)", {"WG_DBG_FLAGS": "768"}),
+  ("[diagnostic] chained, static items, no polls / counts (flags 1792)", {"WG_DBG_FLAGS": "1792"}),
+  ("one launch per layer (WG_CHAIN=0, again)", {"WG_CHAIN": "0"}),
   ("production (again)", {}),
 ]
 VARIANTS_512 = [
@@ -91,13 +95,19 @@ def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--child", nargs=2, type=int, default=None)
   ap.add_argument("--seconds", type=float, default=5.0)
+  ap.add_argument("--only", type=int, default=0, help="256 or 512: only that channel count")
+  ap.add_argument("--match", default="", help="only variants whose name contains one of these comma-separated substrings")
   args = ap.parse_args()
   if args.child:
     return child(args.child[0], args.child[1], args.seconds)
   for channels, batch, variants in ((256, 16, VARIANTS_256), (512, 8, VARIANTS_512)):
+    if args.only and args.only != channels:
+      continue
     print(f"# {channels} channels, {batch} x 861 frames per step; >= {args.seconds:.0f} s of back-to-back steps per variant, NVML energy counter")
     print(f"{'variant':58s} {'ms/step':>8s} {'J/step':>8s} {'avg W':>7s} {'SM MHz':>7s}")
     for name, env in variants:
+      if args.match and not any(m in name for m in args.match.split(",")):
+        continue
       e = dict(os.environ)
       for k in ("WG_CHAIN", "WG_PDL", "WG_PACK4", "WG_FIRST", "WG_TRIM", "WG_DBG_FLAGS", "WG_EXACT_CARRY"):
         e.pop(k, None)

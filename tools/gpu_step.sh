@@ -10,6 +10,8 @@ for step in "$@"; do
     quick256)  TAILN=15 run quick256 300 python -m pytest tests/test_gpu_parity.py -q -x -s -k "gemm or (stagewise and 256) or golden and not 512" ;;
     big)       TAILN=30 run big 600 python -m pytest tests/test_gpu_baseline_shapes.py -q -s -k "beyond_4_gib" --timeout 400 ;;
     energy)    python tools/energy_ab.py 2>&1 | tee $OUT/energy_ab.txt ;;
+    energy_chain) python tools/energy_ab.py --only 256 --match "production,one launch,diagnostic" 2>&1 | tee $OUT/energy_chain.txt ;;
+    energy256) python tools/energy_ab.py --only 256 2>&1 | tee $OUT/energy_ab.txt ;;
     hparams)   TAILN=30 run hparams 600 python -m pytest tests/test_gpu_parity.py -q -s -k "non_default_hparams" --timeout 300 ;;
     quick512)  TAILN=30 run quick512 300 python -m pytest tests/test_gpu_parity.py -q -x -s -k "(stagewise and 512) or 512_channel" ;;
     tests)     TAILN=8 run tests 1500 python -m pytest tests -q -m gpu -x --timeout 600 --durations=12 ;;

@@ -72,7 +72,8 @@ struct LayerTcParams {
   uint32_t* flags;        // n_layers > 1: [n_layers][pair-tiles] completion counters, zero at launch (see kTileDoneCount)
   uint32_t* counter;      // n_layers > 1: the next unclaimed work item of this launch, zero at launch
   int dbg_flags;          // diagnostics only (results invalid): 1 skip all operand loads, 4 skip the gate math, 8 skip the x' stores,
-                          // 16 skip the skip-end GEMM, 64 stamp the start of every tile, 128 no identity carry
+                          // 16 skip the skip-end GEMM, 64 stamp the start of every tile, 128 no identity carry; chained launches:
+                          // 256 no dependency polls, 512 no completion counts, 1024 static round-robin items (only with 256)
   long long* timeline;    // optional [n_ctas][16] clock64 stamps (diagnostics; nullptr in production)
 };
 

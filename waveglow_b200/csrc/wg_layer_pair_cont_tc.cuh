@@ -179,7 +179,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
   // even if part of the grid is not resident (another kernel holding SMs), and a pair that starts late just claims later items.
   // The roles of a CTA are at most 3 items apart (operand ring, TMEM regions, e_done), so 8 slots are never overrun.
   const int n_items = p.n_layers * n_ptiles;
-  const bool claimed = p.n_layers > 1;
+  const bool claimed = p.n_layers > 1 && !(p.dbg_flags & 1024);      // (diagnostics: 1024 = static round-robin items, use with 256)
 
   struct Coord {
     int ph, en, l, pt;      // phase; entry; layer (index into p.ly); pair-tile
@@ -196,7 +196,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
   // the it-th work item of this CTA pair (>= n_items: no more work); every role of both CTAs calls this once per iteration
   auto item_of = [&](int it) -> int {
     if (!claimed) return pair + it * n_pairs;
-    ptx::mbar_wait_cluster(&item_bar[it & 7], (it >> 3) & 1);
+    ptx::mbar_wait(&item_bar[it & 7], (it >> 3) & 1);      // completed by the bytes of the leader's st.async: the word is visible
     return static_cast<int>(s_items[it & 7]);
   };
   // (utterance, frame) -> entry that holds it (blocks and packed modes)
@@ -376,7 +376,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
     auto deps_begin = [&](const Coord& tc) {
       const LayerDesc& L = p.ly[tc.l];
       const int tap = lane >> 3, u = (lane >> 1) & 3, last = lane & 1;
-      bool need = tc.l > 0 && tap < 3 && (tr.packed || u == 0);
+      bool need = tc.l > 0 && tap < 3 && (tr.packed || u == 0) && !(p.dbg_flags & 256);      // (diagnostics: 256 = no dependency polls)
       int pt_dep = 0;
       if (need) {
         const int pp = tc.ph + (tap - 1) * L.dilation;
@@ -392,6 +392,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
       dep_seen = need ? ptx::ld_acquire_gpu(dep_flag) : kTileDoneCount;
     };
     auto deps_finish = [&]() {
+      if (p.dbg_flags & 256) return;
       if (dep_seen < kTileDoneCount) ptx::wait_flag_at_least(dep_flag, kTileDoneCount);
       __syncwarp();
       ptx::fence_proxy_async_global();      // the generic-proxy stores just acquired -> this warp's TMA (async proxy) loads
@@ -428,20 +429,35 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
         __syncwarp();
       }
     };
-    // leader CTA, chained launch: claim the next work item for this pair and publish it to both CTAs (slot = iteration % 8)
-    auto claim = [&](int slot_it) {
-      if (ptx::elect_one()) {
-        const uint32_t w_new = atomicAdd(p.counter, 1u);
-        s_items[slot_it & 7] = w_new;
-        ptx::st_shared_cluster_u32(ptx::map_to_cta(const_cast<uint32_t*>(&s_items[slot_it & 7]), 1), w_new);
-        ptx::mbar_arrive(&item_bar[slot_it & 7]);
-        ptx::mbar_arrive_release_cluster(ptx::map_to_cta(&item_bar[slot_it & 7], 1));
+    // leader CTA, chained launch: work items are claimed from the global counter TWO ahead, in two steps, so that neither the
+    // round trip of the atomic (~1 us) nor the publication stalls this warp: the atomic for item it + 2 is ISSUED at the top of
+    // item it and its result is first touched -- published to both CTAs, slot = iteration % 8 -- after chunk 0's loads, when the
+    // ring is full (claiming one ahead with the atomic waited for on the spot cost 2.2 % of a config-2 step,
+    // profiles/r02/energy_ab.txt).  Progress does not depend on the depth: a pair runs its items in increasing order, so the
+    // lowest unfinished item of the grid is always some pair's CURRENT item, and its dependencies are all finished.
+    uint32_t pending_item = 0;      // lane 0: item it + 2, in flight
+    auto claim_issue = [&]() {
+      if (lane == 0) pending_item = atomicAdd(p.counter, 1u);
+    };
+    auto claim_publish = [&](int slot_it) {
+      if (lane == 0) {
+#pragma unroll
+        for (uint32_t r = 0; r < 2; ++r) {      // both CTAs the same way: one arrival that expects 4 bytes, then the word itself
+          const uint32_t bar_r = ptx::map_to_cta(&item_bar[slot_it & 7], r);
+          ptx::mbar_arrive_expect_tx_cluster(bar_r, 4);
+          ptx::st_async_u32(ptx::map_to_cta(const_cast<uint32_t*>(&s_items[slot_it & 7]), r), pending_item, bar_r);
+        }
       }
       __syncwarp();
     };
     Coord prev{};
     int it = 0;
-    if (claimed && rank == 0) claim(0);
+    if (claimed && rank == 0) {
+      claim_issue();
+      claim_publish(0);
+      claim_issue();
+      claim_publish(1);
+    }
     for (;; ++it) {
       const int w = item_of(it);
       if (w >= n_items) break;
@@ -449,7 +465,8 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
       const LayerDesc& L = p.ly[tc.l];
       const bool prev_res = it > 0 && p.ly[prev.l].has_res;
       tr = rows_of(tc.en);
-      if (claimed) deps_begin(tc);
+      if (claimed && rank == 0) claim_issue();
+      if (p.n_layers > 1) deps_begin(tc);
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
 #pragma unroll 1
@@ -493,9 +510,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
           }
           __syncwarp();
         }
-        // The next item is claimed one ahead, here, after chunk 0's loads: the cluster-scope release of the publication is a
-        // heavy fence, and at this point the ring is full and this warp has slack (at the top of an item it cost ~1 % of the step)
-        if (c == 0 && claimed && rank == 0) claim(it + 1);
+        if (c == 0 && claimed && rank == 0) claim_publish(it + 2);
       }
       prev = tc;
     }
@@ -789,15 +804,12 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
           }
           if (tl && h == NH - 1) stamp(p, 11);
         }
-        if (tc.l + 1 < p.n_layers) {
+        if (tc.l + 1 < p.n_layers && !(p.dbg_flags & 512)) {      // (diagnostics: 512 = no completion counts)
           // chained launch: this warp's share of the tile's x' is stored -- count it on the tile's flag (release at gpu scope
           // after the warp's stores; the consumers are TMA loads in other CTAs, hence the proxy fence)
           ptx::fence_proxy_async_global();
           __syncwarp();
-          if (lane == 0) {
-            __threadfence();
-            ptx::red_release_gpu_add(p.flags + static_cast<size_t>(tc.l) * n_ptiles + tc.pt, 1u);
-          }
+          if (lane == 0) ptx::red_release_gpu_add(p.flags + static_cast<size_t>(tc.l) * n_ptiles + tc.pt, 1u);
         }
       }
     }
@@ -881,13 +893,10 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
           }
         }
       }
-      if (tc.l + 1 < p.n_layers) {
+      if (tc.l + 1 < p.n_layers && !(p.dbg_flags & 512)) {
         // chained launch: this warp's share of the tile's e rows is stored (the next layer read-modify-writes them)
         __syncwarp();
-        if (lane == 0) {
-          __threadfence();
-          ptx::red_release_gpu_add(p.flags + static_cast<size_t>(tc.l) * n_ptiles + tc.pt, 1u);
-        }
+        if (lane == 0) ptx::red_release_gpu_add(p.flags + static_cast<size_t>(tc.l) * n_ptiles + tc.pt, 1u);
       }
     }
   }

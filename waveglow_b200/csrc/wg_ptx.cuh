@@ -263,35 +263,16 @@ __device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// Release at CLUSTER scope: the arriving thread's earlier writes to the other CTA's shared memory (st_shared_cluster_u32) are
-// visible to a thread of that CTA that observes the phase with an acquire at cluster scope (mbar_wait_cluster).  Costs a
-// heavier fence than mbar_arrive_cluster; used once per work item, off every critical path.
-__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// One word to (any CTA of the cluster)'s shared memory, completing 4 bytes of transaction count on an mbarrier of that CTA:
+// a thread that observes the barrier phase (plain try_wait) sees the word -- no fence on either side.  The barrier must expect
+// those bytes (mbar_arrive_expect_tx_cluster).  A `st.shared::cluster` + `mbarrier.arrive.release.cluster` pair does the same
+// with MEMBAR.ALL.GPU in the sender and CCTL.IVALL in every acquiring receiver (SASS), 2 % of a step when done once per tile.
+__device__ __forceinline__ void st_async_u32(uint32_t cluster_addr, uint32_t v, uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];" ::"r"(cluster_addr), "r"(v), "r"(cluster_mbar)
+               : "memory");
 }
-__device__ __forceinline__ void st_shared_cluster_u32(uint32_t cluster_addr, uint32_t v) {
-  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait_cluster(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) {
-      printf("waveglow_b200: work-item barrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
-      __trap();
-    }
-  }
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_mbar), "r"(bytes) : "memory");
 }
 // TMA load whose completion bytes are signalled on a barrier that may live in the PEER CTA of the pair
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
