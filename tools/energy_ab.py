@@ -30,6 +30,7 @@ VARIANTS_256 = [
   ("[invalid] operand loads off (flags 1, per-layer launches)", {"WG_DBG_FLAGS": "1", "WG_CHAIN": "0"}),
   ("[invalid] gate math off (flags 4)", {"WG_DBG_FLAGS": "4"}),
   ("[invalid] x' stores off (flags 8)", {"WG_DBG_FLAGS": "8"}),
+  ("[invalid] x' stores as full 128-byte lines, rows scrambled (flags 8192)", {"WG_DBG_FLAGS": "8192"}),
   ("[invalid] skip-end GEMM off (flags 16)", {"WG_DBG_FLAGS": "16"}),
   ("[invalid] identity carry off (flags 128)", {"WG_DBG_FLAGS": "128"}),
   ("[invalid] all of the above off (flags 157, per-layer launches)", {"WG_DBG_FLAGS": "157", "WG_CHAIN": "0"}),

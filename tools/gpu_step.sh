@@ -11,6 +11,11 @@ for step in "$@"; do
     big)       TAILN=30 run big 600 python -m pytest tests/test_gpu_baseline_shapes.py -q -s -k "beyond_4_gib" --timeout 400 ;;
     energy)    python tools/energy_ab.py 2>&1 | tee $OUT/energy_ab.txt ;;
     energy_chain) python tools/energy_ab.py --only 256 --match "production,one launch,diagnostic" 2>&1 | tee $OUT/energy_chain.txt ;;
+    energy_st) python tools/energy_ab.py --only 256 --match "production,x' stores" 2>&1 | tee $OUT/energy_stores.txt ;;
+    energy_b)  for b in 2 4 8 16 32; do echo "batch $b"; python tools/energy_ab.py --child 256 $b --seconds 4 2>/dev/null | tail -1; done | tee $OUT/energy_batch.txt ;;
+    energy_nx) WG_CHAIN=0 WG_NX=2 python bench.py --batch 2 --steps 3 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('parity with 2 x buffers:', d['parity']['max_abs'], d['parity']['pass'])"
+               for b in 2 16; do for nx in 8 2; do echo "batch $b, WG_CHAIN=0, x buffers $nx"; WG_CHAIN=0 WG_NX=$nx python tools/energy_ab.py --child 256 $b --seconds 4 2>/dev/null | tail -1; done; done | tee $OUT/energy_nx.txt ;;
+    energy_lib) for ch in "256 16" "512 8"; do for rep in 1 2; do for v in "WG_B200_LIB=$PWD/waveglow_b200/libwaveglow_b200_prev.so" "WG_CHAIN=1"; do echo "channels / batch $ch, ${v##*/}"; env $v python tools/energy_ab.py --child $ch --seconds 4 2>/dev/null | tail -1; done; done; done | tee $OUT/energy_lib.txt ;;
     energy256) python tools/energy_ab.py --only 256 2>&1 | tee $OUT/energy_ab.txt ;;
     hparams)   TAILN=30 run hparams 600 python -m pytest tests/test_gpu_parity.py -q -s -k "non_default_hparams" --timeout 300 ;;
     quick512)  TAILN=30 run quick512 300 python -m pytest tests/test_gpu_parity.py -q -x -s -k "(stagewise and 512) or 512_channel" ;;

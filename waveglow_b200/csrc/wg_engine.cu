@@ -92,6 +92,7 @@ struct wg_engine {
   long long* dbg_timeline = nullptr;  // device buffer for clock64 stamps of layer launches (tests/diagnostics)
   int num_sms = 148;
   int dbg_flags = 0;                  // WG_DBG_FLAGS env (diagnostics; see LayerTcParams::dbg_flags)
+  int nx_override = 0;                // WG_NX env (diagnostics, only with WG_CHAIN=0): number of x buffers a flow's layers rotate through
   // device arrays that make up the packed weights, by tag: what wg_save_packed writes and wg_load_packed restores
   std::map<std::string, std::pair<void**, size_t>> sections;
   // tensor maps over the caller's workspace of the last call (ActMaps, heap): re-encoding ~45 maps costs the host ~1 ms per call,
@@ -332,6 +333,7 @@ WsLayout ws_layout(const wg_engine* e, int B, int T) {
                      : static_cast<size_t>(B) * ((T + kUpPhases - 1) / kUpPhases) * kUpKdim * L.elt;
   off = align_up(off + L.cond_bytes, 1024);
   L.n_x = e->cfg.precision == WG_PRECISION_FP16 ? e->cfg.n_layers : 2;
+  if (e->cfg.precision == WG_PRECISION_FP16 && !e->chain && e->nx_override >= 2 && e->nx_override < L.n_x) L.n_x = e->nx_override;
   for (int i = 0; i < L.n_x; ++i) {
     L.x[i] = off;
     off = align_up(off + nppos * e->cfg.n_channels * L.elt, 1024);
@@ -504,6 +506,8 @@ int wg_create(const wg_config* cfg, wg_engine** out) {
   e->force_seg = seg_env ? atoi(seg_env) : 0;
   if (e->force_seg != 0 && e->force_seg != 128 && e->force_seg != 64 && e->force_seg != 32)
     return fail(e, WG_ERR_INVALID_ARGUMENT, "WG_SEG must be 128, 64 or 32 (got %d)", e->force_seg);
+  const char* nx_env = getenv("WG_NX");
+  e->nx_override = nx_env ? atoi(nx_env) : 0;
   const char* dbg_env = getenv("WG_DBG_FLAGS");
   e->dbg_flags = dbg_env ? atoi(dbg_env) : 0;
   if (tc)
@@ -545,11 +549,25 @@ void wg_destroy(wg_engine* e) {
   delete e;
 }
 
+// What the tensor-core layer kernel's gate expects of the packed weights (gate_one, wg_layer_common.cuh): the constants of the
+// gate live in the weights / biases.  Approximate form (256 channels): sigmoid-half rows and bias x 0.5, W_res / W_se x 0.5
+// (the gate emits 2 x acts).  Accurate form (512 channels): weights as they are, biases pre-multiplied by 2 log2 e / -log2 e.
+struct GatePackScales {
+  float sig_w, act_w;      // weight scales (powers of two only: exact in fp16)
+  float tanh_b, sig_b;     // bias scales
+};
+GatePackScales gate_pack_scales(bool tc, int nc) {
+  if (!tc) return {1.f, 1.f, 1.f, 1.f};
+  if (nc == 512) return {1.f, 1.f, kGateTanhScale, kGateSigScale};      // kAccurate = (NC == 512) in wn_layer_pair_cont_kernel
+  return {0.5f, 0.5f, 1.f, 0.5f};
+}
+
 int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) {
   if (!e || !descs || n_descs <= 0) return WG_ERR_INVALID_ARGUMENT;
   if (!e->encode) return fail(e, WG_ERR_INVALID_ARGUMENT, "engine was not created successfully");
   WG_DEVICE(e, e->cfg.device);
   const int nc = e->cfg.n_channels, L = e->cfg.n_layers, NF = e->cfg.n_flows;
+  const GatePackScales gs = gate_pack_scales(e->cfg.precision == WG_PRECISION_FP16, nc);
   e->sections.clear();
   e->loaded = false;
   HostWeights hw;
@@ -639,7 +657,17 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
     if ((rc = upload(e, &fp.d_w_start, *w_start, "w_start." + std::to_string(k)))) return rc;
     if ((rc = upload(e, &fp.d_b_start, *b_start, "b_start." + std::to_string(k)))) return rc;
     // tensor-core mode: W_cond stays on the device (fp32); V = W_cond . Wup_p is composed from it in finish_tensor_core_load
-    if (tc && (rc = upload(e, &fp.d_w_cond, *w_cond, "w_cond." + std::to_string(k)))) return rc;
+    // (its sigmoid-half rows carry the gate's input scale, see gate_one)
+    if (tc) {
+      std::vector<float> wcs(*w_cond);
+      if (gs.sig_w != 1.f)
+        for (int i = 0; i < L; ++i)
+          for (int oc = nc; oc < 2 * nc; ++oc) {
+            float* row = &wcs[(static_cast<size_t>(2 * nc) * i + oc) * kCond];
+            for (int m = 0; m < kCond; ++m) row[m] *= gs.sig_w;
+          }
+      if ((rc = upload(e, &fp.d_w_cond, wcs, "w_cond." + std::to_string(k)))) return rc;
+    }
     {
       double a[kGroup * kGroup], inv[kGroup * kGroup];
       for (int i = 0; i < C * C; ++i) {
@@ -676,13 +704,15 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
           const int chunk = np / 256, half = (np % 256) / 128, j = np % 128;
           const int oc = half * nc + chunk * 128 + j;
           uint16_t* row = w1 + static_cast<size_t>(np) * K1x;
+          const float sw = half ? gs.sig_w : 1.f;                  // weight scale of this pre-activation row (exact: 1 or 0.5)
+          const float sb = half ? gs.sig_b : gs.tanh_b;            // what its bias is multiplied by
           for (int tap = 0; tap < 3; ++tap)
-            for (int ci = 0; ci < nc; ++ci) row[tap * nc + ci] = f2h((*w_in)[(static_cast<size_t>(oc) * nc + ci) * 3 + tap], e->op_fmt);
+            for (int ci = 0; ci < nc; ++ci) row[tap * nc + ci] = f2h(sw * (*w_in)[(static_cast<size_t>(oc) * nc + ci) * 3 + tap], e->op_fmt);
           // the upsampler's bias enters every kept group-step: fold W_cond . b_up into the layer bias
           const float* wc = &(*w_cond)[(static_cast<size_t>(2 * nc) * i + oc) * kCond];
           double bfold = 0.0;
           for (int m = 0; m < kCond; ++m) bfold += static_cast<double>(wc[m]) * (*up_bias)[m / kGroup];
-          bias1[li * 2 * nc + np] = static_cast<float>((*b_in)[oc] + (*b_cond)[2 * nc * i + oc] + bfold);
+          bias1[li * 2 * nc + np] = static_cast<float>(sb * ((*b_in)[oc] + (*b_cond)[2 * nc * i + oc] + bfold));
           if (i == 0 && e->first_comp) {
             // in_layers[0](start(a0)) (model.py:117, 125): per tap, W_in[:, :, tap] . W_start (h columns) and
             // W_in[:, :, tap] . b_start (column 4, multiplied by the operand's `1`, which is 0 in the zero padding)
@@ -696,10 +726,10 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
               }
               // columns match the operand rows [a_hi | a_lo | a_hi | 1 | 1]: [W_hi | W_hi | W_lo | b_hi | b_lo]
               for (int j = 0; j < h; ++j) {
-                split16(acc[j], e->op_fmt, &crow[j], &crow[8 + j]);
+                split16(sw * acc[j], e->op_fmt, &crow[j], &crow[8 + j]);
                 crow[4 + j] = crow[j];
               }
-              split16(acc[4], e->op_fmt, &crow[12], &crow[13]);
+              split16(sw * acc[4], e->op_fmt, &crow[12], &crow[13]);
             }
           }
         }
@@ -717,12 +747,13 @@ int wg_load_weights(wg_engine* e, const wg_weight_desc* descs, int32_t n_descs) 
         uint16_t* w2 = &w2h[li * w2rows * nc];
         if (i < L - 1) {
           for (int n = 0; n < nc; ++n) {
-            for (int c = 0; c < nc; ++c) w2[static_cast<size_t>(n) * nc + c] = f2h((*w_rs)[static_cast<size_t>(n) * nc + c], e->op_fmt);
+            for (int c = 0; c < nc; ++c) w2[static_cast<size_t>(n) * nc + c] = f2h(gs.act_w * (*w_rs)[static_cast<size_t>(n) * nc + c], e->op_fmt);
             bias_res[li * nc + n] = (*b_rs)[n];
           }
         }
         for (int r = 0; r < 2 * h; ++r)
-          for (int c = 0; c < nc; ++c) w2[static_cast<size_t>(nc + r) * nc + c] = f2h(static_cast<float>(wse[static_cast<size_t>(r) * nc + c]), e->op_fmt);
+          for (int c = 0; c < nc; ++c)
+            w2[static_cast<size_t>(nc + r) * nc + c] = f2h(gs.act_w * static_cast<float>(wse[static_cast<size_t>(r) * nc + c]), e->op_fmt);
       } else {
         float* w1 = &w1f[li * K1 * 2 * nc];
         for (int oc = 0; oc < 2 * nc; ++oc) {
@@ -824,7 +855,7 @@ int wg_debug_view(const wg_engine* e, const char* name, int32_t batch, int32_t f
 // ------------------------------------------------------------------------------------------ packed-weight cache
 namespace {
 
-constexpr uint32_t kPackVersion = 5;
+constexpr uint32_t kPackVersion = 6;      // 6: gate constants folded into the packed weights / biases
 
 struct PackHeader {
   char magic[8];             // "WGB200PK"
@@ -1178,10 +1209,10 @@ int run_wn_layers(wg_engine* e, int k, int B, int T, uint8_t* ws, const WsLayout
       for (int j = 0; j < lp.n_layers; ++j) {
         lp.ly[j] = desc(i0 + j);
         lp.ly[j].x_in = j;
-        xm.m3[j] = am->x3[best_idx][i0 + j];
-        xm.m4[j] = am->x4[i0 + j];
-        xl.m3[j] = am->xl3[best_idx][i0 + j];
-        xl.m4[j] = am->xl4[i0 + j];
+        xm.m3[j] = am->x3[best_idx][(i0 + j) % L.n_x];
+        xm.m4[j] = am->x4[(i0 + j) % L.n_x];
+        xl.m3[j] = am->xl3[best_idx][(i0 + j) % L.n_x];
+        xl.m4[j] = am->xl4[(i0 + j) % L.n_x];
       }
       for (int j = lp.n_layers; j < kMaxLayersPerLaunch; ++j) {      // unused slots: valid maps, never dereferenced
         xm.m3[j] = xm.m3[0];

@@ -101,13 +101,23 @@ __device__ __forceinline__ void stamp(const LayerTcParams& p, int slot) {
 //     gate (8 x 861 frames against the fp32 engine: 2.09e-3 with the approximate form, <= 2e-3 with this one) and whose
 //     epilogue has slack.  |a| is clamped at 15 (tanh(15) = 1 - 2e-13: exact in fp32) so that u stays finite; b needs no clamp:
 //     v = inf gives rcp(inf) = 0, v = 0 gives sigmoid = 1.
+// The constants of both forms are folded into what wg_load_weights packs (kGateTanhScale / kGateSigScale below, gate_pack_scales in wg_engine.cu), so that the gate spends no
+// instruction on them:
+//   approximate: the sigmoid-half rows of W_in / V / the composed start weights and their bias are packed x 0.5 (exact: a power
+//     of two commutes with every rounding on the path), so the accumulator already holds b / 2; the gate returns
+//     2 tanh(a) sigmoid(b) = ta + ta * tanh(b / 2) (ONE fma), and W_res / W_se are packed x 0.5.  3 FP32 + 2 MUFU per activation
+//     (5 + 2 with the constants in the gate; the gate is 12.5 % of a step's energy, profiles/r02/energy_ab.txt);
+//   accurate: the biases are packed pre-multiplied (tanh half x 2 log2 e, sigmoid half x -log2 e): one fma per pre-activation.
+constexpr float kGateTanhScale = 2.8853900817779268f;      // 2 log2(e)
+constexpr float kGateSigScale = -1.4426950408889634f;      // -log2(e)
 template <bool kAccurate>
-__device__ __forceinline__ float gate_one(float a, float b) {
+__device__ __forceinline__ float gate_one(float acc_t, float acc_s, float bt, float bs) {
   if constexpr (!kAccurate) {
-    return ptx::tanh_approx(a) * fmaf(0.5f, ptx::tanh_approx(0.5f * b), 0.5f);
+    const float ta = ptx::tanh_approx(acc_t + bt);
+    return fmaf(ta, ptx::tanh_approx(acc_s + bs), ta);
   } else {
-    const float u = ptx::ex2_approx(fminf(fmaxf(a, -15.f), 15.f) * 2.8853900817779268f);      // e^(2a) = 2^(2a log2 e)
-    const float v = ptx::ex2_approx(b * -1.4426950408889634f);                                // e^(-b)
+    const float u = ptx::ex2_approx(fminf(fmaxf(fmaf(acc_t, kGateTanhScale, bt), -15.f * kGateTanhScale), 15.f * kGateTanhScale));      // e^(2a)
+    const float v = ptx::ex2_approx(fmaf(acc_s, kGateSigScale, bs));                                                                      // e^(-b)
     return (u - 1.f) * ptx::rcp_approx(fmaf(u, v, u) + v + 1.f);                              // (u + 1)(1 + v) = uv + u + v + 1
   }
 }
@@ -132,16 +142,16 @@ __device__ __forceinline__ void gate_chunk_quarter(uint32_t rc, uint8_t* acts, i
     float bt_[16], bs_[16];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float4 t4 = kGlobalBias ? __ldg(reinterpret_cast<const float4*>(bt + g * 16) + i) : reinterpret_cast<const float4*>(bt + g * 16)[i];
-      const float4 s4 = kGlobalBias ? __ldg(reinterpret_cast<const float4*>(bs + g * 16) + i) : reinterpret_cast<const float4*>(bs + g * 16)[i];
+      const float4 t4 = kGlobalBias ? __ldg(reinterpret_cast<const float4*>(bt + g * 16) + i) : ptx::lds_f4(bt + g * 16 + 4 * i);
+      const float4 s4 = kGlobalBias ? __ldg(reinterpret_cast<const float4*>(bs + g * 16) + i) : ptx::lds_f4(bs + g * 16 + 4 * i);
       bt_[4 * i] = t4.x; bt_[4 * i + 1] = t4.y; bt_[4 * i + 2] = t4.z; bt_[4 * i + 3] = t4.w;
       bs_[4 * i] = s4.x; bs_[4 * i + 1] = s4.y; bs_[4 * i + 2] = s4.z; bs_[4 * i + 3] = s4.w;
     }
     uint32_t pk[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      pk[i] = ptx::pack_half2(gate_one<kAccurate>(__uint_as_float(vt[2 * i]) + bt_[2 * i], __uint_as_float(vs[2 * i]) + bs_[2 * i]),
-                              gate_one<kAccurate>(__uint_as_float(vt[2 * i + 1]) + bt_[2 * i + 1], __uint_as_float(vs[2 * i + 1]) + bs_[2 * i + 1]));
+      pk[i] = ptx::pack_half2(gate_one<kAccurate>(__uint_as_float(vt[2 * i]), __uint_as_float(vs[2 * i]), bt_[2 * i], bs_[2 * i]),
+                              gate_one<kAccurate>(__uint_as_float(vt[2 * i + 1]), __uint_as_float(vs[2 * i + 1]), bt_[2 * i + 1], bs_[2 * i + 1]));
     }
     // 16-byte chunk index inside the 128-byte slab row, XOR-swizzled by (row mod 8)
     const int c0 = ((cq & 1) * 4 + 2 * g) ^ (row & 7);

@@ -757,7 +757,16 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
             ptx::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(ptx::map_to_cta(&res_drained[h], 0));
-            if (in_buf && !(p.dbg_flags & 8)) {
+            if (p.dbg_flags & 8192) {
+              // diagnostics (rows scrambled): every warp store covers 8 rows x one full 128-byte line instead of 32 rows x 32 bytes
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int src = (lane >> 2) + 8 * k;
+                const unsigned long long d = __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(dst), src);
+                const int ib = __shfl_sync(0xffffffffu, static_cast<int>(in_buf), src);
+                if (ib) ptx::st_global_v8(reinterpret_cast<uint8_t*>(d) + h * 512 + (lane & 3) * 32, *reinterpret_cast<uint32_t(*)[8]>(&pk[8 * k]));
+              }
+            } else if (in_buf && !(p.dbg_flags & 8)) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) ptx::st_global_v8(dst + h * 512 + k * 32, *reinterpret_cast<uint32_t(*)[8]>(&pk[8 * k]));
             }

@@ -81,6 +81,13 @@ __device__ __forceinline__ void tc_fence_after_sync() {
 __device__ __forceinline__ void fence_proxy_async_global() {
   asm volatile("fence.proxy.async.global;" ::: "memory");
 }
+// 16 bytes from shared memory through the shared window (a generic `float4` load of a pointer the compiler cannot prove to be
+// shared compiles to LD.E: generic address translation on every access)
+__device__ __forceinline__ float4 lds_f4(const void* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
 // inter-CTA completion flags in global memory (tile-level dependencies between the layers of one launch)
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   uint32_t v;
