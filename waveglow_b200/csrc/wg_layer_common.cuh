@@ -156,8 +156,8 @@ __device__ __forceinline__ void gate_chunk_quarter(uint32_t rc, uint8_t* acts, i
     // 16-byte chunk index inside the 128-byte slab row, XOR-swizzled by (row mod 8)
     const int c0 = ((cq & 1) * 4 + 2 * g) ^ (row & 7);
     const int c1 = ((cq & 1) * 4 + 2 * g + 1) ^ (row & 7);
-    *reinterpret_cast<uint4*>(slab_row + c0 * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    *reinterpret_cast<uint4*>(slab_row + c1 * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    ptx::sts_u4(slab_row + c0 * 16, pk[0], pk[1], pk[2], pk[3]);
+    ptx::sts_u4(slab_row + c1 * 16, pk[4], pk[5], pk[6], pk[7]);
   }
 }
 

@@ -197,7 +197,7 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
   auto item_of = [&](int it) -> int {
     if (!claimed) return pair + it * n_pairs;
     ptx::mbar_wait(&item_bar[it & 7], (it >> 3) & 1);      // completed by the bytes of the leader's st.async: the word is visible
-    return static_cast<int>(s_items[it & 7]);
+    return static_cast<int>(ptx::lds_u32(const_cast<const uint32_t*>(&s_items[it & 7])));
   };
   // (utterance, frame) -> entry that holds it (blocks and packed modes)
   auto entry_of = [&](int b, int q) {
@@ -744,8 +744,8 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
               const float4* bp = reinterpret_cast<const float4*>(bias_res + h * 256 + cq * 64 + g2 * 32);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float4 b4 = C::kConstSmem ? bp[i] : __ldg(bp + i);
-                const float4 c4 = C::kConstSmem ? bp[4 + i] : __ldg(bp + 4 + i);
+                const float4 b4 = C::kConstSmem ? ptx::lds_f4(bp + i) : __ldg(bp + i);
+                const float4 c4 = C::kConstSmem ? ptx::lds_f4(bp + 4 + i) : __ldg(bp + 4 + i);
                 pk[g2 * 16 + 2 * i] = live ? ptx::pack_half2(__uint_as_float(v0[4 * i]) + b4.x, __uint_as_float(v0[4 * i + 1]) + b4.y) : 0u;
                 pk[g2 * 16 + 2 * i + 1] = live ? ptx::pack_half2(__uint_as_float(v0[4 * i + 2]) + b4.z, __uint_as_float(v0[4 * i + 3]) + b4.w) : 0u;
                 pk[g2 * 16 + 8 + 2 * i] = live ? ptx::pack_half2(__uint_as_float(v1[4 * i]) + c4.x, __uint_as_float(v1[4 * i + 1]) + c4.y) : 0u;
@@ -867,8 +867,8 @@ wn_layer_pair_cont_kernel(const __grid_constant__ XMaps xm,               // x b
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const int ks = s * 4 + kk;
-          const uint32_t b0 = C::kConstSmem ? s_wse[(2 * ks) * 32 + lane] : __ldg(g_wse + ks * 8);
-          const uint32_t b1 = C::kConstSmem ? s_wse[(2 * ks + 1) * 32 + lane] : __ldg(g_wse + ks * 8 + 4);
+          const uint32_t b0 = C::kConstSmem ? ptx::lds_u32(s_wse + (2 * ks) * 32 + lane) : __ldg(g_wse + ks * 8);
+          const uint32_t b1 = C::kConstSmem ? ptx::lds_u32(s_wse + (2 * ks + 1) * 32 + lane) : __ldg(g_wse + ks * 8 + 4);
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt) {
             uint32_t a[4];
