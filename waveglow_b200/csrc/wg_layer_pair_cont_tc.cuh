@@ -18,6 +18,7 @@
 //           kTilePacked -- whole 128-frame blocks first, then the remaining frames of 4 consecutive utterances share tiles of
 //           32 frames x 4 utterances (one 4-D box); kTileSegments -- 128 / seg_rows segments of seg_rows (64 or 32) frames, a
 //           tile may span utterances (one 3-D box per segment; short training segments).
+//   kLo     512 channels: the residual stream is carried exactly as fp16 hi + fp16 lo (see the comment above the kernel).
 //
 // Measured bounds that shaped the schedule (profiles/r01): an `if (lane == 0)` issue loop paces the pipe at 159 cycles per MMA
 // (converged warps + elect.sync: 128.7, the hardware rate); tcgen05.ld is slow while the pipe is busy and a warp-level
