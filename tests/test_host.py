@@ -145,3 +145,19 @@ def test_bench_reference_arm_prints_the_contract_line():
   assert "configs[1]" in d["config"]["workload"] and "ONE utterance" in d["config"]["reference_arm_sample"]
   assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
   assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_roofline_traffic_entries_name_a_committed_capture():
+  """bench.py copies `roofline.traffic` from profiles/traffic.json (an ncu capture cannot run inside the timed program): every
+  entry must carry a positive byte count and point at a summary file that is committed, and the headline workload must have one."""
+  import json
+  import re
+  with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+    tr = json.load(f)
+  entries = {k: v for k, v in tr.items() if not k.startswith("_")}
+  assert "c256_b16_f861_fp16" in entries
+  for key, ent in entries.items():
+    assert re.fullmatch(r"c(256|512)_b\d+_f\d+_(fp16|fp32)", key), key
+    assert ent["bytes_per_launch"] > 0
+    m = re.match(r"(profiles/\S+)", ent["source"])
+    assert m and os.path.isfile(os.path.join(ROOT, m.group(1))), ent["source"]
